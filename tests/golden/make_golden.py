@@ -1,0 +1,280 @@
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference's three Python files are imported unmodified through a stub shim for its unused
+plotting imports and called with device="cpu", dtype=float64.  Nothing
+from the reference is copied; only its OUTPUTS on small seeded meshes are stored (.npz).
+`c3d4_to_c3d10` is called through a one-identifier patch of its globals (`elems` -> the argument),
+because the reference iterates an undefined name (solver/element.py:824).
+"""
+import contextlib
+import io
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "cuda-powered-mesh-handling-and-iterative-solvers_b200"))
+from femb200 import meshgen  # noqa: E402
+
+for name in ("plotly", "plotly.graph_objects", "pyvista"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["plotly"].graph_objects = sys.modules["plotly.graph_objects"]
+sys.dont_write_bytecode = True
+sys.path.insert(0, "/root/reference/solver")
+import element as R   # noqa: E402  (the reference)
+import shell as RS    # noqa: E402
+import solver as RV   # noqa: E402
+
+KW = dict(device="cpu", dtype=torch.float64)
+E, NU = 1.0, 0.3
+MEMB = torch.tensor([1.0, 0.3, 0.1], dtype=torch.float64)
+BEND = torch.tensor([1.0, 0.3, 0.1], dtype=torch.float64)
+
+
+def npy(x):
+    if isinstance(x, (list, tuple)):
+        return [npy(v) for v in x]
+    if not torch.is_tensor(x):
+        return np.asarray(x)
+    return x.detach().cpu().numpy()
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrs.items()})
+    print(f"{name}: {os.path.getsize(path)/1024:.1f} KiB, {len(arrs)} arrays")
+
+
+def quiet(fn, *a, **k):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out = fn(*a, **k)
+    return out, buf.getvalue()
+
+
+def iters_of(text):
+    m = re.search(r"Converged after (\d+) iterations", text)
+    return int(m.group(1)) if m else -1
+
+
+def gen_tets():
+    coords, tets = meshgen.kuhn_cube(2, jitter=0.2)
+    o = dict(coords=coords, tets=tets)
+    o["vol"] = R.compute_tetrahedral_volumes(coords, tets, **KW)
+    o["B"] = R.compute_c3d4_B_matrix(coords, tets, **KW)
+    o["K"] = R.compute_c3d4_K_matrix(coords, tets, E, NU, **KW)
+    sf, s4 = R.compute_tetrahedral_surface_faces_with_fourth_node(tets, device="cpu")
+    o["surf_faces"], o["surf_fourth"] = sf, s4
+    o["shared"] = R.identify_tetrahedral_shared_faces(tets, device="cpu")
+    o["surf_normals"] = R.compute_tetrahdral_surface_normals(coords, tets, **KW)
+    o["face_normals"] = R.compute_tetrahedral_normals_and_area(coords, tets, **KW)
+    o["edges"] = R.element_to_edge(tets, device="cpu")
+    # P1 -> P2 (patched identifier), on positively oriented (for the reference's convention) tets
+    t01 = meshgen.swap01(tets)
+    R.c3d4_to_c3d10.__globals__["elems"] = t01
+    c2, e10, _, _ = R.c3d4_to_c3d10(coords, t01, dtype=torch.float64)
+    del R.c3d4_to_c3d10.__globals__["elems"]
+    e10 = e10.to(torch.int64)
+    o["coords10"], o["elems10"] = c2, e10
+    ip = torch.tensor([0.2, 0.3, 0.15], dtype=torch.float64)
+    o["ip10"] = ip
+    o["J10"] = R.compute_c3d10_Jacobian(c2, e10, ip, **KW)
+    o["g10"] = R.compute_c3d10_shape_gradients(c2, e10, ip, **KW)
+    o["B10"] = R.compute_c3d10_B_matrix(c2, e10, ip, **KW)
+    o["K10"] = R.compute_c3d10_K_matrix(c2, e10, E, NU, **KW)
+    o["K10_multi"] = R.compute_c3d10_K_matrix(c2, e10[:5], E, NU, single=False, **KW)
+    pts = torch.tensor([[0.25, 0.25, 0.25, 1 / 6], [0.1, 0.2, 0.3, 0.05]], dtype=torch.float64)
+    o["pts10_custom"] = pts
+    o["K10_custom"] = R.compute_c3d10_K_matrix(c2, e10, E, NU, integral_point=pts, **KW)
+    o["tets_from10"] = R.c3d10_to_c3d4(e10, device="cpu")
+    p, w = R.c3d10_integration_points(**KW)
+    o["pts10"], o["w10"] = p, w
+    u = torch.randn(c2.shape[0], 3, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    o["u10"] = u
+    o["f10"] = R.compute_nodal_forces(o["K10"], e10, u, **KW)
+    save("tets", **{k: npy(v) for k, v in o.items()})
+
+
+def gen_hex():
+    coords, hexes = meshgen.hex_cube(2, jitter=0.2)
+    o = dict(coords=coords, hexes=hexes)
+    o["vol"] = R.compute_hexahedral_volumes(coords, hexes, **KW)
+    ip = torch.tensor([0.3, -0.2, 0.5], dtype=torch.float64)
+    o["ip"] = ip
+    o["J"] = R.compute_c3d8_Jacobian(coords, hexes, ip, **KW)
+    o["g"] = R.compute_c3d8_shape_gradients(coords, hexes, ip, **KW)
+    o["B"] = R.compute_c3d8_B_matrix(coords, hexes, ip, **KW)
+    o["K"] = R.compute_c3d8_K_matrix(coords, hexes, E, NU, **KW)
+    o["K_multi"] = R.compute_c3d8_K_matrix(coords, hexes[:3], E, NU, single=False, **KW)
+    p, w = R.c3d8_integration_points(**KW)
+    o["pts"], o["w"] = p, w
+    sf, ex = R.compute_hexahedral_surface_faces_with_extra_node(hexes, device="cpu")
+    o["surf_faces"], o["surf_extra"] = sf, ex
+    o["shared"] = R.identify_hexahedral_shared_faces(hexes, device="cpu")
+    o["surf_normals"] = R.compute_hexahedral_surface_normals(coords, hexes, **KW)
+    o["face_normals"] = R.compute_hexahedral_normals_and_area(coords, hexes, **KW)
+    o["tets"] = R.c3d8_to_c3d4(hexes, device="cpu")
+    save("hexes", **{k: npy(v) for k, v in o.items()})
+
+
+def gen_wedge():
+    coords, w6 = meshgen.wedge_cube(2, jitter=0.2)
+    o = dict(coords=coords, wedges=w6)
+    o["vol"] = R.compute_wedge_volumes(coords, w6, **KW)
+    ip = torch.tensor([0.2, 0.3, -0.4], dtype=torch.float64)
+    o["ip"] = ip
+    o["J"] = R.compute_c3d6_Jacobian(coords, w6, ip, **KW)
+    o["g"] = R.compute_c3d6_shape_gradients(coords, w6, ip, **KW)
+    o["B"] = R.compute_c3d6_B_matrix(coords, w6, ip, **KW)
+    o["K_single"] = R.compute_c3d6_K_matrix(coords, w6, E, NU, single=True, **KW)
+    o["K_full"] = R.compute_c3d6_K_matrix(coords, w6, E, NU, single=False, **KW)
+    p, w = R.c3d6_integration_points(**KW)
+    o["pts"], o["w"] = p, w
+    (q, t), (qe, te) = R.compute_wedge_surface_faces_with_extra_node(w6, device="cpu")
+    o["surf_quads"], o["surf_tris"], o["quad_extra"], o["tri_extra"] = q, t, qe, te
+    nq, nt = R.compute_wedge_surface_normals(coords, w6, **KW)
+    o["nq"], o["nt"] = nq, nt
+    o["tets"] = R.c3d6_to_c3d4(w6, device="cpu")
+    save("wedges", **{k: npy(v) for k, v in o.items()})
+
+
+def gen_shells():
+    c3, s3 = meshgen.tri_sheet(3, warp=0.15)
+    c4, s4 = meshgen.quad_sheet(3, warp=0.15)
+    o = dict(c3=c3, s3=s3, c4=c4, s4=s4, membrane=MEMB, bending=BEND)
+    o["D"] = RS.compute_kirchoff_D_matrix(MEMB, BEND, **KW)
+    o["unit3"] = RS.compute_s3_local_unitvector(c3, s3, device="cpu")
+    o["J3"] = RS.compute_s3_jacobian(c3, s3, **KW)
+    o["g3"] = RS.compute_s3_shape_gradient(c3, s3, **KW)
+    o["B3"] = RS.compute_s3_B_matrix(c3, s3, **KW)
+    o["K3"] = RS.compute_s3_K_matrix(c3, s3, MEMB, BEND, **KW)
+    o["shared3"] = RS.identify_s3_shared_edges(s3, device="cpu")
+    e, t = RS.compute_triangle_surface_faces_with_third_node(s3, device="cpu")
+    o["bedges3"], o["bthird3"] = e, t
+    o["unit4"] = RS.compute_s4_local_unitvector(c4, s4, device="cpu")
+    xi, eta = 0.3, -0.6
+    o["xieta"] = np.array([xi, eta])
+    o["J4"] = RS.compute_s4_jacobian(c4, s4, xi, eta, **KW)
+    o["g4"] = RS.compute_s4_shape_gradient(c4, s4, xi, eta, **KW)
+    o["B4"] = RS.compute_s4_B_matrix_single(c4, s4, xi, eta, **KW)
+    o["K4"] = RS.compute_s4_K_matrix(c4, s4, MEMB, BEND, **KW)
+    o["K4_multi"] = RS.compute_s4_K_matrix(c4, s4, MEMB, BEND, single=False, **KW)
+    p, w = RS.s4_integration_points(device="cpu")
+    o["pts4"], o["w4"] = p.double(), w.double()
+    o["shared4"] = RS.identify_s4_shared_edges(s4, device="cpu")
+    e, t = RS.compute_square_surface_faces_with_fourth_node(s4, device="cpu")
+    o["bedges4"], o["bfourth4"] = e, t
+    g = torch.Generator().manual_seed(5)
+    u3 = torch.randn(c3.shape[0], 6, dtype=torch.float64, generator=g)
+    u4 = torch.randn(c4.shape[0], 6, dtype=torch.float64, generator=g)
+    o["u3"], o["u4"] = u3, u4
+    o["f3"] = RS.compute_shell_nodal_forces(o["K3"], s3, u3, o["unit3"], **KW)
+    o["f4"] = RS.compute_shell_nodal_forces(o["K4"], s4, u4, o["unit4"], **KW)
+    save("shells", **{k: npy(v) for k, v in o.items()})
+
+
+def gen_units():
+    """The known-answer table of SURVEY.md section 4 (unit elements, E=1, nu=0.3)."""
+    o = {}
+    c = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]], dtype=torch.float64)
+    t = torch.tensor([[0, 1, 2, 3]])
+    o["c3d4"] = R.compute_c3d4_K_matrix(c, t, E, NU, **KW)
+    R.c3d4_to_c3d10.__globals__["elems"] = t
+    c2, e10, _, _ = R.c3d4_to_c3d10(c, t, dtype=torch.float64)
+    del R.c3d4_to_c3d10.__globals__["elems"]
+    o["c3d10"] = R.compute_c3d10_K_matrix(c2, e10.long(), E, NU, **KW)
+    ch, h = meshgen.hex_cube(1)
+    o["c3d8"] = R.compute_c3d8_K_matrix(ch, h, E, NU, **KW)
+    w = h[:, [0, 1, 2, 4, 5, 6]]
+    o["c3d6_single"] = R.compute_c3d6_K_matrix(ch, w, E, NU, single=True, **KW)
+    o["c3d6_full"] = R.compute_c3d6_K_matrix(ch, w, E, NU, single=False, **KW)
+    cs = torch.tensor([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0.0]], dtype=torch.float64)
+    o["s3"] = RS.compute_s3_K_matrix(cs, torch.tensor([[0, 1, 3]]), MEMB, BEND, **KW)
+    o["s4"] = RS.compute_s4_K_matrix(cs, torch.tensor([[0, 1, 2, 3]]), MEMB, BEND, **KW)
+    o["D"] = R.compute_elasticity_matrix(E, NU, **KW)
+    save("units", **{k: npy(v) for k, v in o.items()})
+
+
+def gen_solve():
+    n = 4
+    coords, tets = meshgen.kuhn_cube(n)
+    N = coords.shape[0]
+    K = R.compute_c3d4_K_matrix(coords, tets, E, NU, **KW)
+    fixed = torch.nonzero(coords[:, 2] == 0).reshape(-1)
+    top = torch.nonzero(coords[:, 2] == 1).reshape(-1)
+    F = torch.zeros(N, 3, dtype=torch.float64)
+    F[top, 2] = 1.0 / top.numel()
+    o = dict(coords=coords, tets=tets, fixed=fixed, F=F)
+    u, txt = quiet(RV.stable_conjugate_gradient_solver, K, tets, F, fixed, tol=1e-8, max_iter=1000, **KW)
+    o["u_cg"], o["it_cg"] = u, iters_of(txt)
+    u2, txt = quiet(RV.final_solver, K, tets, F, fixed, tol=1e-8, max_iter=1000, **KW)
+    o["u_final"], o["it_final"] = u2.detach(), iters_of(txt)
+    # reference (buggy) diagonal builder, stored for the oracle's reproduction of it
+    o["Minv_ref"] = RV.compute_diagonal_preconditioner(K, tets, N, **KW)
+    # PCG loop driven by the correct Jacobi diagonal with fixed rows zeroed
+    diag = torch.zeros(N * 3, dtype=torch.float64)
+    dofs = (tets.unsqueeze(-1) * 3 + torch.arange(3)).reshape(-1)
+    diag.index_add_(0, dofs, K.diagonal(dim1=1, dim2=2).reshape(-1))
+    Minv = (1.0 / diag).reshape(N, 3)
+    Minv[fixed] = 0.0
+    o["Minv"] = Minv
+    u3, txt = quiet(RV.preconditioned_conjugate_gradient_solver, K, tets, F, Minv, tol=1e-8, max_iter=1000, **KW)
+    o["u_pcg"], o["it_pcg"] = u3, iters_of(txt)
+    # coalesced CSR of the notebook's COO (subdivision.ipynb cell 6), via torch semantics
+    M = K.shape[0]
+    dof = (tets.unsqueeze(-1).repeat(1, 1, 3) * 3 + torch.arange(3).view(1, 1, 3)).view(M, -1)
+    row = dof.unsqueeze(2).repeat(1, 1, 12).view(-1)
+    col = dof.unsqueeze(1).repeat(1, 12, 1).view(-1)
+    csr = torch.sparse_coo_tensor(torch.stack([row, col]), K.view(-1), size=(3 * N, 3 * N)).coalesce().to_sparse_csr()
+    o["crow"], o["col"], o["val"] = csr.crow_indices(), csr.col_indices(), csr.values()
+    save("solve_c3d4", **{k: npy(v) if torch.is_tensor(v) else v for k, v in o.items()})
+
+    # mixed static_structure_solver: hex | wedge | tet slabs plus a quad+tri skin on z=1
+    n = 3
+    coords, parts = meshgen.mixed_box(n)
+    N = coords.shape[0]
+    m = n + 1
+    top_ids = torch.tensor([[(i * m + j) * m + n for j in range(m)] for i in range(m)])
+    quads = torch.stack([top_ids[:-1, :-1], top_ids[1:, :-1], top_ids[1:, 1:], top_ids[:-1, 1:]], -1).reshape(-1, 4)
+    s4 = quads[: quads.shape[0] // 2]
+    tq = quads[quads.shape[0] // 2:]
+    s3 = torch.cat([tq[:, [0, 1, 2]], tq[:, [0, 2, 3]]], 0)
+    fixed = torch.nonzero(coords[:, 2] == 0).reshape(-1)
+    force = torch.zeros(N, 6, dtype=torch.float64)
+    force[top_ids.reshape(-1), 2] = -1.0 / top_ids.numel()
+    material = {"E": E, "nu": NU, "membrane": MEMB, "bending": BEND}
+    u, txt = quiet(RV.static_structure_solver, coords, force, fixed, c3d4=parts["c3d4"], c3d6=parts["c3d6"],
+                   c3d8=parts["c3d8"], s3=s3, s4=s4, material=material, tol=1e-8, max_iter=2000, **KW)
+    save("solve_mixed", coords=npy(coords), c3d4=npy(parts["c3d4"]), c3d6=npy(parts["c3d6"]), c3d8=npy(parts["c3d8"]),
+         s3=npy(s3), s4=npy(s4), fixed=npy(fixed), force=npy(force), u=npy(u), it=iters_of(txt))
+
+    # shell CG on a flat triangle sheet (local frame == global frame, so the load stays in the
+    # range of the w/theta_z-free Kirchhoff operator and the reference loop converges)
+    c3, s3 = meshgen.tri_sheet(4, warp=0.0)
+    K3 = RS.compute_s3_K_matrix(c3, s3, MEMB, BEND, **KW)
+    unit = RS.compute_s3_local_unitvector(c3, s3, device="cpu")
+    fixed = torch.nonzero(c3[:, 0] == 0).reshape(-1)
+    Fs = torch.zeros(c3.shape[0], 6, dtype=torch.float64)
+    Fs[c3[:, 0] == 1, 0] = 0.2
+    Fs[c3[:, 0] == 1, 4] = 0.01
+    us, txt = quiet(RV.stable_conjugate_gradient_shell_solver, K3, s3, Fs, fixed, unit=unit, tol=1e-9, max_iter=3000, **KW)
+    save("solve_shell", c3=npy(c3), s3=npy(s3), fixed=npy(fixed), F=npy(Fs), u=npy(us), it=iters_of(txt))
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    gen_units()
+    gen_tets()
+    gen_hex()
+    gen_wedge()
+    gen_shells()
+    gen_solve()
