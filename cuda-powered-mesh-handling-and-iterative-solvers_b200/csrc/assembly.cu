@@ -1,0 +1,506 @@
+// Global assembly: element matrices -> CSR, deterministic, no atomics on values.
+//
+// Replaces the un-coalesced torch.sparse_coo_tensor of subdivision.ipynb cell 6 (reference) with
+//   plan   : node->element incidence lists (stable radix sort of (node, flat slot)) and the node-level sparsity pattern
+//            (segmented sort + unique of each node's candidate columns)
+//   values : one warp per node row; contributions are added in incidence order (ascending element id), i.e. a
+//            sort-based segmented reduction into the precomputed pattern.  Either from materialised Ke
+//            (any element type / dofs per node) or fused from coordinates for P1 tets.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+struct femb_csr_plan {
+  long long M = 0, N = 0, nnzn = 0;
+  int nen = 0, max_row = 0, max_inc = 0;
+  int* conn32 = nullptr;    // [M,nen]
+  int* inc_ptr = nullptr;   // [N+1]
+  int* inc = nullptr;       // [M*nen] flat slot e*nen+a, grouped by node, ascending
+  int* node_ptr = nullptr;  // [N+1]
+  int* node_col = nullptr;  // [nnzn] sorted within a row
+};
+
+namespace femb {
+
+template <typename I>
+__global__ void conn_to_i32(const I* __restrict__ conn, long long L, int* __restrict__ out, int* __restrict__ iota) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L; t += (long long)gridDim.x * blockDim.x) {
+    out[t] = (int)ldidx(conn + t);
+    iota[t] = (int)t;
+  }
+}
+
+// inc_ptr from the sorted node keys (handles nodes without elements)
+__global__ void ptr_from_sorted(const int* __restrict__ keys, long long L, long long N, int* __restrict__ ptr) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < L; k += (long long)gridDim.x * blockDim.x) {
+    const int prev = k == 0 ? -1 : keys[k - 1], cur = keys[k];
+    for (int n = prev + 1; n <= cur; ++n) ptr[n] = (int)k;
+    if (k == L - 1)
+      for (long long n = cur + 1; n <= N; ++n) ptr[n] = (int)L;
+  }
+}
+
+__global__ void emit_candidates(const int* __restrict__ conn32, const int* __restrict__ inc, long long L, int nen, int* __restrict__ cand) {
+  const long long total = L * nen;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long k = t / nen;
+    const int b = (int)(t - k * nen);
+    const int e = inc[k] / nen;
+    cand[t] = conn32[(long long)e * nen + b];
+  }
+}
+
+__global__ void scale_offsets(const int* __restrict__ ptr, long long n, int nen, int* __restrict__ off) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) off[t] = ptr[t] * nen;
+}
+
+// one warp per node: count (fill==nullptr) or write the distinct values of its sorted candidate segment
+__global__ void unique_rows(const int* __restrict__ cand, const int* __restrict__ off, long long N, int* __restrict__ cnt,
+                            const int* __restrict__ node_ptr, int* __restrict__ node_col) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp; i < N; i += nwarps) {
+    const int s = off[i], t = off[i + 1];
+    int base = node_col ? node_ptr[i] : 0, total = 0;
+    for (int k0 = s; k0 < t; k0 += 32) {
+      const int k = k0 + lane;
+      bool head = false;
+      int v = 0;
+      if (k < t) {
+        v = cand[k];
+        head = (k == s) || (cand[k - 1] != v);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, head);
+      if (node_col && head) node_col[base + total + __popc(m & ((1u << lane) - 1))] = v;
+      total += __popc(m);
+    }
+    if (!node_col && lane == 0) cnt[i] = total;
+  }
+}
+
+__global__ void inc_counts(const int* __restrict__ inc_ptr, long long N, int* __restrict__ out) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) out[t] = inc_ptr[t + 1] - inc_ptr[t];
+}
+
+__global__ void pattern_kernel(const int* __restrict__ node_ptr, const int* __restrict__ node_col, long long N, int d, int* __restrict__ crow,
+                               int* __restrict__ col) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp; i < N; i += nwarps) {
+    const int s = node_ptr[i], len = node_ptr[i + 1] - s;
+    const long long base = (long long)d * d * s;
+    if (lane < d) crow[i * d + lane] = (int)(base + (long long)lane * len * d);
+    if (i == N - 1 && lane == 0) crow[N * d] = (int)((long long)d * d * node_ptr[N]);
+    const int per_row = len * d;
+    for (int t = lane; t < d * per_row; t += 32) {
+      const int within = t % per_row;
+      col[base + t] = node_col[s + within / d] * d + within % d;
+    }
+  }
+}
+
+__device__ __forceinline__ int lower_bound_i32(const int* a, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// ---- values from materialised Ke -----------------------------------------------------------------
+// warp per node; shared accumulator laid out exactly like the node's d rows of the CSR value array
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) assemble_gather(const int* __restrict__ conn32, const int* __restrict__ inc_ptr,
+                                                              const int* __restrict__ inc, const int* __restrict__ node_ptr,
+                                                              const int* __restrict__ node_col, long long N, int nen, int d, int max_row,
+                                                              const double* __restrict__ Ke, double* __restrict__ vals) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* acc = sm + (size_t)w * max_row * d * d;
+  const int nd = nen * d;
+  const long long warp = (long long)blockIdx.x * WARPS + w, nwarps = (long long)gridDim.x * WARPS;
+  for (long long i = warp; i < N; i += nwarps) {
+    const int s = node_ptr[i], len = node_ptr[i + 1] - s;
+    const int nacc = len * d * d;
+    for (int t = lane; t < nacc; t += 32) acc[t] = 0.0;
+    __syncwarp();
+    const int* cols = node_col + s;
+    for (int k = inc_ptr[i]; k < inc_ptr[i + 1]; ++k) {
+      const int slot = inc[k], e = slot / nen, a = slot - e * nen;
+      int pos = 0;
+      if (lane < nen) pos = lower_bound_i32(cols, len, conn32[(long long)e * nen + lane]);
+      const double* src = Ke + ((long long)e * nd + (long long)a * d) * nd;  // d consecutive rows of Ke
+      for (int t0 = 0; t0 < d * nd; t0 += 32) {  // warp-uniform trip count: every lane takes part in the shuffle
+        const int t = t0 + lane;
+        const bool valid = t < d * nd;
+        const int tt = valid ? t : 0;
+        const int alpha = tt / nd, c = tt - alpha * nd, b = c / d, beta = c - b * d;
+        const int p = __shfl_sync(0xffffffffu, pos, b);
+        if (valid) acc[(alpha * len + p) * d + beta] += __ldg(src + t);
+      }
+      __syncwarp();
+    }
+    double* dst = vals + (long long)d * d * s;
+    for (int t = lane; t < nacc; t += 32) dst[t] = acc[t];
+    __syncwarp();
+  }
+}
+
+// ---- fused P1 tet assembly -------------------------------------------------------------------------
+// warp per node, one lane per incident element (batches of 32).  Each lane rebuilds the element's cofactor vectors from
+// the coordinates and produces row `a` of Ke; off-diagonal columns are merged in lane (= element) order through
+// match/rank rounds, the diagonal through a fixed shuffle tree.  KIND 0: Poisson (d=1), 1: elasticity (d=3).
+template <int KIND, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) assemble_c3d4_fused(const int* __restrict__ conn32, const int* __restrict__ inc_ptr,
+                                                                  const int* __restrict__ inc, const int* __restrict__ node_ptr,
+                                                                  const int* __restrict__ node_col, long long N, int max_row,
+                                                                  const double* __restrict__ coords, double lam, double mu,
+                                                                  double* __restrict__ vals, int* __restrict__ flag) {
+  constexpr int D = KIND == 0 ? 1 : 3, DD = D * D;
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* acc = sm + (size_t)w * (max_row * DD + (max_row + 1) / 2);
+  int* cols = reinterpret_cast<int*>(acc + (size_t)max_row * DD);
+  const long long warp = (long long)blockIdx.x * WARPS + w, nwarps = (long long)gridDim.x * WARPS;
+  for (long long i = warp; i < N; i += nwarps) {
+    const int s = node_ptr[i], len = node_ptr[i + 1] - s;
+    const int nacc = len * DD;
+    for (int t = lane; t < nacc; t += 32) acc[t] = 0.0;
+    for (int t = lane; t < len; t += 32) cols[t] = node_col[s + t];
+    __syncwarp();
+    const int pdiag = lower_bound_i32(cols, len, (int)i);
+    const int k0 = inc_ptr[i], k1 = inc_ptr[i + 1];
+    for (int kb = k0; kb < k1; kb += 32) {
+      const int k = kb + lane;
+      const bool on = k < k1;
+      int nd4[4] = {0, 0, 0, 0}, a = 0;
+      double c[4][3], scale = 0.0;
+      if (on) {
+        const int slot = inc[k], e = slot >> 2;
+        a = slot & 3;
+        const int4 q = __ldg(reinterpret_cast<const int4*>(conn32) + e);
+        nd4[0] = q.x, nd4[1] = q.y, nd4[2] = q.z, nd4[3] = q.w;
+        double x[4][3];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+          for (int t = 0; t < 3; ++t) x[v][t] = __ldg(coords + 3ll * nd4[v] + t);
+        double e1[3], e2[3], e3[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          e1[t] = x[1][t] - x[0][t];
+          e2[t] = x[2][t] - x[0][t];
+          e3[t] = x[3][t] - x[0][t];
+        }
+        c[1][0] = e2[1] * e3[2] - e2[2] * e3[1], c[1][1] = e2[2] * e3[0] - e2[0] * e3[2], c[1][2] = e2[0] * e3[1] - e2[1] * e3[0];
+        c[2][0] = e3[1] * e1[2] - e3[2] * e1[1], c[2][1] = e3[2] * e1[0] - e3[0] * e1[2], c[2][2] = e3[0] * e1[1] - e3[1] * e1[0];
+        c[3][0] = e1[1] * e2[2] - e1[2] * e2[1], c[3][1] = e1[2] * e2[0] - e1[0] * e2[2], c[3][2] = e1[0] * e2[1] - e1[1] * e2[0];
+        const double det = e1[0] * c[1][0] + e1[1] * c[1][1] + e1[2] * c[1][2];
+        if (fabs(det) < 1e-12 && flag) *flag = 1;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) c[0][t] = -(c[1][t] + c[2][t] + c[3][t]);
+        scale = 1.0 / (6.0 * fabs(det));  // V g_a.g_b = c_a.c_b / (6 |det|)
+      }
+      // gradient-cofactor of this lane's own row node
+      double ca[3] = {0, 0, 0};
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (v == a) ca[0] = c[v][0], ca[1] = c[v][1], ca[2] = c[v][2];
+      // diagonal block (row node with itself): fixed shuffle tree over the batch
+      {
+        const double dot = ca[0] * ca[0] + ca[1] * ca[1] + ca[2] * ca[2];
+#pragma unroll
+        for (int r = 0; r < DD; ++r) {
+          double v;
+          if (KIND == 0) {
+            v = dot;
+          } else {
+            v = (lam + mu) * ca[r / D] * ca[r % D];
+            if (r / D == r % D) v += mu * dot;
+          }
+          v = warp_sum(on ? v * scale : 0.0);
+          if (lane == 0) acc[((r / D) * len + pdiag) * D + (r % D)] += v;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        double blk[DD];
+        const bool off = on && (b != a);
+        if (off) {
+          const double dot = ca[0] * c[b][0] + ca[1] * c[b][1] + ca[2] * c[b][2];
+          if (KIND == 0) {
+            blk[0] = dot * scale;
+          } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {
+                double v = lam * ca[r] * c[b][t] + mu * ca[t] * c[b][r];
+                if (r == t) v += mu * dot;
+                blk[r * D + t] = v * scale;
+              }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < DD; ++r) blk[r] = 0.0;
+        }
+        // off-diagonal columns: equal columns are merged in lane order
+        const int p = off ? lower_bound_i32(cols, len, nd4[b]) : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, p);
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        const int rounds = __reduce_max_sync(0xffffffffu, off ? __popc(peers) : 0);
+        for (int t = 0; t < rounds; ++t) {
+          if (off && rank == t) {
+#pragma unroll
+            for (int r = 0; r < DD; ++r) acc[((r / D) * len + p) * D + (r % D)] += blk[r];
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+    double* dst = vals + (long long)DD * s;
+    for (int t = lane; t < nacc; t += 32) dst[t] = acc[t];
+    __syncwarp();
+  }
+}
+
+// ---- element-by-element operator (compute_nodal_forces / compute_shell_nodal_forces) -------------------
+template <typename T>
+__global__ void ebe_apply_kernel(const int* __restrict__ conn32, const int* __restrict__ inc_ptr, const int* __restrict__ inc, long long N,
+                                 int nen, int d, const T* __restrict__ Ke, const T* __restrict__ u, T* __restrict__ y) {
+  const int nd = nen * d;
+  const long long rows = N * d;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const long long i = r / d;
+    const int alpha = (int)(r - i * d);
+    T sum = 0;
+    for (int k = inc_ptr[i]; k < inc_ptr[i + 1]; ++k) {
+      const int slot = inc[k], e = slot / nen, a = slot - e * nen;
+      const T* row = Ke + ((long long)e * nd + a * d + alpha) * nd;
+      const int* cn = conn32 + (long long)e * nen;
+      T part = 0;
+      for (int b = 0; b < nen; ++b) {
+        const T* ub = u + (long long)cn[b] * d;
+        for (int beta = 0; beta < d; ++beta) part += __ldg(row + b * d + beta) * __ldg(ub + beta);
+      }
+      sum += part;
+    }
+    y[r] = sum;
+  }
+}
+
+// shells: rotate each element's nodal vectors into its frame, apply Ke, rotate the row-node's force back (shell.py:58-102)
+template <typename T>
+__global__ void ebe_shell_kernel(const int* __restrict__ conn32, const int* __restrict__ inc_ptr, const int* __restrict__ inc, long long N,
+                                 int nen, const T* __restrict__ Ke, const T* __restrict__ u, const T* __restrict__ unit, T* __restrict__ y) {
+  const int nd = nen * 6;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    T out[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = inc_ptr[i]; k < inc_ptr[i + 1]; ++k) {
+      const int slot = inc[k], e = slot / nen, a = slot - e * nen;
+      const T* R = unit + (long long)e * 9;
+      T Rm[9];
+      for (int t = 0; t < 9; ++t) Rm[t] = __ldg(R + t);
+      T fl[6] = {0, 0, 0, 0, 0, 0};
+      for (int b = 0; b < nen; ++b) {
+        const T* ub = u + (long long)conn32[(long long)e * nen + b] * 6;
+        T loc[6];
+        for (int h = 0; h < 2; ++h)
+          for (int dd = 0; dd < 3; ++dd)
+            loc[3 * h + dd] = __ldg(ub + 3 * h) * Rm[dd * 3] + __ldg(ub + 3 * h + 1) * Rm[dd * 3 + 1] + __ldg(ub + 3 * h + 2) * Rm[dd * 3 + 2];
+        for (int r = 0; r < 6; ++r) {
+          const T* row = Ke + ((long long)e * nd + a * 6 + r) * nd + b * 6;
+          T s = 0;
+          for (int c = 0; c < 6; ++c) s += __ldg(row + c) * loc[c];
+          fl[r] += s;
+        }
+      }
+      for (int h = 0; h < 2; ++h)
+        for (int g = 0; g < 3; ++g) out[3 * h + g] += Rm[g] * fl[3 * h] + Rm[3 + g] * fl[3 * h + 1] + Rm[6 + g] * fl[3 * h + 2];
+    }
+    for (int r = 0; r < 6; ++r) y[i * 6 + r] = out[r];
+  }
+}
+
+static void plan_free(femb_csr_plan* p) {
+  if (!p) return;
+  cudaFree(p->conn32);
+  cudaFree(p->inc_ptr);
+  cudaFree(p->inc);
+  cudaFree(p->node_ptr);
+  cudaFree(p->node_col);
+  delete p;
+}
+
+template <typename I>
+static int plan_build(const I* conn, femb_csr_plan* p, cudaStream_t s) {
+  const long long M = p->M, N = p->N, L = M * p->nen;
+  const int nen = p->nen;
+  FEMB_CUDA(cudaMalloc(&p->conn32, sizeof(int) * std::max<long long>(L, 1)));
+  FEMB_CUDA(cudaMalloc(&p->inc_ptr, sizeof(int) * (N + 1)));
+  FEMB_CUDA(cudaMalloc(&p->inc, sizeof(int) * std::max<long long>(L, 1)));
+  FEMB_CUDA(cudaMalloc(&p->node_ptr, sizeof(int) * (N + 1)));
+  Scratch scr(s);
+  int *iota, *keys_sorted, *cand, *cand_sorted, *off, *cnt;
+  FEMB_CUDA(scr.alloc(&iota, L));
+  FEMB_CUDA(scr.alloc(&keys_sorted, L));
+  conn_to_i32<I><<<grid_for(L, 256), 256, 0, s>>>(conn, L, p->conn32, iota);
+  FEMB_LAUNCH_CHECK();
+  int bits = 1;
+  while ((1ll << bits) < N) ++bits;
+  size_t tb = 0;
+  FEMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, p->conn32, keys_sorted, iota, p->inc, (int)L, 0, bits, s));
+  void* tmp;
+  FEMB_CUDA(scr.alloc((char**)&tmp, tb));
+  FEMB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, p->conn32, keys_sorted, iota, p->inc, (int)L, 0, bits, s));
+  if (L > 0) {
+    ptr_from_sorted<<<grid_for(L, 256), 256, 0, s>>>(keys_sorted, L, N, p->inc_ptr);
+  } else {
+    FEMB_CUDA(cudaMemsetAsync(p->inc_ptr, 0, sizeof(int) * (N + 1), s));
+  }
+  FEMB_LAUNCH_CHECK();
+  // candidate columns of every node, grouped by node; sorted per segment, then made unique
+  const long long LC = L * nen;
+  FEMB_CUDA(scr.alloc(&cand, LC));
+  FEMB_CUDA(scr.alloc(&cand_sorted, LC));
+  FEMB_CUDA(scr.alloc(&off, N + 1));
+  FEMB_CUDA(scr.alloc(&cnt, N + 1));
+  if (LC > 0) emit_candidates<<<grid_for(LC, 256), 256, 0, s>>>(p->conn32, p->inc, L, nen, cand);
+  scale_offsets<<<grid_for(N + 1, 256), 256, 0, s>>>(p->inc_ptr, N + 1, nen, off);
+  FEMB_LAUNCH_CHECK();
+  size_t tb2 = 0;
+  FEMB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tb2, cand, cand_sorted, (int)LC, (int)N, off, off + 1, s));
+  void* tmp2;
+  FEMB_CUDA(scr.alloc((char**)&tmp2, tb2));
+  FEMB_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp2, tb2, cand, cand_sorted, (int)LC, (int)N, off, off + 1, s));
+  FEMB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (N + 1), s));
+  unique_rows<<<grid_for(N * 32, 256), 256, 0, s>>>(cand_sorted, off, N, cnt, nullptr, nullptr);
+  FEMB_LAUNCH_CHECK();
+  size_t tb3 = 0;
+  FEMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb3, cnt, p->node_ptr, (int)(N + 1), s));
+  void* tmp3;
+  FEMB_CUDA(scr.alloc((char**)&tmp3, tb3));
+  FEMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp3, tb3, cnt, p->node_ptr, (int)(N + 1), s));
+  // maxima for shared-memory sizing
+  int *dmax, *inccnt;
+  FEMB_CUDA(scr.alloc(&dmax, 2));
+  FEMB_CUDA(scr.alloc(&inccnt, N));
+  inc_counts<<<grid_for(N, 256), 256, 0, s>>>(p->inc_ptr, N, inccnt);
+  size_t tb4 = 0, tb5 = 0;
+  FEMB_CUDA(cub::DeviceReduce::Max(nullptr, tb4, cnt, dmax, (int)N, s));
+  FEMB_CUDA(cub::DeviceReduce::Max(nullptr, tb5, inccnt, dmax + 1, (int)N, s));
+  void* tmp4;
+  FEMB_CUDA(scr.alloc((char**)&tmp4, std::max(tb4, tb5)));
+  FEMB_CUDA(cub::DeviceReduce::Max(tmp4, tb4, cnt, dmax, (int)N, s));
+  FEMB_CUDA(cub::DeviceReduce::Max(tmp4, tb5, inccnt, dmax + 1, (int)N, s));
+  int hmax[2] = {0, 0}, hn = 0;
+  FEMB_CUDA(cudaMemcpyAsync(hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaMemcpyAsync(&hn, p->node_ptr + N, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaStreamSynchronize(s));
+  p->max_row = hmax[0];
+  p->max_inc = hmax[1];
+  p->nnzn = hn;
+  FEMB_CUDA(cudaMalloc(&p->node_col, sizeof(int) * std::max<long long>(p->nnzn, 1)));
+  unique_rows<<<grid_for(N * 32, 256), 256, 0, s>>>(cand_sorted, off, N, nullptr, p->node_ptr, p->node_col);
+  FEMB_LAUNCH_CHECK();
+  FEMB_CUDA(cudaStreamSynchronize(s));
+  return FEMB_OK;
+}
+
+}  // namespace femb
+
+using namespace femb;
+
+extern "C" int femb_csr_plan_create(const void* conn, int ib, int64_t M, int nen, int64_t n_nodes, femb_stream stream, femb_csr_plan** plan,
+                                    int64_t* nnz_nodes) {
+  FEMB_CHECK_ARG(ib == 4 || ib == 8, "ib in {4,8}");
+  FEMB_CHECK_ARG(plan != nullptr && M >= 0 && nen >= 1 && nen <= 32 && n_nodes >= 1, "plan/M/nen(1..32)/n_nodes");
+  FEMB_CHECK_ARG(n_nodes < (1ll << 31) - 1 && (long long)M * nen * nen < (1ll << 31) - 1, "index range: M*nen^2 and n_nodes must fit int32");
+  auto* p = new femb_csr_plan();
+  p->M = M, p->N = n_nodes, p->nen = nen;
+  cudaStream_t s = as_stream(stream);
+  const int rc = ib == 8 ? plan_build<long long>((const long long*)conn, p, s) : plan_build<int>((const int*)conn, p, s);
+  if (rc != FEMB_OK) {
+    plan_free(p);
+    return rc;
+  }
+  *plan = p;
+  if (nnz_nodes) *nnz_nodes = p->nnzn;
+  return FEMB_OK;
+}
+
+extern "C" int femb_csr_plan_destroy(femb_csr_plan* plan) {
+  plan_free(plan);
+  return FEMB_OK;
+}
+
+extern "C" int femb_csr_plan_pattern(femb_csr_plan* p, int ndof, int32_t* crow, int32_t* col, femb_stream stream) {
+  FEMB_CHECK_ARG(p && ndof >= 1 && ndof <= 6, "plan, 1 <= ndof <= 6");
+  FEMB_CHECK_ARG(p->nnzn * ndof * ndof < (1ll << 31) - 1, "nnz must fit int32");
+  pattern_kernel<<<grid_for(p->N * 32, 256), 256, 0, as_stream(stream)>>>(p->node_ptr, p->node_col, p->N, ndof, crow, col);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+extern "C" int femb_csr_assemble(femb_csr_plan* p, int ndof, const double* Ke, double* vals, femb_stream stream) {
+  FEMB_CHECK_ARG(p && ndof >= 1 && ndof <= 6, "plan, 1 <= ndof <= 6");
+  const size_t per_warp = sizeof(double) * (size_t)p->max_row * ndof * ndof;
+  FEMB_CHECK_ARG(per_warp <= 200 * 1024, "row too long for the shared-memory accumulator");
+  cudaStream_t s = as_stream(stream);
+#define LAUNCH_GATHER(W)                                                                                             \
+  {                                                                                                                  \
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_gather<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * W))); \
+    assemble_gather<W><<<grid_for(p->N, W, 16), W * 32, per_warp * W, s>>>(p->conn32, p->inc_ptr, p->inc, p->node_ptr, p->node_col, p->N, \
+                                                                          p->nen, ndof, p->max_row, Ke, vals);      \
+  }
+  if (per_warp * 8 <= 96 * 1024) LAUNCH_GATHER(8)
+  else if (per_warp * 4 <= 200 * 1024) LAUNCH_GATHER(4)
+  else LAUNCH_GATHER(1)
+#undef LAUNCH_GATHER
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+extern "C" int femb_csr_assemble_c3d4(femb_csr_plan* p, int kind, const double* coords, double E, double nu, double* vals, int32_t* flag,
+                                      femb_stream stream) {
+  FEMB_CHECK_ARG(p && p->nen == 4 && (kind == 0 || kind == 1), "plan must be a 4-node plan; kind in {0,1}");
+  const int dd = kind == 0 ? 1 : 9;
+  constexpr int W = 8;
+  const size_t per_warp = sizeof(double) * ((size_t)p->max_row * dd + (p->max_row + 1) / 2);
+  FEMB_CHECK_ARG(per_warp * W <= 200 * 1024, "row too long for the shared-memory accumulator");
+  const double c = E / ((1 + nu) * (1 - 2 * nu));
+  cudaStream_t s = as_stream(stream);
+  const int grid = grid_for(p->N, W, 16);
+  if (kind == 0) {
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_c3d4_fused<0, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * W)));
+    assemble_c3d4_fused<0, W><<<grid, W * 32, per_warp * W, s>>>(p->conn32, p->inc_ptr, p->inc, p->node_ptr, p->node_col, p->N, p->max_row, coords,
+                                                                 0.0, 0.0, vals, flag);
+  } else {
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_c3d4_fused<1, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * W)));
+    assemble_c3d4_fused<1, W><<<grid, W * 32, per_warp * W, s>>>(p->conn32, p->inc_ptr, p->inc, p->node_ptr, p->node_col, p->N, p->max_row, coords,
+                                                                 c * nu, c * (1 - 2 * nu) / 2, vals, flag);
+  }
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+extern "C" int femb_ebe_apply(femb_csr_plan* p, int ndof, const void* Ke, const void* u, const void* unit, int fp, void* y, femb_stream stream) {
+  FEMB_CHECK_ARG(p && (fp == 4 || fp == 8), "plan, fp in {4,8}");
+  cudaStream_t s = as_stream(stream);
+  if (unit) {
+    FEMB_CHECK_ARG(ndof == 6, "shell operator has 6 dofs per node");
+    const int grid = grid_for(p->N, 128);
+    if (fp == 8) ebe_shell_kernel<double><<<grid, 128, 0, s>>>(p->conn32, p->inc_ptr, p->inc, p->N, p->nen, (const double*)Ke, (const double*)u, (const double*)unit, (double*)y);
+    else ebe_shell_kernel<float><<<grid, 128, 0, s>>>(p->conn32, p->inc_ptr, p->inc, p->N, p->nen, (const float*)Ke, (const float*)u, (const float*)unit, (float*)y);
+  } else {
+    FEMB_CHECK_ARG(ndof >= 1 && ndof <= 6, "1 <= ndof <= 6");
+    const int grid = grid_for(p->N * ndof, 128);
+    if (fp == 8) ebe_apply_kernel<double><<<grid, 128, 0, s>>>(p->conn32, p->inc_ptr, p->inc, p->N, p->nen, ndof, (const double*)Ke, (const double*)u, (double*)y);
+    else ebe_apply_kernel<float><<<grid, 128, 0, s>>>(p->conn32, p->inc_ptr, p->inc, p->N, p->nen, ndof, (const float*)Ke, (const float*)u, (float*)y);
+  }
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}

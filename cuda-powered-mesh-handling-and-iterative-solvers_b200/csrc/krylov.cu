@@ -1,0 +1,375 @@
+// CSR SpMV and the conjugate-gradient loops of the reference (solver/solver.py:144-229 projected CG,
+// :766-812 Jacobi-PCG) on the assembled operator.
+//
+// One CG iteration = three kernels, captured `check_every` at a time in a CUDA graph:
+//   k1  Ap = mask .* (A p), per-CTA partial of p.Ap, last CTA reduces the partials in index order -> pAp, guards, alpha
+//   k2  u += alpha p, r -= alpha Ap, partial of r.r (or r.Minv r), last CTA -> rs_new, convergence test, beta, rs_old
+//   k3  p = r + beta p            (or Minv r + beta p)
+// All scalars stay on the device.  Once the sticky stop flag is set the remaining kernels of the graph are no-ops, so the
+// state returned is exactly the state at the reference's `break`.
+#include "common.cuh"
+
+namespace femb {
+
+struct CGState {
+  double rs_old, rs_new, pAp, alpha, beta;
+  int it, stop, status, iterations;
+  unsigned int ticket1, ticket2, pad0, pad1;
+};
+
+constexpr int SPMV_THREADS = 256;
+
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// L lanes cooperate on one row.  FUSED adds the row mask, the p.Ap partial and the last-CTA scalar epilogue.
+template <int L, bool FUSED>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(long long n, const int* __restrict__ crow, const int* __restrict__ col,
+                                                            const double* __restrict__ val, const double* __restrict__ x,
+                                                            double* __restrict__ y, const unsigned char* __restrict__ mask,
+                                                            double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards) {
+  if (st && st->stop) return;
+  const bool accumulate = (guards & 2) != 0;  // y += A x (operator given as a sum of matrices)
+  guards &= 1;
+  const int sub = threadIdx.x % L;
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / L;
+  const long long ngroups = ((long long)gridDim.x * blockDim.x) / L;
+  double dot = 0.0;
+  for (long long r0 = 0; r0 < n; r0 += ngroups) {  // warp-uniform trip count (shuffles below use the full mask)
+    const long long r = r0 + group;
+    double sum = 0.0;
+    if (r < n) {
+      const int s = __ldg(crow + r), e = __ldg(crow + r + 1);
+      int j = s + sub;
+      for (; j + L < e; j += 2 * L) {
+        const int c0 = ld_stream(col + j), c1 = ld_stream(col + j + L);
+        const double v0 = ld_stream(val + j), v1 = ld_stream(val + j + L);
+        sum += v0 * __ldg(x + c0);
+        sum += v1 * __ldg(x + c1);
+      }
+      if (j < e) sum += ld_stream(val + j) * __ldg(x + ld_stream(col + j));
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (r < n && sub == 0) {
+      if (accumulate) sum += y[r];
+      if (FUSED) {
+        if (mask && !mask[r]) sum = 0.0;
+        dot += sum * __ldg(x + r);
+      }
+      y[r] = sum;
+    }
+  }
+  if (FUSED) {
+    const double t = block_sum<SPMV_THREADS>(dot);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+      partial[blockIdx.x] = t;
+      __threadfence();
+      last = atomicAdd(&st->ticket1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      double a = 0.0;
+      for (int k = threadIdx.x; k < (int)gridDim.x; k += SPMV_THREADS) a += ((volatile double*)partial)[k];
+      a = block_sum<SPMV_THREADS>(a);
+      if (threadIdx.x == 0) {
+        st->ticket1 = 0;
+        st->pAp = a;
+        if (guards && (fabs(a) < eps || a < 0.0)) {  // solver.py:187-192
+          st->stop = 1, st->status = 1, st->iterations = st->it + 1;
+        } else {
+          const double alpha = st->rs_old / (a + eps);
+          st->alpha = alpha;
+          if (guards && !isfinite(alpha)) st->stop = 1, st->status = 1, st->iterations = st->it + 1;  // solver.py:196-198
+        }
+      }
+    }
+  }
+}
+
+constexpr int VEC_THREADS = 256;
+
+// k2: u += alpha p ; r -= alpha Ap ; partial r.r or r.(minv r) ; last CTA: convergence / beta / bookkeeping
+__global__ void __launch_bounds__(VEC_THREADS) cg_update_kernel(long long n, double* __restrict__ u, double* __restrict__ r,
+                                                                const double* __restrict__ p, const double* __restrict__ Ap,
+                                                                const double* __restrict__ minv, double* __restrict__ partial,
+                                                                CGState* __restrict__ st, double tol, double eps, int guards, int max_iter) {
+  if (st->stop) return;
+  const double alpha = st->alpha;
+  double dot = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double pi = p[i], ri = r[i] - alpha * Ap[i];
+    u[i] += alpha * pi;
+    r[i] = ri;
+    dot += minv ? ri * (minv[i] * ri) : ri * ri;
+  }
+  const double t = block_sum<VEC_THREADS>(dot);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(&st->ticket2, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += VEC_THREADS) a += ((volatile double*)partial)[k];
+    a = block_sum<VEC_THREADS>(a);
+    if (threadIdx.x == 0) {
+      st->ticket2 = 0;
+      st->rs_new = a;
+      if (sqrt(a) < tol) {  // solver.py:210-212 / :804-806
+        st->stop = 1, st->status = 0, st->iterations = st->it + 1;
+      } else {
+        const double beta = a / (st->rs_old + eps);
+        st->beta = beta;
+        if (guards && !isfinite(beta)) {  // solver.py:216-218
+          st->stop = 1, st->status = 1, st->iterations = st->it + 1;
+        } else {
+          st->rs_old = a;
+          st->it += 1;
+          if (st->it >= max_iter) st->stop = 2, st->status = 2, st->iterations = max_iter;
+        }
+      }
+    }
+  }
+}
+
+// k3: p = z + beta p with z = r or minv*r.  stop==1 means the reference broke out before this update; stop==2 (max_iter) did not.
+__global__ void __launch_bounds__(VEC_THREADS) cg_direction_kernel(long long n, const double* __restrict__ r, double* __restrict__ p,
+                                                                   const double* __restrict__ minv, const CGState* __restrict__ st) {
+  if (st->stop == 1) return;
+  const double beta = st->beta;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double z = minv ? minv[i] * r[i] : r[i];
+    p[i] = z + beta * p[i];
+  }
+}
+
+// setup: u <- mask.*u ; (after Ap = A u) r = mask.*(F - Ap), p = z, partial r.z -> rs_old
+__global__ void cg_mask_kernel(long long n, double* __restrict__ u, const unsigned char* __restrict__ mask) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!mask[i]) u[i] = 0.0;
+}
+
+__global__ void __launch_bounds__(VEC_THREADS) cg_init_kernel(long long n, const double* __restrict__ F, const double* __restrict__ Au,
+                                                              const unsigned char* __restrict__ mask, const double* __restrict__ minv,
+                                                              double* __restrict__ r, double* __restrict__ p, double* __restrict__ partial) {
+  double dot = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double ri = F[i] - Au[i];
+    if (mask && !mask[i]) ri = 0.0;
+    const double z = minv ? minv[i] * ri : ri;
+    r[i] = ri;
+    p[i] = z;
+    dot += ri * z;
+  }
+  const double t = block_sum<VEC_THREADS>(dot);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(VEC_THREADS) cg_init_finish(int nparts, const double* __restrict__ partial, CGState* __restrict__ st,
+                                                              int max_iter) {
+  double a = 0.0;
+  for (int k = threadIdx.x; k < nparts; k += VEC_THREADS) a += partial[k];
+  a = block_sum<VEC_THREADS>(a);
+  if (threadIdx.x == 0) {
+    CGState s;
+    memset(&s, 0, sizeof(s));
+    s.rs_old = a;
+    s.rs_new = a;
+    if (max_iter <= 0) s.stop = 2, s.status = 2;
+    *st = s;
+  }
+}
+
+__global__ void jacobi_kernel(long long n, const int* __restrict__ crow, const int* __restrict__ col, const double* __restrict__ val,
+                              const unsigned char* __restrict__ mask, double* __restrict__ minv) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    double d = 0.0;
+    int lo = crow[r], hi = crow[r + 1];
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (col[mid] < r) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < crow[r + 1] && col[lo] == r) d = val[lo];
+    minv[r] = (d != 0.0 && (!mask || mask[r])) ? 1.0 / d : 0.0;
+  }
+}
+
+static int pick_lanes(long long n, long long nnz) {
+  const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
+  if (avg <= 3) return 2;
+  if (avg <= 6) return 4;
+  if (avg <= 24) return 8;
+  if (avg <= 48) return 16;
+  return 32;
+}
+
+template <bool FUSED>
+static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const int* crow, const int* col, const double* val, const double* x,
+                        double* y, const unsigned char* mask, double* partial, CGState* st, double eps, int guards) {
+  switch (lanes) {
+    case 2: spmv_kernel<2, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+    case 4: spmv_kernel<4, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+    case 8: spmv_kernel<8, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+    case 16: spmv_kernel<16, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+    default: spmv_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+  }
+}
+
+static int spmv_grid(long long n, int lanes) {
+  const long long rows_per_block = SPMV_THREADS / lanes;
+  long long b = (n + rows_per_block - 1) / rows_per_block;
+  const long long cap = (long long)SMS * 8;  // 8 resident CTAs of 256 threads per SM
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace femb
+
+using namespace femb;
+
+extern "C" int femb_spmv(int64_t n, int64_t nnz, const int32_t* crow, const int32_t* col, const double* val, const double* x, double* y,
+                         femb_stream stream) {
+  FEMB_CHECK_ARG(n >= 0, "n >= 0");
+  if (n == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int lanes = pick_lanes(n, nnz);
+  launch_spmv<false>(lanes, spmv_grid(n, lanes), s, n, crow, col, val, x, y, nullptr, nullptr, nullptr, 0.0, 0);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+extern "C" int femb_csr_jacobi(int64_t n, const int32_t* crow, const int32_t* col, const double* val, const uint8_t* mask, double* minv,
+                               femb_stream stream) {
+  if (n == 0) return FEMB_OK;
+  jacobi_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(n, crow, col, val, mask, minv);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+// Stream capture is illegal on the legacy default stream (torch's default current stream), so the solve runs on a private
+// non-blocking stream that is ordered after the caller's stream by an event; the call blocks until the solve is done.
+static cudaStream_t solver_stream(cudaStream_t user) {
+  static thread_local cudaStream_t s = nullptr;
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!s) {
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  }
+  cudaEventRecord(ev, user);
+  cudaStreamWaitEvent(s, ev, 0);
+  return s;
+}
+
+struct CsrRef {
+  long long nnz;
+  const int *crow, *col;
+  const double* val;
+};
+
+static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* F, const uint8_t* mask, const double* minv, double* u,
+                         double* work, double tol, int max_iter, double eps, int check_every, femb_cg_result* result_host,
+                         femb_stream stream) {
+  FEMB_CHECK_ARG(n > 0 && nmat >= 1 && nmat <= 8 && F && u && work && result_host, "null pointer / n <= 0 / nmat not in 1..8");
+  if (check_every < 1) check_every = 16;
+  cudaStream_t s = solver_stream(as_stream(stream));
+  FEMB_CHECK_ARG(s != nullptr, "could not create the solver stream");
+  const int guards = minv ? 0 : 1;  // the reference's PCG loop carries no guards and no eps (solver.py:795-810)
+  if (minv) eps = 0.0;
+  double *r = work, *p = work + n, *Ap = work + 2 * n;
+  int lanes[8], g1[8], gmax = 1;
+  for (int m = 0; m < nmat; ++m) {
+    lanes[m] = pick_lanes(n, mats[m].nnz);
+    g1[m] = spmv_grid(n, lanes[m]);
+    gmax = std::max(gmax, g1[m]);
+  }
+  const int g2 = grid_for(n, VEC_THREADS, 8);
+  Scratch scr(s);
+  double* partial;
+  CGState* st;
+  FEMB_CUDA(scr.alloc(&partial, (size_t)std::max(gmax, g2)));
+  FEMB_CUDA(scr.alloc(&st, 1));
+  // ---- setup (solver.py:163-181)
+  if (mask) cg_mask_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, mask);
+  for (int m = 0; m < nmat; ++m)
+    launch_spmv<false>(lanes[m], g1[m], s, n, mats[m].crow, mats[m].col, mats[m].val, u, Ap, nullptr, nullptr, nullptr, 0.0, m ? 2 : 0);
+  cg_init_kernel<<<g2, VEC_THREADS, 0, s>>>(n, F, Ap, mask, minv, r, p, partial);
+  cg_init_finish<<<1, VEC_THREADS, 0, s>>>(g2, partial, st, max_iter);
+  FEMB_LAUNCH_CHECK();
+  // ---- capture `check_every` iterations into one graph
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  FEMB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  for (int k = 0; k < check_every; ++k) {
+    for (int m = 0; m + 1 < nmat; ++m)
+      launch_spmv<false>(lanes[m], g1[m], s, n, mats[m].crow, mats[m].col, mats[m].val, p, Ap, nullptr, nullptr, st, 0.0, m ? 2 : 0);
+    const int last = nmat - 1;
+    launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
+                      guards | (last ? 2 : 0));
+    cg_update_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, r, p, Ap, minv, partial, st, tol, eps, guards, max_iter);
+    cg_direction_kernel<<<g2, VEC_THREADS, 0, s>>>(n, r, p, minv, st);
+  }
+  cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  if (ce != cudaSuccess) {
+    set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    return FEMB_ERR_CUDA;
+  }
+  FEMB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  static thread_local CGState* hst = nullptr;
+  if (!hst) FEMB_CUDA(cudaMallocHost(&hst, sizeof(CGState)));
+  int rc = FEMB_OK;
+  const int launches = (max_iter + check_every - 1) / check_every;
+  hst->stop = 0;
+  for (int l = 0; l < launches; ++l) {
+    if (cudaGraphLaunch(exec, s) != cudaSuccess || cudaMemcpyAsync(hst, st, sizeof(CGState), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error(std::string("CG graph launch: ") + cudaGetErrorString(cudaGetLastError()));
+      rc = FEMB_ERR_CUDA;
+      break;
+    }
+    if (hst->stop) break;
+  }
+  if (rc == FEMB_OK && launches == 0) {
+    FEMB_CUDA(cudaMemcpyAsync(hst, st, sizeof(CGState), cudaMemcpyDeviceToHost, s));
+    FEMB_CUDA(cudaStreamSynchronize(s));
+  }
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  if (rc != FEMB_OK) return rc;
+  result_host->iterations = hst->stop ? hst->iterations : max_iter;
+  result_host->status = hst->stop ? hst->status : 2;
+  result_host->rs = hst->rs_new;
+  return FEMB_OK;
+}
+
+extern "C" int femb_cg_solve(int64_t n, int64_t nnz, const int32_t* crow, const int32_t* col, const double* val, const double* F,
+                             const uint8_t* mask, const double* minv, double* u, double* work, double tol, int max_iter, double eps,
+                             int check_every, femb_cg_result* result_host, femb_stream stream) {
+  FEMB_CHECK_ARG(crow && col && val, "null CSR pointer");
+  const CsrRef m{nnz, crow, col, val};
+  return cg_solve_impl(n, 1, &m, F, mask, minv, u, work, tol, max_iter, eps, check_every, result_host, stream);
+}
+
+extern "C" int femb_cg_solve_multi(int64_t n, int nmat, const int64_t* nnz_host, const int32_t* const* crow_host,
+                                   const int32_t* const* col_host, const double* const* val_host, const double* F, const uint8_t* mask,
+                                   const double* minv, double* u, double* work, double tol, int max_iter, double eps, int check_every,
+                                   femb_cg_result* result_host, femb_stream stream) {
+  FEMB_CHECK_ARG(nmat >= 1 && nmat <= 8 && nnz_host && crow_host && col_host && val_host, "nmat in 1..8, non-null arrays");
+  CsrRef m[8];
+  for (int k = 0; k < nmat; ++k) m[k] = CsrRef{nnz_host[k], crow_host[k], col_host[k], val_host[k]};
+  return cg_solve_impl(n, nmat, m, F, mask, minv, u, work, tol, max_iter, eps, check_every, result_host, stream);
+}

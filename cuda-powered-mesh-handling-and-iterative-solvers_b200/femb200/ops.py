@@ -1,0 +1,337 @@
+"""Thin torch <-> C-ABI plumbing: allocate outputs with torch, pass raw device pointers to libfemb200.
+
+PyTorch is used for device memory and streams only.  Every function requires a CUDA device; a CPU
+device raises (the reference's `device="cpu"` path is deliberately not provided: no CPU fallback).
+"""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+import weakref
+
+import torch
+
+from . import _lib
+from ._lib import CGResult, check, lib
+
+C3D4, C3D6, C3D8, C3D10, S3, S4 = 4, 6, 8, 10, 103, 104
+ENT_TET_FACES, ENT_HEX_FACES, ENT_WEDGE_QUADS, ENT_WEDGE_TRIS, ENT_TRI_EDGES, ENT_QUAD_EDGES = range(6)
+_ENT = {ENT_TET_FACES: (4, 3), ENT_HEX_FACES: (6, 4), ENT_WEDGE_QUADS: (3, 4), ENT_WEDGE_TRIS: (2, 3), ENT_TRI_EDGES: (3, 2),
+        ENT_QUAD_EDGES: (4, 2)}
+
+
+def cuda_device(device) -> torch.device:
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise RuntimeError(f"femb200 runs on CUDA devices only (got device={device!r}); there is no CPU fallback")
+    if not torch.cuda.is_available():
+        raise RuntimeError("femb200 needs a CUDA device (sm_100a); none is visible")
+    return d
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def real(t, dev, dtype) -> torch.Tensor:
+    if dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"dtype must be float32 or float64, got {dtype}")
+    return torch.as_tensor(t).to(device=dev, dtype=dtype).contiguous()
+
+
+def index(t, dev) -> torch.Tensor:
+    t = torch.as_tensor(t).to(device=dev)
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+def _fp(t):
+    return t.element_size()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _host_doubles(values):
+    arr = (C.c_double * len(values))(*[float(v) for v in values])
+    return arr
+
+
+def default_points(kind) -> list:
+    buf = (C.c_double * (64 * 4))()
+    n = lib.femb_default_points(kind, buf)
+    if n < 0:
+        check(1, "femb_default_points")
+    return [[buf[4 * q + k] for k in range(4)] for q in range(n)]
+
+
+# ----------------------------------------------------------------------------- element kernels
+
+def c3d4(what, coords, elements, E=0.0, nu=0.0, device="cuda:0", dtype=torch.float32):
+    dev = cuda_device(device)
+    x, conn = real(coords, dev, dtype), index(elements, dev)
+    M = conn.shape[0]
+    shape = {0: (M, 4, 3), 1: (M, 6, 12), 2: (M, 12, 12), 3: (M, 4, 4), 4: (M, 12, 12), 5: (M,)}[what]
+    out = torch.empty(shape, device=dev, dtype=dtype)
+    flag = torch.zeros(1, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        check(lib.femb_c3d4(what, _p(x), _fp(x), _p(conn), _fp(conn), M, float(E), float(nu), _p(out), _p(flag), _stream(dev)), "femb_c3d4")
+    if what in (0, 1, 2, 3) and M and int(flag.item()):   # the reference also synchronises here (torch.any, element.py:857)
+        raise ValueError("Singular matrix encountered while computing B matrix.")
+    return out
+
+
+def volumes(kind, coords, elements, device="cuda:0", dtype=torch.float32):
+    dev = cuda_device(device)
+    x, conn = real(coords, dev, dtype), index(elements, dev)
+    M = conn.shape[0]
+    out = torch.empty((M,), device=dev, dtype=dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_elem_volumes(kind, _p(x), _fp(x), _p(conn), _fp(conn), M, conn.shape[1], _p(out), _stream(dev)), "femb_elem_volumes")
+    return out
+
+
+_NEN = {C3D4: 4, C3D6: 6, C3D8: 8, C3D10: 10, S3: 3, S4: 4}
+
+
+def solid(kind, what, coords, elements, points, E=0.0, nu=0.0, device="cuda:0", dtype=torch.float32):
+    """points: list of [xi,eta,zeta,w] rows (host)."""
+    dev = cuda_device(device)
+    x, conn = real(coords, dev, dtype), index(elements, dev)
+    nen = _NEN[kind]
+    if conn.shape[1] != nen:
+        conn = conn[:, :nen].contiguous()
+    M, nd, nq = conn.shape[0], 3 * nen, len(points)
+    shape = {0: (M, 3, 3), 1: (M, nen, 3), 2: (M, 6, nd), 3: (M, nd, nd), 4: (nq, M, nd, nd), 5: (M, nd, nd)}[what]
+    out = torch.empty(shape, device=dev, dtype=dtype)
+    flat = [v for row in points for v in row]
+    with torch.cuda.device(dev):
+        check(lib.femb_solid(kind, what, _p(x), _fp(x), _p(conn), _fp(conn), M, _host_doubles(flat), nq, float(E), float(nu), _p(out),
+                             _stream(dev)), "femb_solid")
+    return out
+
+
+def shell(kind, what, coords, elements, points=None, D=None, device="cuda:0", dtype=torch.float32):
+    dev = cuda_device(device)
+    x, conn = real(coords, dev, dtype), index(elements, dev)
+    nen = _NEN[kind]
+    M, nd = conn.shape[0], 6 * nen
+    points = points if points is not None else [[0.0, 0.0, 0.0, 1.0]]
+    nq = len(points)
+    shape = {0: (M, 3, 3), 1: (M, 2, 2), 2: (M, nen, 2), 3: (M, 6, nd), 4: (M, nd, nd), 5: (M, nd, nd, nq)}[what]
+    out = torch.empty(shape, device=dev, dtype=dtype)
+    flat = [v for row in points for v in row]
+    Dh = _host_doubles([float(v) for v in D.reshape(-1).tolist()]) if D is not None else None
+    with torch.cuda.device(dev):
+        check(lib.femb_shell(kind, what, _p(x), _fp(x), _p(conn), _fp(conn), M, _host_doubles(flat), nq, Dh, _p(out), _stream(dev)),
+              "femb_shell")
+    return out
+
+
+def to_c3d4(kind, elements, device="cuda:0"):
+    dev = cuda_device(device)
+    conn = index(elements, dev)
+    k = {C3D10: 8, C3D8: 6, C3D6: 3}[kind]
+    if conn.shape[1] != _NEN[kind]:
+        conn = conn[:, :_NEN[kind]].contiguous()
+    out = torch.empty((conn.shape[0] * k, 4), device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        check(lib.femb_to_c3d4(kind, _p(conn), _fp(conn), conn.shape[0], _p(out), _stream(dev)), "femb_to_c3d4")
+    return out
+
+
+# ----------------------------------------------------------------------------- topology
+
+def entities(ent_kind, elements, device="cuda:0", want_surface=True, want_shared=True):
+    """Returns (faces [K,nfn], extra [K], pairs [S,2,2]) -- entries not requested are None."""
+    dev = cuda_device(device)
+    conn = index(elements, dev)
+    M = conn.shape[0]
+    nf, nfn = _ENT[ent_kind]
+    plan, K, S = C.c_void_p(), C.c_int64(), C.c_int64()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        check(lib.femb_entities_create(ent_kind, _p(conn), _fp(conn), M, conn.shape[1], st, C.byref(plan), C.byref(K), C.byref(S)),
+              "femb_entities_create")
+        try:
+            faces = extra = pairs = None
+            if want_surface:
+                faces = torch.empty((K.value, nfn), device=dev, dtype=torch.int64)
+                extra = torch.empty((K.value,), device=dev, dtype=torch.int64)
+                check(lib.femb_entities_surface(plan, _p(faces), _p(extra), st), "femb_entities_surface")
+            if want_shared:
+                pairs = torch.empty((S.value, 2, 2), device=dev, dtype=torch.int64)
+                check(lib.femb_entities_shared(plan, _p(pairs), st), "femb_entities_shared")
+            torch.cuda.current_stream(dev).synchronize()   # plan scratch is freed below
+        finally:
+            lib.femb_entities_destroy(plan)
+    return faces, extra, pairs
+
+
+def surface_normals(coords, faces, extra, second, device="cuda:0", dtype=torch.float32):
+    dev = cuda_device(device)
+    x = real(coords, dev, dtype)
+    out = torch.empty((faces.shape[0], 3), device=dev, dtype=dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_surface_normals(_p(x), _fp(x), _p(faces), _p(extra), faces.shape[0], faces.shape[1], second, _p(out), _stream(dev)),
+              "femb_surface_normals")
+    return out
+
+
+def face_normals_area(kind, coords, elements, device="cuda:0", dtype=torch.float32):
+    dev = cuda_device(device)
+    x, conn = real(coords, dev, dtype), index(elements, dev)
+    nf = 4 if kind == C3D4 else 6
+    out = torch.empty((conn.shape[0], nf, 3), device=dev, dtype=dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_face_normals_area(kind, _p(x), _fp(x), _p(conn), _fp(conn), conn.shape[0], conn.shape[1], _p(out), _stream(dev)),
+              "femb_face_normals_area")
+    return out
+
+
+# ----------------------------------------------------------------------------- assembly plan
+
+class CsrPlan:
+    """Node-level sparsity pattern + node->element incidence of one connectivity array (device resident)."""
+
+    def __init__(self, elements, n_nodes=None, device="cuda:0"):
+        self.dev = cuda_device(device)
+        conn = index(elements, self.dev)
+        self.M, self.nen = conn.shape
+        self.n_nodes = int(n_nodes) if n_nodes is not None else (int(conn.max().item()) + 1 if self.M else 1)
+        h, nnz = C.c_void_p(), C.c_int64()
+        with torch.cuda.device(self.dev):
+            check(lib.femb_csr_plan_create(_p(conn), _fp(conn), self.M, self.nen, self.n_nodes, _stream(self.dev), C.byref(h), C.byref(nnz)),
+                  "femb_csr_plan_create")
+        self.handle, self.nnz_nodes = h, nnz.value
+        self._fin = weakref.finalize(self, lib.femb_csr_plan_destroy, h)
+        self._patterns = {}
+
+    def pattern(self, ndof):
+        """(crow int32 [n+1], col int32 [nnz]) for `ndof` dofs per node."""
+        if ndof not in self._patterns:
+            n = self.n_nodes * ndof
+            crow = torch.empty(n + 1, device=self.dev, dtype=torch.int32)
+            col = torch.empty(self.nnz_nodes * ndof * ndof, device=self.dev, dtype=torch.int32)
+            with torch.cuda.device(self.dev):
+                check(lib.femb_csr_plan_pattern(self.handle, ndof, _p(crow), _p(col), _stream(self.dev)), "femb_csr_plan_pattern")
+            self._patterns[ndof] = (crow, col)
+        return self._patterns[ndof]
+
+    def assemble(self, Ke, ndof, out=None):
+        """CSR values (fp64) from materialised element matrices Ke [M, nen*ndof, nen*ndof]."""
+        Ke = real(Ke, self.dev, torch.float64)
+        assert Ke.shape == (self.M, self.nen * ndof, self.nen * ndof), (Ke.shape, self.M, self.nen, ndof)
+        vals = out if out is not None else torch.empty(self.nnz_nodes * ndof * ndof, device=self.dev, dtype=torch.float64)
+        with torch.cuda.device(self.dev):
+            check(lib.femb_csr_assemble(self.handle, ndof, _p(Ke), _p(vals), _stream(self.dev)), "femb_csr_assemble")
+        return vals
+
+    def assemble_c3d4(self, coords, kind, E=0.0, nu=0.0, out=None, check_singular=True):
+        """Fused P1-tet assembly from coordinates. kind: 'poisson' (1 dof) or 'elasticity' (3 dofs)."""
+        k = {"poisson": 0, "elasticity": 1}[kind]
+        d2 = 1 if k == 0 else 9
+        x = real(coords, self.dev, torch.float64)
+        vals = out if out is not None else torch.empty(self.nnz_nodes * d2, device=self.dev, dtype=torch.float64)
+        flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        with torch.cuda.device(self.dev):
+            check(lib.femb_csr_assemble_c3d4(self.handle, k, _p(x), float(E), float(nu), _p(vals), _p(flag), _stream(self.dev)),
+                  "femb_csr_assemble_c3d4")
+        if check_singular and int(flag.item()):
+            raise ValueError("Singular matrix encountered while computing B matrix.")
+        return vals
+
+    def ebe_apply(self, Ke, u, ndof, unit=None, dtype=torch.float64):
+        Ke, u = real(Ke, self.dev, dtype), real(u, self.dev, dtype)
+        un = real(unit, self.dev, dtype) if unit is not None else None
+        y = torch.empty((self.n_nodes, ndof), device=self.dev, dtype=dtype)
+        assert u.shape[0] == self.n_nodes, "displacement rows must equal the plan's node count"
+        with torch.cuda.device(self.dev):
+            check(lib.femb_ebe_apply(self.handle, ndof, _p(Ke), _p(u), _p(un), _fp(u), _p(y), _stream(self.dev)), "femb_ebe_apply")
+        return y
+
+
+_PLAN_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+
+
+def cached_plan(elements, n_nodes, device) -> CsrPlan:
+    """Plans are keyed on the connectivity tensor's identity/version so that repeated operator applications on
+    the same mesh (every CG iteration of the reference calls compute_nodal_forces) reuse one plan."""
+    e = torch.as_tensor(elements)
+    key = (e.data_ptr(), tuple(e.shape), e.dtype, e._version, str(e.device), int(n_nodes), str(device))
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = CsrPlan(e, n_nodes, device)
+        plan._keepalive = e   # keeps data_ptr from being recycled while cached
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > 8:
+            _PLAN_CACHE.popitem(last=False)
+    else:
+        _PLAN_CACHE.move_to_end(key)
+    return plan
+
+
+# ----------------------------------------------------------------------------- Krylov
+
+def spmv(crow, col, val, x):
+    dev = val.device
+    n = crow.numel() - 1
+    xx = x.reshape(-1).contiguous()
+    y = torch.empty(n, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        check(lib.femb_spmv(n, val.numel(), _p(crow), _p(col), _p(val), _p(xx), _p(y), _stream(dev)), "femb_spmv")
+    return y.reshape(x.shape)
+
+
+def jacobi(crow, col, val, mask=None):
+    dev = val.device
+    n = crow.numel() - 1
+    out = torch.empty(n, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        check(lib.femb_csr_jacobi(n, _p(crow), _p(col), _p(val), _p(mask), _p(out), _stream(dev)), "femb_csr_jacobi")
+    return out
+
+
+STATUS = {0: "converged", 1: "breakdown", 2: "maxiter"}
+
+
+def cg_solve(crow, col, val, F, mask=None, minv=None, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, check_every=16):
+    """Runs the reference CG (mask: uint8 per dof, 0 = held at zero) or PCG (minv given) loop on the device.
+    Returns (u [same shape as F], info dict)."""
+    dev = val.device
+    n = crow.numel() - 1
+    Ff = F.to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+    assert Ff.numel() == n, (Ff.numel(), n)
+    u = torch.zeros(n, device=dev, dtype=torch.float64) if u_init is None else \
+        u_init.to(device=dev, dtype=torch.float64).reshape(-1).clone().contiguous()
+    work = torch.empty(4 * n, device=dev, dtype=torch.float64)
+    res = CGResult()
+    with torch.cuda.device(dev):
+        check(lib.femb_cg_solve(n, val.numel(), _p(crow), _p(col), _p(val), _p(Ff), _p(mask), _p(minv), _p(u), _p(work), float(tol),
+                                int(max_iter), float(eps), int(check_every), C.byref(res), _stream(dev)), "femb_cg_solve")
+    info = {"iterations": res.iterations, "status": STATUS.get(res.status, "?"), "rs": res.rs}
+    return u.reshape(F.shape), info
+
+
+def cg_solve_multi(mats, F, mask=None, minv=None, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, check_every=16):
+    """cg_solve with the operator given as a sum of CSR triples [(crow, col, val), ...] over the same rows."""
+    dev = mats[0][2].device
+    n = mats[0][0].numel() - 1
+    Ff = F.to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+    assert Ff.numel() == n and all(m[0].numel() - 1 == n for m in mats)
+    u = torch.zeros(n, device=dev, dtype=torch.float64) if u_init is None else \
+        u_init.to(device=dev, dtype=torch.float64).reshape(-1).clone().contiguous()
+    work = torch.empty(4 * n, device=dev, dtype=torch.float64)
+    k = len(mats)
+    nnz = (C.c_int64 * k)(*[m[2].numel() for m in mats])
+    crow = (C.c_void_p * k)(*[m[0].data_ptr() for m in mats])
+    col = (C.c_void_p * k)(*[m[1].data_ptr() for m in mats])
+    val = (C.c_void_p * k)(*[m[2].data_ptr() for m in mats])
+    res = CGResult()
+    with torch.cuda.device(dev):
+        check(lib.femb_cg_solve_multi(n, k, nnz, crow, col, val, _p(Ff), _p(mask), _p(minv), _p(u), _p(work), float(tol), int(max_iter),
+                                      float(eps), int(check_every), C.byref(res), _stream(dev)), "femb_cg_solve_multi")
+    info = {"iterations": res.iterations, "status": STATUS.get(res.status, "?"), "rs": res.rs}
+    return u.reshape(F.shape), info

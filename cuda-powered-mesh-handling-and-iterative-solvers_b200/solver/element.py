@@ -1,0 +1,406 @@
+"""Drop-in mirror of the reference's `solver/element.py` function API on hand-written sm_100a kernels.
+
+Use exactly like the reference (`sys.path.append(<this dir>); import element`): same function names,
+positional order, defaults (device="cuda:0", dtype=torch.float32) and return shapes; tensors in and
+out stay on the device.  Every function is a thin wrapper that allocates outputs with torch and calls
+libfemb200 through ctypes (femb200/ops.py); there is no CPU path and no torch op chain behind them.
+Each docstring names the reference lines it replaces (paths relative to the reference's solver/).
+
+Deliberately reproduced quirks: the type dispatchers drop `dtype` (q2), C3D6 and S4
+quadrature constants are fp32-rounded (q1), detJ is signed (q3), C3D10/C3D6 weights are the reference's (q4),
+shared-face pairs are emitted lower-element-first (the reference's order is implementation-defined, q5).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+
+from femb200 import ops as _ops  # noqa: E402
+from femb200.ops import CsrPlan  # noqa: E402,F401
+
+
+def _pts(kind, integral_point, dtype, single_point=False):
+    """Resolve quadrature input to a host list of [xi,eta,zeta,w] rows, rounded through `dtype` as the reference does."""
+    if integral_point is None:
+        rows = torch.tensor(_ops.default_points(kind), dtype=torch.float64)
+    else:
+        ip = torch.as_tensor(integral_point).detach().to("cpu")
+        if single_point:
+            ip = torch.cat([ip.reshape(3).to(torch.float64), torch.ones(1, dtype=torch.float64)]).reshape(1, 4)
+        rows = torch.stack([ip[:, 0], ip[:, 1], ip[:, 2], ip[:, -1]], dim=1)
+    return rows.to(dtype).to(torch.float64).tolist()
+
+
+# ------------------------------------------------------------------------------------------- constants
+
+def compute_elasticity_matrix(E, nu, device="cuda:0", dtype=torch.float32):
+    """Isotropic 6x6 D in Voigt order xx,yy,zz,xy,yz,zx (reference element.py:282-306)."""
+    c = E / ((1 + nu) * (1 - 2 * nu))
+    s = (1 - 2 * nu) / 2
+    rows = [[1 - nu, nu, nu, 0, 0, 0], [nu, 1 - nu, nu, 0, 0, 0], [nu, nu, 1 - nu, 0, 0, 0],
+            [0, 0, 0, s, 0, 0], [0, 0, 0, 0, s, 0], [0, 0, 0, 0, 0, s]]
+    return c * torch.tensor(rows, device=device, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------- dispatchers
+
+def to_c3d4(elements, device="cuda:0"):
+    """element.py:355-364"""
+    n = elements.shape[1]
+    if n == 6:
+        return c3d6_to_c3d4(elements, device)
+    if n == 8:
+        return c3d8_to_c3d4(elements, device)
+    if n == 10:
+        return c3d10_to_c3d4(elements, device)
+    return None
+
+
+def to_2nd_order(coords, elements, rbe2=None, rbe3=None, device="cuda:0", dtype=torch.float32):
+    """element.py:366-369"""
+    if elements.shape[1] == 4:
+        return c3d4_to_c3d10(coords, elements, rbe2, rbe3, dtype=dtype)
+    return None
+
+
+def _unsupported(element_type):
+    raise ValueError(f"Unsupported element type: {element_type}")
+
+
+def integral_points(element_type, device="cuda:0"):
+    """element.py:371-378 -- always float32 (the dispatcher drops dtype, quirk q2)."""
+    t = element_type.lower()
+    fn = {"c3d8": c3d8_integration_points, "c3d10": c3d10_integration_points, "c3d6": c3d6_integration_points}.get(t)
+    return fn(device) if fn else _unsupported(element_type)
+
+
+def compute_Jacobian(coords, elements, element_type, integral_point=None, device="cuda:0"):
+    """element.py:380-388 (float32 result, q2; 'c3d8i' aliases C3D8 here only)."""
+    t = element_type.lower()
+    fn = {"c3d8": compute_c3d8_Jacobian, "c3d8i": compute_c3d8_Jacobian, "c3d10": compute_c3d10_Jacobian,
+          "c3d6": compute_c3d6_Jacobian}.get(t)
+    return fn(coords, elements, integral_point, device) if fn else _unsupported(element_type)
+
+
+def compute_shape_gradients(coords, elements, element_type, integral_point=None, device="cuda:0"):
+    """element.py:390-397 (float32 result, q2)."""
+    t = element_type.lower()
+    fn = {"c3d8": compute_c3d8_shape_gradients, "c3d10": compute_c3d10_shape_gradients, "c3d6": compute_c3d6_shape_gradients}.get(t)
+    return fn(coords, elements, integral_point, device) if fn else _unsupported(element_type)
+
+
+def compute_B_matrix(coords, elements, integral_point, element_type, device="cuda:0", dtype=torch.float32):
+    """element.py:399-407 (dtype honoured for C3D4 only, q2)."""
+    t = element_type.lower()
+    if t == "c3d4":
+        return compute_c3d4_B_matrix(coords, elements, device, dtype)
+    fn = {"c3d8": compute_c3d8_B_matrix, "c3d10": compute_c3d10_B_matrix, "c3d6": compute_c3d6_B_matrix}.get(t)
+    return fn(coords, elements, integral_point, device) if fn else _unsupported(element_type)
+
+
+def compute_K_matrix(coords, elements, element_type, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32):
+    """element.py:419-427"""
+    t = element_type.lower()
+    if t == "c3d4":
+        return compute_c3d4_K_matrix(coords, elements, E, nu, device, dtype)
+    fn = {"c3d8": compute_c3d8_K_matrix, "c3d10": compute_c3d10_K_matrix, "c3d6": compute_c3d6_K_matrix}.get(t)
+    return fn(coords, elements, E, nu, integral_point, single, device, dtype) if fn else _unsupported(element_type)
+
+
+def compute_nodal_forces(K, elements, displacement, device="cuda:0", dtype=torch.float32):
+    """Matrix-free y = K u (element.py:429-464).  Instead of gather -> bmm -> atomic index_add, one thread per dof row
+    walks the node's incidence list in ascending element order (deterministic).  The incidence plan of `elements` is
+    cached across calls (the reference rebuilds its dof table on every call)."""
+    dev = _ops.cuda_device(device)
+    u = _ops.real(displacement, dev, dtype)
+    N, ndof = u.shape
+    plan = _ops.cached_plan(elements, N, dev)
+    return plan.ebe_apply(K, u, ndof, None, dtype)
+
+
+# ------------------------------------------------------------------------------------------- tetrahedra
+
+def compute_tetrahedral_volumes(coords, elements, device="cuda:0", dtype=torch.float32):
+    """|det[v1,v2,v3]|/6 (element.py:514-541)."""
+    return _ops.volumes(_ops.C3D4, coords, elements, device, dtype)
+
+
+def compute_tetrahedral_surface_faces_with_fourth_node(elements, device="cuda:0"):
+    """Faces that occur once, slot-major order, plus the off-face node (element.py:543-579)."""
+    f, x, _ = _ops.entities(_ops.ENT_TET_FACES, elements, device, want_shared=False)
+    return f, x
+
+
+def compute_tetrahdral_surface_normals(coords, elements, device="cuda:0", dtype=torch.float32):
+    """Outward unit normals of the surface faces (element.py:581-619)."""
+    f, x = compute_tetrahedral_surface_faces_with_fourth_node(elements, device)
+    return _ops.surface_normals(coords, f, x, 2, device, dtype)
+
+
+def compute_tetrahedral_normals_and_area(coords, elements, device="cuda:0", dtype=torch.float32):
+    """[M,4,3] area-weighted outward face normals (element.py:652-705)."""
+    return _ops.face_normals_area(_ops.C3D4, coords, elements, device, dtype)
+
+
+def identify_tetrahedral_shared_faces(elements, device="cuda:0"):
+    """[S,2,2] = ((elem,face),(elem,face)), rows lexicographic by sorted node triple (element.py:707-762)."""
+    return _ops.entities(_ops.ENT_TET_FACES, elements, device, want_surface=False)[2]
+
+
+def c3d4_to_c3d10(coords, elements, rbe2_ids=None, rbe3_ids=None, dtype=torch.float32, device=None):
+    """Mid-edge insertion with the reference's first-encounter numbering (element.py:777-833), done with parallel device
+    primitives instead of a Python dict loop: an edge's new id is N + (rank of its first occurrence in element-major,
+    slot (0,1),(1,2),(2,0),(0,3),(1,3),(2,3) order).  Returns (coords', elems[int32], rbe2', rbe3') on the CPU like the
+    reference unless `device` is given."""
+    dev = torch.as_tensor(elements).device if device is None else torch.device(device)
+    work = dev if dev.type == "cuda" else (torch.device("cuda:0") if torch.cuda.is_available() else dev)
+    x = torch.as_tensor(coords).to(work)
+    e = torch.as_tensor(elements).to(work).long()
+    N, M = x.shape[0], e.shape[0]
+    slots = torch.tensor([[0, 1], [1, 2], [2, 0], [0, 3], [1, 3], [2, 3]], device=work)
+    pr = e[:, slots]                                     # [M,6,2]
+    lo, hi = pr.min(dim=2).values, pr.max(dim=2).values
+    key = (lo * N + hi).reshape(-1)
+    uniq, inv = torch.unique(key, return_inverse=True)
+    first = torch.full((uniq.numel(),), key.numel(), device=work, dtype=torch.long)
+    first.scatter_reduce_(0, inv, torch.arange(key.numel(), device=work), reduce="amin")
+    rank = torch.empty_like(first)
+    rank[torch.argsort(first)] = torch.arange(uniq.numel(), device=work)
+    mids = (N + rank[inv]).reshape(M, 6)
+    new_elems = torch.cat([e, mids], dim=1).to(torch.int32)
+    ulo, uhi = uniq // N, uniq % N
+    mid_xyz = torch.empty((uniq.numel(), 3), device=work, dtype=x.dtype)
+    mid_xyz[rank] = (x[ulo] + x[uhi]) / 2
+    new_coords = torch.cat([x, mid_xyz], dim=0).to(dtype)
+
+    def grow(ids):
+        if ids is None:
+            return torch.tensor([], dtype=torch.int32)
+        m = torch.zeros(N, dtype=torch.bool, device=work)
+        m[torch.as_tensor(ids).to(work).long()] = True
+        both = torch.zeros(uniq.numel(), dtype=torch.bool, device=work)
+        both[rank] = m[ulo] & m[uhi]
+        return torch.cat([torch.nonzero(m).reshape(-1), N + torch.nonzero(both).reshape(-1)]).to(torch.int32)
+
+    out_dev = torch.device("cpu") if device is None else dev
+    return new_coords.to(out_dev), new_elems.to(out_dev), grow(rbe2_ids).to(out_dev), grow(rbe3_ids).to(out_dev)
+
+
+def compute_c3d4_B_matrix(coords, elements, device="cuda:0", dtype=torch.float32):
+    """[M,6,12]; raises ValueError when any |det[1,x,y,z]| < 1e-12 (element.py:835-881)."""
+    return _ops.c3d4(1, coords, elements, device=device, dtype=dtype)
+
+
+def compute_c3d4_shape_gradients(coords, elements, device="cuda:0", dtype=torch.float32):
+    """[M,4,3] P1 gradients (the `grads` of element.py:862-866; additive helper)."""
+    return _ops.c3d4(0, coords, elements, device=device, dtype=dtype)
+
+
+def compute_c3d4_K_matrix(coords, elements, E, nu, device="cuda:0", dtype=torch.float32):
+    """K = B^T D B V, [M,12,12] (element.py:883-903)."""
+    return _ops.c3d4(2, coords, elements, E, nu, device, dtype)
+
+
+def compute_c3d4_poisson_K_matrix(coords, elements, device="cuda:0", dtype=torch.float32):
+    """Scalar Laplace stiffness V G G^T [M,4,4].  Not in the reference (parity unpinned); additive."""
+    return _ops.c3d4(3, coords, elements, device=device, dtype=dtype)
+
+
+def compute_c3d4_M_matrix(coords, elements, rho, device="cuda:0", dtype=torch.float32):
+    """Consistent mass [M,12,12].  Called by the reference's notebook but defined nowhere (parity unpinned)."""
+    return _ops.c3d4(4, coords, elements, rho, 0.0, device, dtype)
+
+
+def c3d10_to_c3d4(c3d10_elements, device="cuda:0"):
+    """8 children per C3D10 (element.py:963-993)."""
+    return _ops.to_c3d4(_ops.C3D10, c3d10_elements, device)
+
+
+def _points_out(kind, device, dtype):
+    rows = torch.tensor(_ops.default_points(kind), dtype=torch.float64)
+    return rows[:, :3].to(dtype).to(device), rows[:, 3].to(dtype).to(device)
+
+
+def c3d10_integration_points(device="cuda:0", dtype=torch.float32):
+    """The reference's 11-point rule, weights summing to 0.45 (element.py:995-1024)."""
+    return _points_out(_ops.C3D10, device, dtype)
+
+
+def _solid(kind, what, coords, elements, integral_point, device, dtype, E=0.0, nu=0.0, single_point=True):
+    pts = _pts(kind, integral_point, dtype, single_point=single_point)
+    return _ops.solid(kind, what, coords, elements, pts, E, nu, device, dtype)
+
+
+def _solid_K(kind, coords, elements, E, nu, integral_point, single, device, dtype):
+    return _solid(kind, 3 if single else 4, coords, elements, integral_point, device, dtype, E, nu, single_point=False)
+
+
+def compute_c3d10_Jacobian(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """[M,3,3] (element.py:1026-1060)."""
+    return _solid(_ops.C3D10, 0, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d10_shape_gradients(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """[M,10,3] (element.py:1062-1095)."""
+    return _solid(_ops.C3D10, 1, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d10_B_matrix(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """[M,6,30] (element.py:1097-1125)."""
+    return _solid(_ops.C3D10, 2, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d10_K_matrix(coords, elements, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32):
+    """sum_q w_q detJ_q B^T D B with signed detJ; single=False -> [n_int,M,30,30] unweighted (element.py:1191-1239)."""
+    return _solid_K(_ops.C3D10, coords, elements, E, nu, integral_point, single, device, dtype)
+
+
+# ------------------------------------------------------------------------------------------- hexahedra
+
+def compute_hexahedral_volumes(coords, elements, device="cuda:0", dtype=torch.float32):
+    """Sum of six |tet| volumes with the reference's table (element.py:1248-1291)."""
+    return _ops.volumes(_ops.C3D8, coords, elements, device, dtype)
+
+
+def compute_hexahedral_surface_faces_with_extra_node(elements, device="cuda:0"):
+    """element.py:1293-1334 (works on [M,20] too: corner columns only)."""
+    f, x, _ = _ops.entities(_ops.ENT_HEX_FACES, elements, device, want_shared=False)
+    return f, x
+
+
+def compute_hexahedral_surface_normals(coords, elements, device="cuda:0", dtype=torch.float32):
+    """element.py:1336-1374"""
+    f, x = compute_hexahedral_surface_faces_with_extra_node(elements, device)
+    return _ops.surface_normals(coords, f, x, 2, device, dtype)
+
+
+def compute_hexahedral_normals_and_area(coords, elements, device="cuda:0", dtype=torch.float32):
+    """[M,6,3] cross(e01,e03), oriented with the element routine's own off-face table (element.py:1418-1472)."""
+    return _ops.face_normals_area(_ops.C3D8, coords, elements, device, dtype)
+
+
+def identify_hexahedral_shared_faces(elements, device="cuda:0"):
+    """element.py:1474-1532"""
+    return _ops.entities(_ops.ENT_HEX_FACES, elements, device, want_surface=False)[2]
+
+
+def c3d8_to_c3d4(c3d8_elements, device="cuda:0"):
+    """The reference's 6-tet table, reproduced as is although it is not a partition of the hex (element.py:1555-1581)."""
+    return _ops.to_c3d4(_ops.C3D8, c3d8_elements, device)
+
+
+def c3d8_integration_points(device="cuda:0", dtype=torch.float32):
+    """2x2x2 Gauss, xi slowest (element.py:1583-1599)."""
+    return _points_out(_ops.C3D8, device, dtype)
+
+
+def compute_c3d8_Jacobian(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """element.py:1601-1632"""
+    return _solid(_ops.C3D8, 0, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d8_shape_gradients(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """element.py:1634-1664"""
+    return _solid(_ops.C3D8, 1, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d8_B_matrix(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """element.py:1666-1694"""
+    return _solid(_ops.C3D8, 2, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d8_K_matrix(coords, elements, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32):
+    """element.py:1754-1803"""
+    return _solid_K(_ops.C3D8, coords, elements, E, nu, integral_point, single, device, dtype)
+
+
+# ------------------------------------------------------------------------------------------- wedges
+
+def compute_wedge_volumes(coords, elements, device="cuda:0", dtype=torch.float32):
+    """element.py:2198-2232"""
+    return _ops.volumes(_ops.C3D6, coords, elements, device, dtype)
+
+
+def compute_wedge_surface_faces_with_extra_node(elements, device="cuda:0"):
+    """([quads, tris], [quad_extra, tri_extra]); the two kinds are grouped separately (element.py:2234-2283)."""
+    q, qe, _ = _ops.entities(_ops.ENT_WEDGE_QUADS, elements, device, want_shared=False)
+    t, te, _ = _ops.entities(_ops.ENT_WEDGE_TRIS, elements, device, want_shared=False)
+    return [q, t], [qe, te]
+
+
+def compute_wedge_surface_normals(coords, elements, device="cuda:0", dtype=torch.float32):
+    """element.py:2285-2338 (quads use nodes 0,1,3 of the face; triangles 0,1,2)."""
+    (q, t), (qe, te) = compute_wedge_surface_faces_with_extra_node(elements, device)
+    return [_ops.surface_normals(coords, q, qe, 3, device, dtype), _ops.surface_normals(coords, t, te, 2, device, dtype)]
+
+
+def c3d6_to_c3d4(element, device="cuda:0"):
+    """element.py:2424-2446"""
+    return _ops.to_c3d4(_ops.C3D6, element, device)
+
+
+def c3d6_integration_points(device="cuda:0", dtype=torch.float32):
+    """3 triangle points x 2 fp32-rounded line points, weights summing to 2 (element.py:2448-2480)."""
+    return _points_out(_ops.C3D6, device, dtype)
+
+
+def compute_c3d6_Jacobian(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """element.py:2482-2509"""
+    return _solid(_ops.C3D6, 0, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d6_shape_gradients(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """element.py:2511-2539"""
+    return _solid(_ops.C3D6, 1, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d6_B_matrix(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """element.py:2541-2568"""
+    return _solid(_ops.C3D6, 2, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d6_K_matrix(coords, elements, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32):
+    """single=True (the reference's default) is the one-point centroid rule times the 3-tet |volume|; single=False the
+    weighted 6-point rule with signed detJ (element.py:2631-2676)."""
+    if single:
+        centroid = _pts(_ops.C3D6, torch.tensor([[1 / 3, 1 / 3, 0.0, 1.0]], dtype=torch.float64), dtype)
+        return _ops.solid(_ops.C3D6, 5, coords, elements, centroid, E, nu, device, dtype)
+    return _solid(_ops.C3D6, 3, coords, elements, integral_point, device, dtype, E, nu, single_point=False)
+
+
+# ------------------------------------------------------------------------------------------- misc topology
+
+def element_to_edge(elements, device="cuda:0"):
+    """Unique sorted tet edges [2,E] (element.py:2687-2713) = strictly upper part of the node-level CSR pattern."""
+    dev = _ops.cuda_device(device)
+    e = _ops.index(elements, dev)[:, :4].contiguous()
+    plan = CsrPlan(e, None, dev)
+    crow, col = plan.pattern(1)
+    rows = torch.repeat_interleave(torch.arange(plan.n_nodes, device=dev), (crow[1:] - crow[:-1]).long())
+    keep = col.long() > rows
+    return torch.stack([rows[keep], col[keep].long()])
+
+
+# ------------------------------------------------------------------------------------------- global assembly (additive API)
+
+def assemble_csr(K, elements, N=None, device="cuda:0", plan=None):
+    """COO of subdivision.ipynb cell 6 -> coalesced CSR (the reference never coalesces).  Returns a
+    torch.sparse_csr_tensor [N*ndof, N*ndof] (int32 indices, fp64 values) whose pattern equals
+    torch.sparse_coo_tensor(...).coalesce().to_sparse_csr() of that COO; duplicates are summed in ascending
+    element order (deterministic)."""
+    dev = _ops.cuda_device(device)
+    K = torch.as_tensor(K)
+    nen = elements.shape[1]
+    ndof = K.shape[1] // nen
+    if plan is None:
+        plan = _ops.cached_plan(elements, N if N is not None else int(torch.as_tensor(elements).max().item()) + 1, dev)
+    crow, col = plan.pattern(ndof)
+    vals = plan.assemble(K, ndof)
+    n = plan.n_nodes * ndof
+    return torch.sparse_csr_tensor(crow, col, vals, size=(n, n), device=dev)

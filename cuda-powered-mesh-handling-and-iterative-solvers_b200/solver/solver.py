@@ -1,0 +1,188 @@
+"""Drop-in mirror of the CG family of the reference's `solver/solver.py` on sm_100a kernels.
+
+Same names, argument order, defaults and return values as the reference.  Where the reference applies the
+operator element by element in every iteration (gather -> bmm -> atomic index_add, solver.py:184), these solvers
+assemble the operator once into CSR (deterministic sort-based assembly) and run the whole loop on the device:
+three fused kernels per iteration captured in a CUDA graph, scalars never leave the GPU, and the convergence /
+breakdown tests are the reference's own (absolute sqrt(r.r) < tol, +eps denominators, pAp guards, node-level
+fixing by projection).  Each solver also accepts `return_info=True` (additive) to get the iteration count the
+reference only prints.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if _HERE not in sys.path:
+    sys.path.insert(0, _HERE)
+
+from element import *  # noqa: E402,F401,F403  (the reference does the same: solver.py:1-2)
+from shell import *    # noqa: E402,F401,F403
+import element as _el  # noqa: E402
+import shell as _sh    # noqa: E402
+from femb200 import ops as _ops  # noqa: E402
+
+
+def _dof_mask(n_nodes, ndof, fixed, dev):
+    mask = torch.ones((n_nodes, ndof), device=dev, dtype=torch.uint8)
+    if fixed is not None and torch.as_tensor(fixed).numel():
+        mask[torch.as_tensor(fixed).to(dev).long()] = 0
+    return mask.reshape(-1).contiguous()
+
+
+def _report(kind, info, max_iter):
+    # the reference prints these lines (solver.py:188-226); kept so notebook output reads the same
+    if info["status"] == "converged":
+        print(f"Converged after {info['iterations']} iterations. Residual norm: {info['rs']:.3e}")
+    elif info["status"] == "breakdown":
+        print(f"Terminating early at iteration {info['iterations']}: CG breakdown (p^T K p invalid or NaN/Inf step).")
+    else:
+        print(f"{kind} did not converge within the maximum number of iterations.")
+
+
+def _operator(K, elements, N, dev):
+    """CSR of sum_e K_e (or pass-through of an already assembled torch CSR tensor)."""
+    if isinstance(K, torch.Tensor) and K.layout == torch.sparse_csr:
+        return K.crow_indices().to(torch.int32), K.col_indices().to(torch.int32), K.values().to(torch.float64), None
+    K = torch.as_tensor(K)
+    ndof = K.shape[1] // elements.shape[1]
+    plan = _ops.cached_plan(elements, N, dev)
+    crow, col = plan.pattern(ndof)
+    return crow, col, plan.assemble(K, ndof), plan
+
+
+def stable_conjugate_gradient_solver(K, elements, F, rbe2, u_init=None, tol=1e-10, max_iter=1000, device="cuda:0", dtype=torch.float64,
+                                     eps=1e-30, return_info=False, verbose=True):
+    """Projected CG with node fixing (solver.py:144-229).  K: element matrices [M,nd,nd] (assembled internally) or a
+    torch CSR tensor.  Arithmetic is fp64 (the reference's default); the result is cast to `dtype`."""
+    dev = _ops.cuda_device(device)
+    F = torch.as_tensor(F).to(dev)
+    N, ndof = F.shape
+    crow, col, val, _ = _operator(K, elements, N, dev)
+    u, info = _ops.cg_solve(crow, col, val, F, mask=_dof_mask(N, ndof, rbe2, dev), u_init=u_init, tol=tol, max_iter=max_iter, eps=eps)
+    if verbose:
+        _report("CG", info, max_iter)
+    u = u.to(dtype)
+    return (u, info) if return_info else u
+
+
+def final_solver(K, elements, F, rbe2, u_init=None, tol=1e-10, max_iter=1000, device="cuda:0", dtype=torch.float64, eps=1e-30,
+                 return_info=False, verbose=True):
+    """Same mathematics as stable_conjugate_gradient_solver written out of place with a 0/1 mask in the reference
+    (solver.py:231-295); identical iterates, so it shares the device loop."""
+    return stable_conjugate_gradient_solver(K, elements, F, rbe2, u_init, tol, max_iter, device, dtype, eps, return_info, verbose)
+
+
+def _shell_global_K(K, unit):
+    """T^T K T with T = blockdiag(R,R,...) per node: the element operator of shell.py:58-102 in global axes."""
+    M, nd, _ = K.shape
+    nb = nd // 3
+    Kb = K.reshape(M, nb, 3, nb, 3)
+    return torch.einsum("mia,mpiqj,mjb->mpaqb", unit, Kb, unit).reshape(M, nd, nd).contiguous()
+
+
+def stable_conjugate_gradient_shell_solver(K, elements, F, rbe2, coords=None, unit=None, u_init=None, tol=1e-10, max_iter=1000,
+                                           device="cuda:0", dtype=torch.float64, eps=1e-30, return_info=False, verbose=True):
+    """Shell CG on 6 dofs per node (solver.py:297-389).  The element operator R^T K_e R is assembled once."""
+    dev = _ops.cuda_device(device)
+    F = torch.as_tensor(F).to(dev)
+    if unit is None:
+        if coords is None:
+            raise ValueError("Neither coords or units data were provided")
+        unit = _sh.compute_s3_local_unitvector(coords, elements, device=dev)
+    N = F.shape[0]
+    Kg = _shell_global_K(torch.as_tensor(K).to(dev, torch.float64), torch.as_tensor(unit).to(dev, torch.float64))
+    crow, col, val, _ = _operator(Kg, elements, N, dev)
+    u, info = _ops.cg_solve(crow, col, val, F, mask=_dof_mask(N, 6, rbe2, dev), u_init=u_init, tol=tol, max_iter=max_iter, eps=eps)
+    if verbose:
+        _report("CG", info, max_iter)
+    u = u.to(dtype)
+    return (u, info) if return_info else u
+
+
+def compute_diagonal_preconditioner(K, elements, N, device="cuda:0", dtype=torch.float32, fixed=None, reference_bug=False):
+    """1/diag(K_global) as [N,3] without assembling K (solver.py:814-833).
+
+    DEVIATION (documented): the reference's strided view `K.view(-1,nd)[:, ::nd+1]` selects COLUMN 0 of
+    every row, not the diagonal, and yields a useless preconditioner.  The default here is the correct Jacobi diagonal
+    (rows of `fixed` nodes set to 0); `reference_bug=True` reproduces the reference's numbers."""
+    dev = _ops.cuda_device(device)
+    K = torch.as_tensor(K).to(dev)
+    e = torch.as_tensor(elements).to(dev).long()
+    nd = K.shape[-1]
+    ndof = nd // e.shape[1]
+    dofs = (e.unsqueeze(-1) * ndof + torch.arange(ndof, device=dev)).reshape(-1)
+    entries = K[:, :, 0].reshape(-1) if reference_bug else K.diagonal(dim1=1, dim2=2).reshape(-1)
+    diag = torch.zeros(N * ndof, device=dev, dtype=dtype).index_add_(0, dofs, entries.to(dtype))
+    m = 1.0 / diag
+    m[m == float("inf")] = 0.0
+    m = m.view(N, ndof)
+    if fixed is not None and not reference_bug:
+        m[torch.as_tensor(fixed).to(dev).long()] = 0.0
+    return m
+
+
+def preconditioned_conjugate_gradient_solver(K, elements, F, M_inv, u_init=None, tol=1e-8, max_iter=1000, device="cuda:0",
+                                             dtype=torch.float32, return_info=False, verbose=True):
+    """Textbook Jacobi-PCG exactly as the reference writes it (solver.py:766-812): z = M_inv*r, converged iff
+    sqrt(r.z) < tol, no node fixing, no guards.  The loop runs in fp64 on the device; the result is cast to `dtype`."""
+    dev = _ops.cuda_device(device)
+    F = torch.as_tensor(F).to(dev)
+    N = F.shape[0]
+    crow, col, val, _ = _operator(K, elements, N, dev)
+    minv = torch.as_tensor(M_inv).to(dev, torch.float64).reshape(-1).contiguous()
+    u, info = _ops.cg_solve(crow, col, val, F, mask=None, minv=minv, u_init=u_init, tol=tol, max_iter=max_iter, eps=0.0)
+    if verbose:
+        if info["status"] == "converged":
+            print(f"Converged after {info['iterations']} iterations.")
+        else:
+            print("Preconditioned CG did not converge within the maximum number of iterations.")
+    u = u.to(dtype)
+    return (u, info) if return_info else u
+
+
+def static_structure_solver(coords, force, fixed, c3d4=None, c3d6=None, c3d8=None, s3=None, s4=None, material=None, u_init=None,
+                            tol=1e-10, max_iter=1000, device="cuda:0", dtype=torch.float64, eps=1e-30, return_info=False, verbose=True):
+    """Mixed-element static solve on [N,6] (solver.py:11-135): solids act on the translations, shells on all six dofs
+    in their own frames.  Every element family is brought to global 6-dof element matrices and assembled into ONE CSR
+    (padded connectivity is avoided by assembling each family on its own plan and summing the CSR triplets)."""
+    dev = _ops.cuda_device(device)
+    coords = torch.as_tensor(coords).to(dev, torch.float64)
+    force = torch.as_tensor(force).to(dev, torch.float64)
+    N = coords.shape[0]
+    E, nu = (material or {}).get("E"), (material or {}).get("nu")
+    fams = []
+
+    def solid6(K3):
+        M, nd, _ = K3.shape
+        nen = nd // 3
+        K6 = torch.zeros((M, nen, 6, nen, 6), device=dev, dtype=torch.float64)
+        K6[:, :, :3, :, :3] = K3.reshape(M, nen, 3, nen, 3)
+        return K6.reshape(M, nen * 6, nen * 6)
+
+    if c3d4 is not None:
+        fams.append((solid6(_el.compute_c3d4_K_matrix(coords, c3d4, E, nu, device=dev, dtype=torch.float64)), c3d4))
+    if c3d8 is not None:
+        fams.append((solid6(_el.compute_c3d8_K_matrix(coords, c3d8, E, nu, device=dev, dtype=torch.float64)), c3d8))
+    if c3d6 is not None:
+        fams.append((solid6(_el.compute_c3d6_K_matrix(coords, c3d6, E, nu, device=dev, dtype=torch.float64)), c3d6))
+    if s3 is not None:
+        K = _sh.compute_s3_K_matrix(coords, s3, material["membrane"], material["bending"], device=dev, dtype=torch.float64)
+        fams.append((_shell_global_K(K, _sh.compute_s3_local_unitvector(coords, s3, device=dev)), s3))
+    if s4 is not None:
+        K = _sh.compute_s4_K_matrix(coords, s4, material["membrane"], material["bending"], device=dev, dtype=torch.float64)
+        fams.append((_shell_global_K(K, _sh.compute_s4_local_unitvector(coords, s4, device=dev)), s4))
+    if verbose:
+        print("Preprocessing done.")
+    mats = []
+    for K6, conn in fams:
+        crow, col, val, _ = _operator(K6, torch.as_tensor(conn).to(dev), N, dev)
+        mats.append((crow, col, val))
+    u, info = _ops.cg_solve_multi(mats, force, mask=_dof_mask(N, 6, fixed, dev), u_init=u_init, tol=tol, max_iter=max_iter, eps=eps)
+    if verbose:
+        _report("CG", info, max_iter)
+    u = u.to(dtype)
+    return (u, info) if return_info else u

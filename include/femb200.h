@@ -1,0 +1,180 @@
+/*
+ * libfemb200 -- C ABI of the B200-native (sm_100a) FEM hot path.
+ *
+ * The reference (sml2004/CUDA-powered-mesh-handling-and-Iterative-solvers) has no FFI: its boundary
+ * is the module-level Python API of solver/element.py, solver/shell.py and solver/solver.py.  Each
+ * entry point below names the reference function (file:line under /root/reference/solver/) whose torch
+ * op chain it replaces; the Python mirror in <package>/solver/ binds them with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; tensors are contiguous row-major
+ *  - `fp` = 4 (float) or 8 (double) bytes per real; `ib` = 4 (int32) or 8 (int64) bytes per index
+ *  - the library never allocates user-visible memory: the caller passes outputs; data-dependent sizes use
+ *    a plan handle (create -> query counts -> fill -> destroy); scratch comes from the stream-ordered pool
+ *  - every call is asynchronous on `stream` (a cudaStream_t) unless it returns a count to the host
+ *  - return value 0 = ok; otherwise femb_last_error() holds a message (thread-local)
+ */
+#ifndef FEMB200_H
+#define FEMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* femb_stream; /* cudaStream_t */
+
+enum {
+  FEMB_OK = 0,
+  FEMB_ERR_ARG = 1,
+  FEMB_ERR_CUDA = 2,
+  FEMB_ERR_SINGULAR = 3, /* reference raises ValueError (element.py:857-858) */
+  FEMB_ERR_NCCL = 4,
+  FEMB_ERR_UNSUPPORTED = 5
+};
+
+const char* femb_last_error(void);
+int femb_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Element kernels (solver/element.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* element kinds */
+enum { FEMB_C3D4 = 4, FEMB_C3D6 = 6, FEMB_C3D8 = 8, FEMB_C3D10 = 10, FEMB_S3 = 103, FEMB_S4 = 104 };
+
+/* compute_tetrahedral_volumes :514-541, compute_hexahedral_volumes :1248-1291, compute_wedge_volumes :2198-2232.
+ * vol[M] = sum of |det|/6 over the reference's sub-tet table of `kind`. */
+int femb_elem_volumes(int kind, const void* coords, int fp, const void* conn, int ib, int64_t M, int conn_stride,
+                      void* vol, femb_stream stream);
+
+/* compute_c3d4_B_matrix :835-881 (what = 0: gradients [M,4,3]; 1: B [M,6,12]) and compute_c3d4_K_matrix :883-903
+ * (what = 2: K [M,12,12] = B^T D B V; 3: Poisson V G G^T [M,4,4] (not in the reference); 4: consistent mass
+ * rho V/20 (1+delta) (x) I3 [M,12,12] with rho passed in `E` (not in the reference)).
+ * `flag` (device int32, zeroed by the caller) is set to 1 when any |det[1,x,y,z]| < 1e-12 (-> ValueError). */
+int femb_c3d4(int what, const void* coords, int fp, const void* conn, int ib, int64_t M, double E, double nu, void* out,
+              int32_t* flag, femb_stream stream);
+
+/* Isoparametric solids C3D10/C3D8/C3D6:
+ *   compute_c3d10_{Jacobian,shape_gradients,B_matrix,K_matrix} :1026-1125,:1191-1239
+ *   compute_c3d8_*  :1601-1694,:1754-1803     compute_c3d6_* :2482-2568,:2631-2676
+ * `pts_host` = [nq,4] doubles (xi,eta,zeta,w) on the HOST (the caller resolves defaults; the library ships
+ * the reference's rules through femb_default_points).
+ * what = 0: J [M,3,3] at pts[0]; 1: gradients [M,nen,3] at pts[0]; 2: B [M,6,3nen] at pts[0];
+ *        3: K [M,nd,nd] = sum_q w_q detJ_q B^T D B (signed detJ);
+ *        4: per-point K [nq,M,nd,nd] = detJ_q B^T D B, unweighted (single=False);
+ *        5: (C3D6 single=True) K = B^T D B at pts[0] times the 3-tet |volume|. */
+int femb_solid(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* pts_host,
+               int nq, double E, double nu, void* out, femb_stream stream);
+
+/* c3d10_integration_points :995-1024, c3d8_integration_points :1583-1599, c3d6_integration_points :2448-2480,
+ * s4_integration_points shell.py:651-672.  Fills pts_host[nq*4] (shells: xi,eta,0,w), returns nq (or -1). */
+int femb_default_points(int kind, double* pts_host);
+
+/* Shell elements (solver/shell.py): compute_s3_* :297-453, compute_s4_* :597-861.
+ * what = 0: unit [M,3,3]; 1: J [M,2,2]; 2: gradients [M,nen,2]; 3: B [M,6,6nen]; 4: K [M,6nen,6nen];
+ *        5: (S4) per-point K [M,24,24,nq] (single=False).  S3 ignores pts. D6 = Kirchhoff D as 36 doubles (host). */
+int femb_shell(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* pts_host,
+               int nq, const double* D6_host, void* out, femb_stream stream);
+
+/* Fixed-table connectivity expansion: c3d10_to_c3d4 :963-993, c3d8_to_c3d4 :1555-1581, c3d6_to_c3d4 :2424-2446.
+ * out[k*M,4] int64, k = 8/6/3. */
+int femb_to_c3d4(int kind, const void* conn, int ib, int64_t M, int64_t* out, femb_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Topology (bit-exact): faces of solids, edges of shells
+ *   surface: compute_tetrahedral_surface_faces_with_fourth_node :543-579, hex :1293-1334, wedge :2234-2283,
+ *            shell.py compute_triangle_surface_faces_with_third_node :261-295, square :561-597
+ *   shared : identify_tetrahedral_shared_faces :707-762, hex :1474-1532, shell.py S3 :205-259, S4 :504-559
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  FEMB_ENT_TET_FACES = 0,
+  FEMB_ENT_HEX_FACES = 1,
+  FEMB_ENT_WEDGE_QUADS = 2,
+  FEMB_ENT_WEDGE_TRIS = 3,
+  FEMB_ENT_TRI_EDGES = 4,
+  FEMB_ENT_QUAD_EDGES = 5
+};
+typedef struct femb_entity_plan femb_entity_plan;
+/* Sorts the canonical (ascending) node tuples of all entities once; synchronises the stream to return counts. */
+int femb_entities_create(int ent_kind, const void* conn, int ib, int64_t M, int conn_stride, femb_stream stream,
+                         femb_entity_plan** plan, int64_t* n_surface, int64_t* n_shared);
+/* faces[K,nfn] int64 in slot-major order with the element's node order, extra[K] = off-entity node */
+int femb_entities_surface(femb_entity_plan* plan, int64_t* faces, int64_t* extra, femb_stream stream);
+/* pairs[S,2,2] int64 = ((elem,local),(elem,local)), rows lexicographic by sorted tuple, lower element id first */
+int femb_entities_shared(femb_entity_plan* plan, int64_t* pairs, femb_stream stream);
+int femb_entities_destroy(femb_entity_plan* plan);
+
+/* Outward normals: compute_tetrahdral_surface_normals :581-619, hex :1336-1374, wedge :2285-2338.
+ * faces[K,nfn] + extra[K] as returned above; `second` = which face node forms the second edge (2; wedge quads 3). */
+int femb_surface_normals(const void* coords, int fp, const int64_t* faces, const int64_t* extra, int64_t K, int nfn,
+                         int second, void* normals, femb_stream stream);
+/* compute_tetrahedral_normals_and_area :652-705 (kind=FEMB_C3D4, [M,4,3]),
+ * compute_hexahedral_normals_and_area :1418-1472 (kind=FEMB_C3D8, [M,6,3]) */
+int femb_face_normals_area(int kind, const void* coords, int fp, const void* conn, int ib, int64_t M, int conn_stride,
+                           void* out, femb_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Global assembly: COO (subdivision.ipynb cell 6) -> CSR, deterministic
+ * ------------------------------------------------------------------------------------------- */
+typedef struct femb_csr_plan femb_csr_plan;
+/* Builds the node-level sparsity pattern and the node->element incidence lists (sort based).
+ * n_nodes = elements.max()+1 as in cell 6 line 11.  Synchronises the stream to return nnz_nodes. */
+int femb_csr_plan_create(const void* conn, int ib, int64_t M, int nen, int64_t n_nodes, femb_stream stream,
+                         femb_csr_plan** plan, int64_t* nnz_nodes);
+/* dof-level pattern for `ndof` dofs per node: crow[n_nodes*ndof+1], col[nnz_nodes*ndof^2] (int32), identical to
+ * torch.sparse_coo_tensor(...).coalesce().to_sparse_csr() of the cell-6 COO. */
+int femb_csr_plan_pattern(femb_csr_plan* plan, int ndof, int32_t* crow, int32_t* col, femb_stream stream);
+/* vals[nnz] (fp64) = ordered (element-ascending) sums of the materialised element matrices Ke[M,nen*ndof,nen*ndof] */
+int femb_csr_assemble(femb_csr_plan* plan, int ndof, const double* Ke, double* vals, femb_stream stream);
+/* fused P1-tet assembly straight from coordinates (never materialises Ke): kind 0 = Poisson (ndof 1),
+ * 1 = elasticity (ndof 3, E/nu). */
+int femb_csr_assemble_c3d4(femb_csr_plan* plan, int kind, const double* coords, double E, double nu, double* vals,
+                           int32_t* flag, femb_stream stream);
+int femb_csr_plan_destroy(femb_csr_plan* plan);
+
+/* ---------------------------------------------------------------------------------------------
+ * Operator application and Krylov solvers
+ * ------------------------------------------------------------------------------------------- */
+/* y = A x, CSR with int32 indices and fp64 values */
+int femb_spmv(int64_t n_rows, int64_t nnz, const int32_t* crow, const int32_t* col, const double* val, const double* x, double* y,
+              femb_stream stream);
+
+/* compute_nodal_forces element.py:429-464: y[N,ndof] = sum_e K_e u_e, deterministic (incidence ordered).
+ * compute_shell_nodal_forces shell.py:58-102 when unit != NULL (ndof = 6, rotates into/out of the element frame). */
+int femb_ebe_apply(femb_csr_plan* plan, int ndof, const void* Ke, const void* u, const void* unit, int fp, void* y,
+                   femb_stream stream);
+
+typedef struct femb_cg_result {
+  int32_t iterations; /* the count the reference prints: i+1 at exit, max_iter when not converged */
+  int32_t status;     /* 0 converged, 1 breakdown (pAp guard / NaN), 2 max_iter */
+  double rs;          /* last r.r (or r.z) */
+} femb_cg_result;
+
+/* stable_conjugate_gradient_solver solver.py:144-229 (also the loops of :11-135, :231-295, :297-389) on the
+ * assembled operator: projected CG, rows with mask[i]==0 are held at zero, absolute test sqrt(r.r)<tol,
+ * +eps denominators, pAp guards.  minv != NULL selects preconditioned_conjugate_gradient_solver :766-812
+ * (z = minv*r, test sqrt(r.z)<tol, no guards, no eps).  u holds u_init on entry and the solution on exit.
+ * work = 4*n doubles of caller scratch.  The loop is captured in a CUDA graph; blocks until done. */
+int femb_cg_solve(int64_t n, int64_t nnz, const int32_t* crow, const int32_t* col, const double* val, const double* F,
+                  const uint8_t* mask, const double* minv, double* u, double* work, double tol, int max_iter, double eps,
+                  int check_every, femb_cg_result* result_host, femb_stream stream);
+
+/* Same loop with the operator given as a SUM of up to 8 CSR matrices over the same n rows (static_structure_solver
+ * solver.py:11-135 sums one operator per element family: C3D4/C3D8/C3D6 on the translations, S3/S4 on all six dofs).
+ * The *_host arguments are host arrays of nmat device pointers / sizes. */
+int femb_cg_solve_multi(int64_t n, int nmat, const int64_t* nnz_host, const int32_t* const* crow_host,
+                        const int32_t* const* col_host, const double* const* val_host, const double* F, const uint8_t* mask,
+                        const double* minv, double* u, double* work, double tol, int max_iter, double eps, int check_every,
+                        femb_cg_result* result_host, femb_stream stream);
+
+/* Jacobi diagonal of a CSR matrix: minv[i] = mask[i] ? 1/A_ii : 0 (the documented replacement for the
+ * reference's broken compute_diagonal_preconditioner solver.py:814-833) */
+int femb_csr_jacobi(int64_t n, const int32_t* crow, const int32_t* col, const double* val, const uint8_t* mask,
+                    double* minv, femb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMB200_H */

@@ -1,0 +1,435 @@
+"""GPU parity tests: the CUDA path (through the reference-shaped Python API -> ctypes -> libfemb200 C ABI) against
+(a) outputs of the reference itself (tests/golden/*.npz) and (b) the CPU oracle on seeded inputs.
+Bars (north_star): topology and CSR pattern bit-exact; fp64 element matrices / assembled values 1e-12 relative;
+CG solution 1e-8 relative with iteration counts within +-1."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(PKG, "solver"))
+
+TOL = 1e-12
+E, NU = 1.0, 0.3
+DEV = "cuda:0"
+KW = dict(device=DEV, dtype=torch.float64)
+MB = torch.tensor([1.0, 0.3, 0.1], dtype=torch.float64)
+
+
+@pytest.fixture(scope="module")
+def api():
+    import element
+    import shell
+    import solver
+    return element, shell, solver
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import fem_oracle
+    return fem_oracle
+
+
+def T(a, dtype=None):
+    t = torch.as_tensor(np.asarray(a))
+    return t.to(dtype) if dtype is not None else t
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, tol=TOL):
+    a, b = N(a) if torch.is_tensor(a) else np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert rel_err(a, b) <= tol, rel_err(a, b)
+
+
+def same(a, b):
+    a, b = N(a) if torch.is_tensor(a) else np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(a.astype(np.int64), b.astype(np.int64))
+
+
+def test_library_loaded_is_in_tree():
+    from femb200 import _lib
+    assert os.path.dirname(_lib.LIB_PATH) == PKG and _lib.lib.femb_version() >= 100
+
+
+def test_c3d4(api, O):
+    el = api[0]
+    g = load_golden("tets")
+    c, t = T(g["coords"]), T(g["tets"])
+    close(el.compute_tetrahedral_volumes(c, t, **KW), g["vol"])
+    close(el.compute_c3d4_B_matrix(c, t, **KW), g["B"])
+    close(el.compute_c3d4_K_matrix(c, t, E, NU, **KW), g["K"])
+    close(el.compute_K_matrix(c, t, "C3D4", E, NU, **KW), g["K"])
+    close(el.compute_c3d4_poisson_K_matrix(c, t, **KW), O.c3d4_poisson_K(g["coords"], g["tets"]))
+    close(el.compute_c3d4_M_matrix(c, t, 2.5, **KW), O.c3d4_mass(g["coords"], g["tets"], 2.5))
+    close(el.compute_c3d4_K_matrix(c, t.to(torch.int32), E, NU, **KW), g["K"])       # int32 connectivity accepted
+    k32 = el.compute_c3d4_K_matrix(c, t, E, NU, device=DEV)                            # default dtype float32
+    assert k32.dtype == torch.float32
+    close(k32.double(), g["K"], 2e-5)
+    close(el.compute_elasticity_matrix(E, NU, **KW), load_golden("units")["D"])
+
+
+def test_c3d4_singular_raises(api):
+    el = api[0]
+    c = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.0]], dtype=torch.float64)   # coplanar
+    with pytest.raises(ValueError):
+        el.compute_c3d4_B_matrix(c, torch.tensor([[0, 1, 2, 3]]), **KW)
+    with pytest.raises(ValueError):
+        el.compute_c3d4_K_matrix(c, torch.tensor([[0, 1, 2, 3]]), E, NU, **KW)
+
+
+def test_empty_inputs(api):
+    el = api[0]
+    c = torch.zeros((4, 3), dtype=torch.float64)
+    e = torch.zeros((0, 4), dtype=torch.int64)
+    assert el.compute_c3d4_K_matrix(c, e, E, NU, **KW).shape == (0, 12, 12)
+    assert el.compute_c3d10_K_matrix(c, torch.zeros((0, 10), dtype=torch.int64), E, NU, **KW).shape == (0, 30, 30)
+    f, x = el.compute_tetrahedral_surface_faces_with_fourth_node(e, device=DEV)
+    assert f.shape == (0, 3) and x.shape == (0,)
+    assert el.identify_tetrahedral_shared_faces(e, device=DEV).shape == (0, 2, 2)
+
+
+def test_c3d10(api, O):
+    el = api[0]
+    g = load_golden("tets")
+    c2, e10, ip = T(g["coords10"]), T(g["elems10"]), T(g["ip10"])
+    close(el.compute_c3d10_Jacobian(c2, e10, ip, **KW), g["J10"])
+    close(el.compute_c3d10_shape_gradients(c2, e10, ip, **KW), g["g10"])
+    close(el.compute_c3d10_B_matrix(c2, e10, ip, **KW), g["B10"])
+    close(el.compute_c3d10_K_matrix(c2, e10, E, NU, **KW), g["K10"])
+    close(el.compute_K_matrix(c2, e10, "c3d10", E, NU, **KW), g["K10"])
+    close(el.compute_c3d10_K_matrix(c2, e10[:5], E, NU, single=False, **KW), g["K10_multi"])
+    close(el.compute_c3d10_K_matrix(c2, e10, E, NU, integral_point=T(g["pts10_custom"]), **KW), g["K10_custom"])
+    same(el.c3d10_to_c3d4(e10, device=DEV), g["tets_from10"])
+    same(el.to_c3d4(e10, device=DEV), g["tets_from10"])
+    p, w = el.c3d10_integration_points(**KW)
+    close(p, g["pts10"], 0); close(w, g["w10"], 0)
+    # dtype-dropping dispatchers (quirk q2): float32 out even for float64 in
+    assert el.compute_Jacobian(c2, e10, "c3d10", ip, device=DEV).dtype == torch.float32
+    assert el.integral_points("c3d10", device=DEV)[0].dtype == torch.float32
+    # P1 -> P2 with the reference's first-encounter numbering
+    t01 = T(g["tets"])[:, [1, 0, 2, 3]]
+    nc, ne, _, _ = el.c3d4_to_c3d10(T(g["coords"]).to(DEV), t01.to(DEV), dtype=torch.float64)
+    assert ne.dtype == torch.int32 and nc.device.type == "cpu"
+    same(ne, g["elems10"]); close(nc, g["coords10"], 1e-15)
+
+
+def test_c3d8(api):
+    el = api[0]
+    g = load_golden("hexes")
+    c, h, ip = T(g["coords"]), T(g["hexes"]), T(g["ip"])
+    close(el.compute_hexahedral_volumes(c, h, **KW), g["vol"])
+    close(el.compute_c3d8_Jacobian(c, h, ip, **KW), g["J"])
+    close(el.compute_c3d8_shape_gradients(c, h, ip, **KW), g["g"])
+    close(el.compute_c3d8_B_matrix(c, h, ip, **KW), g["B"])
+    close(el.compute_c3d8_K_matrix(c, h, E, NU, **KW), g["K"])
+    close(el.compute_c3d8_K_matrix(c, h[:3], E, NU, single=False, **KW), g["K_multi"])
+    p, w = el.c3d8_integration_points(**KW)
+    close(p, g["pts"], 0); close(w, g["w"], 0)
+    f, x = el.compute_hexahedral_surface_faces_with_extra_node(h, device=DEV)
+    same(f, g["surf_faces"]); same(x, g["surf_extra"])
+    from oracle import fem_oracle as O
+    same(el.identify_hexahedral_shared_faces(h, device=DEV), O.canonical_pairs(g["shared"]))
+    close(el.compute_hexahedral_surface_normals(c, h, **KW), g["surf_normals"])
+    close(el.compute_hexahedral_normals_and_area(c, h, **KW), g["face_normals"])
+    same(el.c3d8_to_c3d4(h, device=DEV), g["tets"])
+
+
+def test_c3d6(api):
+    el = api[0]
+    g = load_golden("wedges")
+    c, w6, ip = T(g["coords"]), T(g["wedges"]), T(g["ip"])
+    close(el.compute_wedge_volumes(c, w6, **KW), g["vol"])
+    close(el.compute_c3d6_Jacobian(c, w6, ip, **KW), g["J"])
+    close(el.compute_c3d6_shape_gradients(c, w6, ip, **KW), g["g"])
+    close(el.compute_c3d6_B_matrix(c, w6, ip, **KW), g["B"])
+    close(el.compute_c3d6_K_matrix(c, w6, E, NU, single=True, **KW), g["K_single"])
+    close(el.compute_c3d6_K_matrix(c, w6, E, NU, single=False, **KW), g["K_full"])
+    p, w = el.c3d6_integration_points(**KW)
+    close(p, g["pts"], 0); close(w, g["w"], 0)
+    (q, t), (qe, te) = el.compute_wedge_surface_faces_with_extra_node(w6, device=DEV)
+    same(q, g["surf_quads"]); same(t, g["surf_tris"]); same(qe, g["quad_extra"]); same(te, g["tri_extra"])
+    nq, nt = el.compute_wedge_surface_normals(c, w6, **KW)
+    close(nq, g["nq"]); close(nt, g["nt"])
+    same(el.c3d6_to_c3d4(w6, device=DEV), g["tets"])
+
+
+def test_tet_topology(api, O):
+    el = api[0]
+    g = load_golden("tets")
+    c, t = T(g["coords"]), T(g["tets"])
+    f, x = el.compute_tetrahedral_surface_faces_with_fourth_node(t, device=DEV)
+    same(f, g["surf_faces"]); same(x, g["surf_fourth"])
+    same(el.identify_tetrahedral_shared_faces(t, device=DEV), O.canonical_pairs(g["shared"]))
+    close(el.compute_tetrahdral_surface_normals(c, t, **KW), g["surf_normals"])
+    close(el.compute_tetrahedral_normals_and_area(c, t, **KW), g["face_normals"])
+    same(el.element_to_edge(t, device=DEV), g["edges"])
+
+
+def test_topology_vs_oracle_shuffled(api, O):
+    """Node ids permuted and elements shuffled: nothing may depend on lattice order."""
+    el = api[0]
+    from femb200 import meshgen
+    rng = np.random.default_rng(7)
+    for gen, surf, shared, o_surf, o_shared in (
+            (meshgen.kuhn_cube, el.compute_tetrahedral_surface_faces_with_fourth_node, el.identify_tetrahedral_shared_faces,
+             O.tet_surface_faces, O.tet_shared_faces),
+            (meshgen.hex_cube, el.compute_hexahedral_surface_faces_with_extra_node, el.identify_hexahedral_shared_faces,
+             O.hex_surface_faces, O.hex_shared_faces)):
+        c, e = gen(5)
+        perm = rng.permutation(c.shape[0])
+        e = torch.as_tensor(perm)[e][torch.as_tensor(rng.permutation(e.shape[0]))]
+        f, x = surf(e, device=DEV)
+        of, ox = o_surf(N(e))
+        same(f, of); same(x, ox)
+        same(shared(e, device=DEV), o_shared(N(e)))
+        nf = 4 if e.shape[1] == 4 else 6
+        assert 2 * o_shared(N(e)).shape[0] + of.shape[0] == nf * e.shape[0]
+
+
+def test_topology_wide_node_ids(api, O):
+    """Node ids needing > 21 bits force the multi-pass (96-bit key) path."""
+    el = api[0]
+    from femb200 import meshgen
+    _, e = meshgen.kuhn_cube(3)
+    big = e * 1_000_003 + 5
+    f, x = el.compute_tetrahedral_surface_faces_with_fourth_node(big, device=DEV)
+    of, ox = O.tet_surface_faces(N(big))
+    same(f, of); same(x, ox)
+    same(el.identify_tetrahedral_shared_faces(big, device=DEV), O.tet_shared_faces(N(big)))
+
+
+def test_shells(api, O):
+    sh = api[1]
+    g = load_golden("shells")
+    c3, s3, c4, s4 = T(g["c3"]), T(g["s3"]), T(g["c4"]), T(g["s4"])
+    close(sh.compute_kirchoff_D_matrix(MB, MB, **KW), g["D"])
+    close(sh.compute_s3_local_unitvector(c3, s3, device=DEV), g["unit3"])
+    close(sh.compute_s3_jacobian(c3, s3, **KW), g["J3"])
+    close(sh.compute_s3_shape_gradient(c3, s3, **KW), g["g3"])
+    close(sh.compute_s3_B_matrix(c3, s3, **KW), g["B3"])
+    close(sh.compute_s3_K_matrix(c3, s3, MB, MB, **KW), g["K3"])
+    same(sh.identify_s3_shared_edges(s3, device=DEV), O.canonical_pairs(g["shared3"]))
+    e, t = sh.compute_triangle_surface_faces_with_third_node(s3, device=DEV)
+    same(e, g["bedges3"]); same(t, g["bthird3"])
+    xi, eta = g["xieta"]
+    close(sh.compute_s4_local_unitvector(c4, s4, device=DEV), g["unit4"])
+    close(sh.compute_s4_jacobian(c4, s4, xi, eta, **KW), g["J4"])
+    close(sh.compute_s4_shape_gradient(c4, s4, xi, eta, **KW), g["g4"])
+    close(sh.compute_s4_B_matrix_single(c4, s4, xi, eta, **KW), g["B4"])
+    close(sh.compute_s4_K_matrix(c4, s4, MB, MB, **KW), g["K4"])
+    close(sh.compute_s4_K_matrix(c4, s4, MB, MB, single=False, **KW), g["K4_multi"])
+    p, w = sh.s4_integration_points(device=DEV)
+    assert p.dtype == torch.float32
+    close(p.double(), g["pts4"], 0)
+    same(sh.identify_s4_shared_edges(s4, device=DEV), O.canonical_pairs(g["shared4"]))
+    e, t = sh.compute_square_surface_faces_with_fourth_node(s4, device=DEV)
+    same(e, g["bedges4"]); same(t, g["bfourth4"])
+    close(sh.compute_shell_nodal_forces(T(g["K3"]), s3, T(g["u3"]), T(g["unit3"]), **KW), g["f3"])
+    close(sh.compute_shell_nodal_forces(T(g["K4"]), s4, T(g["u4"]), T(g["unit4"]), **KW), g["f4"])
+
+
+def test_unit_known_answers(api):
+    """SURVEY.md section 4 table on the GPU path."""
+    el, sh, _ = api
+    g = load_golden("units")
+    c = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]], dtype=torch.float64)
+    K = el.compute_c3d4_K_matrix(c, torch.tensor([[0, 1, 2, 3]]), E, NU, **KW)
+    assert abs(K[0, 0, 0].item() - 0.35256410256410248) < 1e-14 and abs(K[0, 0, 1].item() - 0.16025641025641024) < 1e-14
+    close(K, g["c3d4"])
+    from femb200 import meshgen
+    ch, h = meshgen.hex_cube(1)
+    close(el.compute_c3d8_K_matrix(ch, h, E, NU, **KW), g["c3d8"])
+    w = h[:, [0, 1, 2, 4, 5, 6]]
+    close(el.compute_c3d6_K_matrix(ch, w, E, NU, single=True, **KW), g["c3d6_single"])
+    close(el.compute_c3d6_K_matrix(ch, w, E, NU, single=False, **KW), g["c3d6_full"])
+    cs = torch.tensor([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0.0]], dtype=torch.float64)
+    close(sh.compute_s3_K_matrix(cs, torch.tensor([[0, 1, 3]]), MB, MB, **KW), g["s3"])
+    close(sh.compute_s4_K_matrix(cs, torch.tensor([[0, 1, 2, 3]]), MB, MB, **KW), g["s4"])
+
+
+def test_nodal_forces(api):
+    el = api[0]
+    g = load_golden("tets")
+    close(el.compute_nodal_forces(T(g["K10"]), T(g["elems10"]), T(g["u10"]), **KW), g["f10"])
+    f32 = el.compute_nodal_forces(T(g["K10"]), T(g["elems10"]), T(g["u10"]), device=DEV)
+    assert f32.dtype == torch.float32
+    close(f32.double(), g["f10"], 1e-4)
+
+
+def test_assembly_csr(api, O):
+    el = api[0]
+    g = load_golden("solve_c3d4")
+    c, t = T(g["coords"]), T(g["tets"])
+    K = el.compute_c3d4_K_matrix(c, t, E, NU, **KW)
+    A = el.assemble_csr(K, t, c.shape[0], device=DEV)
+    same(A.crow_indices(), g["crow"]); same(A.col_indices(), g["col"])       # pattern bit-exact vs torch coalesce
+    close(A.values(), g["val"])
+    # fused P1 assembly (never materialises Ke) gives the same matrix; Poisson vs oracle
+    plan = el.CsrPlan(t, c.shape[0], DEV)
+    close(plan.assemble_c3d4(c, "elasticity", E, NU), g["val"])
+    crow, col, val, _ = O.assemble_csr(O.c3d4_poisson_K(g["coords"], g["tets"]), g["tets"], 1, c.shape[0])
+    pc, pcol = plan.pattern(1)
+    same(pc, crow); same(pcol, col)
+    close(plan.assemble_c3d4(c, "poisson"), val)
+    close(plan.assemble(el.compute_c3d4_poisson_K_matrix(c, t, **KW), 1), val)
+    # run-to-run determinism: bit-identical values
+    v1, v2 = plan.assemble_c3d4(c, "elasticity", E, NU), plan.assemble_c3d4(c, "elasticity", E, NU)
+    assert torch.equal(v1, v2)
+    # SpMV equals the element-by-element operator
+    from femb200 import ops
+    x = torch.randn(c.shape[0], 3, dtype=torch.float64, device=DEV, generator=torch.Generator(DEV).manual_seed(0))
+    y = ops.spmv(A.crow_indices(), A.col_indices(), A.values(), x)
+    close(y, N(el.compute_nodal_forces(K, t, x, **KW)), 1e-13)
+
+
+def test_assembly_p2_and_mixed_types(api, O):
+    el = api[0]
+    g = load_golden("tets")
+    c2, e10 = T(g["coords10"]), T(g["elems10"])
+    A = el.assemble_csr(T(g["K10"]), e10, c2.shape[0], device=DEV)
+    crow, col, val, _ = O.assemble_csr(g["K10"], g["elems10"], 3, c2.shape[0])
+    same(A.crow_indices(), crow); same(A.col_indices(), col); close(A.values(), val)
+    gh = load_golden("hexes")
+    A = el.assemble_csr(T(gh["K"]), T(gh["hexes"]), gh["coords"].shape[0], device=DEV)
+    crow, col, val, _ = O.assemble_csr(gh["K"], gh["hexes"], 3, gh["coords"].shape[0])
+    same(A.crow_indices(), crow); same(A.col_indices(), col); close(A.values(), val)
+
+
+def test_cg_family(api, O):
+    el, _, sv = api
+    g = load_golden("solve_c3d4")
+    c, t, fixed, F = T(g["coords"]), T(g["tets"]), T(g["fixed"]), T(g["F"])
+    K = el.compute_c3d4_K_matrix(c, t, E, NU, **KW)
+    u, info = sv.stable_conjugate_gradient_solver(K, t, F, fixed, tol=1e-8, return_info=True, **KW)
+    assert info["status"] == "converged" and abs(info["iterations"] - int(g["it_cg"])) <= 1
+    close(u, g["u_cg"], 1e-8)
+    u2, info2 = sv.final_solver(K, t, F, fixed, tol=1e-8, return_info=True, **KW)
+    assert abs(info2["iterations"] - int(g["it_final"])) <= 1
+    close(u2, g["u_final"], 1e-8)
+    # already-assembled CSR operator is accepted too
+    A = el.assemble_csr(K, t, c.shape[0], device=DEV)
+    u3 = sv.stable_conjugate_gradient_solver(A, t, F, fixed, tol=1e-8, **KW)
+    close(u3, g["u_cg"], 1e-8)
+    # Jacobi PCG with the corrected diagonal (documented deviation) and the reference's own loop semantics
+    Minv = sv.compute_diagonal_preconditioner(K, t, c.shape[0], fixed=fixed, **KW)
+    close(Minv, g["Minv"])
+    u4, info4 = sv.preconditioned_conjugate_gradient_solver(K, t, F, Minv, tol=1e-8, return_info=True, **KW)
+    assert info4["status"] == "converged" and abs(info4["iterations"] - int(g["it_pcg"])) <= 1
+    close(u4, g["u_pcg"], 1e-8)
+    # max_iter exhausted: same partial iterate as the oracle loop
+    u5, info5 = sv.stable_conjugate_gradient_solver(K, t, F, fixed, tol=1e-8, max_iter=10, return_info=True, **KW)
+    ou, oit, ost = O.stable_cg(N(K), g["tets"], g["F"], g["fixed"], tol=1e-8, max_iter=10)
+    assert info5["status"] == "maxiter" == ost and info5["iterations"] == 10
+    close(u5, ou, 1e-10)
+    # warm start from the solution converges immediately
+    u6, info6 = sv.stable_conjugate_gradient_solver(K, t, F, fixed, u_init=T(g["u_cg"]), tol=1e-6, return_info=True, **KW)
+    assert info6["iterations"] <= 2
+
+
+def test_cg_breakdown_guard(api):
+    """A negatively oriented C3D10 element gives a negative-definite K (quirk q3): the reference exits on pAp<0."""
+    el, _, sv = api
+    g = load_golden("tets")
+    c, t = T(g["coords"]), T(g["tets"])        # NOT swapped: reference detJ < 0
+    nc, ne, _, _ = el.c3d4_to_c3d10(c.to(DEV), t.to(DEV), dtype=torch.float64)
+    K = el.compute_c3d10_K_matrix(nc, ne.long(), E, NU, **KW)
+    F = torch.zeros(nc.shape[0], 3, dtype=torch.float64)
+    F[-1, 2] = 1.0
+    u, info = sv.stable_conjugate_gradient_solver(K, ne.long(), F, torch.tensor([0]), tol=1e-8, return_info=True, **KW)
+    assert info["status"] == "breakdown" and info["iterations"] == 1
+    assert float(u.abs().max()) == 0.0
+
+
+def test_static_structure_mixed(api):
+    sv = api[2]
+    g = load_golden("solve_mixed")
+    mat = {"E": E, "nu": NU, "membrane": MB, "bending": MB}
+    u, info = sv.static_structure_solver(T(g["coords"]), T(g["force"]), T(g["fixed"]), c3d4=T(g["c3d4"]), c3d6=T(g["c3d6"]),
+                                         c3d8=T(g["c3d8"]), s3=T(g["s3"]), s4=T(g["s4"]), material=mat, tol=1e-8, max_iter=2000,
+                                         return_info=True, **KW)
+    assert info["status"] == "converged" and abs(info["iterations"] - int(g["it"])) <= 1
+    close(u, g["u"], 1e-8)
+
+
+def test_shell_cg(api):
+    _, sh, sv = api
+    g = load_golden("solve_shell")
+    c3, s3 = T(g["c3"]), T(g["s3"])
+    K = sh.compute_s3_K_matrix(c3, s3, MB, MB, **KW)
+    u, info = sv.stable_conjugate_gradient_shell_solver(K, s3, T(g["F"]), T(g["fixed"]), coords=c3, tol=1e-9, max_iter=3000,
+                                                        return_info=True, **KW)
+    assert info["status"] == "converged" and abs(info["iterations"] - int(g["it"])) <= 25
+    close(u, g["u"], 1e-6)
+
+
+def test_kuhn20_known_counts_and_cg(api, O):
+    """BASELINE config 1 / 1': 20^3 Kuhn cube.  Counts from SURVEY.md section 4; CG within +-1 iteration of the oracle."""
+    el, _, sv = api
+    from femb200 import meshgen
+    c, t = meshgen.kuhn_cube(20)
+    f, _ = el.compute_tetrahedral_surface_faces_with_fourth_node(t, device=DEV)
+    s = el.identify_tetrahedral_shared_faces(t, device=DEV)
+    assert f.shape[0] == 4800 and s.shape[0] == 93600
+    plan = el.CsrPlan(t, c.shape[0], DEV)
+    assert plan.nnz_nodes == 128581 and plan.pattern(3)[1].numel() == 1157229
+    # Poisson (config 1): z=0 Dirichlet, f=1 lumped
+    vals = plan.assemble_c3d4(c, "poisson")
+    crow, col = plan.pattern(1)
+    fixed = torch.nonzero(c[:, 2] == 0).reshape(-1)
+    Kp = O.c3d4_poisson_K(N(c), N(t))
+    load = np.bincount(N(t).reshape(-1), weights=np.repeat(O.tet_volumes(N(c), N(t)) / 4, 4), minlength=c.shape[0])
+    from femb200 import ops
+    mask = torch.ones(c.shape[0], dtype=torch.uint8, device=DEV)
+    mask[fixed.to(DEV)] = 0
+    u, info = ops.cg_solve(crow, col, vals, T(load).reshape(-1, 1).to(DEV), mask=mask, tol=1e-8)
+    ou, oit, ost = O.stable_cg(Kp, N(t), load.reshape(-1, 1), N(fixed), tol=1e-8, ndof=1)
+    assert info["status"] == ost == "converged" and abs(info["iterations"] - oit) <= 1
+    close(u, ou, 1e-8)
+    assert abs(float(u.max()) - 0.50102) < 1e-4          # SURVEY.md section 6 probe
+
+
+def test_invariants_large(api):
+    """Size-independent properties on a 24^3 jittered cube (83k tets): symmetry, rigid-body null space,
+    2S+K = 4M, assembled row sums, CSR vs element-by-element operator."""
+    el = api[0]
+    from femb200 import meshgen, ops
+    c, t = meshgen.kuhn_cube(24, jitter=0.2)
+    c, t = c.to(DEV), t.to(DEV)
+    K = el.compute_c3d4_K_matrix(c, t, E, NU, **KW)
+    assert float((K - K.transpose(1, 2)).abs().max()) <= 1e-13 * float(K.abs().max())
+    rb = torch.zeros(c.shape[0], 3, dtype=torch.float64, device=DEV)
+    rb[:, 0] = -c[:, 1]; rb[:, 1] = c[:, 0]                       # rotation about z
+    assert float(el.compute_nodal_forces(K, t, rb, **KW).abs().max()) < 1e-11
+    f, _ = el.compute_tetrahedral_surface_faces_with_fourth_node(t, device=DEV)
+    s = el.identify_tetrahedral_shared_faces(t, device=DEV)
+    assert 2 * s.shape[0] + f.shape[0] == 4 * t.shape[0] and f.shape[0] == 12 * 24 * 24
+    plan = el.CsrPlan(t, c.shape[0], DEV)
+    vals = plan.assemble_c3d4(c, "poisson")
+    crow, col = plan.pattern(1)
+    ones = torch.ones(c.shape[0], dtype=torch.float64, device=DEV)
+    assert float(ops.spmv(crow, col, vals, ones).abs().max()) < 1e-11      # constants in the Laplace null space
+    x = torch.randn(c.shape[0], 3, dtype=torch.float64, device=DEV, generator=torch.Generator(DEV).manual_seed(1))
+    ve = plan.assemble_c3d4(c, "elasticity", E, NU)
+    cr3, co3 = plan.pattern(3)
+    y1, y2 = ops.spmv(cr3, co3, ve, x), el.compute_nodal_forces(K, t, x, **KW)
+    assert float((y1 - y2).abs().max()) <= 1e-12 * float(y2.abs().max())
+    assert torch.equal(plan.assemble(K, 3), plan.assemble(K, 3))
+    assert float((plan.assemble(K, 3) - ve).abs().max()) <= 1e-12 * float(ve.abs().max())
+
+
+def test_no_cpu_fallback(api):
+    el = api[0]
+    c = torch.zeros((4, 3)); e = torch.tensor([[0, 1, 2, 3]])
+    with pytest.raises(RuntimeError):
+        el.compute_c3d4_K_matrix(c, e, E, NU, device="cpu")
