@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the FEM hot path (BASELINE.json metric: assembled elems/s; CG iters/s with SpMV GB/s vs HBM peak).
+
+Workload (config.workload): BASELINE config 4, "P1 tet Poisson 64M tets" -- the configuration the north-star targets are
+quoted on: Kuhn cube n=220, 63,888,000 C3D4 tets, 10,793,861 nodes, CSR nnz 160,738,381, fp64.  It fits one B200.
+A step = one CG iteration of the reference's projected CG (solver.py:144-229) on the assembled CSR operator.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 220] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = CG iterations/s with everything resident in HBM (device events around the
+graph-captured loop), `e2e` = the same through the public solver API with the load vector in pinned host memory and the
+solution read back to the host inside the timed region.  `roofline` is for the dominant kernel (the CSR SpMV).
+`assembly` reports the second half of the metric (assembled elems/s, fused coords->CSR values) with its own roofline.
+`--impl reference` times the CPU restatement of the reference (oracle/, the numpy port or its C/OpenMP build) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cuda-powered-mesh-handling-and-iterative-solvers_b200")
+for p in (ROOT, PKG, os.path.join(PKG, "solver")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC, UNIT = "cg_iters_per_s", "iter/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = float(rows[0][2])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for k, n in enumerate(names) if any("Active" in r[5 + k] and "Not" not in r[5 + k] for r in rows)]
+        out["samples"] = len(rows)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU side (oracle)
+def cpu_cg_rate(n_sample, iters, full_nnz):
+    """Times the oracle's CSR CG loop (the reference's loop, solver.py:144-229) on a Kuhn-cube Poisson operator of size
+    n_sample built on the CPU, and scales the measured rate by nnz_sample/nnz_full to the benchmark workload (CG is
+    memory-bound and linear in nnz far beyond the last-level cache).  Returns (iters/s at full size, description, cores)."""
+    import numpy as np
+    import torch
+    from femb200 import meshgen
+    from oracle import fem_oracle as O
+    c, t = meshgen.kuhn_cube(n_sample)
+    c, t = c.numpy(), t.numpy()
+    Ke = O.c3d4_poisson_K(c, t)
+    crow, col, val, n = O.assemble_csr(Ke, t, 1, c.shape[0])
+    load = np.bincount(t.reshape(-1), weights=np.repeat(O.tet_volumes(c, t) / 4, 4), minlength=c.shape[0]).reshape(-1, 1)
+    fixed = np.flatnonzero(c[:, 2] == 0)
+    cores = os.cpu_count() or 1
+    kind = "port"
+    try:
+        from oracle import c_oracle
+        apply_fn, used = c_oracle.csr_apply(crow, col, val, cores)
+        impl = f"C/OpenMP build of the oracle CG loop ({used} threads)"
+        threads = used
+    except Exception:
+        apply_fn = lambda v: O.csr_matvec(crow, col, val, v).reshape(-1, 1)  # noqa: E731
+        impl, threads = "numpy oracle CG loop", 1
+    O.cg_solve(apply_fn, load, fixed, tol=0.0, max_iter=2)           # warm-up
+    t0 = time.perf_counter()
+    O.cg_solve(apply_fn, load, fixed, tol=0.0, max_iter=iters)
+    dt = time.perf_counter() - t0
+    rate_sample = iters / dt
+    rate_full = rate_sample * (val.size / full_nnz)
+    desc = (f"{impl}; sample = {iters} CG iterations on the n={n_sample} Kuhn-cube Poisson operator ({t.shape[0]} tets, nnz {val.size}), "
+            f"{rate_sample:.1f} it/s measured, scaled by nnz ratio {val.size / full_nnz:.4f} to the full workload")
+    return rate_full, desc, threads, kind
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import element as el
+    import solver as sv
+    from femb200 import meshgen, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    n = args.n
+    K, W = args.steps, max(args.warmup, 3)
+
+    if world > 1:
+        from femb200 import dist_cg
+        return dist_cg.bench(args, dev, rank, world, METRIC, UNIT)
+
+    # ---- mesh + operator (resident in HBM before any timed region)
+    coords, tets = meshgen.kuhn_cube(n, device=dev)
+    M, N = tets.shape[0], coords.shape[0]
+    t0 = time.perf_counter()
+    plan = el.CsrPlan(tets, N, dev)
+    torch.cuda.synchronize()
+    t_plan = time.perf_counter() - t0
+    crow, col = plan.pattern(1)
+    vals = plan.assemble_c3d4(coords, "poisson")
+    nnz = vals.numel()
+    fixed = torch.nonzero(coords[:, 2] == 0).reshape(-1)
+    mask = torch.ones(N, dtype=torch.uint8, device=dev)
+    mask[fixed] = 0
+    F = torch.full((N, 1), 1.0 / N, dtype=torch.float64, device=dev)
+    hbm, peak_src = peaks()
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    # ---- assembly: fused coords -> CSR values, K passes
+    for _ in range(W):
+        plan.assemble_c3d4(coords, "poisson", out=vals, check_singular=False)
+    a0, a1 = ev(), ev()
+    reps_a = max(3, min(K, 10))
+    torch.cuda.synchronize()
+    a0.record()
+    for _ in range(reps_a):
+        plan.assemble_c3d4(coords, "poisson", out=vals, check_singular=False)
+    a1.record()
+    torch.cuda.synchronize()
+    ms_asm = a0.elapsed_time(a1) / reps_a
+    bytes_asm = M * 4 * 8 + N * 24 + nnz * 8          # conn as the API receives it (int64) + coords + values
+    # drop-in element matrices (compute_K_matrix path), Poisson 4x4
+    Ke = el.compute_c3d4_poisson_K_matrix(coords, tets, device=dev, dtype=torch.float64)
+    k0, k1 = ev(), ev()
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(3):
+        Ke = el.compute_c3d4_poisson_K_matrix(coords, tets, device=dev, dtype=torch.float64)
+    k1.record()
+    torch.cuda.synchronize()
+    ms_ke = k0.elapsed_time(k1) / 3
+    bytes_ke = M * (4 * 8 + 16 * 8) + N * 24
+    g0, g1 = ev(), ev()
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(3):
+        plan.assemble(Ke, 1, out=vals)
+    g1.record()
+    torch.cuda.synchronize()
+    ms_gather = g0.elapsed_time(g1) / 3
+    del Ke
+    plan.assemble_c3d4(coords, "poisson", out=vals, check_singular=False)
+
+    # ---- dominant kernel alone: CSR SpMV, K launches on the current stream
+    x = torch.randn(N, dtype=torch.float64, device=dev)
+    for _ in range(W):
+        ops.spmv(crow, col, vals, x)
+    s0, s1 = ev(), ev()
+    torch.cuda.synchronize()
+    s0.record()
+    for _ in range(K):
+        ops.spmv(crow, col, vals, x)
+    s1.record()
+    torch.cuda.synchronize()
+    ms_spmv = s0.elapsed_time(s1) / K
+    bytes_spmv = nnz * 12 + N * 20
+
+    # ---- CG: W warm-up iterations, then exactly K timed iterations (tol=0 never converges)
+    ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=W, check_every=W)
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    c0, c1 = ev(), ev()
+    c0.record()
+    u, info = ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=K, check_every=min(K, 50))
+    c1.record()
+    torch.cuda.synchronize()
+    ms_call = c0.elapsed_time(c1)
+    ms_loop = info["loop_ms"]
+    assert info["iterations"] == K, info
+    bytes_iter = bytes_spmv + 9 * N * 8
+
+    # ---- e2e: public solver API, load vector from pinned host memory, solution read back to the host
+    F_host = torch.full((N, 1), 1.0 / N, dtype=torch.float64).pin_memory()
+    u_host = torch.empty((N, 1), dtype=torch.float64).pin_memory()
+    A = torch.sparse_csr_tensor(crow, col, vals, size=(N, N))
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record()
+    u2 = sv.stable_conjugate_gradient_solver(A, tets, F_host.to(dev, non_blocking=True), fixed, tol=0.0, max_iter=K, device=dev, verbose=False)
+    u_host.copy_(u2, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    value = K / (ms_loop * 1e-3)
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_loop / K, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"P1 tet Poisson, Kuhn cube n={n}: {M} C3D4 tets, {N} nodes, CSR nnz {nnz} (BASELINE config 4); "
+                               "step = one CG iteration of the reference loop", "index_dtype": "int32 CSR / int64 API connectivity",
+                   "l2": "inputs larger than L2 (CSR operator %.2f GB)" % (nnz * 12 / 1e9), "tol": 0.0, "partition": "none (1 GPU)"},
+        "clocks": clocks,
+        "e2e": {"value": round(K / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(F_host.numel() * 8 / K),
+                "d2h_bytes_per_step": int(u_host.numel() * 8 / K),
+                "note": f"one solver-API call of {K} iterations: F pinned host -> device, CG, u -> pinned host; bytes are per call / K"},
+        "gpu_launches": 3 * K + 4,
+        "roofline": {"kernel": "spmv_kernel<8,false> (CSR SpMV, the kernel fused into CG step k1)", "bound": "hbm",
+                     "achieved": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
+                     "frac": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9 / hbm, 4), "traffic": None, "peak_source": peak_src,
+                     "ms_per_launch": round(ms_spmv, 4), "algorithmic_bytes": bytes_spmv},
+        "cg_iteration": {"ms": round(ms_loop / K, 4), "algorithmic_bytes": bytes_iter,
+                         "achieved_GBps": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9, 1),
+                         "frac": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9 / hbm, 4), "api_call_ms": round(ms_call, 2)},
+        "assembly": {"metric": "assembled_elems_per_s", "value": round(M / (ms_asm * 1e-3), 1), "ms": round(ms_asm, 3),
+                     "kernel": "assemble_c3d4_fused<0> (coords+conn -> CSR values, pattern prebuilt)",
+                     "algorithmic_bytes": bytes_asm, "achieved_GBps": round(bytes_asm / (ms_asm * 1e-3) / 1e9, 1),
+                     "frac": round(bytes_asm / (ms_asm * 1e-3) / 1e9 / hbm, 4), "plan_build_s": round(t_plan, 3),
+                     "element_K_elems_per_s": round(M / (ms_ke * 1e-3), 1), "element_K_GBps": round(bytes_ke / (ms_ke * 1e-3) / 1e9, 1),
+                     "element_K_frac": round(bytes_ke / (ms_ke * 1e-3) / 1e9 / hbm, 4),
+                     "two_step_gather_ms": round(ms_gather, 3)},
+    }
+    if not args.no_cpu:
+        rate, desc, cores, kind = cpu_cg_rate(args.cpu_n, args.cpu_iters, nnz)
+        out["cpu_baseline"] = {"value": round(rate, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+    print(json.dumps(out), flush=True)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.n
+    N = (n + 1) ** 3
+    M = 6 * n ** 3
+    edges = 3 * n * (n + 1) ** 2 + 3 * n * n * (n + 1) + n ** 3 + 0  # axis + face-diagonal + body-diagonal edges of the Kuhn cube
+    nnz = N + 2 * edges
+    K, W = args.steps, max(args.warmup, 3)
+    iters = max(3, min(K, args.cpu_iters))
+    t0 = time.perf_counter()
+    rate, desc, cores, kind = cpu_cg_rate(args.cpu_n, iters, nnz)
+    out = {"impl": "reference", "metric": METRIC, "value": round(rate, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+           "ms_per_step": round(1e3 / rate, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": f"P1 tet Poisson, Kuhn cube n={n}: {M} C3D4 tets, {N} nodes, CSR nnz {nnz} (BASELINE config 4); "
+                                  "step = one CG iteration of the reference loop"},
+           "cpu_baseline": {"value": round(rate, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+           "e2e": {"value": round(rate, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": round(time.perf_counter() - t0, 1)}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--n", type=int, default=220, help="Kuhn cube cells per edge (220 -> 63.9M tets)")
+    ap.add_argument("--impl", default="femb200", choices=["femb200", "reference"])
+    ap.add_argument("--cpu-n", type=int, default=96, help="cube size of the CPU sample")
+    ap.add_argument("--cpu-iters", type=int, default=30)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

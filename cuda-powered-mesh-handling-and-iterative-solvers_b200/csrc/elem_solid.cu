@@ -218,7 +218,7 @@ struct SolidTab {
 };
 
 template <typename T, typename I, int NEN, int EPB>
-__global__ void solid_K_kernel(const T* __restrict__ coords, const I* __restrict__ conn, long long M, SolidTab tab, int nq, int mode,
+__global__ void __launch_bounds__(512) solid_K_kernel(const T* __restrict__ coords, const I* __restrict__ conn, long long M, SolidTab tab, int nq, int mode,
                                T lam, T mu, T* __restrict__ out) {
   constexpr int ND = 3 * NEN;
   constexpr int NPAIR = NEN * (NEN + 1) / 2;

@@ -329,30 +329,51 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
     return FEMB_ERR_CUDA;
   }
   FEMB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-  static thread_local CGState* hst = nullptr;
-  if (!hst) FEMB_CUDA(cudaMallocHost(&hst, sizeof(CGState)));
+  // Host polling is pipelined one graph deep: graph l+1 is already queued while the stop flag of graph l travels back
+  // (kernels after the stop are no-ops), so the GPU never idles on the host round trip.
+  static thread_local CGState* hst = nullptr;  // [2] pinned
+  static thread_local cudaEvent_t ev[2] = {nullptr, nullptr}, tev[2] = {nullptr, nullptr};
+  if (!hst) {
+    FEMB_CUDA(cudaMallocHost(&hst, 2 * sizeof(CGState)));
+    for (int k = 0; k < 2; ++k) {
+      FEMB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+      FEMB_CUDA(cudaEventCreate(&tev[k]));
+    }
+  }
   int rc = FEMB_OK;
   const int launches = (max_iter + check_every - 1) / check_every;
-  hst->stop = 0;
-  for (int l = 0; l < launches; ++l) {
-    if (cudaGraphLaunch(exec, s) != cudaSuccess || cudaMemcpyAsync(hst, st, sizeof(CGState), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaStreamSynchronize(s) != cudaSuccess) {
+  hst[0].stop = hst[1].stop = 0;
+  bool stopped = false;
+  cudaEventRecord(tev[0], s);
+  for (int l = 0; l < launches && !stopped; ++l) {
+    if (cudaGraphLaunch(exec, s) != cudaSuccess || cudaMemcpyAsync(&hst[l & 1], st, sizeof(CGState), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaEventRecord(ev[l & 1], s) != cudaSuccess) {
       set_error(std::string("CG graph launch: ") + cudaGetErrorString(cudaGetLastError()));
       rc = FEMB_ERR_CUDA;
       break;
     }
-    if (hst->stop) break;
+    if (l >= 1) {
+      cudaEventSynchronize(ev[(l - 1) & 1]);
+      stopped = hst[(l - 1) & 1].stop != 0;
+    }
   }
-  if (rc == FEMB_OK && launches == 0) {
-    FEMB_CUDA(cudaMemcpyAsync(hst, st, sizeof(CGState), cudaMemcpyDeviceToHost, s));
-    FEMB_CUDA(cudaStreamSynchronize(s));
+  cudaEventRecord(tev[1], s);
+  CGState* fin = &hst[0];
+  if (rc == FEMB_OK) {
+    if (cudaMemcpyAsync(fin, st, sizeof(CGState), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error(std::string("CG final state: ") + cudaGetErrorString(cudaGetLastError()));
+      rc = FEMB_ERR_CUDA;
+    }
   }
+  float ms = 0.f;
+  if (rc == FEMB_OK) cudaEventElapsedTime(&ms, tev[0], tev[1]);
   cudaGraphExecDestroy(exec);
   cudaGraphDestroy(graph);
   if (rc != FEMB_OK) return rc;
-  result_host->iterations = hst->stop ? hst->iterations : max_iter;
-  result_host->status = hst->stop ? hst->status : 2;
-  result_host->rs = hst->rs_new;
+  result_host->iterations = fin->stop ? fin->iterations : max_iter;
+  result_host->status = fin->stop ? fin->status : 2;
+  result_host->rs = fin->rs_new;
+  result_host->loop_ms = ms;
   return FEMB_OK;
 }
 

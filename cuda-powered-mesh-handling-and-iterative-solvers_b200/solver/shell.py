@@ -127,8 +127,11 @@ def s4_integration_points(device="cuda:0"):
 
 
 def _s4_pts(points, weights=None):
-    p = torch.as_tensor(points).detach().to("cpu", torch.float64).reshape(-1, 2)
-    w = torch.ones(p.shape[0], dtype=torch.float64) if weights is None else torch.as_tensor(weights).detach().to("cpu", torch.float64)
+    def f64(v):  # python floats must not pass through torch's float32 default
+        return v.detach().to("cpu", torch.float64) if torch.is_tensor(v) else torch.tensor(v, dtype=torch.float64)
+
+    p = f64(points).reshape(-1, 2)
+    w = torch.ones(p.shape[0], dtype=torch.float64) if weights is None else f64(weights).reshape(-1)
     return [[float(p[q, 0]), float(p[q, 1]), 0.0, float(w[q])] for q in range(p.shape[0])]
 
 

@@ -150,6 +150,7 @@ typedef struct femb_cg_result {
   int32_t iterations; /* the count the reference prints: i+1 at exit, max_iter when not converged */
   int32_t status;     /* 0 converged, 1 breakdown (pAp guard / NaN), 2 max_iter */
   double rs;          /* last r.r (or r.z) */
+  double loop_ms;     /* device time of the iteration loop (CUDA events on the solver stream) */
 } femb_cg_result;
 
 /* stable_conjugate_gradient_solver solver.py:144-229 (also the loops of :11-135, :231-295, :297-389) on the
