@@ -18,6 +18,7 @@ struct femb_csr_plan {
   int* inc = nullptr;       // [M*nen] flat slot e*nen+a, grouped by node, ascending
   int* node_ptr = nullptr;  // [N+1]
   int* node_col = nullptr;  // [nnzn] sorted within a row
+  unsigned char* inc_slots = nullptr;  // [M*nen*nen] position of conn[e][b] in the row of the incidence's node (max_row <= 255)
 };
 
 namespace femb {
@@ -107,6 +108,81 @@ __device__ __forceinline__ int lower_bound_i32(const int* a, int n, int v) {
     else hi = mid;
   }
   return lo;
+}
+
+// slot table: for incidence k (node i = keys[k], element e, local a) and every local b, where conn[e][b] sits in row i
+__global__ void fill_slots(const int* __restrict__ conn32, const int* __restrict__ inc, const int* __restrict__ keys, const int* __restrict__ node_ptr,
+                           const int* __restrict__ node_col, long long L, int nen, unsigned char* __restrict__ slots) {
+  const long long total = L * nen;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long k = t / nen;
+    const int b = (int)(t - k * nen), i = keys[k], e = inc[k] / nen;
+    const int s = node_ptr[i];
+    slots[t] = (unsigned char)lower_bound_i32(node_col + s, node_ptr[i + 1] - s, conn32[(long long)e * nen + b]);
+  }
+}
+
+// ---- thread-per-row P1 Poisson assembly ------------------------------------------------------------
+// One THREAD owns one node row and walks its incidence list in ascending element order, so the sum order is fixed without
+// any cross-lane merge.  SRC 0: the element's cofactor vectors are rebuilt from the coordinates (fused path, Ke never
+// exists); SRC 1: row `a` of a materialised Ke[M,4,4] is read as one 32-byte sector.  The row accumulator lives in shared
+// memory as acc[slot][thread] (bank-conflict free, no dynamic register indexing).
+template <int SRC, int BD>
+__global__ void __launch_bounds__(BD) assemble_p1_scalar_rows(const int* __restrict__ conn32, const int* __restrict__ inc_ptr,
+                                                              const int* __restrict__ inc, const unsigned int* __restrict__ slots4,
+                                                              const int* __restrict__ node_ptr, long long N, const double* __restrict__ coords,
+                                                              const double* __restrict__ Ke, double* __restrict__ vals, int* __restrict__ flag) {
+  extern __shared__ __align__(16) double acc[];  // [max_row][BD]
+  const int tid = threadIdx.x;
+  for (long long i0 = (long long)blockIdx.x * BD; i0 < N; i0 += (long long)gridDim.x * BD) {
+    const long long i = i0 + tid;
+    if (i >= N) continue;
+    const int s = node_ptr[i], len = node_ptr[i + 1] - s;
+    for (int p = 0; p < len; ++p) acc[p * BD + tid] = 0.0;
+    const int k1 = inc_ptr[i + 1];
+    for (int k = inc_ptr[i]; k < k1; ++k) {
+      const int slot = __ldg(inc + k), e = slot >> 2, a = slot & 3;
+      const unsigned int sl = __ldg(slots4 + k);
+      double v[4];
+      if (SRC == 1) {
+        const double* row = Ke + ((long long)e * 4 + a) * 4;
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(row));
+      } else {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(conn32) + e);
+        const int nd4[4] = {q.x, q.y, q.z, q.w};
+        double x[4][3];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int t = 0; t < 3; ++t) x[n][t] = __ldg(coords + 3ll * nd4[n] + t);
+        double e1[3], e2[3], e3[3], c[4][3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          e1[t] = x[1][t] - x[0][t];
+          e2[t] = x[2][t] - x[0][t];
+          e3[t] = x[3][t] - x[0][t];
+        }
+        c[1][0] = e2[1] * e3[2] - e2[2] * e3[1], c[1][1] = e2[2] * e3[0] - e2[0] * e3[2], c[1][2] = e2[0] * e3[1] - e2[1] * e3[0];
+        c[2][0] = e3[1] * e1[2] - e3[2] * e1[1], c[2][1] = e3[2] * e1[0] - e3[0] * e1[2], c[2][2] = e3[0] * e1[1] - e3[1] * e1[0];
+        c[3][0] = e1[1] * e2[2] - e1[2] * e2[1], c[3][1] = e1[2] * e2[0] - e1[0] * e2[2], c[3][2] = e1[0] * e2[1] - e1[1] * e2[0];
+        const double det = e1[0] * c[1][0] + e1[1] * c[1][1] + e1[2] * c[1][2];
+        if (fabs(det) < 1e-12 && flag) *flag = 1;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) c[0][t] = -(c[1][t] + c[2][t] + c[3][t]);
+        const double scale = 1.0 / (6.0 * fabs(det));  // V g_a.g_b = c_a.c_b / (6|det|)
+        double ca[3] = {c[0][0], c[0][1], c[0][2]};
+#pragma unroll
+        for (int n = 1; n < 4; ++n)
+          if (a == n) ca[0] = c[n][0], ca[1] = c[n][1], ca[2] = c[n][2];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[b] = (ca[0] * c[b][0] + ca[1] * c[b][1] + ca[2] * c[b][2]) * scale;
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[((sl >> (8 * b)) & 255u) * BD + tid] += v[b];
+    }
+    double* dst = vals + s;
+    for (int p = 0; p < len; ++p) dst[p] = acc[p * BD + tid];
+  }
 }
 
 // ---- values from materialised Ke -----------------------------------------------------------------
@@ -332,6 +408,7 @@ static void plan_free(femb_csr_plan* p) {
   cudaFree(p->inc);
   cudaFree(p->node_ptr);
   cudaFree(p->node_col);
+  cudaFree(p->inc_slots);
   delete p;
 }
 
@@ -406,6 +483,11 @@ static int plan_build(const I* conn, femb_csr_plan* p, cudaStream_t s) {
   FEMB_CUDA(cudaMalloc(&p->node_col, sizeof(int) * std::max<long long>(p->nnzn, 1)));
   unique_rows<<<grid_for(N * 32, 256), 256, 0, s>>>(cand_sorted, off, N, nullptr, p->node_ptr, p->node_col);
   FEMB_LAUNCH_CHECK();
+  if (p->max_row <= 255 && LC > 0) {
+    FEMB_CUDA(cudaMalloc(&p->inc_slots, (size_t)LC));
+    fill_slots<<<grid_for(LC, 256), 256, 0, s>>>(p->conn32, p->inc, keys_sorted, p->node_ptr, p->node_col, L, nen, p->inc_slots);
+    FEMB_LAUNCH_CHECK();
+  }
   FEMB_CUDA(cudaStreamSynchronize(s));
   return FEMB_OK;
 }
@@ -450,7 +532,17 @@ extern "C" int femb_csr_assemble(femb_csr_plan* p, int ndof, const double* Ke, d
   const size_t per_warp = sizeof(double) * (size_t)p->max_row * ndof * ndof;
   FEMB_CHECK_ARG(per_warp <= 200 * 1024, "row too long for the shared-memory accumulator");
   cudaStream_t s = as_stream(stream);
-#define LAUNCH_GATHER(W)                                                                                             \
+  if (ndof == 1 && p->nen == 4 && p->inc_slots && (size_t)p->max_row * 8 * 128 <= 160 * 1024) {
+    // scalar P1: one thread per row (a warp-per-row tile would leave 28 of 32 lanes idle on 4 entries per incidence)
+    constexpr int BD = 128;
+    const size_t smem = sizeof(double) * (size_t)p->max_row * BD;
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_scalar_rows<1, BD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assemble_p1_scalar_rows<1, BD><<<grid_for(p->N, BD, 16), BD, smem, s>>>(p->conn32, p->inc_ptr, p->inc, (const unsigned int*)p->inc_slots,
+                                                                            p->node_ptr, p->N, nullptr, Ke, vals, nullptr);
+    FEMB_LAUNCH_CHECK();
+    return FEMB_OK;
+  }
+#define LAUNCH_GATHER(W)                                                                                            \
   {                                                                                                                  \
     FEMB_CUDA(cudaFuncSetAttribute(assemble_gather<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * W))); \
     assemble_gather<W><<<grid_for(p->N, W, 16), W * 32, per_warp * W, s>>>(p->conn32, p->inc_ptr, p->inc, p->node_ptr, p->node_col, p->N, \
@@ -474,7 +566,13 @@ extern "C" int femb_csr_assemble_c3d4(femb_csr_plan* p, int kind, const double* 
   const double c = E / ((1 + nu) * (1 - 2 * nu));
   cudaStream_t s = as_stream(stream);
   const int grid = grid_for(p->N, W, 16);
-  if (kind == 0) {
+  if (kind == 0 && p->inc_slots && (size_t)p->max_row * 8 * 128 <= 160 * 1024) {
+    constexpr int BD = 128;
+    const size_t smem = sizeof(double) * (size_t)p->max_row * BD;
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_scalar_rows<0, BD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assemble_p1_scalar_rows<0, BD><<<grid_for(p->N, BD, 16), BD, smem, s>>>(p->conn32, p->inc_ptr, p->inc, (const unsigned int*)p->inc_slots,
+                                                                            p->node_ptr, p->N, coords, nullptr, vals, flag);
+  } else if (kind == 0) {
     FEMB_CUDA(cudaFuncSetAttribute(assemble_c3d4_fused<0, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * W)));
     assemble_c3d4_fused<0, W><<<grid, W * 32, per_warp * W, s>>>(p->conn32, p->inc_ptr, p->inc, p->node_ptr, p->node_col, p->N, p->max_row, coords,
                                                                  0.0, 0.0, vals, flag);

@@ -21,8 +21,12 @@ struct Tet {
 template <typename T, typename I>
 __device__ __forceinline__ void tet_setup(const T* __restrict__ coords, const I* __restrict__ conn, long long e, Tet<T>& t) {
   long long n[4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) n[a] = ldidx(conn + 4 * e + a);
+  if (sizeof(I) == 8) {  // one 256-bit load of the element's four int64 ids
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(n[0]), "=l"(n[1]), "=l"(n[2]), "=l"(n[3]) : "l"(conn + 4 * e));
+  } else {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(conn) + e);
+    n[0] = q.x, n[1] = q.y, n[2] = q.z, n[3] = q.w;
+  }
   T x[4][3];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -60,6 +64,16 @@ __device__ __forceinline__ void store_row12<double>(double* p, const double* v) 
   st256(p, v[0], v[1], v[2], v[3]);
   st256(p + 4, v[4], v[5], v[6], v[7]);
   st256(p + 8, v[8], v[9], v[10], v[11]);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_row4(T* p, const T* v) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) p[k] = v[k];
+}
+template <>
+__device__ __forceinline__ void store_row4<double>(double* p, const double* v) {
+  st256(p, v[0], v[1], v[2], v[3]);
 }
 
 // WHAT: 0 gradients [M,4,3]; 1 B [M,6,12]; 2 K [M,12,12]; 3 Poisson [M,4,4]; 4 mass [M,12,12]; 5 volume [M]
@@ -121,10 +135,12 @@ __global__ void __launch_bounds__(128) c3d4_kernel(const T* __restrict__ coords,
     } else if (WHAT == 3) {
       T* o = out + e * 16;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 4; ++a) {
+        T v[4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          o[4 * a + b] = (t.g[a][0] * t.g[b][0] + t.g[a][1] * t.g[b][1] + t.g[a][2] * t.g[b][2]) * V;
+        for (int b = 0; b < 4; ++b) v[b] = (t.g[a][0] * t.g[b][0] + t.g[a][1] * t.g[b][1] + t.g[a][2] * t.g[b][2]) * V;
+        store_row4(o + 4 * a, v);
+      }
     } else if (WHAT == 4) {
       T* o = out + e * 144;
       const T m = lam * V / T(20);  // lam carries rho

@@ -7,6 +7,8 @@
 //   k3  p = r + beta p            (or Minv r + beta p)
 // All scalars stay on the device.  Once the sticky stop flag is set the remaining kernels of the graph are no-ops, so the
 // state returned is exactly the state at the reference's `break`.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace femb {
@@ -28,6 +30,36 @@ __device__ __forceinline__ int ld_stream(const int* p) {
   int v;
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
+}
+
+// Last-CTA-done epilogue of CG step k1: per-CTA partial of p.Ap, then the last CTA to arrive sums the partials in index
+// order (deterministic), applies the reference's guards (solver.py:187-198) and publishes alpha.
+__device__ __forceinline__ void cg_k1_epilogue(double dot, double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards) {
+  const double t = block_sum<SPMV_THREADS>(dot);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(&st->ticket1, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += SPMV_THREADS) a += ((volatile double*)partial)[k];
+    a = block_sum<SPMV_THREADS>(a);
+    if (threadIdx.x == 0) {
+      st->ticket1 = 0;
+      st->pAp = a;
+      if (guards && (fabs(a) < eps || a < 0.0)) {  // solver.py:187-192
+        st->stop = 1, st->status = 1, st->iterations = st->it + 1;
+      } else {
+        const double alpha = st->rs_old / (a + eps);
+        st->alpha = alpha;
+        if (guards && !isfinite(alpha)) st->stop = 1, st->status = 1, st->iterations = st->it + 1;  // solver.py:196-198
+      }
+    }
+  }
 }
 
 // L lanes cooperate on one row.  FUSED adds the row mask, the p.Ap partial and the last-CTA scalar epilogue.
@@ -68,33 +100,71 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(long long n, const i
       y[r] = sum;
     }
   }
-  if (FUSED) {
-    const double t = block_sum<SPMV_THREADS>(dot);
-    __shared__ bool last;
-    if (threadIdx.x == 0) {
-      partial[blockIdx.x] = t;
-      __threadfence();
-      last = atomicAdd(&st->ticket1, 1u) == gridDim.x - 1;
+  if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards);
+}
+
+// CSR-stream SpMV: a CTA owns R = 256/LR consecutive rows.  Their nonzeros form one contiguous slice of val/col, which the
+// whole CTA streams with fully coalesced loads, multiplies by the gathered x and parks in shared memory; then LR lanes per
+// row add up that row's products (in index order within a lane, fixed shuffle tree across lanes).  Short FEM rows
+// (~15 nonzeros for P1) therefore cost no idle lanes and no per-row pointer chasing in the streaming phase.
+constexpr int STREAM_CAP = 5632;  // products per CTA (44 KB of static shared memory)
+
+template <int LR, bool FUSED>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(long long n, const int* __restrict__ crow, const int* __restrict__ col,
+                                                                   const double* __restrict__ val, const double* __restrict__ x,
+                                                                   double* __restrict__ y, const unsigned char* __restrict__ mask,
+                                                                   double* __restrict__ partial, CGState* __restrict__ st, double eps,
+                                                                   int guards) {
+  if (st && st->stop) return;
+  const bool accumulate = (guards & 2) != 0;
+  guards &= 1;
+  constexpr int R = SPMV_THREADS / LR;
+  __shared__ double prod[STREAM_CAP];
+  __shared__ int rp[R + 1];
+  const int tid = threadIdx.x, sub = tid % LR, lr = tid / LR;
+  double dot = 0.0;
+  for (long long r0 = (long long)blockIdx.x * R; r0 < n; r0 += (long long)gridDim.x * R) {
+    const int nr = (int)min((long long)R, n - r0);
+    for (int t = tid; t <= nr; t += SPMV_THREADS) rp[t] = __ldg(crow + r0 + t);
+    __syncthreads();
+    const int s = rp[0], e = rp[nr];
+    const bool fits = (e - s) <= STREAM_CAP;
+    if (fits) {
+      int j = s + tid;
+      for (; j + 3 * SPMV_THREADS < e; j += 4 * SPMV_THREADS) {
+        int c[4];
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[q] = ld_stream(col + j + q * SPMV_THREADS), v[q] = ld_stream(val + j + q * SPMV_THREADS);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) prod[j - s + q * SPMV_THREADS] = v[q] * __ldg(x + c[q]);
+      }
+      for (; j < e; j += SPMV_THREADS) prod[j - s] = ld_stream(val + j) * __ldg(x + ld_stream(col + j));
     }
     __syncthreads();
-    if (last) {
-      __threadfence();
-      double a = 0.0;
-      for (int k = threadIdx.x; k < (int)gridDim.x; k += SPMV_THREADS) a += ((volatile double*)partial)[k];
-      a = block_sum<SPMV_THREADS>(a);
-      if (threadIdx.x == 0) {
-        st->ticket1 = 0;
-        st->pAp = a;
-        if (guards && (fabs(a) < eps || a < 0.0)) {  // solver.py:187-192
-          st->stop = 1, st->status = 1, st->iterations = st->it + 1;
-        } else {
-          const double alpha = st->rs_old / (a + eps);
-          st->alpha = alpha;
-          if (guards && !isfinite(alpha)) st->stop = 1, st->status = 1, st->iterations = st->it + 1;  // solver.py:196-198
-        }
+    double sum = 0.0;
+    if (lr < nr) {
+      const int a = rp[lr], b = rp[lr + 1];
+      if (fits) {
+        for (int j = a - s + sub; j < b - s; j += LR) sum += prod[j];
+      } else {  // oversized slice (very long rows): read straight from global memory
+        for (int j = a + sub; j < b; j += LR) sum += ld_stream(val + j) * __ldg(x + ld_stream(col + j));
       }
     }
+#pragma unroll
+    for (int o = LR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lr < nr && sub == 0) {
+      const long long r = r0 + lr;
+      if (accumulate) sum += y[r];
+      if (FUSED) {
+        if (mask && !mask[r]) sum = 0.0;
+        dot += sum * __ldg(x + r);
+      }
+      y[r] = sum;
+    }
+    __syncthreads();
   }
+  if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards);
 }
 
 constexpr int VEC_THREADS = 256;
@@ -209,31 +279,40 @@ __global__ void jacobi_kernel(long long n, const int* __restrict__ crow, const i
   }
 }
 
+// lanes per row of the stream kernel: the smallest LR whose R = 256/LR rows keep the CTA's slice within STREAM_CAP
 static int pick_lanes(long long n, long long nnz) {
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
-  if (avg <= 3) return 2;
-  if (avg <= 6) return 4;
-  if (avg <= 24) return 8;
-  if (avg <= 48) return 16;
+  static const bool force_vector = getenv("FEMB_SPMV_VECTOR") != nullptr;  // A/B switch for profiling
+  if (force_vector) return -(avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 24 ? 8 : avg <= 48 ? 16 : 32);
+  for (int lr = 1; lr <= 32; lr *= 2)
+    if ((SPMV_THREADS / lr) * avg * 1.25 <= STREAM_CAP) return lr;
   return 32;
 }
 
 template <bool FUSED>
 static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const int* crow, const int* col, const double* val, const double* x,
                         double* y, const unsigned char* mask, double* partial, CGState* st, double eps, int guards) {
+#define FEMB_SPMV_ARGS n, crow, col, val, x, y, mask, partial, st, eps, guards
   switch (lanes) {
-    case 2: spmv_kernel<2, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
-    case 4: spmv_kernel<4, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
-    case 8: spmv_kernel<8, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
-    case 16: spmv_kernel<16, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
-    default: spmv_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(n, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+    case 1: spmv_stream_kernel<1, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case 2: spmv_stream_kernel<2, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case 4: spmv_stream_kernel<4, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case 8: spmv_stream_kernel<8, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case 16: spmv_stream_kernel<16, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case 32: spmv_stream_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case -2: spmv_kernel<2, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case -4: spmv_kernel<4, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case -8: spmv_kernel<8, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    case -16: spmv_kernel<16, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
+    default: spmv_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
   }
+#undef FEMB_SPMV_ARGS
 }
 
 static int spmv_grid(long long n, int lanes) {
-  const long long rows_per_block = SPMV_THREADS / lanes;
+  const long long rows_per_block = SPMV_THREADS / (lanes < 0 ? -lanes : lanes);
   long long b = (n + rows_per_block - 1) / rows_per_block;
-  const long long cap = (long long)SMS * 8;  // 8 resident CTAs of 256 threads per SM
+  const long long cap = (long long)SMS * 4 * 8;  // a few waves of the 4 CTAs (48 KB each) that fit an SM; partial array is sized by this
   if (b > cap) b = cap;
   return (int)(b < 1 ? 1 : b);
 }
