@@ -6,6 +6,7 @@
 //   values : one warp per node row; contributions are added in incidence order (ascending element id), i.e. a
 //            sort-based segmented reduction into the precomputed pattern.  Either from materialised Ke
 //            (any element type / dofs per node) or fused from coordinates for P1 tets.
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -19,6 +20,12 @@ struct femb_csr_plan {
   int* node_ptr = nullptr;  // [N+1]
   int* node_col = nullptr;  // [nnzn] sorted within a row
   unsigned char* inc_slots = nullptr;  // [M*nen*nen] position of conn[e][b] in the row of the incidence's node (max_row <= 255)
+  // P1 fused-assembly acceleration structure (built lazily): per tile of 32 consecutive rows, step-major records
+  // rec[tile_ptr[t]*32 + step*32 + lane] = {other node 1, 2, 3, their three row slots packed in bytes}; x = -1 pads
+  int4* rec = nullptr;
+  int* tile_ptr = nullptr;          // [ntiles+1] in steps
+  unsigned char* pdiag = nullptr;   // [N] slot of the diagonal entry
+  long long ntiles = 0, total_steps = 0;
 };
 
 namespace femb {
@@ -126,7 +133,63 @@ __global__ void fill_slots(const int* __restrict__ conn32, const int* __restrict
 // One THREAD owns one node row and walks its incidence list in ascending element order, so the sum order is fixed without
 // any cross-lane merge.  SRC 0: the element's cofactor vectors are rebuilt from the coordinates (fused path, Ke never
 // exists); SRC 1: row `a` of a materialised Ke[M,4,4] is read as one 32-byte sector.  The row accumulator lives in shared
-// memory as acc[slot][thread] (bank-conflict free, no dynamic register indexing).
+// memory as acc[slot][thread] (bank-conflict free, no dynamic register indexing).  The dependent load chain
+// inc[k] -> conn[e] -> coords[n] is software-pipelined three deep (index data two incidences ahead, connectivity one
+// ahead, coordinates one ahead of the arithmetic), which is what turns the kernel from latency-bound into fp64-bound.
+struct P1Idx {
+  int slot;
+  unsigned int sl;
+};
+
+template <int SRC>
+__device__ __forceinline__ void p1_load_payload(bool on, const int4& q, int slot, const double* __restrict__ coords, const double* __restrict__ Ke,
+                                                double* x) {
+  if (!on) return;
+  if (SRC == 1) {
+    const double* row = Ke + ((long long)(slot >> 2) * 4 + (slot & 3)) * 4;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(row));
+  } else {
+    const int nd4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) x[3 * n + t] = __ldg(coords + 3ll * nd4[n] + t);
+  }
+}
+
+template <int SRC, int BD>
+__device__ __forceinline__ void p1_accumulate(const double* x, int slot, unsigned int sl, double* acc, int tid, int* flag) {
+  double v[4];
+  if (SRC == 1) {
+    v[0] = x[0], v[1] = x[1], v[2] = x[2], v[3] = x[3];
+  } else {
+    const int a = slot & 3;
+    double e1[3], e2[3], e3[3], c[4][3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      e1[t] = x[3 + t] - x[t];
+      e2[t] = x[6 + t] - x[t];
+      e3[t] = x[9 + t] - x[t];
+    }
+    c[1][0] = e2[1] * e3[2] - e2[2] * e3[1], c[1][1] = e2[2] * e3[0] - e2[0] * e3[2], c[1][2] = e2[0] * e3[1] - e2[1] * e3[0];
+    c[2][0] = e3[1] * e1[2] - e3[2] * e1[1], c[2][1] = e3[2] * e1[0] - e3[0] * e1[2], c[2][2] = e3[0] * e1[1] - e3[1] * e1[0];
+    c[3][0] = e1[1] * e2[2] - e1[2] * e2[1], c[3][1] = e1[2] * e2[0] - e1[0] * e2[2], c[3][2] = e1[0] * e2[1] - e1[1] * e2[0];
+    const double det = e1[0] * c[1][0] + e1[1] * c[1][1] + e1[2] * c[1][2];
+    if (fabs(det) < 1e-12 && flag) *flag = 1;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) c[0][t] = -(c[1][t] + c[2][t] + c[3][t]);
+    const double scale = 1.0 / (6.0 * fabs(det));  // V g_a.g_b = c_a.c_b / (6|det|)
+    double ca[3] = {c[0][0], c[0][1], c[0][2]};
+#pragma unroll
+    for (int n = 1; n < 4; ++n)
+      if (a == n) ca[0] = c[n][0], ca[1] = c[n][1], ca[2] = c[n][2];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) v[b] = (ca[0] * c[b][0] + ca[1] * c[b][1] + ca[2] * c[b][2]) * scale;
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) acc[((sl >> (8 * b)) & 255u) * BD + tid] += v[b];
+}
+
 template <int SRC, int BD>
 __global__ void __launch_bounds__(BD) assemble_p1_scalar_rows(const int* __restrict__ conn32, const int* __restrict__ inc_ptr,
                                                               const int* __restrict__ inc, const unsigned int* __restrict__ slots4,
@@ -134,54 +197,159 @@ __global__ void __launch_bounds__(BD) assemble_p1_scalar_rows(const int* __restr
                                                               const double* __restrict__ Ke, double* __restrict__ vals, int* __restrict__ flag) {
   extern __shared__ __align__(16) double acc[];  // [max_row][BD]
   const int tid = threadIdx.x;
+  constexpr int NX = SRC == 1 ? 4 : 12;
   for (long long i0 = (long long)blockIdx.x * BD; i0 < N; i0 += (long long)gridDim.x * BD) {
     const long long i = i0 + tid;
     if (i >= N) continue;
     const int s = node_ptr[i], len = node_ptr[i + 1] - s;
+    const int k0 = inc_ptr[i], k1 = inc_ptr[i + 1];
+    auto load_idx = [&](int k) {
+      P1Idx r{0, 0u};
+      if (k < k1) r.slot = __ldg(inc + k), r.sl = __ldg(slots4 + k);
+      return r;
+    };
+    auto load_conn = [&](int k, const P1Idx& id) {
+      int4 q = make_int4(0, 0, 0, 0);
+      if (SRC == 0 && k < k1) q = __ldg(reinterpret_cast<const int4*>(conn32) + (id.slot >> 2));
+      return q;
+    };
+    // prologue: fill the pipeline
+    P1Idx ia = load_idx(k0), ib = load_idx(k0 + 1), ic = load_idx(k0 + 2);
+    int4 qa = load_conn(k0, ia), qb = load_conn(k0 + 1, ib);
+    double xa[NX], xb[NX];
+    p1_load_payload<SRC>(k0 < k1, qa, ia.slot, coords, Ke, xa);
     for (int p = 0; p < len; ++p) acc[p * BD + tid] = 0.0;
-    const int k1 = inc_ptr[i + 1];
-    for (int k = inc_ptr[i]; k < k1; ++k) {
-      const int slot = __ldg(inc + k), e = slot >> 2, a = slot & 3;
-      const unsigned int sl = __ldg(slots4 + k);
-      double v[4];
-      if (SRC == 1) {
-        const double* row = Ke + ((long long)e * 4 + a) * 4;
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(row));
-      } else {
-        const int4 q = __ldg(reinterpret_cast<const int4*>(conn32) + e);
-        const int nd4[4] = {q.x, q.y, q.z, q.w};
-        double x[4][3];
-#pragma unroll
-        for (int n = 0; n < 4; ++n)
-#pragma unroll
-          for (int t = 0; t < 3; ++t) x[n][t] = __ldg(coords + 3ll * nd4[n] + t);
-        double e1[3], e2[3], e3[3], c[4][3];
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          e1[t] = x[1][t] - x[0][t];
-          e2[t] = x[2][t] - x[0][t];
-          e3[t] = x[3][t] - x[0][t];
-        }
-        c[1][0] = e2[1] * e3[2] - e2[2] * e3[1], c[1][1] = e2[2] * e3[0] - e2[0] * e3[2], c[1][2] = e2[0] * e3[1] - e2[1] * e3[0];
-        c[2][0] = e3[1] * e1[2] - e3[2] * e1[1], c[2][1] = e3[2] * e1[0] - e3[0] * e1[2], c[2][2] = e3[0] * e1[1] - e3[1] * e1[0];
-        c[3][0] = e1[1] * e2[2] - e1[2] * e2[1], c[3][1] = e1[2] * e2[0] - e1[0] * e2[2], c[3][2] = e1[0] * e2[1] - e1[1] * e2[0];
-        const double det = e1[0] * c[1][0] + e1[1] * c[1][1] + e1[2] * c[1][2];
-        if (fabs(det) < 1e-12 && flag) *flag = 1;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) c[0][t] = -(c[1][t] + c[2][t] + c[3][t]);
-        const double scale = 1.0 / (6.0 * fabs(det));  // V g_a.g_b = c_a.c_b / (6|det|)
-        double ca[3] = {c[0][0], c[0][1], c[0][2]};
-#pragma unroll
-        for (int n = 1; n < 4; ++n)
-          if (a == n) ca[0] = c[n][0], ca[1] = c[n][1], ca[2] = c[n][2];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) v[b] = (ca[0] * c[b][0] + ca[1] * c[b][1] + ca[2] * c[b][2]) * scale;
-      }
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[((sl >> (8 * b)) & 255u) * BD + tid] += v[b];
+    for (int k = k0; k < k1; k += 2) {
+      // even half: payload k+1 and index data further ahead go out before the arithmetic of k
+      p1_load_payload<SRC>(k + 1 < k1, qb, ib.slot, coords, Ke, xb);
+      qa = load_conn(k + 2, ic);
+      P1Idx id = load_idx(k + 3);
+      p1_accumulate<SRC, BD>(xa, ia.slot, ia.sl, acc, tid, flag);
+      if (k + 1 >= k1) break;
+      // odd half
+      p1_load_payload<SRC>(k + 2 < k1, qa, ic.slot, coords, Ke, xa);
+      qb = load_conn(k + 3, id);
+      P1Idx ie = load_idx(k + 4);
+      p1_accumulate<SRC, BD>(xb, ib.slot, ib.sl, acc, tid, flag);
+      ia = ic, ib = id, ic = ie;
     }
     double* dst = vals + s;
     for (int p = 0; p < len; ++p) dst[p] = acc[p * BD + tid];
+  }
+}
+
+// ---- tiled fused P1 Poisson assembly ----------------------------------------------------------------------
+// Same ownership (thread = row, ascending element order) but every per-lane gather of index data is replaced by ONE
+// coalesced 16-byte record per step: the plan stores, for each tile of 32 consecutive rows, step-major records holding the
+// three OTHER nodes of the incident element and their row slots.  The row's own node is taken as local node 0 (the
+// element matrix is invariant under the renumbering), so only three padded 32-byte coordinate loads remain per step.
+// L1 wavefronts per warp-step drop from ~176 (three strided index streams + 12 strided 8-byte coordinate loads) to ~28.
+__global__ void tile_degrees(const int* __restrict__ inc_ptr, long long N, long long ntiles, int* __restrict__ deg) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t <= ntiles; t += (long long)gridDim.x * blockDim.x) {
+    int m = 0;
+    if (t < ntiles)
+      for (long long i = t * 32; i < min(N, t * 32 + 32); ++i) m = max(m, inc_ptr[i + 1] - inc_ptr[i]);
+    deg[t] = m;
+  }
+}
+
+__global__ void build_records(const int* __restrict__ conn32, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                              const unsigned char* __restrict__ slots, const int* __restrict__ tile_ptr, long long N, long long ntiles,
+                              int4* __restrict__ rec, unsigned char* __restrict__ pdiag) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long t = warp; t < ntiles; t += nwarps) {
+    const long long i = t * 32 + lane;
+    const int s0 = tile_ptr[t], steps = tile_ptr[t + 1] - s0;
+    const int k0 = i < N ? inc_ptr[i] : 0, k1 = i < N ? inc_ptr[i + 1] : 0;
+    for (int st = 0; st < steps; ++st) {
+      int4 r = make_int4(-1, -1, -1, 0);
+      const int k = k0 + st;
+      if (k < k1) {
+        const int slot = inc[k], e = slot >> 2, a = slot & 3;
+        int ids[3], sl[3], n = 0;
+        for (int b = 0; b < 4; ++b) {
+          if (b == a) {
+            if (st == 0) pdiag[i] = slots[4ll * k + b];
+            continue;
+          }
+          ids[n] = conn32[4ll * e + b];
+          sl[n] = slots[4ll * k + b];
+          ++n;
+        }
+        r = make_int4(ids[0], ids[1], ids[2], sl[0] | (sl[1] << 8) | (sl[2] << 16));
+      }
+      rec[((long long)s0 + st) * 32 + lane] = r;
+    }
+  }
+}
+
+__global__ void pad_coords(const double* __restrict__ coords, long long N, double* __restrict__ out) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x)
+    st256(out + 4 * t, coords[3 * t], coords[3 * t + 1], coords[3 * t + 2], 0.0);
+}
+
+__device__ __forceinline__ void ld_xyz(const double* __restrict__ c4, int node, double* x) {
+  double w;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(w) : "l"(c4 + 4ll * node));
+}
+
+template <int BD, int OCC>
+__global__ void __launch_bounds__(BD, OCC) assemble_p1_poisson_tiles(const int4* __restrict__ rec, const int* __restrict__ tile_ptr,
+                                                                const int* __restrict__ node_ptr, const unsigned char* __restrict__ pdiag,
+                                                                long long N, long long ntiles, const double* __restrict__ c4,
+                                                                double* __restrict__ vals, int* __restrict__ flag) {
+  extern __shared__ __align__(16) double acc[];  // [max_row][BD]
+  const int tid = threadIdx.x, lane = tid & 31;
+  constexpr int WPB = BD / 32;
+  for (long long t = (long long)blockIdx.x * WPB + (tid >> 5); t < ntiles; t += (long long)gridDim.x * WPB) {
+    const long long i = t * 32 + lane;
+    const bool live = i < N;
+    const int s = live ? node_ptr[i] : 0, len = live ? node_ptr[i + 1] - s : 0;
+    const int s0 = tile_ptr[t], steps = tile_ptr[t + 1] - s0;
+    const int4* rp = rec + (long long)s0 * 32 + lane;
+    double x0[3] = {0, 0, 0};
+    if (live) ld_xyz(c4, (int)i, x0);
+    const int pd = live ? pdiag[i] : 0;
+    for (int p = 0; p < len; ++p) acc[p * BD + tid] = 0.0;
+    double diag = 0.0;
+    // two-deep pipeline: record of step+2 and coordinates of step+1 are in flight during the arithmetic of `step`
+    int4 ra = steps > 0 ? __ldg(rp) : make_int4(-1, 0, 0, 0);
+    int4 rb = steps > 1 ? __ldg(rp + 32) : make_int4(-1, 0, 0, 0);
+    double xa[9], xb[9];
+    if (ra.x >= 0) ld_xyz(c4, ra.x, xa), ld_xyz(c4, ra.y, xa + 3), ld_xyz(c4, ra.z, xa + 6);
+    auto contribute = [&](const int4& r, const double* x) {
+      if (r.x < 0) return;
+      double e1[3], e2[3], e3[3], c1[3], c2[3], c3[3], c0[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) e1[q] = x[q] - x0[q], e2[q] = x[3 + q] - x0[q], e3[q] = x[6 + q] - x0[q];
+      c1[0] = e2[1] * e3[2] - e2[2] * e3[1], c1[1] = e2[2] * e3[0] - e2[0] * e3[2], c1[2] = e2[0] * e3[1] - e2[1] * e3[0];
+      c2[0] = e3[1] * e1[2] - e3[2] * e1[1], c2[1] = e3[2] * e1[0] - e3[0] * e1[2], c2[2] = e3[0] * e1[1] - e3[1] * e1[0];
+      c3[0] = e1[1] * e2[2] - e1[2] * e2[1], c3[1] = e1[2] * e2[0] - e1[0] * e2[2], c3[2] = e1[0] * e2[1] - e1[1] * e2[0];
+      const double det = e1[0] * c1[0] + e1[1] * c1[1] + e1[2] * c1[2];
+      if (fabs(det) < 1e-12 && flag) *flag = 1;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) c0[q] = -(c1[q] + c2[q] + c3[q]);
+      const double scale = 1.0 / (6.0 * fabs(det));  // V g_a.g_b = c_a.c_b / (6|det|)
+      diag += (c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2]) * scale;
+      acc[(r.w & 255) * BD + tid] += (c0[0] * c1[0] + c0[1] * c1[1] + c0[2] * c1[2]) * scale;
+      acc[((r.w >> 8) & 255) * BD + tid] += (c0[0] * c2[0] + c0[1] * c2[1] + c0[2] * c2[2]) * scale;
+      acc[((r.w >> 16) & 255) * BD + tid] += (c0[0] * c3[0] + c0[1] * c3[1] + c0[2] * c3[2]) * scale;
+    };
+    for (int st = 0; st < steps; st += 2) {
+      if (rb.x >= 0) ld_xyz(c4, rb.x, xb), ld_xyz(c4, rb.y, xb + 3), ld_xyz(c4, rb.z, xb + 6);
+      const int4 rc = st + 2 < steps ? __ldg(rp + (st + 2) * 32) : make_int4(-1, 0, 0, 0);
+      contribute(ra, xa);
+      if (rc.x >= 0) ld_xyz(c4, rc.x, xa), ld_xyz(c4, rc.y, xa + 3), ld_xyz(c4, rc.z, xa + 6);
+      const int4 rd = st + 3 < steps ? __ldg(rp + (st + 3) * 32) : make_int4(-1, 0, 0, 0);
+      contribute(rb, xb);
+      ra = rc, rb = rd;
+    }
+    if (live) {
+      if (len > 0) acc[pd * BD + tid] += diag;
+      double* dst = vals + s;
+      for (int p = 0; p < len; ++p) dst[p] = acc[p * BD + tid];
+    }
   }
 }
 
@@ -409,7 +577,36 @@ static void plan_free(femb_csr_plan* p) {
   cudaFree(p->node_ptr);
   cudaFree(p->node_col);
   cudaFree(p->inc_slots);
+  cudaFree(p->rec);
+  cudaFree(p->tile_ptr);
+  cudaFree(p->pdiag);
   delete p;
+}
+
+static int build_p1_records(femb_csr_plan* p, cudaStream_t s) {
+  const long long N = p->N, nt = (N + 31) / 32;
+  p->ntiles = nt;
+  Scratch scr(s);
+  int* deg;
+  FEMB_CUDA(scr.alloc(&deg, nt + 1));
+  FEMB_CUDA(cudaMalloc(&p->tile_ptr, sizeof(int) * (nt + 1)));
+  FEMB_CUDA(cudaMalloc(&p->pdiag, (size_t)N));
+  FEMB_CUDA(cudaMemsetAsync(p->pdiag, 0, (size_t)N, s));
+  tile_degrees<<<grid_for(nt + 1, 256), 256, 0, s>>>(p->inc_ptr, N, nt, deg);
+  FEMB_LAUNCH_CHECK();
+  size_t tb = 0;
+  FEMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, deg, p->tile_ptr, (int)(nt + 1), s));
+  void* tmp;
+  FEMB_CUDA(scr.alloc((char**)&tmp, tb));
+  FEMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, deg, p->tile_ptr, (int)(nt + 1), s));
+  int total = 0;
+  FEMB_CUDA(cudaMemcpyAsync(&total, p->tile_ptr + nt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaStreamSynchronize(s));
+  p->total_steps = total;
+  FEMB_CUDA(cudaMalloc(&p->rec, sizeof(int4) * 32 * (size_t)std::max(total, 1)));
+  build_records<<<grid_for(nt * 32, 256), 256, 0, s>>>(p->conn32, p->inc_ptr, p->inc, p->inc_slots, p->tile_ptr, N, nt, p->rec, p->pdiag);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
 }
 
 template <typename I>
@@ -566,7 +763,28 @@ extern "C" int femb_csr_assemble_c3d4(femb_csr_plan* p, int kind, const double* 
   const double c = E / ((1 + nu) * (1 - 2 * nu));
   cudaStream_t s = as_stream(stream);
   const int grid = grid_for(p->N, W, 16);
-  if (kind == 0 && p->inc_slots && (size_t)p->max_row * 8 * 128 <= 160 * 1024) {
+  static const bool no_tiles = getenv("FEMB_ASM_ROWS") != nullptr;  // A/B switch: previous thread-per-row kernel
+  if (kind == 0 && p->inc_slots && (size_t)p->max_row * 8 * 128 <= 160 * 1024 && !no_tiles) {
+    constexpr int BD = 128;
+    if (!p->rec) {  // lazily built, topology only
+      const int rc = build_p1_records(p, s);
+      if (rc != FEMB_OK) return rc;
+    }
+    Scratch scr(s);
+    double* c4;
+    FEMB_CUDA(scr.alloc(&c4, (size_t)4 * p->N));
+    pad_coords<<<grid_for(p->N, 256), 256, 0, s>>>(coords, p->N, c4);
+    const size_t smem = sizeof(double) * (size_t)p->max_row * BD;
+    static const int occ = getenv("FEMB_ASM_OCC") ? atoi(getenv("FEMB_ASM_OCC")) : 4;
+#define LAUNCH_TILES(O)                                                                                                          \
+  {                                                                                                                              \
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_poisson_tiles<BD, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    assemble_p1_poisson_tiles<BD, O><<<grid_for(p->ntiles, BD / 32, 16), BD, smem, s>>>(p->rec, p->tile_ptr, p->node_ptr, p->pdiag, p->N, \
+                                                                                        p->ntiles, c4, vals, flag);             \
+  }
+    if (occ >= 6) LAUNCH_TILES(6) else if (occ == 5) LAUNCH_TILES(5) else LAUNCH_TILES(4)
+#undef LAUNCH_TILES
+  } else if (kind == 0 && p->inc_slots && (size_t)p->max_row * 8 * 128 <= 160 * 1024) {
     constexpr int BD = 128;
     const size_t smem = sizeof(double) * (size_t)p->max_row * BD;
     FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_scalar_rows<0, BD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -41,7 +41,20 @@ struct Scratch {
   cudaStream_t stream;
   void* ptrs[32];
   int n = 0;
-  explicit Scratch(cudaStream_t s) : stream(s) {}
+  explicit Scratch(cudaStream_t s) : stream(s) { keep_pool_warm(); }
+  // The default pool hands memory back to the driver at every synchronisation unless a release threshold is set;
+  // re-acquiring hundreds of MB per call costs milliseconds.
+  static void keep_pool_warm() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+  }
   template <typename T>
   cudaError_t alloc(T** p, size_t count) {
     void* q = nullptr;
