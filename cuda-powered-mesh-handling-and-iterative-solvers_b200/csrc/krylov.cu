@@ -9,7 +9,7 @@
 // state returned is exactly the state at the reference's `break`.
 #include <cstdlib>
 
-#include "common.cuh"
+#include "spmv_dev.cuh"
 
 namespace femb {
 
@@ -18,19 +18,6 @@ struct CGState {
   int it, stop, status, iterations;
   unsigned int ticket1, ticket2, pad0, pad1;
 };
-
-constexpr int SPMV_THREADS = 256;
-
-__device__ __forceinline__ double ld_stream(const double* p) {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ int ld_stream(const int* p) {
-  int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
 
 // Last-CTA-done epilogue of CG step k1: per-CTA partial of p.Ap, then the last CTA to arrive sums the partials in index
 // order (deterministic), applies the reference's guards (solver.py:187-198) and publishes alpha.
@@ -103,12 +90,6 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(long long n, const i
   if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards);
 }
 
-// CSR-stream SpMV: a CTA owns R = 256/LR consecutive rows.  Their nonzeros form one contiguous slice of val/col, which the
-// whole CTA streams with fully coalesced loads, multiplies by the gathered x and parks in shared memory; then LR lanes per
-// row add up that row's products (in index order within a lane, fixed shuffle tree across lanes).  Short FEM rows
-// (~15 nonzeros for P1) therefore cost no idle lanes and no per-row pointer chasing in the streaming phase.
-constexpr int STREAM_CAP = 5632;  // products per CTA (44 KB of static shared memory)
-
 template <int LR, bool FUSED>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(long long n, const int* __restrict__ crow, const int* __restrict__ col,
                                                                    const double* __restrict__ val, const double* __restrict__ x,
@@ -116,55 +97,8 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(long long n, 
                                                                    double* __restrict__ partial, CGState* __restrict__ st, double eps,
                                                                    int guards) {
   if (st && st->stop) return;
-  const bool accumulate = (guards & 2) != 0;
-  guards &= 1;
-  constexpr int R = SPMV_THREADS / LR;
-  __shared__ double prod[STREAM_CAP];
-  __shared__ int rp[R + 1];
-  const int tid = threadIdx.x, sub = tid % LR, lr = tid / LR;
-  double dot = 0.0;
-  for (long long r0 = (long long)blockIdx.x * R; r0 < n; r0 += (long long)gridDim.x * R) {
-    const int nr = (int)min((long long)R, n - r0);
-    for (int t = tid; t <= nr; t += SPMV_THREADS) rp[t] = __ldg(crow + r0 + t);
-    __syncthreads();
-    const int s = rp[0], e = rp[nr];
-    const bool fits = (e - s) <= STREAM_CAP;
-    if (fits) {
-      int j = s + tid;
-      for (; j + 3 * SPMV_THREADS < e; j += 4 * SPMV_THREADS) {
-        int c[4];
-        double v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) c[q] = ld_stream(col + j + q * SPMV_THREADS), v[q] = ld_stream(val + j + q * SPMV_THREADS);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) prod[j - s + q * SPMV_THREADS] = v[q] * __ldg(x + c[q]);
-      }
-      for (; j < e; j += SPMV_THREADS) prod[j - s] = ld_stream(val + j) * __ldg(x + ld_stream(col + j));
-    }
-    __syncthreads();
-    double sum = 0.0;
-    if (lr < nr) {
-      const int a = rp[lr], b = rp[lr + 1];
-      if (fits) {
-        for (int j = a - s + sub; j < b - s; j += LR) sum += prod[j];
-      } else {  // oversized slice (very long rows): read straight from global memory
-        for (int j = a + sub; j < b; j += LR) sum += ld_stream(val + j) * __ldg(x + ld_stream(col + j));
-      }
-    }
-#pragma unroll
-    for (int o = LR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lr < nr && sub == 0) {
-      const long long r = r0 + lr;
-      if (accumulate) sum += y[r];
-      if (FUSED) {
-        if (mask && !mask[r]) sum = 0.0;
-        dot += sum * __ldg(x + r);
-      }
-      y[r] = sum;
-    }
-    __syncthreads();
-  }
-  if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards);
+  const double dot = spmv_stream_rows<LR, true>(n, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED);
+  if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards & 1);
 }
 
 constexpr int VEC_THREADS = 256;

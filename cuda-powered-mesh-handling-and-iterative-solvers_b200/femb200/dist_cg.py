@@ -1,0 +1,179 @@
+"""Multi-GPU CG: one process per GPU (torch.distributed for bootstrap only), rows partitioned with partition.py, local
+operators assembled without communication, and the iteration loop running over NVLink peer memory in libfemb200
+(csrc/dist.cu): halo exchange and all-reduces are peer stores + flags inside the CUDA graph, not NCCL calls.
+
+torch.distributed is used exactly three times per solver object: to exchange the cudaIpc handles, the per-rank sizes /
+halo offsets, and for a barrier after flags are reset.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import ops, partition
+from ._lib import CGResult, check, lib
+
+
+class DistOperator:
+    """A row-partitioned CSR operator plus its peer-memory halo plan on this rank."""
+
+    def __init__(self, part: partition.LocalPart, crow, col, val, device):
+        self.part, self.dev = part, torch.device(device)
+        self.rank, self.P = part.rank, part.nparts
+        no = part.n_owned
+        nnz = int(crow[no].item())
+        self.crow, self.col, self.val = crow[:no + 1].contiguous(), col[:nnz].contiguous(), val[:nnz].contiguous()
+        self.nnz = nnz
+        # ---- symmetric buffers: header + p[max n_local over ranks]
+        sizes = [None] * self.P
+        dist.all_gather_object(sizes, {"n_owned": no, "n_local": part.n_local, "recv_off": part.recv_off})
+        self.sizes = sizes
+        hdr = lib.femb_dist_header_bytes()
+        nmax = max(s["n_local"] for s in sizes)
+        self.sym_bytes = hdr + 8 * nmax
+        own, handle = C.c_void_p(), (C.c_char * 64)()
+        with torch.cuda.device(self.dev):
+            check(lib.femb_dist_alloc(self.sym_bytes, C.byref(own), handle), "femb_dist_alloc")
+        self.own = own
+        handles = [None] * self.P
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self.sym = (C.c_void_p * self.P)()
+        self._opened = []
+        for q in range(self.P):
+            if q == self.rank:
+                self.sym[q] = own.value
+            else:
+                ptr = C.c_void_p()
+                hb = (C.c_char * 64).from_buffer_copy(handles[q])
+                with torch.cuda.device(self.dev):
+                    check(lib.femb_dist_open(hb, C.byref(ptr)), "femb_dist_open")
+                self.sym[q] = ptr.value
+                self._opened.append(ptr)
+        # ---- halo plan
+        nb = part.neighbors
+        self.nnbr = len(nb)
+        self.nbr = (C.c_int32 * max(1, self.nnbr))(*nb)
+        ptrs, idx = [0], []
+        for q in nb:
+            idx.append(part.send_idx[q].to(torch.int32))
+            ptrs.append(ptrs[-1] + int(part.send_idx[q].numel()))
+        self.send_ptr = (C.c_int32 * (self.nnbr + 1))(*ptrs)
+        self.send_idx = (torch.cat(idx) if idx else torch.zeros(1, dtype=torch.int32)).to(self.dev).contiguous()
+        self.ghost_off = (C.c_int64 * max(1, self.nnbr))(*[sizes[q]["n_owned"] + sizes[q]["recv_off"][self.rank] for q in nb])
+        self.halo_bytes = 8 * ptrs[-1]
+
+    def solve(self, F_owned, mask_owned=None, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, check_every=16):
+        no = self.part.n_owned
+        Ff = F_owned.to(self.dev, torch.float64).reshape(-1).contiguous()
+        u = torch.zeros(no, device=self.dev, dtype=torch.float64) if u_init is None else \
+            u_init.to(self.dev, torch.float64).reshape(-1).clone().contiguous()
+        work = torch.empty(2 * no, device=self.dev, dtype=torch.float64)
+        res = CGResult()
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        with torch.cuda.device(self.dev):
+            check(lib.femb_dist_reset(self.own, st), "femb_dist_reset")
+            dist.barrier()          # every rank's flags are zero before anyone starts pushing
+            check(lib.femb_dist_cg_solve(self.rank, self.P, no, self.nnz, ops._p(self.crow), ops._p(self.col), ops._p(self.val), ops._p(Ff),
+                                         ops._p(mask_owned), ops._p(u), ops._p(work), self.sym, self.nnbr, self.nbr, self.send_ptr,
+                                         ops._p(self.send_idx), self.ghost_off, float(tol), int(max_iter), float(eps), int(check_every),
+                                         C.byref(res), st), "femb_dist_cg_solve")
+            dist.barrier()          # nobody frees / resets while a peer may still be storing
+        info = {"iterations": res.iterations, "status": ops.STATUS.get(res.status, "?"), "rs": res.rs, "loop_ms": res.loop_ms}
+        return u, info
+
+    def close(self):
+        dist.barrier()
+        for p in self._opened:
+            lib.femb_dist_close(p)
+        self._opened = []
+        if self.own:
+            lib.femb_dist_free(self.own)
+            self.own = None
+
+
+def setup_poisson_p1(coords, elements, rank, world, dev):
+    """Replicated (coords, elements) -> this rank's partitioned Poisson operator, load and mask.  Assembly is local."""
+    labels = partition.rcb_labels(coords, world)
+    part = partition.build_local_part(elements, labels, rank, world)
+    cl = partition.localize(coords, part).contiguous()
+    plan = ops.CsrPlan(part.elements_local, part.n_local, dev)
+    crow, col = plan.pattern(1)
+    val = plan.assemble_c3d4(cl, "poisson")
+    return part, plan, DistOperator(part, crow, col, val, dev), cl
+
+
+def bench(args, dev, rank, world, metric, unit):
+    """bench.py's N>1 arm: strong scaling of the 64M-tet Poisson CG (BASELINE config 4)."""
+    import json
+    import os
+    import sys
+    from . import meshgen
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from bench import ClockSampler, peaks
+
+    n, K, W = args.n, args.steps, max(args.warmup, 3)
+    coords, tets = meshgen.kuhn_cube(n, device=dev)
+    M, N = tets.shape[0], coords.shape[0]
+    t0 = time.perf_counter()
+    part, plan, op, cl = setup_poisson_p1(coords, tets, rank, world, dev)
+    del tets
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    no = part.n_owned
+    mask = (cl[:no, 2] != 0).to(torch.uint8).contiguous()
+    F = torch.full((no,), 1.0 / N, dtype=torch.float64, device=dev)
+    op.solve(F, mask, tol=0.0, max_iter=W, check_every=W)
+    sampler = ClockSampler(dev.index or 0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    u, info = op.solve(F, mask, tol=0.0, max_iter=K, check_every=min(K, 50))
+    ms = torch.tensor([info["loop_ms"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
+    # e2e through host buffers: load vector from pinned host memory, owned solution back to the host
+    F_host = torch.full((no,), 1.0 / N, dtype=torch.float64).pin_memory()
+    u_host = torch.empty(no, dtype=torch.float64).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    u2, info2 = op.solve(F_host.to(dev, non_blocking=True), mask, tol=0.0, max_iter=K, check_every=min(K, 50))
+    u_host.copy_(u2, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    nnz_tot = torch.tensor([op.nnz], dtype=torch.float64, device=dev)
+    dist.all_reduce(nnz_tot)
+    halo = torch.tensor([op.halo_bytes], dtype=torch.float64, device=dev)
+    dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+    hbm, peak_src = peaks()
+    ms_loop = float(ms.item())
+    nnz = int(nnz_tot.item())
+    bytes_iter = nnz * 12 + N * 20 + 9 * N * 8
+    if rank == 0:
+        out = {
+            "metric": metric, "value": round(K / (ms_loop * 1e-3), 2), "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms_loop / K, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"P1 tet Poisson, Kuhn cube n={n}: {M} C3D4 tets, {N} nodes, CSR nnz {nnz} (BASELINE config 4); "
+                                   "step = one CG iteration of the reference loop", "index_dtype": "int32 CSR / int64 API connectivity",
+                       "l2": "total CSR operator %.2f GB over %d GPUs" % (nnz * 12 / 1e9, world), "tol": 0.0,
+                       "partition": f"RCB on node coordinates, {world} parts, halo exchange + all-reduce over NVLink peer memory (no NCCL in the loop)",
+                       "max_halo_bytes_per_rank": int(halo.item()), "setup_s": round(t_setup, 2)},
+            "clocks": clocks,
+            "e2e": {"value": round(K / (float(ms2.item()) * 1e-3), 2), "unit": unit, "h2d_bytes_per_step": int(N * 8 / K),
+                    "d2h_bytes_per_step": int(N * 8 / K),
+                    "note": f"one solve call of {K} iterations per rank: F pinned host -> device, CG, owned u -> pinned host; bytes are whole-job per call / K"},
+            "gpu_launches": 4 * K + 5,
+            "roofline": {"kernel": "whole CG iteration (dist_push + dist_spmv + dist_update + dist_direction), aggregate over ranks",
+                         "bound": "hbm", "achieved": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9, 1), "peak": hbm * world, "unit": "GB/s",
+                         "frac": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9 / (hbm * world), 4), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": bytes_iter},
+        }
+        print(json.dumps(out), flush=True)
+    op.close()
+    dist.destroy_process_group()

@@ -1,0 +1,94 @@
+"""Row/element partition of a mesh over P ranks and the halo-exchange plan (host-side plumbing, torch ops, any device).
+
+The reference has no distributed code; its only partition is the notebook's element region-growing on one GPU
+(reference subdivision.ipynb cell 9, random first seed -> not reproducible).  Here nodes (= operator rows) are split by a
+deterministic recursive coordinate bisection (a geometric graph partition); every rank also takes each element that
+touches one of its nodes, so assembly needs no communication (ghost elements are recomputed redundantly).
+
+Local numbering on a rank: [owned nodes in ascending global id | ghost nodes grouped by owner rank, ascending id].
+Both sides derive the send/recv lists from the same rule (nodes of rank r that share an element with a node of rank q,
+ascending global id), so the plan needs no communication either.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List
+
+import torch
+
+
+def rcb_labels(coords: torch.Tensor, nparts: int) -> torch.Tensor:
+    """Recursive coordinate bisection: label in [0,nparts) per node; nparts need not be a power of two.
+    Splits along the longest extent at the weighted median; ties are broken by node id (stable sort) -> deterministic."""
+    N = coords.shape[0]
+    labels = torch.zeros(N, dtype=torch.int64, device=coords.device)
+    work = [(torch.arange(N, device=coords.device), 0, nparts)]
+    while work:
+        ids, base, k = work.pop()
+        if k == 1:
+            labels[ids] = base
+            continue
+        kl = k // 2
+        c = coords[ids]
+        ext = c.max(dim=0).values - c.min(dim=0).values if ids.numel() else torch.zeros(3)
+        ax = int(torch.argmax(ext).item()) if ids.numel() else 0
+        order = torch.sort(c[:, ax], stable=True).indices
+        cut = (ids.numel() * kl) // k
+        work.append((ids[order[:cut]], base, kl))
+        work.append((ids[order[cut:]], base + kl, k - kl))
+    return labels
+
+
+@dataclass
+class LocalPart:
+    rank: int
+    nparts: int
+    n_owned: int
+    n_ghost: int
+    owned_global: torch.Tensor            # [n_owned] global ids, ascending
+    ghost_global: torch.Tensor            # [n_ghost] global ids, grouped by owner
+    elements_local: torch.Tensor          # [Ml, nen] in local numbering
+    element_ids: torch.Tensor             # [Ml] global element ids
+    neighbors: List[int] = field(default_factory=list)
+    send_idx: Dict[int, torch.Tensor] = field(default_factory=dict)   # q -> local owned indices to push to q
+    recv_off: Dict[int, int] = field(default_factory=dict)            # q -> offset of q's block inside the ghost region
+    recv_cnt: Dict[int, int] = field(default_factory=dict)
+
+    @property
+    def n_local(self):
+        return self.n_owned + self.n_ghost
+
+
+def build_local_part(elements: torch.Tensor, labels: torch.Tensor, rank: int, nparts: int) -> LocalPart:
+    """Everything rank `rank` needs, computed from the replicated (elements, labels)."""
+    dev = elements.device
+    lab = labels[elements]                                            # [M, nen]
+    touch = (lab == rank).any(dim=1)
+    eids = torch.nonzero(touch).reshape(-1)
+    el = elements[eids]
+    ll = lab[eids]
+    owned = torch.nonzero(labels == rank).reshape(-1)                 # ascending
+    nodes = torch.unique(el)
+    gh = nodes[labels[nodes] != rank]
+    gh_owner = labels[gh]
+    order = torch.sort(gh_owner * (labels.numel() + 1) + gh).indices  # by owner, then id
+    gh, gh_owner = gh[order], gh_owner[order]
+    g2l = torch.full((labels.numel(),), -1, dtype=torch.int64, device=dev)
+    g2l[owned] = torch.arange(owned.numel(), device=dev)
+    g2l[gh] = owned.numel() + torch.arange(gh.numel(), device=dev)
+    part = LocalPart(rank, nparts, int(owned.numel()), int(gh.numel()), owned, gh, g2l[el], eids)
+    for q in sorted(set(gh_owner.tolist())):
+        sel = gh_owner == q
+        part.neighbors.append(q)
+        part.recv_off[q] = int(torch.nonzero(sel)[0].item())
+        part.recv_cnt[q] = int(sel.sum().item())
+        # what q needs from me: my nodes in elements that also hold a node of q (ascending global id)
+        has_q = (ll == q).any(dim=1)
+        mine = torch.unique(el[has_q][ll[has_q] == rank])
+        part.send_idx[q] = g2l[mine]
+    return part
+
+
+def localize(vec_global: torch.Tensor, part: LocalPart) -> torch.Tensor:
+    """Rows of a replicated global [N, ...] array in local numbering (owned then ghost)."""
+    return torch.cat([vec_global[part.owned_global], vec_global[part.ghost_global]], dim=0)

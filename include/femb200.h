@@ -175,6 +175,30 @@ int femb_cg_solve_multi(int64_t n, int nmat, const int64_t* nnz_host, const int3
 int femb_csr_jacobi(int64_t n, const int32_t* crow, const int32_t* col, const double* val, const uint8_t* mask,
                     double* minv, femb_stream stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU CG over NVLink peer memory (one process per GPU; nothing to match in the reference)
+ * ------------------------------------------------------------------------------------------- */
+/* Each rank allocates one "symmetric" buffer = header (femb_dist_header_bytes) + p[n_owned+n_ghost] doubles with
+ * femb_dist_alloc, publishes the 64-byte cudaIpc handle to its peers (any side channel, e.g. torch.distributed),
+ * and maps every peer's buffer with femb_dist_open. */
+int femb_dist_header_bytes(void);
+int femb_dist_alloc(int64_t bytes, void** ptr, void* ipc_handle64);
+int femb_dist_open(const void* ipc_handle64, void** ptr);
+int femb_dist_close(void* ptr);
+int femb_dist_free(void* ptr);
+int femb_dist_reset(void* own_sym, femb_stream stream); /* zero the flags; callers barrier across ranks afterwards */
+
+/* The reference's projected CG (solver.py:144-229) on row-partitioned data.  Local CSR = owned rows only, columns in
+ * local numbering [owned | ghost]; F, mask, u are owned-only.  sym_host[P] = every rank's symmetric buffer as mapped in
+ * this process.  For neighbour k: nbr_host[k] = its rank, send_idx[send_ptr_host[k]..send_ptr_host[k+1]) = my owned
+ * entries it needs, ghost_off_host[k] = index in ITS p where my block starts.  The halo exchange and both all-reduces
+ * are peer stores + epoch flags inside the CUDA-graph-captured iteration; there is no NCCL call.  work = 2*n_owned. */
+int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t nnz, const int32_t* crow, const int32_t* col,
+                       const double* val, const double* F, const uint8_t* mask, double* u, double* work,
+                       void* const* sym_host, int nnbr, const int32_t* nbr_host, const int32_t* send_ptr_host,
+                       const int32_t* send_idx, const int64_t* ghost_off_host, double tol, int max_iter, double eps,
+                       int check_every, femb_cg_result* result_host, femb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

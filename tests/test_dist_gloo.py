@@ -1,0 +1,138 @@
+"""World-size 2/3 CPU (gloo) tests of the multi-GPU host logic: RCB partition, local numbering, halo plan.
+Each rank assembles its local operator with the CPU oracle and runs the reference CG loop with a real halo exchange and
+all-reduce over torch.distributed; the result must equal the single-process oracle solve (1e-8, iterations +-1)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _problem(n=6):
+    from femb200 import meshgen
+    c, t = meshgen.kuhn_cube(n, jitter=0.15)
+    fixed = torch.nonzero(c[:, 2] == 0).reshape(-1)
+    return c, t, fixed
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from femb200 import partition
+    from oracle import fem_oracle as O
+    c, t, fixed = _problem()
+    labels = partition.rcb_labels(c, world)
+    part = partition.build_local_part(t, labels, rank, world)
+    cl = partition.localize(c, part).numpy()
+    el = part.elements_local.numpy()
+    Ke = O.c3d4_poisson_K(cl, el)
+    crow, col, val, _ = O.assemble_csr(Ke, el, 1, part.n_local)
+    no = part.n_owned
+    crow, col, val = crow[:no + 1], col[:crow[no]], val[:crow[no]]        # owned rows are a prefix of the local CSR
+    load = np.bincount(el.reshape(-1), weights=np.repeat(O.tet_volumes(cl, el) / 4, 4), minlength=part.n_local)
+    # loads of owned nodes are complete (all their elements are local)
+    F = load[:no].copy()
+    isfixed = torch.zeros(c.shape[0], dtype=torch.bool)
+    isfixed[fixed] = True
+    free = (~isfixed[part.owned_global]).numpy().astype(np.float64)
+
+    def halo(x_owned):
+        xl = np.zeros(part.n_local)
+        xl[:no] = x_owned
+        reqs, bufs = [], {}
+        for q in part.neighbors:
+            bufs[q] = torch.empty(part.recv_cnt[q], dtype=torch.float64)
+            reqs.append(dist.irecv(bufs[q], src=q))
+            reqs.append(dist.isend(torch.from_numpy(x_owned[part.send_idx[q].numpy()]).contiguous(), dst=q))
+        for r in reqs:
+            r.wait()
+        for q in part.neighbors:
+            o = no + part.recv_off[q]
+            xl[o:o + part.recv_cnt[q]] = bufs[q].numpy()
+        return xl
+
+    def gsum(v):
+        t_ = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t_)
+        return float(t_.item())
+
+    def apply(x_owned):
+        return O.csr_matvec(crow, col, val, halo(x_owned)) * free
+
+    # the reference loop (solver.py:144-229) with global reductions
+    u = np.zeros(no)
+    r = (F - apply(u)) * free
+    p = r.copy()
+    rs_old = gsum(float(r @ r))
+    its, tol, eps = 0, 1e-9, 1e-30
+    for i in range(2000):
+        Ap = apply(p)
+        pAp = gsum(float(p @ Ap))
+        alpha = rs_old / (pAp + eps)
+        u += alpha * p
+        r -= alpha * Ap
+        rs_new = gsum(float(r @ r))
+        its = i + 1
+        if np.sqrt(rs_new) < tol:
+            break
+        p = r + (rs_new / (rs_old + eps)) * p
+        rs_old = rs_new
+    out.put((rank, part.owned_global.numpy(), u, its, part.n_ghost, sorted(part.neighbors)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_cg_matches_single(world):
+    from oracle import fem_oracle as O
+    c, t, fixed = _problem()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29600 + world + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cn, tn = c.numpy(), t.numpy()
+    Ke = O.c3d4_poisson_K(cn, tn)
+    load = np.bincount(tn.reshape(-1), weights=np.repeat(O.tet_volumes(cn, tn) / 4, 4), minlength=cn.shape[0]).reshape(-1, 1)
+    u_ref, it_ref, st = O.stable_cg(Ke, tn, load, fixed.numpy(), tol=1e-9, ndof=1)
+    assert st == "converged"
+    u = np.zeros(cn.shape[0])
+    seen = np.zeros(cn.shape[0], dtype=int)
+    for rank, owned, ul, its, n_ghost, nbrs in res:
+        u[owned] = ul
+        seen[owned] += 1
+        assert abs(its - it_ref) <= 1
+        assert n_ghost > 0 and len(nbrs) >= 1
+    assert (seen == 1).all()                       # every node owned exactly once
+    assert np.abs(u - u_ref[:, 0]).max() <= 1e-8 * np.abs(u_ref).max()
+
+
+def test_rcb_is_balanced_and_deterministic():
+    from femb200 import partition
+    c, t, _ = _problem(8)
+    for P in (2, 3, 4, 8):
+        lab = partition.rcb_labels(c, P)
+        cnt = torch.bincount(lab, minlength=P)
+        assert cnt.max() - cnt.min() <= 1 and torch.equal(lab, partition.rcb_labels(c, P))
+    # halo plans agree pairwise: what r sends to q is what q expects from r, in the same (global id) order
+    lab = partition.rcb_labels(c, 4)
+    parts = [partition.build_local_part(t, lab, r, 4) for r in range(4)]
+    for r in range(4):
+        for q in parts[r].neighbors:
+            sent = parts[r].owned_global[parts[r].send_idx[q]]
+            o = parts[q].recv_off[r]
+            assert torch.equal(sent, parts[q].ghost_global[o:o + parts[q].recv_cnt[r]])
