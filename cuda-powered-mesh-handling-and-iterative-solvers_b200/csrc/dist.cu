@@ -61,9 +61,7 @@ __device__ __forceinline__ bool spin_until(volatile long long* flag, long long e
 
 // block-level wait: thread 0 polls the listed ranks' flags in MY header, everyone else parks on the barrier
 __device__ __forceinline__ void wait_flags(volatile long long* flags, const int* ranks, int count, long long expect, DistState* st) {
-  if (threadIdx.x == 0)
-    for (int k = 0; k < count; ++k)
-      if (!spin_until(flags + ranks[k], expect, st)) break;
+  if (threadIdx.x < count) spin_until(flags + ranks[threadIdx.x], expect, st);  // one lane per flag: the polls overlap
   __syncthreads();
 }
 
@@ -370,7 +368,10 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   const long long n = n_owned;
   double *r = work, *Ap = work + n;
   const int lr = pick_lr(n, nnz);
-  const int g1 = (int)std::min<long long>((n + SPMV_THREADS / lr - 1) / (SPMV_THREADS / lr), (long long)SMS * 4 * 8);
+  // one row tile per CTA up to 32k CTAs, then the smallest equal share: no CTA does one tile more than another
+  const long long tiles = (n + SPMV_THREADS / lr - 1) / (SPMV_THREADS / lr);
+  const long long per = (tiles + SMS * 32 - 1) / (SMS * 32);
+  const int g1 = (int)((tiles + per - 1) / per);
   const int g2 = grid_for(n, DV_THREADS, 8);
   const int gp = std::max(1, std::min(64, (pe.send_ptr[nnbr] + 255) / 256));
   Scratch scr(s);

@@ -245,10 +245,12 @@ static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const 
 
 static int spmv_grid(long long n, int lanes) {
   const long long rows_per_block = SPMV_THREADS / (lanes < 0 ? -lanes : lanes);
-  long long b = (n + rows_per_block - 1) / rows_per_block;
-  const long long cap = (long long)SMS * 4 * 8;  // a few waves of the 4 CTAs (48 KB each) that fit an SM; partial array is sized by this
-  if (b > cap) b = cap;
-  return (int)(b < 1 ? 1 : b);
+  const long long tiles = std::max<long long>(1, (n + rows_per_block - 1) / rows_per_block);
+  if (lanes < 0) return (int)std::min<long long>(tiles, (long long)SMS * 8);  // legacy vector kernel: persistent grid
+  // stream kernel: one row tile per CTA up to 32k CTAs, beyond that the smallest equal share (no CTA gets an extra tile)
+  static const long long max_ctas = getenv("FEMB_SPMV_MAXCTAS") ? atoll(getenv("FEMB_SPMV_MAXCTAS")) : SMS * 32;  // measured: 4736 beats larger grids
+  const long long per = (tiles + max_ctas - 1) / max_ctas;
+  return (int)((tiles + per - 1) / per);
 }
 
 }  // namespace femb
