@@ -12,6 +12,8 @@
 // There is no NCCL call and no host involvement inside the loop: the "collectives" are peer stores plus epoch flags, which
 // costs a few microseconds instead of tens per all-reduce -- the difference between ~4x and >6x strong scaling at 8 GPUs
 // when an iteration is ~85 us of compute.  All spin loops carry a timeout so a lost rank turns into an error, not a hang.
+#include <cstdlib>
+
 #include "spmv_dev.cuh"
 
 namespace femb {
@@ -35,7 +37,17 @@ struct DistState {
   int it, stop, status, iterations;
   long long epochA, epochB, epochC;
   unsigned int ticket_push, ticket1, ticket2, ticket3;
+  long long* trace;  // optional [TRACE_ITERS][12] globaltimer stamps (FEMB_DIST_TRACE=1)
 };
+
+constexpr int TRACE_ITERS = 64;
+__device__ __forceinline__ void trace_stamp(DistState* st, int slot) {
+  if (st->trace && st->it < TRACE_ITERS) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    st->trace[st->it * 12 + slot] = t;
+  }
+}
 
 struct Peers {
   SymHeader* hdr[MAXP];  // every rank's header as mapped in this process (own included)
@@ -68,6 +80,7 @@ __device__ __forceinline__ void wait_flags(volatile long long* flags, const int*
 // ---- push: p boundary -> neighbours' ghost slots, then flag A --------------------------------------------------------
 __global__ void __launch_bounds__(256) dist_push_kernel(Peers pe, const int* __restrict__ send_idx, DistState* st) {
   if (st->stop) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 0);
   const double* p = sym_p(pe.hdr[pe.rank]);
   const int total = pe.send_ptr[pe.nnbr];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -87,6 +100,7 @@ __global__ void __launch_bounds__(256) dist_push_kernel(Peers pe, const int* __r
     st->epochA = e;
     __threadfence_system();
     for (int k = 0; k < pe.nnbr; ++k) pe.hdr[pe.nbr[k]]->flagA[pe.rank] = e;
+    trace_stamp(st, 1);
   }
 }
 
@@ -98,8 +112,10 @@ __global__ void __launch_bounds__(SPMV_THREADS) dist_spmv_kernel(Peers pe, long 
                                                                  double* __restrict__ partial, DistState* st) {
   if (st->stop) return;
   SymHeader* me = pe.hdr[pe.rank];
+  if (FUSED && blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 2);
   wait_flags(me->flagA, pe.nbr, pe.nnbr, st->epochA, st);
   if (st->stop) return;
+  if (FUSED && blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 3);
   const double* x = sym_p(me);
   const double dot = spmv_stream_rows<LR, false>(n_owned, crow, col, val, x, y, mask, false, FUSED);
   if (!FUSED) return;
@@ -123,6 +139,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) dist_spmv_kernel(Peers pe, long 
       for (int q = 0; q < pe.P; ++q) pe.hdr[q]->redB[pe.rank] = a;
       __threadfence_system();
       for (int q = 0; q < pe.P; ++q) pe.hdr[q]->flagB[pe.rank] = e;
+      trace_stamp(st, 4);
     }
   }
 }
@@ -144,8 +161,10 @@ __global__ void __launch_bounds__(DV_THREADS) dist_update_kernel(Peers pe, long 
   __shared__ int all[MAXP];
   if (threadIdx.x < MAXP) all[threadIdx.x] = threadIdx.x;
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 5);
   wait_flags(me->flagB, all, pe.P, st->epochB, st);
   if (st->stop) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 6);
   const double pAp = sum_slots(me->redB, pe.P);
   const double alpha = st->rs_old / (pAp + eps);
   if (guards && (fabs(pAp) < eps || pAp < 0.0 || !isfinite(alpha))) {  // solver.py:187-198, same verdict on every rank/CTA
@@ -181,6 +200,7 @@ __global__ void __launch_bounds__(DV_THREADS) dist_update_kernel(Peers pe, long 
       for (int q = 0; q < pe.P; ++q) pe.hdr[q]->redC[pe.rank] = a;
       __threadfence_system();
       for (int q = 0; q < pe.P; ++q) pe.hdr[q]->flagC[pe.rank] = e;
+      trace_stamp(st, 7);
     }
   }
 }
@@ -193,8 +213,10 @@ __global__ void __launch_bounds__(DV_THREADS) dist_direction_kernel(Peers pe, lo
   __shared__ int all[MAXP];
   if (threadIdx.x < MAXP) all[threadIdx.x] = threadIdx.x;
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 8);
   wait_flags(me->flagC, all, pe.P, st->epochC, st);
   if (st->stop) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 9);
   const double rs_new = sum_slots(me->redC, pe.P);
   const double beta = rs_new / (st->rs_old + eps);
   const bool conv = sqrt(rs_new) < tol;                  // solver.py:210-212
@@ -214,6 +236,7 @@ __global__ void __launch_bounds__(DV_THREADS) dist_direction_kernel(Peers pe, lo
   __syncthreads();
   if (last && threadIdx.x == 0) {  // every CTA has read rs_old by now
     st->ticket3 = 0;
+    trace_stamp(st, 10);
     st->rs_new = rs_new, st->beta = beta, st->rs_old = rs_new;
     st->it += 1;
     if (st->it >= max_iter) st->stop = 2, st->status = 2, st->iterations = max_iter;
@@ -380,6 +403,12 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   FEMB_CUDA(scr.alloc(&partial, (size_t)std::max(g1, g2)));
   FEMB_CUDA(scr.alloc(&st, 1));
   FEMB_CUDA(cudaMemsetAsync(st, 0, sizeof(DistState), s));
+  long long* trace = nullptr;
+  if (getenv("FEMB_DIST_TRACE")) {
+    FEMB_CUDA(scr.alloc(&trace, (size_t)TRACE_ITERS * 12));
+    FEMB_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * TRACE_ITERS * 12, s));
+    FEMB_CUDA(cudaMemcpyAsync(&st->trace, &trace, sizeof(trace), cudaMemcpyHostToDevice, s));
+  }
   const int guards = 1;
   // ---- setup: p <- mask.*u, halo, Ap = A u, r = mask.*(F - Ap), p = r, rs_old = allreduce(r.r)   (solver.py:163-181)
   dist_load_p<<<g2, DV_THREADS, 0, s>>>(pe, n, u, mask);
@@ -449,5 +478,25 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   result_host->status = fin->stop ? fin->status : 2;
   result_host->rs = fin->rs_new;
   result_host->loop_ms = ms;
+  if (trace && fin->it > 20) {  // average phase times over iterations 10..min(it,TRACE_ITERS)-1 (microseconds)
+    static long long h[TRACE_ITERS * 12];
+    cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const int i1 = std::min(fin->it, TRACE_ITERS) - 1;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 10; i < i1; ++i) {
+      const long long* t = h + i * 12;
+      acc[0] += t[1] - t[0];                 // push
+      acc[1] += t[3] - t[2];                 // k1 wait for halo
+      acc[2] += t[4] - t[3];                 // k1 body + reduction + remote stores
+      acc[3] += t[6] - t[5];                 // k2 wait for all-reduce B
+      acc[4] += t[7] - t[6];                 // k2 body
+      acc[5] += t[9] - t[8];                 // k3 wait for all-reduce C
+      acc[6] += t[10] - t[9];                // k3 body
+      acc[7] += (h + (i + 1) * 12)[0] - t[0];  // whole iteration
+    }
+    const double m = 1e-3 / (i1 - 10);
+    fprintf(stderr, "[femb dist trace] rank %d: push %.1f | k1 wait %.1f body %.1f | k2 wait %.1f body %.1f | k3 wait %.1f body %.1f | iteration %.1f us\n",
+            rank, acc[0] * m, acc[1] * m, acc[2] * m, acc[3] * m, acc[4] * m, acc[5] * m, acc[6] * m, acc[7] * m);
+  }
   return FEMB_OK;
 }
