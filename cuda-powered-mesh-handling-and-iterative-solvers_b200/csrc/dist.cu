@@ -104,20 +104,33 @@ __global__ void __launch_bounds__(256) dist_push_kernel(Peers pe, const int* __r
   }
 }
 
+struct GraphHaloWaiter {
+  SymHeader* me;
+  const int* nbr;
+  int nnbr;
+  long long epoch;
+  DistState* st;
+  __device__ __forceinline__ void operator()() const { wait_flags(me->flagA, nbr, nnbr, epoch, st); }
+};
+
 // ---- k1: SpMV on owned rows + p.Ap partial -> everyone ---------------------------------------------------------------
 template <int LR, bool FUSED>
 __global__ void __launch_bounds__(SPMV_THREADS) dist_spmv_kernel(Peers pe, long long n_owned, const int* __restrict__ crow,
                                                                  const int* __restrict__ col, const double* __restrict__ val,
                                                                  double* __restrict__ y, const unsigned char* __restrict__ mask,
-                                                                 double* __restrict__ partial, DistState* st) {
+                                                                 double* __restrict__ partial, DistState* st, long long n_interior) {
   if (st->stop) return;
   SymHeader* me = pe.hdr[pe.rank];
-  if (FUSED && blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 2);
-  wait_flags(me->flagA, pe.nbr, pe.nnbr, st->epochA, st);
-  if (st->stop) return;
-  if (FUSED && blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 3);
+  if (FUSED && blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 2), trace_stamp(st, 3);
+  __shared__ int nbr[MAXP];
+  if (threadIdx.x < MAXP) nbr[threadIdx.x] = pe.nbr[threadIdx.x];
+  __syncthreads();
   const double* x = sym_p(me);
-  const double dot = spmv_stream_rows<LR, false>(n_owned, crow, col, val, x, y, mask, false, FUSED);
+  // interior row tiles need no ghost entry: a CTA waits for the halo only when it reaches its first boundary tile
+  const GraphHaloWaiter hw{me, nbr, pe.nnbr, st->epochA, st};
+  const double dot = spmv_stream_rows<LR, false, GraphHaloWaiter>(n_owned, crow, col, val, x, y, mask, false, FUSED,
+                                                                  pe.nnbr > 0 ? n_interior : 0x7fffffffffffffffll, hw);
+  if (st->stop == 3) return;
   if (!FUSED) return;
   const double t = block_sum<SPMV_THREADS>(dot);
   __shared__ bool last;
@@ -146,10 +159,20 @@ __global__ void __launch_bounds__(SPMV_THREADS) dist_spmv_kernel(Peers pe, long 
 
 constexpr int DV_THREADS = 256;
 
-__device__ __forceinline__ double sum_slots(volatile double* red, int P) {
+__device__ __forceinline__ double sum_slots_serial(volatile double* red, int P) {
   double a = 0.0;
   for (int q = 0; q < P; ++q) a += red[q];  // rank order: identical result on every rank
   return a;
+}
+// block-uniform: ONE thread reads the P slots and broadcasts through shared memory.  (Every thread reading them turns the
+// 64-byte slot line into an L2 hot spot: 1184 CTAs x 8 warps x P requests cost ~17 us per kernel at P = 8.)
+__device__ __forceinline__ double sum_slots(volatile double* red, int P) {
+  __shared__ double bc;
+  if (threadIdx.x == 0) bc = sum_slots_serial(red, P);
+  __syncthreads();
+  const double v = bc;
+  __syncthreads();
+  return v;
 }
 
 // ---- k2: u += alpha p ; r -= alpha Ap ; r.r partial -> everyone -------------------------------------------------------
@@ -206,8 +229,15 @@ __global__ void __launch_bounds__(DV_THREADS) dist_update_kernel(Peers pe, long 
 }
 
 // ---- k3: convergence / beta ; p = r + beta p -------------------------------------------------------------------------
+struct BoundaryPush {     // boundary rows [n_interior, n): destinations of each row's value (CSR over boundary rows)
+  const int* ptr;         // [nb+1], nullptr = no folded push
+  const unsigned char* k; // neighbour index of each destination
+  const int* off;         // offset inside that neighbour's block of ghosts
+  long long n_interior;
+};
+
 __global__ void __launch_bounds__(DV_THREADS) dist_direction_kernel(Peers pe, long long n, const double* __restrict__ r, DistState* st,
-                                                                    double tol, double eps, int guards, int max_iter) {
+                                                                    double tol, double eps, int guards, int max_iter, BoundaryPush bp) {
   if (st->stop) return;
   SymHeader* me = pe.hdr[pe.rank];
   __shared__ int all[MAXP];
@@ -226,7 +256,23 @@ __global__ void __launch_bounds__(DV_THREADS) dist_direction_kernel(Peers pe, lo
     return;
   }
   double* p = sym_p(me);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = r[i] + beta * p[i];
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  const long long n_plain = bp.ptr ? bp.n_interior : n;
+  // boundary rows first (their values have the longest way to go): one thread per row writes it locally and stores it
+  // straight into the ghost slots of every neighbour that needs it
+  if (bp.ptr) {
+    for (long long b = gtid; b < n - bp.n_interior; b += gsz) {
+      const long long i = bp.n_interior + b;
+      const double v = r[i] + beta * p[i];
+      p[i] = v;
+      for (int e = bp.ptr[b]; e < bp.ptr[b + 1]; ++e) {
+        const int k = bp.k[e];
+        (sym_p(pe.hdr[pe.nbr[k]]) + pe.ghost_off[k])[bp.off[e]] = v;
+      }
+    }
+    __threadfence_system();
+  }
+  for (long long i = gtid; i < n_plain; i += gsz) p[i] = r[i] + beta * p[i];
   __shared__ bool last;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -234,12 +280,18 @@ __global__ void __launch_bounds__(DV_THREADS) dist_direction_kernel(Peers pe, lo
     last = atomicAdd(&st->ticket3, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {  // every CTA has read rs_old by now
+  if (last && threadIdx.x == 0) {  // every CTA has read rs_old (and pushed its boundary rows) by now
     st->ticket3 = 0;
-    trace_stamp(st, 10);
     st->rs_new = rs_new, st->beta = beta, st->rs_old = rs_new;
     st->it += 1;
     if (st->it >= max_iter) st->stop = 2, st->status = 2, st->iterations = max_iter;
+    if (bp.ptr) {
+      const long long e = st->epochA + 1;
+      st->epochA = e;
+      __threadfence_system();
+      for (int k = 0; k < pe.nnbr; ++k) pe.hdr[pe.nbr[k]]->flagA[pe.rank] = e;
+    }
+    trace_stamp(st, 10);
   }
 }
 
@@ -253,16 +305,17 @@ __global__ void dist_load_p(Peers pe, long long n, double* __restrict__ u, const
 }
 
 __global__ void __launch_bounds__(DV_THREADS) dist_init_kernel(Peers pe, long long n, const double* __restrict__ F, const double* __restrict__ Au,
-                                                               const unsigned char* __restrict__ mask, double* __restrict__ r,
-                                                               double* __restrict__ partial, DistState* st) {
+                                                               const unsigned char* __restrict__ mask, const double* __restrict__ minv,
+                                                               double* __restrict__ r, double* __restrict__ partial, DistState* st) {
   double* p = sym_p(pe.hdr[pe.rank]);
   double dot = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double ri = F[i] - Au[i];
     if (mask && !mask[i]) ri = 0.0;
+    const double z = minv ? minv[i] * ri : ri;
     r[i] = ri;
-    p[i] = ri;
-    dot += ri * ri;
+    p[i] = z;
+    dot += ri * z;
   }
   const double t = block_sum<DV_THREADS>(dot);
   __shared__ bool last;
@@ -294,10 +347,186 @@ __global__ void dist_init_finish(Peers pe, DistState* st, int max_iter) {
     bool ok = true;
     for (int q = 0; q < pe.P && ok; ++q) ok = spin_until(me->flagC + q, st->epochC, st);
     if (ok) {
-      const double a = sum_slots(me->redC, pe.P);
+      const double a = sum_slots_serial(me->redC, pe.P);
       st->rs_old = a, st->rs_new = a;
       if (max_iter <= 0) st->stop = 2, st->status = 2;
     }
+  }
+}
+
+// ---- persistent variant: the whole solve is ONE cooperative kernel -------------------------------------------------------
+// All CTAs are co-resident (cooperative launch) and walk the phases of every iteration together:
+//   push (peer stores of the boundary of p; last CTA raises flag A on the neighbours)
+//   SpMV (interior row tiles first; a CTA waits for flag A only when it reaches its first boundary tile) + p.Ap partial,
+//        last CTA stores the rank's partial into every rank's slot and raises flag B
+//   wait B -> alpha -> u, r update + r.r partial -> last CTA -> slots + flag C
+//   wait C -> convergence / beta -> p update -> local grid barrier
+// Iteration scalars live in registers of every thread (identical everywhere: they are functions of the rank-ordered sums),
+// so there is no launch boundary, no graph and no host round trip inside the solve.  Because the kernel never ends between
+// iterations the L1 is not flushed for us: every wait is followed by a fence (acquire side of the message-passing pattern)
+// and x is read with plain loads, never through the non-coherent path.
+struct PersistArgs {
+  Peers pe;
+  long long n, n_interior;
+  const int *crow, *col;
+  const double *val, *F, *minv;
+  const unsigned char* mask;
+  double *u, *r, *Ap, *partial;
+  const int* send_idx;
+  DistState* st;
+  unsigned long long* counters;  // [4] monotonic: push tickets, k1 tickets, k2 tickets, grid barrier
+  double tol, eps;
+  int max_iter, guards;
+};
+
+__device__ __forceinline__ void wait_then_fence(volatile long long* flags, const int* ranks, int count, long long expect, DistState* st) {
+  if (threadIdx.x < count) spin_until(flags + ranks[threadIdx.x], expect, st);
+  if (threadIdx.x < 32) __threadfence_system();
+  __syncthreads();
+}
+
+struct HaloWaiter {
+  SymHeader* me;
+  const int* nbr;
+  int nnbr;
+  long long epoch;
+  DistState* st;
+  __device__ __forceinline__ void operator()() const { wait_then_fence(me->flagA, nbr, nnbr, epoch, st); }
+};
+
+template <int LR>
+__global__ void __launch_bounds__(SPMV_THREADS) dist_cg_persistent_kernel(const PersistArgs a) {
+  const Peers& pe = a.pe;
+  SymHeader* me = pe.hdr[pe.rank];
+  double* p = sym_p(me);
+  DistState* st = a.st;
+  const unsigned long long G = gridDim.x;
+  const int tid = threadIdx.x;
+  const long long gtid = blockIdx.x * (long long)blockDim.x + tid, gsz = (long long)gridDim.x * blockDim.x;
+  __shared__ int all[MAXP], nbr[MAXP];
+  __shared__ bool last;
+  if (tid < MAXP) all[tid] = tid, nbr[tid] = pe.nbr[tid];
+  __syncthreads();
+  const bool pre = a.minv != nullptr;
+  double rs_old = st->rs_old;      // set by the setup kernels
+  long long eA = st->epochA, eB = st->epochB, eC = st->epochC;
+  unsigned long long round = 0;    // iterations done by this launch (tickets are monotonic: last CTA sees G*(round+1))
+  int it = 0, stop = a.max_iter <= 0 ? 2 : 0, status = 2, iterations = a.max_iter;
+  double rs_new = rs_old, pAp = 0.0;
+  const int total_send = pe.send_ptr[pe.nnbr];
+  while (!stop) {
+    // ---- push
+    for (long long t = gtid; t < total_send; t += gsz) {
+      int k = 0;
+      while (t >= pe.send_ptr[k + 1]) ++k;
+      (sym_p(pe.hdr[pe.nbr[k]]) + pe.ghost_off[k])[t - pe.send_ptr[k]] = p[a.send_idx[t]];
+    }
+    ++eA;
+    if (pe.nnbr > 0) {
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0 && atomicAdd(&a.counters[0], 1ull) + 1 == G * (round + 1)) {
+        __threadfence_system();
+        for (int k = 0; k < pe.nnbr; ++k) pe.hdr[pe.nbr[k]]->flagA[pe.rank] = eA;
+      }
+    }
+    // ---- SpMV + p.Ap
+    const HaloWaiter hw{me, nbr, pe.nnbr, eA, st};
+    double dot = spmv_stream_rows<LR, false, HaloWaiter>(a.n, a.crow, a.col, a.val, p, a.Ap, a.mask, false, true,
+                                                          pe.nnbr > 0 ? a.n_interior : 0x7fffffffffffffffll, hw);
+    double t = block_sum<SPMV_THREADS>(dot);
+    if (tid == 0) {
+      a.partial[blockIdx.x] = t;
+      __threadfence();
+      last = atomicAdd(&a.counters[1], 1ull) + 1 == G * (round + 1);
+    }
+    __syncthreads();
+    ++eB;
+    if (last) {
+      __threadfence();
+      double s = 0.0;
+      for (int k = tid; k < (int)G; k += SPMV_THREADS) s += ((volatile double*)a.partial)[k];
+      s = block_sum<SPMV_THREADS>(s);
+      if (tid == 0) {
+        for (int q = 0; q < pe.P; ++q) pe.hdr[q]->redB[pe.rank] = s;
+        __threadfence_system();
+        for (int q = 0; q < pe.P; ++q) pe.hdr[q]->flagB[pe.rank] = eB;
+      }
+    }
+    // ---- alpha, u/r update, r.z
+    wait_then_fence(me->flagB, all, pe.P, eB, st);
+    if (st->stop == 3) break;
+    pAp = sum_slots(me->redB, pe.P);
+    const double alpha = rs_old / (pAp + a.eps);
+    if (a.guards && (fabs(pAp) < a.eps || pAp < 0.0 || !isfinite(alpha))) {  // solver.py:187-198
+      stop = 1, status = 1, iterations = it + 1;
+      break;
+    }
+    dot = 0.0;
+    for (long long i = gtid; i < a.n; i += gsz) {
+      const double ri = a.r[i] - alpha * a.Ap[i];
+      a.u[i] += alpha * p[i];
+      a.r[i] = ri;
+      dot += pre ? ri * (a.minv[i] * ri) : ri * ri;
+    }
+    t = block_sum<SPMV_THREADS>(dot);
+    if (tid == 0) {
+      a.partial[blockIdx.x] = t;
+      __threadfence();
+      last = atomicAdd(&a.counters[2], 1ull) + 1 == G * (round + 1);
+    }
+    __syncthreads();
+    ++eC;
+    if (last) {
+      __threadfence();
+      double s = 0.0;
+      for (int k = tid; k < (int)G; k += SPMV_THREADS) s += ((volatile double*)a.partial)[k];
+      s = block_sum<SPMV_THREADS>(s);
+      if (tid == 0) {
+        for (int q = 0; q < pe.P; ++q) pe.hdr[q]->redC[pe.rank] = s;
+        __threadfence_system();
+        for (int q = 0; q < pe.P; ++q) pe.hdr[q]->flagC[pe.rank] = eC;
+      }
+    }
+    // ---- convergence, beta, direction
+    wait_then_fence(me->flagC, all, pe.P, eC, st);
+    if (st->stop == 3) break;
+    rs_new = sum_slots(me->redC, pe.P);
+    if (sqrt(rs_new) < a.tol) {  // solver.py:210-212 / :804-806
+      stop = 1, status = 0, iterations = it + 1;
+      break;
+    }
+    const double beta = rs_new / (rs_old + a.eps);
+    if (a.guards && !isfinite(beta)) {  // solver.py:216-218
+      stop = 1, status = 1, iterations = it + 1;
+      break;
+    }
+    for (long long i = gtid; i < a.n; i += gsz) p[i] = (pre ? a.minv[i] * a.r[i] : a.r[i]) + beta * p[i];
+    rs_old = rs_new;
+    ++it;
+    ++round;
+    if (it >= a.max_iter) stop = 2, status = 2, iterations = a.max_iter;
+    // ---- local grid barrier: p is complete before anyone pushes or gathers it again
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&a.counters[3], 1ull);
+      const long long t0 = clock64();
+      while (*((volatile unsigned long long*)&a.counters[3]) < G * round) {
+        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+          st->stop = 3, st->status = 3;
+          break;
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (st->stop == 3) break;
+  }
+  if (blockIdx.x == 0 && tid == 0 && st->stop != 3) {
+    st->it = it, st->stop = stop ? stop : 2, st->status = status, st->iterations = iterations;
+    st->rs_new = rs_new, st->rs_old = rs_old, st->pAp = pAp;
+    st->epochA = eA, st->epochB = eB, st->epochC = eC;
   }
 }
 
@@ -310,14 +539,14 @@ static int pick_lr(long long n, long long nnz) {
 
 template <bool FUSED>
 static void launch_dist_spmv(int lr, int grid, cudaStream_t s, const Peers& pe, long long n, const int* crow, const int* col, const double* val,
-                             double* y, const unsigned char* mask, double* partial, DistState* st) {
+                             double* y, const unsigned char* mask, double* partial, DistState* st, long long n_interior) {
   switch (lr) {
-    case 1: dist_spmv_kernel<1, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st); break;
-    case 2: dist_spmv_kernel<2, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st); break;
-    case 4: dist_spmv_kernel<4, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st); break;
-    case 8: dist_spmv_kernel<8, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st); break;
-    case 16: dist_spmv_kernel<16, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st); break;
-    default: dist_spmv_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st); break;
+    case 1: dist_spmv_kernel<1, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
+    case 2: dist_spmv_kernel<2, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
+    case 4: dist_spmv_kernel<4, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
+    case 8: dist_spmv_kernel<8, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
+    case 16: dist_spmv_kernel<16, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
+    default: dist_spmv_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
   }
 }
 
@@ -372,11 +601,12 @@ extern "C" int femb_dist_reset(void* own_sym, femb_stream stream) {
   return FEMB_OK;
 }
 
-extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t nnz, const int32_t* crow, const int32_t* col, const double* val,
-                                  const double* F, const uint8_t* mask, double* u, double* work, void* const* sym_host, int nnbr,
+extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t n_interior, int64_t nnz, const int32_t* crow,
+                                  const int32_t* col, const double* val, const double* F, const uint8_t* mask, const double* minv,
+                                  double* u, double* work, void* const* sym_host, int nnbr,
                                   const int32_t* nbr_host, const int32_t* send_ptr_host, const int32_t* send_idx,
-                                  const int64_t* ghost_off_host, double tol, int max_iter, double eps, int check_every,
-                                  femb_cg_result* result_host, femb_stream stream) {
+                                  const int64_t* ghost_off_host, const int32_t* bptr, const uint8_t* bk, const int32_t* boff, double tol,
+                                  int max_iter, double eps, int check_every, femb_cg_result* result_host, femb_stream stream) {
   FEMB_CHECK_ARG(nranks >= 1 && nranks <= MAXP && rank >= 0 && rank < nranks && nnbr >= 0 && nnbr < MAXP, "rank/nranks/nnbr");
   FEMB_CHECK_ARG(n_owned > 0 && crow && col && val && F && u && work && sym_host && result_host, "null pointer / n_owned <= 0");
   if (check_every < 1) check_every = 16;
@@ -409,23 +639,81 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
     FEMB_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * TRACE_ITERS * 12, s));
     FEMB_CUDA(cudaMemcpyAsync(&st->trace, &trace, sizeof(trace), cudaMemcpyHostToDevice, s));
   }
-  const int guards = 1;
+  const int guards = minv ? 0 : 1;  // the reference's PCG loop has no guards and no eps (solver.py:795-810)
+  if (minv) eps = 0.0;
+  if (n_interior < 0 || n_interior > n_owned) n_interior = 0;
   // ---- setup: p <- mask.*u, halo, Ap = A u, r = mask.*(F - Ap), p = r, rs_old = allreduce(r.r)   (solver.py:163-181)
   dist_load_p<<<g2, DV_THREADS, 0, s>>>(pe, n, u, mask);
   dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
-  launch_dist_spmv<false>(lr, g1, s, pe, n, crow, col, val, Ap, nullptr, nullptr, st);
-  dist_init_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, F, Ap, mask, r, partial, st);
+  launch_dist_spmv<false>(lr, g1, s, pe, n, crow, col, val, Ap, nullptr, nullptr, st, 0);
+  dist_init_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, F, Ap, mask, minv, r, partial, st);
   dist_init_finish<<<1, 32, 0, s>>>(pe, st, max_iter);
   FEMB_LAUNCH_CHECK();
-  // ---- iterations
+  // default: three kernels per iteration in a CUDA graph.  FEMB_DIST_PERSISTENT=1 (and PCG) selects the single persistent
+  // cooperative kernel, which measured slower so far (grid-wide software barriers cost more than launch boundaries)
+  static const bool use_persistent = getenv("FEMB_DIST_PERSISTENT") != nullptr;
+  if (use_persistent || minv) {
+    // ---- iterations: one persistent cooperative kernel
+    PersistArgs pa;
+    pa.pe = pe, pa.n = n, pa.n_interior = n_interior, pa.crow = crow, pa.col = col, pa.val = val, pa.F = F, pa.minv = minv, pa.mask = mask;
+    pa.u = u, pa.r = r, pa.Ap = Ap, pa.send_idx = send_idx, pa.st = st, pa.tol = tol, pa.eps = eps, pa.max_iter = max_iter, pa.guards = guards;
+    const void* kern = nullptr;
+    switch (lr) {
+      case 1: kern = (const void*)dist_cg_persistent_kernel<1>; break;
+      case 2: kern = (const void*)dist_cg_persistent_kernel<2>; break;
+      case 4: kern = (const void*)dist_cg_persistent_kernel<4>; break;
+      case 8: kern = (const void*)dist_cg_persistent_kernel<8>; break;
+      case 16: kern = (const void*)dist_cg_persistent_kernel<16>; break;
+      default: kern = (const void*)dist_cg_persistent_kernel<32>; break;
+    }
+    int per_sm = 0, dev = 0, sms = SMS;
+    FEMB_CUDA(cudaGetDevice(&dev));
+    FEMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FEMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SPMV_THREADS, 0));
+    FEMB_CHECK_ARG(per_sm >= 1, "persistent CG kernel does not fit on an SM");
+    const int G = per_sm * sms;
+    unsigned long long* counters;
+    FEMB_CUDA(scr.alloc(&pa.partial, (size_t)G));
+    FEMB_CUDA(scr.alloc(&counters, 4));
+    FEMB_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), s));
+    pa.counters = counters;
+    static thread_local DistState* hfin = nullptr;
+    static thread_local cudaEvent_t pev[2] = {nullptr, nullptr};
+    if (!hfin) {
+      FEMB_CUDA(cudaMallocHost(&hfin, sizeof(DistState)));
+      FEMB_CUDA(cudaEventCreate(&pev[0]));
+      FEMB_CUDA(cudaEventCreate(&pev[1]));
+    }
+    void* kargs[] = {(void*)&pa};
+    FEMB_CUDA(cudaEventRecord(pev[0], s));
+    FEMB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(SPMV_THREADS), kargs, 0, s));
+    FEMB_CUDA(cudaEventRecord(pev[1], s));
+    FEMB_CUDA(cudaMemcpyAsync(hfin, st, sizeof(DistState), cudaMemcpyDeviceToHost, s));
+    FEMB_CUDA(cudaStreamSynchronize(s));
+    float pms = 0.f;
+    cudaEventElapsedTime(&pms, pev[0], pev[1]);
+    if (hfin->status == 3 || hfin->stop == 3) {
+      set_error("distributed CG: timed out waiting for a peer rank (flag never arrived)");
+      return FEMB_ERR_NCCL;
+    }
+    result_host->iterations = hfin->iterations;
+    result_host->status = hfin->status;
+    result_host->rs = hfin->rs_new;
+    result_host->loop_ms = pms;
+    return FEMB_OK;
+  }
+  if (bptr != nullptr && nnbr > 0 && n_interior > 0 && !getenv("FEMB_DIST_SEPARATE_PUSH")) dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
+  // ---- iterations: CUDA graph (k1, k2, k3 with the halo push folded into k3)
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   FEMB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  const bool folded = bptr != nullptr && nnbr > 0 && n_interior > 0 && !getenv("FEMB_DIST_SEPARATE_PUSH");
+  BoundaryPush bp{folded ? bptr : nullptr, bk, boff, n_interior};
   for (int k = 0; k < check_every; ++k) {
-    dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
-    launch_dist_spmv<true>(lr, g1, s, pe, n, crow, col, val, Ap, mask, partial, st);
+    if (!folded) dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
+    launch_dist_spmv<true>(lr, g1, s, pe, n, crow, col, val, Ap, mask, partial, st, n_interior);
     dist_update_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, eps, guards);
-    dist_direction_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, r, st, tol, eps, guards, max_iter);
+    dist_direction_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, r, st, tol, eps, guards, max_iter, bp);
   }
   cudaError_t ce = cudaStreamEndCapture(s, &graph);
   if (ce != cudaSuccess) {

@@ -30,17 +30,29 @@ __device__ __forceinline__ double ld_x(const double* p) {
 // memory; then LR lanes per row add up that row's products (index order within a lane, fixed shuffle tree across lanes).
 // Short FEM rows (~15 nonzeros for P1) therefore cost no idle lanes and no per-row pointer chasing while streaming.
 // Returns this thread's partial of sum_r y_r * x_r (only when `fused`), with masked rows forced to zero.
-template <int LR, bool NC>
+struct NoHaloWait {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// `halo_row`: rows >= halo_row may read entries of x that another GPU is still writing; `wait` (block-uniform, may
+// __syncthreads) is called once, right before this CTA touches its first such tile, so interior tiles overlap the exchange.
+template <int LR, bool NC, typename Wait = NoHaloWait>
 __device__ __forceinline__ double spmv_stream_rows(long long n, const int* __restrict__ crow, const int* __restrict__ col,
                                                    const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
-                                                   const unsigned char* __restrict__ mask, bool accumulate, bool fused) {
+                                                   const unsigned char* __restrict__ mask, bool accumulate, bool fused,
+                                                   long long halo_row = 0x7fffffffffffffffll, Wait wait = Wait()) {
   constexpr int R = SPMV_THREADS / LR;
   __shared__ double prod[STREAM_CAP];
   __shared__ int rp[R + 1];
   const int tid = threadIdx.x, sub = tid % LR, lr = tid / LR;
   double dot = 0.0;
+  bool waited = false;
   for (long long r0 = (long long)blockIdx.x * R; r0 < n; r0 += (long long)gridDim.x * R) {
     const int nr = (int)min((long long)R, n - r0);
+    if (!waited && r0 + nr > halo_row) {
+      wait();
+      waited = true;
+    }
     for (int t = tid; t <= nr; t += SPMV_THREADS) rp[t] = __ldg(crow + r0 + t);
     __syncthreads();
     const int s = rp[0], e = rp[nr];

@@ -51,8 +51,8 @@ SIGNATURES = {
     "femb_dist_close": [c_vp],
     "femb_dist_free": [c_vp],
     "femb_dist_reset": [c_vp, c_vp],
-    "femb_dist_cg_solve": [c_i32, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_vp), c_i32,
-                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_vp, C.POINTER(c_i64), c_f64, c_i32, c_f64, c_i32,
+    "femb_dist_cg_solve": [c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_vp), c_i32,
+                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_vp, C.POINTER(c_i64), c_vp, c_vp, c_vp, c_f64, c_i32, c_f64, c_i32,
                            C.POINTER(CGResult), c_vp],
 }
 _RESTYPES = {"femb_last_error": C.c_char_p}

@@ -64,8 +64,25 @@ class DistOperator:
         self.send_idx = (torch.cat(idx) if idx else torch.zeros(1, dtype=torch.int32)).to(self.dev).contiguous()
         self.ghost_off = (C.c_int64 * max(1, self.nnbr))(*[sizes[q]["n_owned"] + sizes[q]["recv_off"][self.rank] for q in nb])
         self.halo_bytes = 8 * ptrs[-1]
+        # destinations of every boundary row (CSR over rows n_interior..n_owned): lets the direction kernel store boundary
+        # values straight into the neighbours' ghost slots instead of running a separate push kernel
+        self.bptr = self.bk = self.boff = None
+        ni = int(getattr(part, "n_interior", 0))
+        if self.nnbr and ni > 0:
+            rows = torch.cat([part.send_idx[q] for q in nb])
+            ks = torch.cat([torch.full((part.send_idx[q].numel(),), k, dtype=torch.int64) for k, q in enumerate(nb)]).to(rows.device)
+            offs = torch.cat([torch.arange(part.send_idx[q].numel()) for q in nb]).to(rows.device)
+            assert int(rows.min().item()) >= ni, "send rows must be boundary rows"
+            order = torch.sort(rows, stable=True).indices
+            rows, ks, offs = rows[order], ks[order], offs[order]
+            cnt = torch.bincount(rows - ni, minlength=no - ni)
+            bptr = torch.zeros(no - ni + 1, dtype=torch.int64, device=rows.device)
+            bptr[1:] = torch.cumsum(cnt, 0)
+            self.bptr = bptr.to(torch.int32).to(self.dev).contiguous()
+            self.bk = ks.to(torch.uint8).to(self.dev).contiguous()
+            self.boff = offs.to(torch.int32).to(self.dev).contiguous()
 
-    def solve(self, F_owned, mask_owned=None, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, check_every=16):
+    def solve(self, F_owned, mask_owned=None, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, check_every=16, minv=None):
         no = self.part.n_owned
         Ff = F_owned.to(self.dev, torch.float64).reshape(-1).contiguous()
         u = torch.zeros(no, device=self.dev, dtype=torch.float64) if u_init is None else \
@@ -76,9 +93,11 @@ class DistOperator:
         with torch.cuda.device(self.dev):
             check(lib.femb_dist_reset(self.own, st), "femb_dist_reset")
             dist.barrier()          # every rank's flags are zero before anyone starts pushing
-            check(lib.femb_dist_cg_solve(self.rank, self.P, no, self.nnz, ops._p(self.crow), ops._p(self.col), ops._p(self.val), ops._p(Ff),
-                                         ops._p(mask_owned), ops._p(u), ops._p(work), self.sym, self.nnbr, self.nbr, self.send_ptr,
-                                         ops._p(self.send_idx), self.ghost_off, float(tol), int(max_iter), float(eps), int(check_every),
+            check(lib.femb_dist_cg_solve(self.rank, self.P, no, int(getattr(self.part, "n_interior", 0)), self.nnz, ops._p(self.crow),
+                                         ops._p(self.col), ops._p(self.val), ops._p(Ff), ops._p(mask_owned), ops._p(minv), ops._p(u),
+                                         ops._p(work), self.sym, self.nnbr, self.nbr, self.send_ptr,
+                                         ops._p(self.send_idx), self.ghost_off, ops._p(self.bptr), ops._p(self.bk), ops._p(self.boff),
+                                         float(tol), int(max_iter), float(eps), int(check_every),
                                          C.byref(res), st), "femb_dist_cg_solve")
             dist.barrier()          # nobody frees / resets while a peer may still be storing
         info = {"iterations": res.iterations, "status": ops.STATUS.get(res.status, "?"), "rs": res.rs, "loop_ms": res.loop_ms}

@@ -53,6 +53,7 @@ class LocalPart:
     send_idx: Dict[int, torch.Tensor] = field(default_factory=dict)   # q -> local owned indices to push to q
     recv_off: Dict[int, int] = field(default_factory=dict)            # q -> offset of q's block inside the ghost region
     recv_cnt: Dict[int, int] = field(default_factory=dict)
+    n_interior: int = 0                   # owned rows [0, n_interior) reference no ghost column
 
     @property
     def n_local(self):
@@ -68,6 +69,14 @@ def build_local_part(elements: torch.Tensor, labels: torch.Tensor, rank: int, np
     el = elements[eids]
     ll = lab[eids]
     owned = torch.nonzero(labels == rank).reshape(-1)                 # ascending
+    # interior rows first: an owned node is "boundary" when one of its elements holds a node of another rank, i.e. its
+    # operator row references ghost columns; interior rows can be multiplied while the halo is still in flight
+    mixed = (ll != rank).any(dim=1)
+    bflag = torch.zeros(labels.numel(), dtype=torch.bool, device=dev)
+    bflag[el[mixed].reshape(-1)] = True
+    is_b = bflag[owned]
+    owned = torch.cat([owned[~is_b], owned[is_b]])
+    n_interior = int((~is_b).sum().item())
     nodes = torch.unique(el)
     gh = nodes[labels[nodes] != rank]
     gh_owner = labels[gh]
@@ -77,6 +86,7 @@ def build_local_part(elements: torch.Tensor, labels: torch.Tensor, rank: int, np
     g2l[owned] = torch.arange(owned.numel(), device=dev)
     g2l[gh] = owned.numel() + torch.arange(gh.numel(), device=dev)
     part = LocalPart(rank, nparts, int(owned.numel()), int(gh.numel()), owned, gh, g2l[el], eids)
+    part.n_interior = n_interior
     for q in sorted(set(gh_owner.tolist())):
         sel = gh_owner == q
         part.neighbors.append(q)

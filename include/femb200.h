@@ -192,11 +192,19 @@ int femb_dist_reset(void* own_sym, femb_stream stream); /* zero the flags; calle
  * local numbering [owned | ghost]; F, mask, u are owned-only.  sym_host[P] = every rank's symmetric buffer as mapped in
  * this process.  For neighbour k: nbr_host[k] = its rank, send_idx[send_ptr_host[k]..send_ptr_host[k+1]) = my owned
  * entries it needs, ghost_off_host[k] = index in ITS p where my block starts.  The halo exchange and both all-reduces
- * are peer stores + epoch flags inside the CUDA-graph-captured iteration; there is no NCCL call.  work = 2*n_owned. */
-int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t nnz, const int32_t* crow, const int32_t* col,
-                       const double* val, const double* F, const uint8_t* mask, double* u, double* work,
+ * are peer stores + epoch flags inside ONE persistent cooperative kernel per solve (FEMB_DIST_GRAPH=1 selects the
+ * four-kernels-per-iteration CUDA graph instead); there is no NCCL call.  Rows [0,n_interior) must not reference ghost
+ * columns (their SpMV overlaps the exchange); pass 0 if the rows are not ordered that way.  minv != NULL = Jacobi-PCG.
+ * work = 2*n_owned. */
+int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t n_interior, int64_t nnz, const int32_t* crow,
+                       const int32_t* col, const double* val, const double* F, const uint8_t* mask, const double* minv,
+                       double* u, double* work,
                        void* const* sym_host, int nnbr, const int32_t* nbr_host, const int32_t* send_ptr_host,
-                       const int32_t* send_idx, const int64_t* ghost_off_host, double tol, int max_iter, double eps,
+                       const int32_t* send_idx, const int64_t* ghost_off_host,
+                       /* optional (NULL = separate push kernel): CSR over the boundary rows [n_interior,n_owned) of their
+                        * destinations, bk = neighbour index, boff = offset in that neighbour's ghost block; lets the
+                        * direction update store boundary values straight into the neighbours' ghost slots */
+                       const int32_t* bptr, const uint8_t* bk, const int32_t* boff, double tol, int max_iter, double eps,
                        int check_every, femb_cg_result* result_host, femb_stream stream);
 
 #ifdef __cplusplus
