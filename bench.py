@@ -239,7 +239,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(u_host.numel() * 8 / K),
                 "note": f"one solver-API call of {K} iterations: F pinned host -> device, CG, u -> pinned host; bytes are per call / K"},
         "gpu_launches": 3 * K + 4,
-        "roofline": {"kernel": "spmv_kernel<8,false> (CSR SpMV, the kernel fused into CG step k1)", "bound": "hbm",
+        "roofline": {"kernel": "spmv_tma_kernel<1,false> (TMA-pipelined CSR SpMV; its fused twin is CG step k1)", "bound": "hbm",
                      "achieved": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
                      "frac": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9 / hbm, 4), "traffic": None, "peak_source": peak_src,
                      "ms_per_launch": round(ms_spmv, 4), "algorithmic_bytes": bytes_spmv},

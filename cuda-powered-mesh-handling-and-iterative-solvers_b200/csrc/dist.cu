@@ -115,10 +115,10 @@ struct GraphHaloWaiter {
 
 // ---- k1: SpMV on owned rows + p.Ap partial -> everyone ---------------------------------------------------------------
 template <int LR, bool FUSED>
-__global__ void __launch_bounds__(SPMV_THREADS) dist_spmv_kernel(Peers pe, long long n_owned, const int* __restrict__ crow,
-                                                                 const int* __restrict__ col, const double* __restrict__ val,
-                                                                 double* __restrict__ y, const unsigned char* __restrict__ mask,
-                                                                 double* __restrict__ partial, DistState* st, long long n_interior) {
+__global__ void __launch_bounds__(TMA_THREADS) dist_spmv_kernel(Peers pe, long long n_owned, long long nnz, const int* __restrict__ crow,
+                                                                const int* __restrict__ col, const double* __restrict__ val,
+                                                                double* __restrict__ y, const unsigned char* __restrict__ mask,
+                                                                double* __restrict__ partial, DistState* st, long long n_interior) {
   if (st->stop) return;
   SymHeader* me = pe.hdr[pe.rank];
   if (FUSED && blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 2), trace_stamp(st, 3);
@@ -126,13 +126,14 @@ __global__ void __launch_bounds__(SPMV_THREADS) dist_spmv_kernel(Peers pe, long 
   if (threadIdx.x < MAXP) nbr[threadIdx.x] = pe.nbr[threadIdx.x];
   __syncthreads();
   const double* x = sym_p(me);
-  // interior row tiles need no ghost entry: a CTA waits for the halo only when it reaches its first boundary tile
+  // TMA-pipelined row tiles; interior tiles need no ghost entry, so a CTA waits for the halo only when it reaches its
+  // first boundary tile.  x is read with plain (L1-cached, L2-coherent) loads: peers write its ghost part.
   const GraphHaloWaiter hw{me, nbr, pe.nnbr, st->epochA, st};
-  const double dot = spmv_stream_rows<LR, false, GraphHaloWaiter>(n_owned, crow, col, val, x, y, mask, false, FUSED,
-                                                                  pe.nnbr > 0 ? n_interior : 0x7fffffffffffffffll, hw);
+  const double dot = spmv_tma_rows<LR, false, TMA_THREADS, TMA_STAGES, TMA_CAP, GraphHaloWaiter>(
+      n_owned, nnz, crow, col, val, x, y, mask, false, FUSED, pe.nnbr > 0 ? n_interior : 0x7fffffffffffffffll, hw);
   if (st->stop == 3) return;
   if (!FUSED) return;
-  const double t = block_sum<SPMV_THREADS>(dot);
+  const double t = block_sum<TMA_THREADS>(dot);
   __shared__ bool last;
   if (threadIdx.x == 0) {
     partial[blockIdx.x] = t;
@@ -143,8 +144,8 @@ __global__ void __launch_bounds__(SPMV_THREADS) dist_spmv_kernel(Peers pe, long 
   if (last) {
     __threadfence();
     double a = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += SPMV_THREADS) a += ((volatile double*)partial)[k];
-    a = block_sum<SPMV_THREADS>(a);
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += TMA_THREADS) a += ((volatile double*)partial)[k];
+    a = block_sum<TMA_THREADS>(a);
     if (threadIdx.x == 0) {
       st->ticket1 = 0;
       const long long e = st->epochB + 1;
@@ -538,16 +539,22 @@ static int pick_lr(long long n, long long nnz) {
 }
 
 template <bool FUSED>
-static void launch_dist_spmv(int lr, int grid, cudaStream_t s, const Peers& pe, long long n, const int* crow, const int* col, const double* val,
-                             double* y, const unsigned char* mask, double* partial, DistState* st, long long n_interior) {
-  switch (lr) {
-    case 1: dist_spmv_kernel<1, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
-    case 2: dist_spmv_kernel<2, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
-    case 4: dist_spmv_kernel<4, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
-    case 8: dist_spmv_kernel<8, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
-    case 16: dist_spmv_kernel<16, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
-    default: dist_spmv_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(pe, n, crow, col, val, y, mask, partial, st, n_interior); break;
+static void launch_dist_spmv(int lr, int grid, cudaStream_t s, const Peers& pe, long long n, long long nnz, const int* crow, const int* col,
+                             const double* val, double* y, const unsigned char* mask, double* partial, DistState* st, long long n_interior) {
+#define FEMB_DSPMV(LRV)                                                                                                         \
+  {                                                                                                                             \
+    cudaFuncSetAttribute(dist_spmv_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);             \
+    dist_spmv_kernel<LRV, FUSED><<<grid, TMA_THREADS, TMA_SMEM, s>>>(pe, n, nnz, crow, col, val, y, mask, partial, st, n_interior); \
   }
+  switch (lr) {
+    case 1: FEMB_DSPMV(1) break;
+    case 2: FEMB_DSPMV(2) break;
+    case 4: FEMB_DSPMV(4) break;
+    case 8: FEMB_DSPMV(8) break;
+    case 16: FEMB_DSPMV(16) break;
+    default: FEMB_DSPMV(32) break;
+  }
+#undef FEMB_DSPMV
 }
 
 static cudaStream_t dist_stream(cudaStream_t user) {
@@ -620,11 +627,8 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   for (int k = 0; k <= nnbr; ++k) pe.send_ptr[k] = send_ptr_host[k];
   const long long n = n_owned;
   double *r = work, *Ap = work + n;
-  const int lr = pick_lr(n, nnz);
-  // one row tile per CTA up to 32k CTAs, then the smallest equal share: no CTA does one tile more than another
-  const long long tiles = (n + SPMV_THREADS / lr - 1) / (SPMV_THREADS / lr);
-  const long long per = (tiles + SMS * 32 - 1) / (SMS * 32);
-  const int g1 = (int)((tiles + per - 1) / per);
+  const int lr = tma_pick_lr(n, nnz);
+  const int g1 = tma_grid(n, lr);
   const int g2 = grid_for(n, DV_THREADS, 8);
   const int gp = std::max(1, std::min(64, (pe.send_ptr[nnbr] + 255) / 256));
   Scratch scr(s);
@@ -645,7 +649,7 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   // ---- setup: p <- mask.*u, halo, Ap = A u, r = mask.*(F - Ap), p = r, rs_old = allreduce(r.r)   (solver.py:163-181)
   dist_load_p<<<g2, DV_THREADS, 0, s>>>(pe, n, u, mask);
   dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
-  launch_dist_spmv<false>(lr, g1, s, pe, n, crow, col, val, Ap, nullptr, nullptr, st, 0);
+  launch_dist_spmv<false>(lr, g1, s, pe, n, nnz, crow, col, val, Ap, nullptr, nullptr, st, 0);
   dist_init_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, F, Ap, mask, minv, r, partial, st);
   dist_init_finish<<<1, 32, 0, s>>>(pe, st, max_iter);
   FEMB_LAUNCH_CHECK();
@@ -658,7 +662,7 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
     pa.pe = pe, pa.n = n, pa.n_interior = n_interior, pa.crow = crow, pa.col = col, pa.val = val, pa.F = F, pa.minv = minv, pa.mask = mask;
     pa.u = u, pa.r = r, pa.Ap = Ap, pa.send_idx = send_idx, pa.st = st, pa.tol = tol, pa.eps = eps, pa.max_iter = max_iter, pa.guards = guards;
     const void* kern = nullptr;
-    switch (lr) {
+    switch (pick_lr(n, nnz)) {
       case 1: kern = (const void*)dist_cg_persistent_kernel<1>; break;
       case 2: kern = (const void*)dist_cg_persistent_kernel<2>; break;
       case 4: kern = (const void*)dist_cg_persistent_kernel<4>; break;
@@ -711,7 +715,7 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   BoundaryPush bp{folded ? bptr : nullptr, bk, boff, n_interior};
   for (int k = 0; k < check_every; ++k) {
     if (!folded) dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
-    launch_dist_spmv<true>(lr, g1, s, pe, n, crow, col, val, Ap, mask, partial, st, n_interior);
+    launch_dist_spmv<true>(lr, g1, s, pe, n, nnz, crow, col, val, Ap, mask, partial, st, n_interior);
     dist_update_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, eps, guards);
     dist_direction_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, r, st, tol, eps, guards, max_iter, bp);
   }

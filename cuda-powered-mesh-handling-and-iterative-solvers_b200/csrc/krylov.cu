@@ -21,8 +21,9 @@ struct CGState {
 
 // Last-CTA-done epilogue of CG step k1: per-CTA partial of p.Ap, then the last CTA to arrive sums the partials in index
 // order (deterministic), applies the reference's guards (solver.py:187-198) and publishes alpha.
-__device__ __forceinline__ void cg_k1_epilogue(double dot, double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards) {
-  const double t = block_sum<SPMV_THREADS>(dot);
+template <int THREADS>
+__device__ __forceinline__ void cg_k1_epilogue_n(double dot, double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards) {
+  const double t = block_sum<THREADS>(dot);
   __shared__ bool last;
   if (threadIdx.x == 0) {
     partial[blockIdx.x] = t;
@@ -33,8 +34,8 @@ __device__ __forceinline__ void cg_k1_epilogue(double dot, double* __restrict__ 
   if (last) {
     __threadfence();
     double a = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += SPMV_THREADS) a += ((volatile double*)partial)[k];
-    a = block_sum<SPMV_THREADS>(a);
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += THREADS) a += ((volatile double*)partial)[k];
+    a = block_sum<THREADS>(a);
     if (threadIdx.x == 0) {
       st->ticket1 = 0;
       st->pAp = a;
@@ -47,6 +48,10 @@ __device__ __forceinline__ void cg_k1_epilogue(double dot, double* __restrict__ 
       }
     }
   }
+}
+
+__device__ __forceinline__ void cg_k1_epilogue(double dot, double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards) {
+  cg_k1_epilogue_n<SPMV_THREADS>(dot, partial, st, eps, guards);
 }
 
 // L lanes cooperate on one row.  FUSED adds the row mask, the p.Ap partial and the last-CTA scalar epilogue.
@@ -99,6 +104,17 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(long long n, 
   if (st && st->stop) return;
   const double dot = spmv_stream_rows<LR, true>(n, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED);
   if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards & 1);
+}
+
+// default SpMV: TMA-pipelined row tiles (spmv_dev.cuh)
+template <int LR, bool FUSED>
+__global__ void __launch_bounds__(TMA_THREADS) spmv_tma_kernel(long long n, long long nnz, const int* __restrict__ crow, const int* __restrict__ col,
+                                                               const double* __restrict__ val, const double* __restrict__ x,
+                                                               double* __restrict__ y, const unsigned char* __restrict__ mask,
+                                                               double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards) {
+  if (st && st->stop) return;
+  const double dot = spmv_tma_rows<LR, true>(n, nnz, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED);
+  if (FUSED) cg_k1_epilogue_n<TMA_THREADS>(dot, partial, st, eps, guards & 1);
 }
 
 constexpr int VEC_THREADS = 256;
@@ -213,21 +229,36 @@ __global__ void jacobi_kernel(long long n, const int* __restrict__ crow, const i
   }
 }
 
-// lanes per row of the stream kernel: the smallest LR whose R = 256/LR rows keep the CTA's slice within STREAM_CAP
+// Kernel selection, encoded in one int: 100+LR = TMA-pipelined (default), LR = LDG-streaming (FEMB_SPMV_STREAM=1),
+// -L = legacy L-lanes-per-row vector kernel (FEMB_SPMV_VECTOR=1).  The env switches exist for A/B profiling.
 static int pick_lanes(long long n, long long nnz) {
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
-  static const bool force_vector = getenv("FEMB_SPMV_VECTOR") != nullptr;  // A/B switch for profiling
+  static const bool force_vector = getenv("FEMB_SPMV_VECTOR") != nullptr, force_stream = getenv("FEMB_SPMV_STREAM") != nullptr;
   if (force_vector) return -(avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 24 ? 8 : avg <= 48 ? 16 : 32);
+  if (!force_stream) return 100 + tma_pick_lr(n, nnz);
   for (int lr = 1; lr <= 32; lr *= 2)
     if ((SPMV_THREADS / lr) * avg * 1.25 <= STREAM_CAP) return lr;
   return 32;
 }
 
+static thread_local long long nnz_hint = 0;  // set by the callers right before launch_spmv (the TMA kernel clamps its copies to nnz)
+
 template <bool FUSED>
 static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const int* crow, const int* col, const double* val, const double* x,
                         double* y, const unsigned char* mask, double* partial, CGState* st, double eps, int guards) {
 #define FEMB_SPMV_ARGS n, crow, col, val, x, y, mask, partial, st, eps, guards
+#define FEMB_TMA(LRV)                                                                                                              \
+  {                                                                                                                                \
+    cudaFuncSetAttribute(spmv_tma_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);                 \
+    spmv_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, TMA_SMEM, s>>>(n, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); \
+  }
   switch (lanes) {
+    case 101: FEMB_TMA(1) break;
+    case 102: FEMB_TMA(2) break;
+    case 104: FEMB_TMA(4) break;
+    case 108: FEMB_TMA(8) break;
+    case 116: FEMB_TMA(16) break;
+    case 132: FEMB_TMA(32) break;
     case 1: spmv_stream_kernel<1, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
     case 2: spmv_stream_kernel<2, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
     case 4: spmv_stream_kernel<4, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
@@ -240,15 +271,17 @@ static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const 
     case -16: spmv_kernel<16, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
     default: spmv_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
   }
+#undef FEMB_TMA
 #undef FEMB_SPMV_ARGS
 }
 
 static int spmv_grid(long long n, int lanes) {
+  if (lanes >= 100) return tma_grid(n, lanes - 100);  // persistent: TMA_CTAS_PER_SM CTAs per SM
   const long long rows_per_block = SPMV_THREADS / (lanes < 0 ? -lanes : lanes);
   const long long tiles = std::max<long long>(1, (n + rows_per_block - 1) / rows_per_block);
   if (lanes < 0) return (int)std::min<long long>(tiles, (long long)SMS * 8);  // legacy vector kernel: persistent grid
-  // stream kernel: one row tile per CTA up to 32k CTAs, beyond that the smallest equal share (no CTA gets an extra tile)
-  static const long long max_ctas = getenv("FEMB_SPMV_MAXCTAS") ? atoll(getenv("FEMB_SPMV_MAXCTAS")) : SMS * 32;  // measured: 4736 beats larger grids
+  // stream kernel: equal share of row tiles over at most 32 CTAs per SM (measured: larger grids lose on the fused tail)
+  const long long max_ctas = SMS * 32;
   const long long per = (tiles + max_ctas - 1) / max_ctas;
   return (int)((tiles + per - 1) / per);
 }
@@ -263,6 +296,7 @@ extern "C" int femb_spmv(int64_t n, int64_t nnz, const int32_t* crow, const int3
   if (n == 0) return FEMB_OK;
   cudaStream_t s = as_stream(stream);
   const int lanes = pick_lanes(n, nnz);
+  nnz_hint = nnz;
   launch_spmv<false>(lanes, spmv_grid(n, lanes), s, n, crow, col, val, x, y, nullptr, nullptr, nullptr, 0.0, 0);
   FEMB_LAUNCH_CHECK();
   return FEMB_OK;
@@ -321,7 +355,7 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   // ---- setup (solver.py:163-181)
   if (mask) cg_mask_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, mask);
   for (int m = 0; m < nmat; ++m)
-    launch_spmv<false>(lanes[m], g1[m], s, n, mats[m].crow, mats[m].col, mats[m].val, u, Ap, nullptr, nullptr, nullptr, 0.0, m ? 2 : 0);
+    nnz_hint = mats[m].nnz, launch_spmv<false>(lanes[m], g1[m], s, n, mats[m].crow, mats[m].col, mats[m].val, u, Ap, nullptr, nullptr, nullptr, 0.0, m ? 2 : 0);
   cg_init_kernel<<<g2, VEC_THREADS, 0, s>>>(n, F, Ap, mask, minv, r, p, partial);
   cg_init_finish<<<1, VEC_THREADS, 0, s>>>(g2, partial, st, max_iter);
   FEMB_LAUNCH_CHECK();
@@ -331,8 +365,9 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   FEMB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   for (int k = 0; k < check_every; ++k) {
     for (int m = 0; m + 1 < nmat; ++m)
-      launch_spmv<false>(lanes[m], g1[m], s, n, mats[m].crow, mats[m].col, mats[m].val, p, Ap, nullptr, nullptr, st, 0.0, m ? 2 : 0);
+      nnz_hint = mats[m].nnz, launch_spmv<false>(lanes[m], g1[m], s, n, mats[m].crow, mats[m].col, mats[m].val, p, Ap, nullptr, nullptr, st, 0.0, m ? 2 : 0);
     const int last = nmat - 1;
+    nnz_hint = mats[last].nnz;
     launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
                       guards | (last ? 2 : 0));
     cg_update_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, r, p, Ap, minv, partial, st, tol, eps, guards, max_iter);

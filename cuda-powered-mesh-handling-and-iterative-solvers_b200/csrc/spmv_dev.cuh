@@ -53,6 +53,17 @@ __device__ __forceinline__ double spmv_stream_rows(long long n, const int* __res
       wait();
       waited = true;
     }
+    // the row's own x entry, mask byte and previous y are requested now so their latency hides behind the streaming phase
+    // instead of sitting between the row sum and the tile's closing barrier
+    double x_own = 0.0, y_prev = 0.0;
+    bool keep = true;
+    if (lr < nr && sub == 0) {
+      if (fused) {
+        x_own = ld_x<NC>(x + r0 + lr);
+        if (mask) keep = mask[r0 + lr] != 0;
+      }
+      if (accumulate) y_prev = y[r0 + lr];
+    }
     for (int t = tid; t <= nr; t += SPMV_THREADS) rp[t] = __ldg(crow + r0 + t);
     __syncthreads();
     const int s = rp[0], e = rp[nr];
@@ -83,16 +94,184 @@ __device__ __forceinline__ double spmv_stream_rows(long long n, const int* __res
     for (int o = LR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lr < nr && sub == 0) {
       const long long r = r0 + lr;
-      if (accumulate) sum += y[r];
+      if (accumulate) sum += y_prev;
       if (fused) {
-        if (mask && !mask[r]) sum = 0.0;
-        dot += sum * ld_x<NC>(x + r);
+        if (!keep) sum = 0.0;
+        dot += sum * x_own;
       }
       y[r] = sum;
     }
     __syncthreads();
   }
   return dot;
+}
+
+// ---- TMA-pipelined CSR SpMV ------------------------------------------------------------------------------------------------
+// Persistent CTAs; the val/col slice of each row tile is brought into shared memory by the TMA engine
+// (cp.async.bulk, 1-D, completion on an mbarrier) STAGES-1 tiles ahead of the arithmetic, so the matrix stream -- 90 % of
+// the bytes -- is always in flight, independent of how many warps are stalled on the x gathers.  Each row is then owned
+// by LR lanes that walk their slice of the staged tile (odd row lengths => conflict-free LDS), gather x through L1/L2
+// eight at a time and accumulate in registers: no product buffer, no second pass.  Slices are aligned down to 4 entries so
+// both copies are 16-byte aligned; tiles that do not fit a stage, and the last tile of the matrix (the aligned copy could
+// run past the end of val/col), take the direct global-load path.
+// Measured on B200, 64 M-tet Poisson operator (2.145 GB algorithmic): 0.38 ms = 5.7 TB/s with (128 threads, 2 stages,
+// 2304 entries) x 4 CTAs/SM or (64, 2, 1152) x 8; 0.66 ms with only 2 CTAs/SM; the LDG-streaming kernel above: 0.52 ms.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int TMA_THREADS = 128, TMA_STAGES = 2, TMA_CAP = 2304, TMA_CTAS_PER_SM = 4;
+constexpr size_t TMA_SMEM = (size_t)TMA_STAGES * TMA_CAP * 12;
+
+// Needs TMA_SMEM bytes of dynamic shared memory and blockDim.x == THREADS.  Returns this thread's partial of y.x (fused).
+template <int LR, bool NC, int THREADS = TMA_THREADS, int STAGES = TMA_STAGES, int CAP = TMA_CAP, typename Wait = NoHaloWait>
+__device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, const int* __restrict__ crow, const int* __restrict__ col,
+                                                const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                                                const unsigned char* __restrict__ mask, bool accumulate, bool fused,
+                                                long long halo_row = 0x7fffffffffffffffll, Wait wait = Wait()) {
+  constexpr int R = THREADS / LR;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  double* vbuf = reinterpret_cast<double*>(tma_smem);                           // [STAGES][CAP]
+  int* cbuf = reinterpret_cast<int*>(tma_smem + sizeof(double) * STAGES * CAP);  // [STAGES][CAP]
+  __shared__ unsigned long long full[STAGES];
+  __shared__ int base[STAGES];  // first staged entry of the tile (aligned down), -1 = not staged (direct path)
+  const int tid = threadIdx.x, sub = tid % LR, lr = tid / LR;
+  const long long ntiles = (n + R - 1) / R;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // producer (thread 0): the row-pointer pair of the tile it will stage next is requested one iteration early, so issuing
+  // the copies never waits on a global load while the other threads sit at the barrier
+  auto bounds = [&](long long k, int& a, int& b) {
+    const long long t = blockIdx.x + k * gridDim.x;
+    a = b = 0;
+    if (t < ntiles) a = __ldg(crow + t * R), b = __ldg(crow + min(n, t * R + R));
+  };
+  auto stage_tile = [&](long long k, int a, int b) {
+    if (blockIdx.x + k * gridDim.x >= ntiles) return;
+    const int s = (int)(k % STAGES);
+    const int a0 = a & ~3, cnt = (b - a0 + 3) & ~3;
+    if (cnt > CAP || (long long)a0 + cnt > nnz || cnt == 0) {
+      base[s] = -1;
+      return;
+    }
+    base[s] = a0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&full[s], (unsigned)cnt * 12u);
+    bulk_g2s(vbuf + (size_t)s * CAP, val + a0, (unsigned)cnt * 8u, &full[s]);
+    bulk_g2s(cbuf + (size_t)s * CAP, col + a0, (unsigned)cnt * 4u, &full[s]);
+  };
+  int na = 0, nb = 0;  // bounds of the next tile to stage (thread 0 only)
+  if (tid == 0) {
+    for (int k = 0; k < STAGES - 1; ++k) {
+      bounds(k, na, nb);
+      stage_tile(k, na, nb);
+    }
+    bounds(STAGES - 1, na, nb);
+  }
+  double dot = 0.0;
+  unsigned phase_bits = 0;  // parity per stage
+  bool waited = false;
+  for (long long k = 0;; ++k) {
+    const long long t = blockIdx.x + k * gridDim.x;
+    if (t >= ntiles) break;
+    const int s = (int)(k % STAGES);
+    if (!waited && min(n, t * R + R) > halo_row) {  // first tile of this CTA that may read ghost entries of x
+      wait();
+      waited = true;
+    }
+    if (tid == 0) {  // refill the stage that was drained in iteration k-1, then request the bounds of the tile after it
+      stage_tile(k + STAGES - 1, na, nb);
+      bounds(k + STAGES, na, nb);
+    }
+    const long long r = t * R + lr;
+    int ra = 0, rb = 0;
+    double x_own = 0.0, y_prev = 0.0;
+    bool keep = true;
+    if (r < n) {
+      ra = __ldg(crow + r), rb = __ldg(crow + r + 1);
+      if (sub == 0) {
+        if (fused) {
+          x_own = ld_x<NC>(x + r);
+          if (mask) keep = mask[r] != 0;
+        }
+        if (accumulate) y_prev = y[r];
+      }
+    }
+    __syncthreads();  // base[s] written by thread 0 (this or an earlier iteration) is visible
+    const int a0 = base[s];
+    double sum = 0.0;
+    if (a0 >= 0) {
+      mbar_wait(&full[s], (phase_bits >> s) & 1u);
+      phase_bits ^= 1u << s;
+      const double* vs = vbuf + (size_t)s * CAP - a0;
+      const int* cs = cbuf + (size_t)s * CAP - a0;
+      int j = ra + sub;
+      for (; j + 7 * LR < rb; j += 8 * LR) {  // eight independent x gathers in flight per lane
+        double xv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xv[q] = ld_x<NC>(x + cs[j + q * LR]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum += vs[j + q * LR] * xv[q];
+      }
+      {  // tail: up to seven more, still issued together
+        double xv[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) xv[q] = (j + q * LR < rb) ? ld_x<NC>(x + cs[j + q * LR]) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 7; ++q)
+          if (j + q * LR < rb) sum += vs[j + q * LR] * xv[q];
+      }
+    } else {
+      for (int j = ra + sub; j < rb; j += LR) sum += ld_stream(val + j) * ld_x<NC>(x + ld_stream(col + j));
+    }
+#pragma unroll
+    for (int o = LR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (r < n && sub == 0) {
+      if (accumulate) sum += y_prev;
+      if (fused) {
+        if (!keep) sum = 0.0;
+        dot += sum * x_own;
+      }
+      y[r] = sum;
+    }
+    __syncthreads();  // the stage is drained: thread 0 may refill it in the next iteration
+  }
+  return dot;
+}
+
+// lanes per row for the TMA kernel: the smallest LR whose R = THREADS/LR rows keep a tile within one stage
+inline int tma_pick_lr(long long n, long long nnz) {
+  const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
+  for (int lr = 1; lr <= 32; lr *= 2)
+    if ((TMA_THREADS / lr) * avg * 1.15 <= TMA_CAP) return lr;
+  return 32;
+}
+inline int tma_grid(long long n, int lr) {
+  const long long tiles = (n + TMA_THREADS / lr - 1) / (TMA_THREADS / lr);
+  return (int)std::max<long long>(1, std::min<long long>(tiles, (long long)SMS * TMA_CTAS_PER_SM));
 }
 
 }  // namespace femb
