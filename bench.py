@@ -46,7 +46,7 @@ class ClockSampler:
     def __init__(self, index=0):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -89,19 +89,19 @@ def cpu_cg_rate(n_sample, iters, full_nnz):
     crow, col, val, n = O.assemble_csr(Ke, t, 1, c.shape[0])
     load = np.bincount(t.reshape(-1), weights=np.repeat(O.tet_volumes(c, t) / 4, 4), minlength=c.shape[0]).reshape(-1, 1)
     fixed = np.flatnonzero(c[:, 2] == 0)
-    cores = os.cpu_count() or 1
     kind = "port"
     try:
-        from oracle import c_oracle
-        apply_fn, used = c_oracle.csr_apply(crow, col, val, cores)
-        impl = f"C/OpenMP build of the oracle CG loop ({used} threads)"
-        threads = used
-    except Exception:
-        apply_fn = lambda v: O.csr_matvec(crow, col, val, v).reshape(-1, 1)  # noqa: E731
+        from oracle import c_oracle          # C + pthreads build of the same loop: all host cores
+        threads = c_oracle.threads()
+        impl = f"compiled oracle CG loop (C + pthreads, {threads} threads)"
+        solve = lambda k: c_oracle.cg_csr(crow, col, val, load, fixed, tol=0.0, max_iter=k)  # noqa: E731
+    except OSError:
         impl, threads = "numpy oracle CG loop", 1
-    O.cg_solve(apply_fn, load, fixed, tol=0.0, max_iter=2)           # warm-up
+        apply_fn = lambda v: O.csr_matvec(crow, col, val, v).reshape(-1, 1)  # noqa: E731
+        solve = lambda k: O.cg_solve(apply_fn, load, fixed, tol=0.0, max_iter=k)  # noqa: E731
+    solve(2)                                   # warm-up
     t0 = time.perf_counter()
-    O.cg_solve(apply_fn, load, fixed, tol=0.0, max_iter=iters)
+    solve(iters)
     dt = time.perf_counter() - t0
     rate_sample = iters / dt
     rate_full = rate_sample * (val.size / full_nnz)
@@ -199,8 +199,8 @@ def run_gpu(args):
     bytes_spmv = nnz * 12 + N * 20
 
     # ---- CG: W warm-up iterations, then exactly K timed iterations (tol=0 never converges)
-    ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=W, check_every=W)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local)          # started before the warm-up so nvidia-smi is already sampling when the timed loop runs
+    ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=max(W, 50), check_every=50)
     torch.cuda.synchronize()
     c0, c1 = ev(), ev()
     c0.record()
