@@ -186,3 +186,13 @@ def static_structure_solver(coords, force, fixed, c3d4=None, c3d6=None, c3d8=Non
         _report("CG", info, max_iter)
     u = u.to(dtype)
     return (u, info) if return_info else u
+
+
+def hybrid_subdivided_solver(coords, elements, levels, load_fn, fixed_fn, E=None, nu=None, kind="elasticity", tol=1e-8, max_iter=10000,
+                             device="cuda:0", verbose=True):
+    """Additive API for the reference's announced "hybrid solver of iterative and inverse methods with sub-divided mesh"
+    (README.md:7; the notebook stops before any solve loop): direct solve on the coarse C3D4 mesh, then `levels` uniform
+    refinements (c3d4_to_c3d10 + c3d10_to_c3d4), each solved by the reference CG loop warm-started from the prolongated
+    coarser solution.  See femb200/hybrid.py.  Returns (u_fine, coords_fine, elements_fine, info)."""
+    from femb200 import hybrid
+    return hybrid.hybrid_solve(coords, elements, levels, load_fn, fixed_fn, E, nu, kind, tol, max_iter, device, _el, verbose)

@@ -433,3 +433,36 @@ def test_no_cpu_fallback(api):
     c = torch.zeros((4, 3)); e = torch.tensor([[0, 1, 2, 3]])
     with pytest.raises(RuntimeError):
         el.compute_c3d4_K_matrix(c, e, E, NU, device="cpu")
+
+
+def test_hybrid_cascade(api, O):
+    """BASELINE config 5 in miniature: coarse direct solve + CG on 2 uniform refinements must equal a cold single-level CG
+    on the same fine mesh (the inner CG is the pinned reference loop; prolongation/coarse solve are unpinned)."""
+    el, _, sv = api
+    from femb200 import meshgen, ops
+    c0, t0 = meshgen.kuhn_cube(3, jitter=0.1)
+
+    def load_fn(c, t):
+        F = torch.zeros(c.shape[0], 3, dtype=torch.float64, device=c.device)
+        top = c[:, 2] > 1 - 1e-9
+        F[top, 2] = -1.0 / float(top.sum())
+        return F
+
+    def fixed_fn(c):
+        return torch.nonzero(c[:, 2] < 1e-9).reshape(-1)
+
+    u, cf, tf, info = sv.hybrid_subdivided_solver(c0, t0, 2, load_fn, fixed_fn, E=E, nu=NU, tol=1e-10, device=DEV, verbose=False)
+    assert tf.shape[0] == 64 * t0.shape[0] and info["levels"][-1]["status"] == "converged"
+    # the refined mesh is conforming: 2S + K = 4M
+    f, _ = el.compute_tetrahedral_surface_faces_with_fourth_node(tf, device=DEV)
+    s = el.identify_tetrahedral_shared_faces(tf, device=DEV)
+    assert 2 * s.shape[0] + f.shape[0] == 4 * tf.shape[0]
+    # cold solve of the same fine problem
+    K = el.compute_c3d4_K_matrix(cf, tf, E, NU, **KW)
+    u_cold, info_cold = sv.stable_conjugate_gradient_solver(K, tf, load_fn(cf, tf), fixed_fn(cf), tol=1e-10, max_iter=10000,
+                                                            return_info=True, verbose=False, **KW)
+    assert float((u - u_cold).abs().max()) <= 1e-8 * float(u_cold.abs().max())
+    assert info["levels"][-1]["iterations"] < info_cold["iterations"]          # the cascade pays off
+    # oracle check of the fine-level solution
+    uo, ito, st = O.stable_cg(N(K), N(tf), N(load_fn(cf, tf)), N(fixed_fn(cf)), tol=1e-10, max_iter=10000)
+    assert st == "converged" and rel_err(N(u), uo) <= 1e-8
