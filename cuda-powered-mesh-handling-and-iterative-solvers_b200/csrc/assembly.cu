@@ -294,7 +294,7 @@ __device__ __forceinline__ void ld_xyz(const double* __restrict__ c4, int node, 
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(w) : "l"(c4 + 4ll * node));
 }
 
-template <int BD, int OCC>
+template <int BD, int OCC, int VARIANT>
 __global__ void __launch_bounds__(BD, OCC) assemble_p1_poisson_tiles(const int4* __restrict__ rec, const int* __restrict__ tile_ptr,
                                                                 const int* __restrict__ node_ptr, const unsigned char* __restrict__ pdiag,
                                                                 long long N, long long ntiles, const double* __restrict__ c4,
@@ -313,13 +313,21 @@ __global__ void __launch_bounds__(BD, OCC) assemble_p1_poisson_tiles(const int4*
     const int pd = live ? pdiag[i] : 0;
     for (int p = 0; p < len; ++p) acc[p * BD + tid] = 0.0;
     double diag = 0.0;
-    // two-deep pipeline: record of step+2 and coordinates of step+1 are in flight during the arithmetic of `step`
-    int4 ra = steps > 0 ? __ldg(rp) : make_int4(-1, 0, 0, 0);
-    int4 rb = steps > 1 ? __ldg(rp + 32) : make_int4(-1, 0, 0, 0);
+    // pipeline: records are resident five steps ahead, the coordinates of step+1 are loaded during the arithmetic of `step`,
+    // and the coordinates of steps +3/+4 are pulled into L1 with prefetch hints (no registers) so that load mostly hits
+    auto rec_at = [&](int st) { return st < steps ? __ldg(rp + st * 32) : make_int4(-1, 0, 0, 0); };
+    auto pf = [&](const int4& r) {
+      if (r.x < 0) return;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(c4 + 4ll * r.x));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(c4 + 4ll * r.y));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(c4 + 4ll * r.z));
+    };
+    int4 ra = rec_at(0), rb = rec_at(1), r2 = rec_at(2), r3 = rec_at(3), r4 = rec_at(4);
     double xa[9], xb[9];
     if (ra.x >= 0) ld_xyz(c4, ra.x, xa), ld_xyz(c4, ra.y, xa + 3), ld_xyz(c4, ra.z, xa + 6);
-    auto contribute = [&](const int4& r, const double* x) {
-      if (r.x < 0) return;
+    pf(rb), pf(r2);
+    // register-only part of one incidence: the row of the element matrix that belongs to local node 0 (= the row node)
+    auto row_of = [&](const int4& r, const double* x, double* v) {  // v[0] diagonal, v[1..3] the three other nodes
       double e1[3], e2[3], e3[3], c1[3], c2[3], c3[3], c0[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q) e1[q] = x[q] - x0[q], e2[q] = x[3 + q] - x0[q], e3[q] = x[6 + q] - x0[q];
@@ -327,23 +335,54 @@ __global__ void __launch_bounds__(BD, OCC) assemble_p1_poisson_tiles(const int4*
       c2[0] = e3[1] * e1[2] - e3[2] * e1[1], c2[1] = e3[2] * e1[0] - e3[0] * e1[2], c2[2] = e3[0] * e1[1] - e3[1] * e1[0];
       c3[0] = e1[1] * e2[2] - e1[2] * e2[1], c3[1] = e1[2] * e2[0] - e1[0] * e2[2], c3[2] = e1[0] * e2[1] - e1[1] * e2[0];
       const double det = e1[0] * c1[0] + e1[1] * c1[1] + e1[2] * c1[2];
-      if (fabs(det) < 1e-12 && flag) *flag = 1;
+      if (r.x >= 0 && fabs(det) < 1e-12 && flag) *flag = 1;
 #pragma unroll
       for (int q = 0; q < 3; ++q) c0[q] = -(c1[q] + c2[q] + c3[q]);
-      const double scale = 1.0 / (6.0 * fabs(det));  // V g_a.g_b = c_a.c_b / (6|det|)
-      diag += (c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2]) * scale;
-      acc[(r.w & 255) * BD + tid] += (c0[0] * c1[0] + c0[1] * c1[1] + c0[2] * c1[2]) * scale;
-      acc[((r.w >> 8) & 255) * BD + tid] += (c0[0] * c2[0] + c0[1] * c2[1] + c0[2] * c2[2]) * scale;
-      acc[((r.w >> 16) & 255) * BD + tid] += (c0[0] * c3[0] + c0[1] * c3[1] + c0[2] * c3[2]) * scale;
+      // V g_a.g_b = c_a.c_b / (6|det|); reciprocal by MUFU seed + two Newton steps (branch-free, ~1 ulp)
+      const double d6 = 6.0 * fabs(det);
+      double rc;
+      if (VARIANT & 2) {
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(d6));
+        rc = rc * (2.0 - d6 * rc);
+        rc = rc * (2.0 - d6 * rc);
+      } else {
+        rc = 1.0 / d6;
+      }
+      const double scale = r.x >= 0 ? rc : 0.0;  // padding steps contribute exactly zero
+      v[0] = (c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2]) * scale;
+      v[1] = (c0[0] * c1[0] + c0[1] * c1[1] + c0[2] * c1[2]) * scale;
+      v[2] = (c0[0] * c2[0] + c0[1] * c2[1] + c0[2] * c2[2]) * scale;
+      v[3] = (c0[0] * c3[0] + c0[1] * c3[1] + c0[2] * c3[2]) * scale;
+    };
+    auto scatter = [&](const int4& r, const double* v) {
+      if (r.x < 0) return;
+      diag += v[0];
+      acc[(r.w & 255) * BD + tid] += v[1];
+      acc[((r.w >> 8) & 255) * BD + tid] += v[2];
+      acc[((r.w >> 16) & 255) * BD + tid] += v[3];
     };
     for (int st = 0; st < steps; st += 2) {
       if (rb.x >= 0) ld_xyz(c4, rb.x, xb), ld_xyz(c4, rb.y, xb + 3), ld_xyz(c4, rb.z, xb + 6);
-      const int4 rc = st + 2 < steps ? __ldg(rp + (st + 2) * 32) : make_int4(-1, 0, 0, 0);
-      contribute(ra, xa);
-      if (rc.x >= 0) ld_xyz(c4, rc.x, xa), ld_xyz(c4, rc.y, xa + 3), ld_xyz(c4, rc.z, xa + 6);
-      const int4 rd = st + 3 < steps ? __ldg(rp + (st + 3) * 32) : make_int4(-1, 0, 0, 0);
-      contribute(rb, xb);
-      ra = rc, rb = rd;
+      const int4 r5 = rec_at(st + 5), r6 = rec_at(st + 6);
+      pf(r3), pf(r4);
+      // the arithmetic of two consecutive incidences is independent: issuing both before the ordered accumulation gives the
+      // fp64 pipe two dependency chains to interleave (the sum order into acc[] is still step order)
+      double va[4], vb[4];
+      if (VARIANT & 1) {
+        row_of(ra, xa, va);
+        row_of(rb, xb, vb);
+        scatter(ra, va);
+        scatter(rb, vb);
+      } else {
+        row_of(ra, xa, va);
+        scatter(ra, va);
+      }
+      if (r2.x >= 0) ld_xyz(c4, r2.x, xa), ld_xyz(c4, r2.y, xa + 3), ld_xyz(c4, r2.z, xa + 6);
+      if (!(VARIANT & 1)) {
+        row_of(rb, xb, vb);
+        scatter(rb, vb);
+      }
+      ra = r2, rb = r3, r2 = r4, r3 = r5, r4 = r6;
     }
     if (live) {
       if (len > 0) acc[pd * BD + tid] += diag;
@@ -775,14 +814,14 @@ extern "C" int femb_csr_assemble_c3d4(femb_csr_plan* p, int kind, const double* 
     FEMB_CUDA(scr.alloc(&c4, (size_t)4 * p->N));
     pad_coords<<<grid_for(p->N, 256), 256, 0, s>>>(coords, p->N, c4);
     const size_t smem = sizeof(double) * (size_t)p->max_row * BD;
-    static const int occ = getenv("FEMB_ASM_OCC") ? atoi(getenv("FEMB_ASM_OCC")) : 4;
-#define LAUNCH_TILES(O)                                                                                                          \
+    static const int occ = getenv("FEMB_ASM_VARIANT") ? atoi(getenv("FEMB_ASM_VARIANT")) : 2;  // measured on C4: 0 = 2.61 ms, 1 = 2.83, 2 = 2.55, 3 = 2.57; bit0: two incidences in flight, bit1: MUFU reciprocal
+#define LAUNCH_TILES(V)                                                                                                          \
   {                                                                                                                              \
-    FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_poisson_tiles<BD, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    assemble_p1_poisson_tiles<BD, O><<<grid_for(p->ntiles, BD / 32, 16), BD, smem, s>>>(p->rec, p->tile_ptr, p->node_ptr, p->pdiag, p->N, \
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_poisson_tiles<BD, 4, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    assemble_p1_poisson_tiles<BD, 4, V><<<grid_for(p->ntiles, BD / 32, 16), BD, smem, s>>>(p->rec, p->tile_ptr, p->node_ptr, p->pdiag, p->N, \
                                                                                         p->ntiles, c4, vals, flag);             \
   }
-    if (occ >= 6) LAUNCH_TILES(6) else if (occ == 5) LAUNCH_TILES(5) else LAUNCH_TILES(4)
+    if (occ == 1) LAUNCH_TILES(1) else if (occ == 2) LAUNCH_TILES(2) else if (occ == 3) LAUNCH_TILES(3) else LAUNCH_TILES(0)
 #undef LAUNCH_TILES
   } else if (kind == 0 && p->inc_slots && (size_t)p->max_row * 8 * 128 <= 160 * 1024) {
     constexpr int BD = 128;
