@@ -29,7 +29,7 @@ class DistOperator:
         self.nnz = nnz
         # ---- symmetric buffers: header + p[max n_local over ranks]
         sizes = [None] * self.P
-        dist.all_gather_object(sizes, {"n_owned": no, "n_local": part.n_local, "recv_off": part.recv_off})
+        dist.all_gather_object(sizes, {"n_owned": no, "ghost_base": part.ghost_base, "n_local": part.n_local, "recv_off": part.recv_off})
         self.sizes = sizes
         hdr = lib.femb_dist_header_bytes()
         nmax = max(s["n_local"] for s in sizes)
@@ -62,7 +62,7 @@ class DistOperator:
             ptrs.append(ptrs[-1] + int(part.send_idx[q].numel()))
         self.send_ptr = (C.c_int32 * (self.nnbr + 1))(*ptrs)
         self.send_idx = (torch.cat(idx) if idx else torch.zeros(1, dtype=torch.int32)).to(self.dev).contiguous()
-        self.ghost_off = (C.c_int64 * max(1, self.nnbr))(*[sizes[q]["n_owned"] + sizes[q]["recv_off"][self.rank] for q in nb])
+        self.ghost_off = (C.c_int64 * max(1, self.nnbr))(*[sizes[q]["ghost_base"] + sizes[q]["recv_off"][self.rank] for q in nb])
         self.halo_bytes = 8 * ptrs[-1]
         # destinations of every boundary row (CSR over rows n_interior..n_owned): lets the direction kernel store boundary
         # values straight into the neighbours' ghost slots instead of running a separate push kernel

@@ -5,7 +5,8 @@ The reference has no distributed code; its only partition is the notebook's elem
 deterministic recursive coordinate bisection (a geometric graph partition); every rank also takes each element that
 touches one of its nodes, so assembly needs no communication (ghost elements are recomputed redundantly).
 
-Local numbering on a rank: [owned nodes in ascending global id | ghost nodes grouped by owner rank, ascending id].
+Local numbering on a rank: [owned nodes, interior rows first | padding to a 128-byte line | ghost nodes grouped by owner
+rank, ascending id].
 Both sides derive the send/recv lists from the same rule (nodes of rank r that share an element with a node of rank q,
 ascending global id), so the plan needs no communication either.
 """
@@ -56,8 +57,14 @@ class LocalPart:
     n_interior: int = 0                   # owned rows [0, n_interior) reference no ghost column
 
     @property
+    def ghost_base(self):
+        """Local index of the first ghost: n_owned rounded up to 16 doubles (one 128-byte line), so that no cache line holds
+        both owned entries (read early by interior rows) and ghost entries (written by peers later in the same kernel)."""
+        return (self.n_owned + 15) // 16 * 16
+
+    @property
     def n_local(self):
-        return self.n_owned + self.n_ghost
+        return self.ghost_base + self.n_ghost
 
 
 def build_local_part(elements: torch.Tensor, labels: torch.Tensor, rank: int, nparts: int) -> LocalPart:
@@ -84,7 +91,7 @@ def build_local_part(elements: torch.Tensor, labels: torch.Tensor, rank: int, np
     gh, gh_owner = gh[order], gh_owner[order]
     g2l = torch.full((labels.numel(),), -1, dtype=torch.int64, device=dev)
     g2l[owned] = torch.arange(owned.numel(), device=dev)
-    g2l[gh] = owned.numel() + torch.arange(gh.numel(), device=dev)
+    g2l[gh] = (owned.numel() + 15) // 16 * 16 + torch.arange(gh.numel(), device=dev)
     part = LocalPart(rank, nparts, int(owned.numel()), int(gh.numel()), owned, gh, g2l[el], eids)
     part.n_interior = n_interior
     for q in sorted(set(gh_owner.tolist())):
@@ -100,5 +107,6 @@ def build_local_part(elements: torch.Tensor, labels: torch.Tensor, rank: int, np
 
 
 def localize(vec_global: torch.Tensor, part: LocalPart) -> torch.Tensor:
-    """Rows of a replicated global [N, ...] array in local numbering (owned then ghost)."""
-    return torch.cat([vec_global[part.owned_global], vec_global[part.ghost_global]], dim=0)
+    """Rows of a replicated global [N, ...] array in local numbering (owned, zero padding up to ghost_base, ghost)."""
+    pad = torch.zeros((part.ghost_base - part.n_owned,) + tuple(vec_global.shape[1:]), dtype=vec_global.dtype, device=vec_global.device)
+    return torch.cat([vec_global[part.owned_global], pad, vec_global[part.ghost_global]], dim=0)

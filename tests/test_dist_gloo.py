@@ -56,7 +56,7 @@ def _worker(rank, world, port, out):
         for r in reqs:
             r.wait()
         for q in part.neighbors:
-            o = no + part.recv_off[q]
+            o = part.ghost_base + part.recv_off[q]
             xl[o:o + part.recv_cnt[q]] = bufs[q].numpy()
         return xl
 

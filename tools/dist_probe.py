@@ -31,7 +31,9 @@ for n in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "32,110,220").s
     if world == 1:
         crow, col = plan.pattern(1)
         val = plan.assemble_c3d4(cl, "poisson")
-        u1, i1 = ops.cg_solve(crow, col, val, F.reshape(-1, 1), mask=mask, tol=0.0, max_iter=K, check_every=50)
+        nz = int(crow[no].item())     # owned rows are a prefix of the (line-padded) local pattern
+        u1, i1 = ops.cg_solve(crow[:no + 1].contiguous(), col[:nz].contiguous(), val[:nz].contiguous(), F.reshape(-1, 1), mask=mask,
+                              tol=0.0, max_iter=K, check_every=50)
         line += f"   (single-GPU path: {1e3 * i1['loop_ms'] / K:.1f} us/iter)"
     if rank == 0:
         print(line, flush=True)
