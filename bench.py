@@ -38,10 +38,24 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(n, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, only for the workload size it was captured on."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(path))
+        return d[kernel]["traffic_bytes"] if d.get("n") == n else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """nvidia-smi sampler (20 ms period).  Started well before the timed region (nvidia-smi needs a second to come up on an
+    8-GPU box) and stopped after it; the reported clock is the median over samples taken while the GPU was busy
+    (utilization >= 50 %), i.e. under the load of the very kernels being timed."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "utilization.gpu")
 
     def __init__(self, index=0):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -61,8 +75,17 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 9]
         os.unlink(self.f.name)
+        out["samples_total"] = len(rows)
+
+        def util(r):
+            try:
+                return float(r[9])
+            except ValueError:
+                return 0.0
+        busy = [r for r in rows if util(r) >= 50.0]
+        rows = busy or rows
         if not rows:
             return out
         sm = sorted(float(r[1]) for r in rows)
@@ -132,6 +155,7 @@ def run_gpu(args):
         from femb200 import dist_cg
         return dist_cg.bench(args, dev, rank, world, METRIC, UNIT)
 
+    sampler = ClockSampler(local)          # started first: nvidia-smi needs up to a second before its first sample
     # ---- mesh + operator (resident in HBM before any timed region)
     coords, tets = meshgen.kuhn_cube(n, device=dev)
     M, N = tets.shape[0], coords.shape[0]
@@ -199,7 +223,6 @@ def run_gpu(args):
     bytes_spmv = nnz * 12 + N * 20
 
     # ---- CG: W warm-up iterations, then exactly K timed iterations (tol=0 never converges)
-    sampler = ClockSampler(local)          # started before the warm-up so nvidia-smi is already sampling when the timed loop runs
     ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=max(W, 50), check_every=50)
     torch.cuda.synchronize()
     c0, c1 = ev(), ev()
@@ -224,6 +247,9 @@ def run_gpu(args):
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
+    t_soak = time.perf_counter()           # untimed: keep the same loop running until the sampler has >= 0.5 s under load
+    while time.perf_counter() - t_soak < 0.5:
+        ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=200, check_every=50)
     clocks = sampler.stop()
 
     value = K / (ms_loop * 1e-3)
@@ -241,7 +267,8 @@ def run_gpu(args):
         "gpu_launches": 3 * K + 4,
         "roofline": {"kernel": "spmv_tma_kernel<1,false> (TMA-pipelined CSR SpMV; its fused twin is CG step k1)", "bound": "hbm",
                      "achieved": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
-                     "frac": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9 / hbm, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9 / hbm, 4), "traffic": ncu_traffic(n, "spmv_tma_kernel"), "peak_source": peak_src,
+                     "traffic_source": "profiles/r01_traffic.json (ncu --set full capture of this kernel on this workload; null for other sizes)",
                      "ms_per_launch": round(ms_spmv, 4), "algorithmic_bytes": bytes_spmv},
         "cg_iteration": {"ms": round(ms_loop / K, 4), "algorithmic_bytes": bytes_iter,
                          "achieved_GBps": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9, 1),

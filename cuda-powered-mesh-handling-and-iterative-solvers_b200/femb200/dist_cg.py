@@ -134,6 +134,7 @@ def bench(args, dev, rank, world, metric, unit):
     from bench import ClockSampler, peaks
 
     n, K, W = args.n, args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(dev.index or 0)   # started first (nvidia-smi needs ~1 s on an 8-GPU box); stopped after a load soak
     coords, tets = meshgen.kuhn_cube(n, device=dev)
     M, N = tets.shape[0], coords.shape[0]
     t0 = time.perf_counter()
@@ -144,7 +145,6 @@ def bench(args, dev, rank, world, metric, unit):
     no = part.n_owned
     mask = (cl[:no, 2] != 0).to(torch.uint8).contiguous()
     F = torch.full((no,), 1.0 / N, dtype=torch.float64, device=dev)
-    sampler = ClockSampler(dev.index or 0)   # spans warm-up, timed loop and e2e: the timed loop alone is tens of ms
     op.solve(F, mask, tol=0.0, max_iter=max(W, 100), check_every=50)
     torch.cuda.synchronize()
     dist.barrier()
@@ -164,6 +164,8 @@ def bench(args, dev, rank, world, metric, unit):
     torch.cuda.synchronize()
     ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    for _ in range(4):                         # untimed: the same loop again so the clock sampler sees >= 0.5 s of this load
+        op.solve(F, mask, tol=0.0, max_iter=1500, check_every=100)
     clocks = sampler.stop()
     nnz_tot = torch.tensor([op.nnz], dtype=torch.float64, device=dev)
     dist.all_reduce(nnz_tot)

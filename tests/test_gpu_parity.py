@@ -466,3 +466,73 @@ def test_hybrid_cascade(api, O):
     # oracle check of the fine-level solution
     uo, ito, st = O.stable_cg(N(K), N(tf), N(load_fn(cf, tf)), N(fixed_fn(cf)), tol=1e-10, max_iter=10000)
     assert st == "converged" and rel_err(N(u), uo) <= 1e-8
+
+
+def test_full_size_properties_c4():
+    """BASELINE config 4 at full size (Kuhn n=220, 63.9 M tets, 10.8 M nodes) through size-independent properties:
+    known counts, 2S+K=4M, Laplace null space, symmetry of the assembled operator, bit-reproducible assembly, and the
+    fused assembly against the element-kernel + generic-reduction path."""
+    import element as el
+    from femb200 import meshgen, ops
+    n = 220
+    c, t = meshgen.kuhn_cube(n, device=DEV)
+    M, Nn = t.shape[0], c.shape[0]
+    assert M == 63_888_000 and Nn == 10_793_861
+    f, x = el.compute_tetrahedral_surface_faces_with_fourth_node(t, device=DEV)
+    assert f.shape[0] == 12 * n * n                                  # two triangles per boundary quad
+    del f, x
+    s = el.identify_tetrahedral_shared_faces(t, device=DEV)
+    assert 2 * s.shape[0] + 12 * n * n == 4 * M
+    assert bool((s[:, 0, 0] < s[:, 1, 0]).all())                     # lower element id first
+    del s
+    torch.cuda.empty_cache()
+    plan = el.CsrPlan(t, Nn, DEV)
+    assert plan.nnz_nodes == 160_738_381                             # N + 2 * (#edges), SURVEY section 8
+    crow, col = plan.pattern(1)
+    v1 = plan.assemble_c3d4(c, "poisson")
+    v2 = plan.assemble_c3d4(c, "poisson")
+    assert torch.equal(v1, v2)                                       # deterministic
+    ones = torch.ones(Nn, dtype=torch.float64, device=DEV)
+    assert float(ops.spmv(crow, col, v1, ones).abs().max()) < 1e-9   # constants are in the null space (entries are O(1/n))
+    g = torch.Generator(DEV).manual_seed(0)
+    a = torch.randn(Nn, dtype=torch.float64, device=DEV, generator=g)
+    b = torch.randn(Nn, dtype=torch.float64, device=DEV, generator=g)
+    lhs, rhs = float(a @ ops.spmv(crow, col, v1, b)), float(b @ ops.spmv(crow, col, v1, a))
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), 1.0)              # symmetric operator
+    Ke = el.compute_c3d4_poisson_K_matrix(c, t, **KW)
+    v3 = plan.assemble(Ke, 1)
+    del Ke
+    assert float((v3 - v1).abs().max()) <= 1e-12 * float(v1.abs().max())
+    # 100 CG iterations reduce the residual and keep fixed rows at zero
+    mask = (c[:, 2] != 0).to(torch.uint8).contiguous()
+    F = torch.full((Nn, 1), 1.0 / Nn, dtype=torch.float64, device=DEV)
+    u, info = ops.cg_solve(crow, col, v1, F, mask=mask, tol=0.0, max_iter=100, check_every=50)
+    assert info["iterations"] == 100 and float(u[c[:, 2] == 0].abs().max()) == 0.0
+    # CG minimises the energy 0.5 u.Au - u.F monotonically (the residual norm itself need not be monotone)
+    uf = u.reshape(-1)
+    energy = 0.5 * float(uf @ ops.spmv(crow, col, v1, uf)) - float(uf @ F.reshape(-1))
+    assert energy < 0.0
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 2 at full size (P2 elasticity, 1.97 M C3D10 tets): symmetry, rigid-body null space of the element
+    matrices, and CSR operator == element-by-element operator."""
+    import element as el
+    from femb200 import meshgen, ops
+    n = 69
+    c1, t1 = meshgen.kuhn_cube(n, device=DEV)
+    c, e10 = meshgen.p1_to_p2_lattice(n, meshgen.swap01(t1), device=DEV)
+    del c1, t1
+    K = el.compute_c3d10_K_matrix(c, e10, E, NU, **KW)
+    assert K.shape == (1_971_054, 30, 30)
+    scale = float(K.abs().max())
+    assert float((K - K.transpose(1, 2)).abs().max()) <= 1e-13 * scale
+    rb = torch.zeros(c.shape[0], 3, dtype=torch.float64, device=DEV)
+    rb[:, 0] = -c[:, 1]; rb[:, 1] = c[:, 0]                          # rigid rotation about z
+    assert float(el.compute_nodal_forces(K, e10, rb, **KW).abs().max()) <= 1e-10 * scale
+    plan = el.CsrPlan(e10, c.shape[0], DEV)
+    crow, col = plan.pattern(3)
+    vals = plan.assemble(K, 3)
+    x = torch.randn(c.shape[0], 3, dtype=torch.float64, device=DEV, generator=torch.Generator(DEV).manual_seed(2))
+    y1, y2 = ops.spmv(crow, col, vals, x), el.compute_nodal_forces(K, e10, x, **KW)
+    assert float((y1 - y2).abs().max()) <= 1e-12 * float(y2.abs().max())
