@@ -392,6 +392,75 @@ __global__ void __launch_bounds__(BD, OCC) assemble_p1_poisson_tiles(const int4*
   }
 }
 
+// ---- tiled fused P1 elasticity assembly ---------------------------------------------------------------------------------
+// Same records and ownership as the Poisson kernel; three warps share a tile of 32 nodes, warp alpha owning dof row
+// (node, alpha).  Each thread rebuilds the cofactor vectors (3x redundant fp64 work, but the output is 9x larger than for
+// Poisson, so the kernel stays within ~4x of its write roofline) and accumulates its row's 3*len entries in shared memory
+// laid out like the CSR row: acc[(slot*3+beta)][thread].
+__global__ void __launch_bounds__(96) assemble_p1_elasticity_tiles(const int4* __restrict__ rec, const int* __restrict__ tile_ptr,
+                                                                   const int* __restrict__ node_ptr, const unsigned char* __restrict__ pdiag,
+                                                                   long long N, long long ntiles, const double* __restrict__ c4, double lam,
+                                                                   double mu, double* __restrict__ vals, int* __restrict__ flag) {
+  constexpr int BD = 96;
+  extern __shared__ __align__(16) double acc[];  // [max_row*3][BD]
+  const int tid = threadIdx.x, lane = tid & 31, alpha = tid >> 5;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long long i = t * 32 + lane;
+    const bool live = i < N;
+    const int s = live ? node_ptr[i] : 0, len = live ? node_ptr[i + 1] - s : 0;
+    const int s0 = tile_ptr[t], steps = tile_ptr[t + 1] - s0;
+    const int4* rp = rec + (long long)s0 * 32 + lane;
+    double x0[3] = {0, 0, 0};
+    if (live) ld_xyz(c4, (int)i, x0);
+    const int pd = live ? pdiag[i] : 0;
+    for (int p = 0; p < 3 * len; ++p) acc[p * BD + tid] = 0.0;
+    auto rec_at = [&](int st) { return st < steps ? __ldg(rp + st * 32) : make_int4(-1, 0, 0, 0); };
+    int4 ra = rec_at(0), rb = rec_at(1), r2 = rec_at(2);
+    double xa[9], xb[9];
+    if (ra.x >= 0) ld_xyz(c4, ra.x, xa), ld_xyz(c4, ra.y, xa + 3), ld_xyz(c4, ra.z, xa + 6);
+    auto contribute = [&](const int4& r, const double* x) {
+      if (r.x < 0) return;
+      double e1[3], e2[3], e3[3], c[4][3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) e1[q] = x[q] - x0[q], e2[q] = x[3 + q] - x0[q], e3[q] = x[6 + q] - x0[q];
+      c[1][0] = e2[1] * e3[2] - e2[2] * e3[1], c[1][1] = e2[2] * e3[0] - e2[0] * e3[2], c[1][2] = e2[0] * e3[1] - e2[1] * e3[0];
+      c[2][0] = e3[1] * e1[2] - e3[2] * e1[1], c[2][1] = e3[2] * e1[0] - e3[0] * e1[2], c[2][2] = e3[0] * e1[1] - e3[1] * e1[0];
+      c[3][0] = e1[1] * e2[2] - e1[2] * e2[1], c[3][1] = e1[2] * e2[0] - e1[0] * e2[2], c[3][2] = e1[0] * e2[1] - e1[1] * e2[0];
+      const double det = e1[0] * c[1][0] + e1[1] * c[1][1] + e1[2] * c[1][2];
+      if (fabs(det) < 1e-12 && flag) *flag = 1;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) c[0][q] = -(c[1][q] + c[2][q] + c[3][q]);
+      const double scale = 1.0 / (6.0 * fabs(det));  // V g_a (x) g_b = c_a (x) c_b / (6|det|)
+      const double ca = alpha == 0 ? c[0][0] : alpha == 1 ? c[0][1] : c[0][2];  // c0[alpha]
+      const int slot[4] = {pd, r.w & 255, (r.w >> 8) & 255, (r.w >> 16) & 255};
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double dot = mu * (c[0][0] * c[b][0] + c[0][1] * c[b][1] + c[0][2] * c[b][2]);
+        const double cba = alpha == 0 ? c[b][0] : alpha == 1 ? c[b][1] : c[b][2];  // cb[alpha]
+#pragma unroll
+        for (int beta = 0; beta < 3; ++beta) {
+          double v = lam * ca * c[b][beta] + mu * cba * c[0][beta];
+          if (beta == alpha) v += dot;
+          acc[(slot[b] * 3 + beta) * BD + tid] += v * scale;
+        }
+      }
+    };
+    for (int st = 0; st < steps; st += 2) {
+      if (rb.x >= 0) ld_xyz(c4, rb.x, xb), ld_xyz(c4, rb.y, xb + 3), ld_xyz(c4, rb.z, xb + 6);
+      const int4 r3 = rec_at(st + 3);
+      contribute(ra, xa);
+      if (r2.x >= 0) ld_xyz(c4, r2.x, xa), ld_xyz(c4, r2.y, xa + 3), ld_xyz(c4, r2.z, xa + 6);
+      const int4 r4 = rec_at(st + 4);
+      contribute(rb, xb);
+      ra = r2, rb = r3, r2 = r4;
+    }
+    if (live) {
+      double* dst = vals + 9ll * s + (long long)alpha * 3 * len;  // row (node i, alpha) of the dof-level CSR
+      for (int p = 0; p < 3 * len; ++p) dst[p] = acc[p * BD + tid];
+    }
+  }
+}
+
 // ---- values from materialised Ke -----------------------------------------------------------------
 // warp per node; shared accumulator laid out exactly like the node's d rows of the CSR value array
 template <int WARPS>
@@ -829,6 +898,19 @@ extern "C" int femb_csr_assemble_c3d4(femb_csr_plan* p, int kind, const double* 
     FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_scalar_rows<0, BD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     assemble_p1_scalar_rows<0, BD><<<grid_for(p->N, BD, 16), BD, smem, s>>>(p->conn32, p->inc_ptr, p->inc, (const unsigned int*)p->inc_slots,
                                                                             p->node_ptr, p->N, coords, nullptr, vals, flag);
+  } else if (kind == 1 && p->inc_slots && (size_t)p->max_row * 3 * 8 * 96 <= 200 * 1024 && !no_tiles) {
+    if (!p->rec) {
+      const int rc = build_p1_records(p, s);
+      if (rc != FEMB_OK) return rc;
+    }
+    Scratch scr(s);
+    double* c4;
+    FEMB_CUDA(scr.alloc(&c4, (size_t)4 * p->N));
+    pad_coords<<<grid_for(p->N, 256), 256, 0, s>>>(coords, p->N, c4);
+    const size_t smem = sizeof(double) * (size_t)p->max_row * 3 * 96;
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_elasticity_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assemble_p1_elasticity_tiles<<<grid_for(p->ntiles, 1, 24), 96, smem, s>>>(p->rec, p->tile_ptr, p->node_ptr, p->pdiag, p->N, p->ntiles, c4, c * nu,
+                                                                              c * (1 - 2 * nu) / 2, vals, flag);
   } else if (kind == 0) {
     FEMB_CUDA(cudaFuncSetAttribute(assemble_c3d4_fused<0, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * W)));
     assemble_c3d4_fused<0, W><<<grid, W * 32, per_warp * W, s>>>(p->conn32, p->inc_ptr, p->inc, p->node_ptr, p->node_col, p->N, p->max_row, coords,
