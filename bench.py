@@ -274,9 +274,14 @@ def run_gpu(args):
                          "achieved_GBps": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9, 1),
                          "frac": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9 / hbm, 4), "api_call_ms": round(ms_call, 2)},
         "assembly": {"metric": "assembled_elems_per_s", "value": round(M / (ms_asm * 1e-3), 1), "ms": round(ms_asm, 3),
-                     "kernel": "assemble_c3d4_fused<0> (coords+conn -> CSR values, pattern prebuilt)",
+                     "kernel": "pad_coords + assemble_p1_poisson_tiles (coords -> CSR values; pattern and per-incidence records prebuilt)",
                      "algorithmic_bytes": bytes_asm, "achieved_GBps": round(bytes_asm / (ms_asm * 1e-3) / 1e9, 1),
-                     "frac": round(bytes_asm / (ms_asm * 1e-3) / 1e9 / hbm, 4), "plan_build_s": round(t_plan, 3),
+                     "frac": round(bytes_asm / (ms_asm * 1e-3) / 1e9 / hbm, 4),
+                     # SURVEY 8d lists the slot map (M*nd^2*4 bytes) as an add-on when one is read; this kernel reads a
+                     # 16-byte record per incidence (the three other node ids + their slots) instead of conn + slot map
+                     "algorithmic_bytes_with_slot_map": bytes_asm + M * 16 * 4,
+                     "frac_with_slot_map": round((bytes_asm + M * 16 * 4) / (ms_asm * 1e-3) / 1e9 / hbm, 4),
+                     "traffic": ncu_traffic(n, "assemble_p1_poisson_tiles"), "plan_build_s": round(t_plan, 3),
                      "element_K_elems_per_s": round(M / (ms_ke * 1e-3), 1), "element_K_GBps": round(bytes_ke / (ms_ke * 1e-3) / 1e9, 1),
                      "element_K_frac": round(bytes_ke / (ms_ke * 1e-3) / 1e9 / hbm, 4),
                      "two_step_gather_ms": round(ms_gather, 3)},

@@ -3,9 +3,10 @@
 // Replaces the un-coalesced torch.sparse_coo_tensor of subdivision.ipynb cell 6 (reference) with
 //   plan   : node->element incidence lists (stable radix sort of (node, flat slot)) and the node-level sparsity pattern
 //            (segmented sort + unique of each node's candidate columns)
-//   values : one warp per node row; contributions are added in incidence order (ascending element id), i.e. a
-//            sort-based segmented reduction into the precomputed pattern.  Either from materialised Ke
-//            (any element type / dofs per node) or fused from coordinates for P1 tets.
+//   values : every CSR row has ONE owner (a thread for P1 tets, a warp for the generic path) that adds the row's
+//            contributions in incidence order (ascending element id), i.e. a sort-based segmented reduction into the
+//            precomputed pattern: bit-reproducible, no atomics.  Either from materialised Ke (any element type / dofs
+//            per node) or fused from coordinates for P1 tets (Poisson and elasticity; Ke never exists).
 #include <cstdlib>
 #include <cub/cub.cuh>
 

@@ -1,17 +1,22 @@
 // Multi-GPU conjugate gradient over NVLink peer memory (one process per GPU, rows partitioned).
 //
-// The reference has no distributed code.  Each rank owns a block of rows (local numbering [owned | ghost]) and keeps its
-// search direction p in a cudaIpc-shared "symmetric" buffer.  One CG iteration is four kernels, all in one CUDA graph:
-//   push  boundary entries of p are stored straight into the neighbours' ghost slots (st.global on mapped peer pointers
-//         through NVSwitch), then flag A is raised on every neighbour
-//   k1    waits for flag A of its neighbours, CSR-stream SpMV on the owned rows, p.Ap partial; the last CTA stores the
-//         partial into slot[rank] of EVERY rank's reduction array and raises flag B everywhere
+// The reference has no distributed code.  Each rank owns a block of rows (local numbering [owned, interior rows first |
+// padding to a cache line | ghost]) and keeps its search direction p in a cudaIpc-shared "symmetric" buffer.  One CG
+// iteration is three kernels in one CUDA graph:
+//   k1    TMA-pipelined SpMV on the owned rows (spmv_dev.cuh): interior row tiles first; a CTA waits for halo flag A of its
+//         neighbours only before its first boundary tile.  p.Ap partial; the last CTA stores the rank's partial into
+//         slot[rank] of EVERY rank's reduction array and raises flag B everywhere
 //   k2    waits for flag B of all ranks, sums the P partials in rank order (deterministic, identical on every rank),
 //         guards/alpha, u += alpha p, r -= alpha Ap, r.r partial -> slot[rank] everywhere, flag C
-//   k3    waits for flag C, rs_new, convergence test / beta (identical on every rank), p = r + beta p
-// There is no NCCL call and no host involvement inside the loop: the "collectives" are peer stores plus epoch flags, which
-// costs a few microseconds instead of tens per all-reduce -- the difference between ~4x and >6x strong scaling at 8 GPUs
-// when an iteration is ~85 us of compute.  All spin loops carry a timeout so a lost rank turns into an error, not a hang.
+//   k3    waits for flag C, rs_new, convergence test / beta (identical on every rank), p = r + beta p; the thread that
+//         updates a boundary row also stores the new value straight into the ghost slots of the neighbours that need it
+//         (st.global on mapped peer pointers through NVSwitch); the last CTA raises flag A on the neighbours
+// There is no NCCL call and no host involvement inside the loop: the "collectives" are peer stores plus epoch flags.
+// All spin loops carry a timeout so a lost rank turns into an error, not a hang.  Lessons measured on 8 B200:
+// let ONE thread per CTA read the reduction slots (every thread doing it made the slot line an L2 hot spot worth 17 us per
+// kernel); read x through the read-only path (plain loads cost 17 %), which is safe because ghosts start on their own
+// 128-byte line and are first touched after flag A while L1 is flushed at every launch; a single persistent cooperative
+// kernel with software grid barriers (dist_cg_persistent_kernel, FEMB_DIST_PERSISTENT=1) is slower than launch boundaries.
 #include <cstdlib>
 
 #include "spmv_dev.cuh"
