@@ -536,3 +536,50 @@ def test_full_size_properties_c2():
     x = torch.randn(c.shape[0], 3, dtype=torch.float64, device=DEV, generator=torch.Generator(DEV).manual_seed(2))
     y1, y2 = ops.spmv(crow, col, vals, x), el.compute_nodal_forces(K, e10, x, **KW)
     assert float((y1 - y2).abs().max()) <= 1e-12 * float(y2.abs().max())
+
+
+def test_edge_cases_topology_and_assembly(api, O):
+    """Non-manifold faces (shared by three elements), isolated nodes / id gaps, int32 connectivity, repeated calls."""
+    el = api[0]
+    # three tets around the same face (0,1,2): the face is neither surface (count 1) nor shared (count 2)
+    t = torch.tensor([[0, 1, 2, 3], [0, 1, 2, 4], [0, 1, 2, 5], [3, 4, 5, 9]])
+    f, x = el.compute_tetrahedral_surface_faces_with_fourth_node(t, device=DEV)
+    of, ox = O.tet_surface_faces(N(t))
+    same(f, of); same(x, ox)
+    same(el.identify_tetrahedral_shared_faces(t, device=DEV), O.tet_shared_faces(N(t)))
+    assert not any((sorted(r) == [0, 1, 2]) for r in N(f).tolist())
+    # node ids with gaps (6,7,8 unused) and trailing isolated nodes: empty CSR rows, pattern still equals the oracle's
+    c = torch.rand(12, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(4))
+    K = el.compute_c3d4_K_matrix(c, t, E, NU, **KW)
+    A = el.assemble_csr(K, t, 12, device=DEV)
+    crow, col, val, _ = O.assemble_csr(N(K), N(t), 3, 12)
+    same(A.crow_indices(), crow); same(A.col_indices(), col); close(A.values(), val)
+    A32 = el.assemble_csr(K, t.to(torch.int32), 12, device=DEV)
+    same(A32.crow_indices(), crow); close(A32.values(), val)
+    plan = el.CsrPlan(t, 12, DEV)
+    close(plan.assemble_c3d4(c, "elasticity", E, NU), val)
+    pc, pcol, pval, _ = O.assemble_csr(O.c3d4_poisson_K(N(c), N(t)), N(t), 1, 12)
+    close(plan.assemble_c3d4(c, "poisson"), pval)
+    # operator application on a mesh with isolated nodes: their rows are zero
+    u = torch.randn(12, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    y = el.compute_nodal_forces(K, t, u, **KW)
+    close(y, O.nodal_forces(N(K), N(t), N(u)))
+    assert float(y[6:9].abs().max()) == 0.0 and float(y[10:].abs().max()) == 0.0
+
+
+def test_mixed_family_topology(api, O):
+    """Hex / wedge surface extraction on shuffled multi-element meshes against the oracle (bit-exact)."""
+    el = api[0]
+    from femb200 import meshgen
+    rng = np.random.default_rng(11)
+    _, w = meshgen.wedge_cube(4)
+    w = w[torch.as_tensor(rng.permutation(w.shape[0]))]
+    (q, t3), (qe, te) = el.compute_wedge_surface_faces_with_extra_node(w, device=DEV)
+    (oq, ot), (oqe, ote) = O.wedge_surface_faces(N(w))
+    same(q, oq); same(t3, ot); same(qe, oqe); same(te, ote)
+    _, h = meshgen.hex_cube(4)
+    h20 = torch.cat([h, h.max() + 1 + torch.arange(h.shape[0] * 12).reshape(-1, 12)], dim=1)   # [M,20]: corner columns only are used
+    f, x = el.compute_hexahedral_surface_faces_with_extra_node(h20, device=DEV)
+    of, ox = O.hex_surface_faces(N(h))
+    same(f, of); same(x, ox)
+    same(el.identify_hexahedral_shared_faces(h20, device=DEV), O.hex_shared_faces(N(h)))
