@@ -270,6 +270,38 @@ def gen_solve():
     save("solve_shell", c3=npy(c3), s3=npy(s3), fixed=npy(fixed), F=npy(Fs), u=npy(us), it=iters_of(txt))
 
 
+def gen_stress():
+    """Stress recovery (SURVEY 8f next #1): reference outputs on the small seeded meshes."""
+    g = torch.Generator().manual_seed(9)
+    o = {}
+    coords, tets = meshgen.kuhn_cube(2, jitter=0.2)
+    u = torch.randn(coords.shape[0], 3, dtype=torch.float64, generator=g) * 0.01
+    o["c"], o["t"], o["u"] = coords, tets, u
+    s, v = R.compute_c3d4_element_stress(coords, tets, u, E, NU, **KW)
+    o["s4"], o["v4"] = s, v
+    o["node_vm4"] = R.compute_node_vm_stress(coords, tets, v, **KW)
+    t01 = meshgen.swap01(tets)
+    R.c3d4_to_c3d10.__globals__["elems"] = t01
+    c2, e10, _, _ = R.c3d4_to_c3d10(coords, t01, dtype=torch.float64)
+    del R.c3d4_to_c3d10.__globals__["elems"]
+    e10 = e10.long()
+    u10 = torch.randn(c2.shape[0], 3, dtype=torch.float64, generator=g) * 0.01
+    o["c10"], o["e10"], o["u10"] = c2, e10, u10
+    o["s10"], o["v10"] = R.compute_c3d10_element_stress(c2, e10, u10, E, NU, **KW)
+    sm, vm = R.compute_c3d10_element_stress(c2, e10[:6], u10, E, NU, single=False, **KW)
+    o["s10m"], o["v10m"] = sm, vm
+    ch, h = meshgen.hex_cube(2, jitter=0.2)
+    uh = torch.randn(ch.shape[0], 3, dtype=torch.float64, generator=g) * 0.01
+    o["ch"], o["h"], o["uh"] = ch, h, uh
+    o["s8"], o["v8"] = R.compute_c3d8_element_stress(ch, h, uh, E, NU, **KW)
+    o["s8m"], o["v8m"] = R.compute_c3d8_element_stress(ch, h, uh, E, NU, single=False, **KW)
+    cw, w6 = meshgen.wedge_cube(2, jitter=0.2)
+    o["w6"] = w6
+    o["s6"], o["v6"] = R.compute_c3d6_element_stress(cw, w6, uh, E, NU, **KW)
+    o["s6m"], o["v6m"] = R.compute_c3d6_element_stress(cw, w6, uh, E, NU, single=False, **KW)
+    save("stress", **{k: npy(v) for k, v in o.items()})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_units()
@@ -278,3 +310,4 @@ if __name__ == "__main__":
     gen_wedge()
     gen_shells()
     gen_solve()
+    gen_stress()

@@ -217,3 +217,21 @@ def test_unpinned_invariants():
     Mm = O.c3d4_mass(c, t, 2.0)
     V = O.tet_volumes(c, t)
     close(Mm[:, 0::3, 0::3].sum(axis=(1, 2)), 2.0 * V, 1e-14)
+
+
+def test_stress_recovery():
+    """SURVEY 8f next #1: element stress and nodal averaging against the reference's outputs."""
+    g = load_golden("stress")
+    s, v = O.c3d4_element_stress(g["c"], g["t"], g["u"], E, NU)
+    close(s, g["s4"]); close(v, g["v4"])
+    close(O.node_vm_stress(g["c"].shape[0], g["t"], g["v4"]), g["node_vm4"])
+    s, v = O.solid_element_stress("c3d10", g["c10"], g["e10"], g["u10"], E, NU)
+    close(s, g["s10"]); close(v, g["v10"])
+    s, v = O.solid_element_stress("c3d10", g["c10"], g["e10"][:6], g["u10"], E, NU, single=False)
+    close(s, g["s10m"]); close(v, g["v10m"])
+    for kind, conn, cc in (("c3d8", g["h"], g["ch"]), ("c3d6", g["w6"], g["ch"])):
+        tag = kind[-1]
+        s, v = O.solid_element_stress(kind, cc, conn, g["uh"], E, NU)
+        close(s, g["s" + tag]); close(v, g["v" + tag])
+        s, v = O.solid_element_stress(kind, cc, conn, g["uh"], E, NU, single=False)
+        close(s, g["s" + tag + "m"]); close(v, g["v" + tag + "m"])
