@@ -925,6 +925,33 @@ extern "C" int femb_csr_assemble_c3d4(femb_csr_plan* p, int kind, const double* 
   return FEMB_OK;
 }
 
+namespace femb {
+// compute_node_vm_stress element.py:466-504: node value = mean of the values of the elements containing the node
+// (0 for isolated nodes).  The reference scatters with atomic index_add; here each node sums its incidence list in
+// ascending element order, so the result is bit-reproducible.
+template <typename T>
+__global__ void node_average_kernel(const int* __restrict__ inc_ptr, const int* __restrict__ inc, long long N, int nen,
+                                    const T* __restrict__ ev, T* __restrict__ out) {
+  for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const int b = inc_ptr[n], e = inc_ptr[n + 1];
+    T sum = 0;
+    for (int k = b; k < e; ++k) sum += __ldg(ev + inc[k] / nen);
+    out[n] = e > b ? sum / (T)(e - b) : T(0);
+  }
+}
+}  // namespace femb
+
+extern "C" int femb_node_average(femb_csr_plan* p, const void* elem_values, int fp, void* out, femb_stream stream) {
+  FEMB_CHECK_ARG(p && (fp == 4 || fp == 8), "plan, fp in {4,8}");
+  if (p->N == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int grid = grid_for(p->N, 128);
+  if (fp == 8) node_average_kernel<double><<<grid, 128, 0, s>>>(p->inc_ptr, p->inc, p->N, p->nen, (const double*)elem_values, (double*)out);
+  else node_average_kernel<float><<<grid, 128, 0, s>>>(p->inc_ptr, p->inc, p->N, p->nen, (const float*)elem_values, (float*)out);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
 extern "C" int femb_ebe_apply(femb_csr_plan* p, int ndof, const void* Ke, const void* u, const void* unit, int fp, void* y, femb_stream stream) {
   FEMB_CHECK_ARG(p && (fp == 4 || fp == 8), "plan, fp in {4,8}");
   cudaStream_t s = as_stream(stream);

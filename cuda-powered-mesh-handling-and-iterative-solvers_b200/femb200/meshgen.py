@@ -115,3 +115,71 @@ def quad_sheet(n, device="cpu", dtype=torch.float64, warp=0.0):
     I, J = torch.meshgrid(torch.arange(n, device=device), torch.arange(n, device=device), indexing="ij")
     q = torch.stack([I * (n + 1) + J, (I + 1) * (n + 1) + J, (I + 1) * (n + 1) + J + 1, I * (n + 1) + J + 1], dim=-1)
     return c, q.reshape(-1, 4).to(torch.int64).contiguous()
+
+
+# ---- quadratic (mid-edge) versions on the (2n+1)^3 lattice -----------------------------------------------------------
+HEX20_EDGES = ((0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7))   # VTK / Abaqus order
+WEDGE15_EDGES = ((0, 1), (1, 2), (2, 0), (3, 4), (4, 5), (5, 3), (0, 3), (1, 4), (2, 5))
+
+
+def to_quadratic_lattice(n, coords, conn, edges, compact=False):
+    """Mid-edge nodes for any linear lattice connectivity: corner (i,j,k) -> site (2i,2j,2k) of the (2n+1)^3 lattice, the
+    mid-edge node of corners a,b -> the site at the sum of their (i,j,k).  Coordinates of mid-edge nodes are the mean of
+    the (possibly jittered) corner coordinates, so edges stay straight.  compact=True renumbers the used sites
+    0..N'-1 in ascending site order (the full lattice keeps face- and body-centre sites as isolated nodes)."""
+    m, m2 = n + 1, 2 * n + 1
+    k, j, i = conn % m, (conn // m) % m, conn // (m * m)
+
+    def nid(a, b):
+        return ((i[:, a] + i[:, b]) * m2 + (j[:, a] + j[:, b])) * m2 + (k[:, a] + k[:, b])
+
+    nen = conn.shape[1]
+    pairs = [(a, a) for a in range(nen)] + list(edges)
+    q = torch.stack([nid(a, b) for (a, b) in pairs], dim=-1).to(torch.int64).contiguous()
+    c2 = torch.zeros((m2 ** 3, 3), device=coords.device, dtype=coords.dtype)
+    for col, (a, b) in enumerate(pairs):
+        c2[q[:, col]] = (coords[conn[:, a]] + coords[conn[:, b]]) / 2
+    if compact:
+        used, inv = torch.unique(q.reshape(-1), return_inverse=True)
+        return c2[used].contiguous(), inv.reshape(q.shape).contiguous()
+    return c2, q
+
+
+def hex20_cube(n, device="cpu", dtype=torch.float64, jitter=0.0, compact=True):
+    c, h = hex_cube(n, device, dtype, jitter)
+    return to_quadratic_lattice(n, c, h, HEX20_EDGES, compact)
+
+
+def wedge15_cube(n, device="cpu", dtype=torch.float64, jitter=0.0, compact=True):
+    c, w = wedge_cube(n, device, dtype, jitter)
+    return to_quadratic_lattice(n, c, w, WEDGE15_EDGES, compact)
+
+
+def tet10_cube(n, device="cpu", dtype=torch.float64, jitter=0.0, compact=True):
+    """Kuhn tets with local nodes 0<->1 swapped (reference detJ > 0) and mid-edge nodes in the reference order."""
+    c, t = kuhn_cube(n, device, dtype, jitter)
+    return to_quadratic_lattice(n, c, swap01(t), P2_EDGES, compact)
+
+
+def mixed_box_quadratic(n, device="cpu", dtype=torch.float64, jitter=0.0):
+    """BASELINE config 3: the hex | wedge | tet slabs of mixed_box with mid-edge nodes, one shared node numbering.
+    Returns (coords [N',3], {"c3d20": [.,20], "c3d15": [.,15], "c3d10": [.,10]}); numbering is compact."""
+    coords, lin = mixed_box(n, device, dtype, jitter)
+    m2 = 2 * n + 1
+    parts, c2 = {}, None
+    for name, key, edges in (("c3d20", "c3d8", HEX20_EDGES), ("c3d15", "c3d6", WEDGE15_EDGES), ("c3d10", "c3d4", P2_EDGES)):
+        conn = swap01(lin[key]) if key == "c3d4" else lin[key]
+        cc, q = to_quadratic_lattice(n, coords, conn, edges, compact=False)
+        parts[name] = q
+        if c2 is None:
+            c2 = cc
+        else:
+            touched = torch.zeros(m2 ** 3, dtype=torch.bool, device=cc.device)
+            touched[q.reshape(-1)] = True
+            c2[touched] = cc[touched]
+    used, inv = torch.unique(torch.cat([p.reshape(-1) for p in parts.values()]), return_inverse=True)
+    out, off = {}, 0
+    for name, q in parts.items():
+        out[name] = inv[off:off + q.numel()].reshape(q.shape).contiguous()
+        off += q.numel()
+    return c2[used].contiguous(), out

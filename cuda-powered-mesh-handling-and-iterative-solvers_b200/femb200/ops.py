@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._lib import CGResult, check, lib
 
-C3D4, C3D6, C3D8, C3D10, S3, S4 = 4, 6, 8, 10, 103, 104
+C3D4, C3D6, C3D8, C3D10, C3D15, C3D20, S3, S4 = 4, 6, 8, 10, 15, 20, 103, 104
 ENT_TET_FACES, ENT_HEX_FACES, ENT_WEDGE_QUADS, ENT_WEDGE_TRIS, ENT_TRI_EDGES, ENT_QUAD_EDGES = range(6)
 _ENT = {ENT_TET_FACES: (4, 3), ENT_HEX_FACES: (6, 4), ENT_WEDGE_QUADS: (3, 4), ENT_WEDGE_TRIS: (2, 3), ENT_TRI_EDGES: (3, 2),
         ENT_QUAD_EDGES: (4, 2)}
@@ -67,6 +67,14 @@ def default_points(kind) -> list:
     return [[buf[4 * q + k] for k in range(4)] for q in range(n)]
 
 
+def mass_points(kind) -> list:
+    buf = (C.c_double * (64 * 4))()
+    n = lib.femb_mass_points(kind, buf)
+    if n < 0:
+        check(1, "femb_mass_points")
+    return [[buf[4 * q + k] for k in range(4)] for q in range(n)]
+
+
 # ----------------------------------------------------------------------------- element kernels
 
 def c3d4(what, coords, elements, E=0.0, nu=0.0, device="cuda:0", dtype=torch.float32):
@@ -93,7 +101,7 @@ def volumes(kind, coords, elements, device="cuda:0", dtype=torch.float32):
     return out
 
 
-_NEN = {C3D4: 4, C3D6: 6, C3D8: 8, C3D10: 10, S3: 3, S4: 4}
+_NEN = {C3D4: 4, C3D6: 6, C3D8: 8, C3D10: 10, C3D15: 15, C3D20: 20, S3: 3, S4: 4}
 
 
 def solid(kind, what, coords, elements, points, E=0.0, nu=0.0, device="cuda:0", dtype=torch.float32):
@@ -104,12 +112,44 @@ def solid(kind, what, coords, elements, points, E=0.0, nu=0.0, device="cuda:0", 
     if conn.shape[1] != nen:
         conn = conn[:, :nen].contiguous()
     M, nd, nq = conn.shape[0], 3 * nen, len(points)
-    shape = {0: (M, 3, 3), 1: (M, nen, 3), 2: (M, 6, nd), 3: (M, nd, nd), 4: (nq, M, nd, nd), 5: (M, nd, nd)}[what]
+    shape = {0: (M, 3, 3), 1: (M, nen, 3), 2: (M, 6, nd), 3: (M, nd, nd), 4: (nq, M, nd, nd), 5: (M, nd, nd), 6: (M, nd, nd)}[what]
     out = torch.empty(shape, device=dev, dtype=dtype)
     flat = [v for row in points for v in row]
     with torch.cuda.device(dev):
         check(lib.femb_solid(kind, what, _p(x), _fp(x), _p(conn), _fp(conn), M, _host_doubles(flat), nq, float(E), float(nu), _p(out),
                              _stream(dev)), "femb_solid")
+    return out
+
+
+def solid_stress(kind, coords, elements, displacement, points, E, nu, single=True, device="cuda:0", dtype=torch.float32):
+    """(stress, vm): single -> [M,3,3],[M]; else point-major [nq,M,3,3],[nq,M]."""
+    dev = cuda_device(device)
+    x, conn, u = real(coords, dev, dtype), index(elements, dev), real(displacement, dev, dtype)
+    nen = _NEN[kind]
+    if conn.shape[1] != nen:
+        conn = conn[:, :nen].contiguous()
+    if u.shape != x.shape:
+        raise ValueError(f"displacement must be [N,3] like coords, got {tuple(u.shape)} vs {tuple(x.shape)}")
+    M, nq = conn.shape[0], len(points)
+    lead = (M,) if single else (nq, M)
+    S = torch.empty(lead + (3, 3), device=dev, dtype=dtype)
+    V = torch.empty(lead, device=dev, dtype=dtype)
+    flat = [v for row in points for v in row]
+    with torch.cuda.device(dev):
+        check(lib.femb_solid_stress(kind, _p(x), _fp(x), _p(conn), _fp(conn), M, _p(u), _host_doubles(flat), nq, float(E), float(nu),
+                                    1 if single else 0, _p(S), _p(V), _stream(dev)), "femb_solid_stress")
+    return S, V
+
+
+def stress_helper(what, t):
+    """what 0: Voigt [M,6] -> [M,3,3]; 1: [M,3,3] -> von Mises [M].  Works on the tensor's own device/dtype like the reference."""
+    t = torch.as_tensor(t)
+    dev = cuda_device(t.device)
+    t = real(t, dev, t.dtype)
+    M = t.shape[0]
+    out = torch.empty((M, 3, 3) if what == 0 else (M,), device=dev, dtype=t.dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_stress_helper(what, _p(t), _fp(t), M, _p(out), _stream(dev)), "femb_stress_helper")
     return out
 
 
@@ -133,7 +173,7 @@ def shell(kind, what, coords, elements, points=None, D=None, device="cuda:0", dt
 def to_c3d4(kind, elements, device="cuda:0"):
     dev = cuda_device(device)
     conn = index(elements, dev)
-    k = {C3D10: 8, C3D8: 6, C3D6: 3}[kind]
+    k = {C3D10: 8, C3D8: 6, C3D6: 3, C3D20: 24}[kind]
     if conn.shape[1] != _NEN[kind]:
         conn = conn[:, :_NEN[kind]].contiguous()
     out = torch.empty((conn.shape[0] * k, 4), device=dev, dtype=torch.int64)
@@ -251,6 +291,16 @@ class CsrPlan:
         with torch.cuda.device(self.dev):
             check(lib.femb_ebe_apply(self.handle, ndof, _p(Ke), _p(u), _p(un), _fp(u), _p(y), _stream(self.dev)), "femb_ebe_apply")
         return y
+
+    def node_average(self, elem_values, dtype=None):
+        """[N] mean over the elements containing each node (0 for isolated nodes), ascending element order."""
+        v = torch.as_tensor(elem_values)
+        v = real(v, self.dev, dtype if dtype is not None else (v.dtype if v.dtype in (torch.float32, torch.float64) else torch.float64))
+        assert v.shape == (self.M,), (v.shape, self.M)
+        out = torch.empty(self.n_nodes, device=self.dev, dtype=v.dtype)
+        with torch.cuda.device(self.dev):
+            check(lib.femb_node_average(self.handle, _p(v), _fp(v), _p(out), _stream(self.dev)), "femb_node_average")
+        return out
 
 
 _PLAN_CACHE: "collections.OrderedDict" = collections.OrderedDict()

@@ -59,7 +59,7 @@ def to_c3d4(elements, device="cuda:0"):
         return c3d8_to_c3d4(elements, device)
     if n == 10:
         return c3d10_to_c3d4(elements, device)
-    return None
+    return None   # the reference's dispatcher does not route C3D20 either; call c3d20_to_c3d4 directly
 
 
 def to_2nd_order(coords, elements, rbe2=None, rbe3=None, device="cuda:0", dtype=torch.float32):
@@ -76,7 +76,8 @@ def _unsupported(element_type):
 def integral_points(element_type, device="cuda:0"):
     """element.py:371-378 -- always float32 (the dispatcher drops dtype, quirk q2)."""
     t = element_type.lower()
-    fn = {"c3d8": c3d8_integration_points, "c3d10": c3d10_integration_points, "c3d6": c3d6_integration_points}.get(t)
+    fn = {"c3d8": c3d8_integration_points, "c3d10": c3d10_integration_points, "c3d6": c3d6_integration_points,
+          "c3d20": c3d20_integration_points, "c3d15": c3d15_integration_points}.get(t)
     return fn(device) if fn else _unsupported(element_type)
 
 
@@ -84,14 +85,15 @@ def compute_Jacobian(coords, elements, element_type, integral_point=None, device
     """element.py:380-388 (float32 result, q2; 'c3d8i' aliases C3D8 here only)."""
     t = element_type.lower()
     fn = {"c3d8": compute_c3d8_Jacobian, "c3d8i": compute_c3d8_Jacobian, "c3d10": compute_c3d10_Jacobian,
-          "c3d6": compute_c3d6_Jacobian}.get(t)
+          "c3d6": compute_c3d6_Jacobian, "c3d20": compute_c3d20_Jacobian, "c3d15": compute_c3d15_Jacobian}.get(t)
     return fn(coords, elements, integral_point, device) if fn else _unsupported(element_type)
 
 
 def compute_shape_gradients(coords, elements, element_type, integral_point=None, device="cuda:0"):
     """element.py:390-397 (float32 result, q2)."""
     t = element_type.lower()
-    fn = {"c3d8": compute_c3d8_shape_gradients, "c3d10": compute_c3d10_shape_gradients, "c3d6": compute_c3d6_shape_gradients}.get(t)
+    fn = {"c3d8": compute_c3d8_shape_gradients, "c3d10": compute_c3d10_shape_gradients, "c3d6": compute_c3d6_shape_gradients,
+          "c3d20": compute_c3d20_shape_gradients, "c3d15": compute_c3d15_shape_gradients}.get(t)
     return fn(coords, elements, integral_point, device) if fn else _unsupported(element_type)
 
 
@@ -100,7 +102,8 @@ def compute_B_matrix(coords, elements, integral_point, element_type, device="cud
     t = element_type.lower()
     if t == "c3d4":
         return compute_c3d4_B_matrix(coords, elements, device, dtype)
-    fn = {"c3d8": compute_c3d8_B_matrix, "c3d10": compute_c3d10_B_matrix, "c3d6": compute_c3d6_B_matrix}.get(t)
+    fn = {"c3d8": compute_c3d8_B_matrix, "c3d10": compute_c3d10_B_matrix, "c3d6": compute_c3d6_B_matrix,
+          "c3d20": compute_c3d20_B_matrix, "c3d15": compute_c3d15_B_matrix}.get(t)
     return fn(coords, elements, integral_point, device) if fn else _unsupported(element_type)
 
 
@@ -109,8 +112,58 @@ def compute_K_matrix(coords, elements, element_type, E, nu, integral_point=None,
     t = element_type.lower()
     if t == "c3d4":
         return compute_c3d4_K_matrix(coords, elements, E, nu, device, dtype)
-    fn = {"c3d8": compute_c3d8_K_matrix, "c3d10": compute_c3d10_K_matrix, "c3d6": compute_c3d6_K_matrix}.get(t)
+    fn = {"c3d8": compute_c3d8_K_matrix, "c3d10": compute_c3d10_K_matrix, "c3d6": compute_c3d6_K_matrix,
+          "c3d20": compute_c3d20_K_matrix, "c3d15": compute_c3d15_K_matrix}.get(t)
     return fn(coords, elements, E, nu, integral_point, single, device, dtype) if fn else _unsupported(element_type)
+
+
+def compute_element_stress(coords, elements, displacement, E, nu, element_type, integral_point=None, single=True, device="cuda:0",
+                           dtype=torch.float32):
+    """element.py:409-417"""
+    t = element_type.lower()
+    if t == "c3d4":
+        return compute_c3d4_element_stress(coords, elements, displacement, E, nu, device, dtype)
+    fn = {"c3d8": compute_c3d8_element_stress, "c3d10": compute_c3d10_element_stress, "c3d6": compute_c3d6_element_stress,
+          "c3d20": compute_c3d20_element_stress, "c3d15": compute_c3d15_element_stress}.get(t)
+    return fn(coords, elements, displacement, E, nu, integral_point, single, device, dtype) if fn else _unsupported(element_type)
+
+
+def compute_M_matrix(coords, elements, element_type, rho, integral_point=None, device="cuda:0", dtype=torch.float32):
+    """Consistent mass [M,nd,nd] by element type.  Additive: the reference only calls an undefined
+    compute_c3d4_M_matrix (solver_example.ipynb cell 13) -- parity unpinned, see compute_c3d10_M_matrix."""
+    t = element_type.lower()
+    if t == "c3d4":
+        return compute_c3d4_M_matrix(coords, elements, rho, device, dtype)
+    kind = {"c3d8": _ops.C3D8, "c3d10": _ops.C3D10, "c3d6": _ops.C3D6, "c3d20": _ops.C3D20, "c3d15": _ops.C3D15}.get(t)
+    return _solid_M(kind, coords, elements, rho, integral_point, device, dtype) if kind else _unsupported(element_type)
+
+
+# ------------------------------------------------------------------------------------------- stress helpers
+
+def compute_stress_tensor(stress_vector):
+    """Voigt [M,6] (xx,yy,zz,xy,yz,zx) -> [M,3,3] on the tensor's own device and dtype (element.py:308-330)."""
+    return _ops.stress_helper(0, stress_vector)
+
+
+def compute_von_mises_stress(stress_tensor):
+    """[M,3,3] -> [M] (element.py:332-353)."""
+    return _ops.stress_helper(1, stress_tensor)
+
+
+def compute_node_vm_stress(coords, elements, element_vm_stress, device="cuda:0", dtype=torch.float32):
+    """Node value = mean over the elements containing the node (element.py:466-504); the reference scatters with atomic
+    index_add, here each node sums its incidence list in ascending element order (deterministic)."""
+    dev = _ops.cuda_device(device)
+    plan = _ops.cached_plan(elements, torch.as_tensor(coords).shape[0], dev)
+    return plan.node_average(element_vm_stress, dtype)
+
+
+def _stress(kind, coords, elements, displacement, E, nu, integral_point, single, device, dtype, point_major):
+    pts = _pts(kind, integral_point, dtype)
+    S, V = _ops.solid_stress(kind, coords, elements, displacement, pts, E, nu, single, device, dtype)
+    if single or point_major:
+        return S, V
+    return S.permute(1, 0, 2, 3).contiguous(), V.t().contiguous()
 
 
 def compute_nodal_forces(K, elements, displacement, device="cuda:0", dtype=torch.float32):
@@ -217,6 +270,11 @@ def compute_c3d4_M_matrix(coords, elements, rho, device="cuda:0", dtype=torch.fl
     return _ops.c3d4(4, coords, elements, rho, 0.0, device, dtype)
 
 
+def compute_c3d4_element_stress(coords, elements, displacement, E, nu, device="cuda:0", dtype=torch.float32):
+    """([M,3,3], [M]) constant-strain stress and von Mises (element.py:905-939)."""
+    return _ops.solid_stress(_ops.C3D4, coords, elements, displacement, [[0.25, 0.25, 0.25, 1.0]], E, nu, True, device, dtype)
+
+
 def c3d10_to_c3d4(c3d10_elements, device="cuda:0"):
     """8 children per C3D10 (element.py:963-993)."""
     return _ops.to_c3d4(_ops.C3D10, c3d10_elements, device)
@@ -241,6 +299,14 @@ def _solid_K(kind, coords, elements, E, nu, integral_point, single, device, dtyp
     return _solid(kind, 3 if single else 4, coords, elements, integral_point, device, dtype, E, nu, single_point=False)
 
 
+def _solid_M(kind, coords, elements, rho, integral_point, device, dtype):
+    if integral_point is None:
+        pts = torch.tensor(_ops.mass_points(kind), dtype=torch.float64).to(dtype).to(torch.float64).tolist()
+    else:
+        pts = _pts(kind, integral_point, dtype)
+    return _ops.solid(kind, 6, coords, elements, pts, rho, 0.0, device, dtype)
+
+
 def compute_c3d10_Jacobian(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
     """[M,3,3] (element.py:1026-1060)."""
     return _solid(_ops.C3D10, 0, coords, elements, integral_point, device, dtype)
@@ -259,6 +325,19 @@ def compute_c3d10_B_matrix(coords, elements, integral_point, device="cuda:0", dt
 def compute_c3d10_K_matrix(coords, elements, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32):
     """sum_q w_q detJ_q B^T D B with signed detJ; single=False -> [n_int,M,30,30] unweighted (element.py:1191-1239)."""
     return _solid_K(_ops.C3D10, coords, elements, E, nu, integral_point, single, device, dtype)
+
+
+def compute_c3d10_element_stress(coords, elements, displacement, E, nu, integral_point=None, single=True, device="cuda:0",
+                                 dtype=torch.float32):
+    """single=True: ([M,3,3],[M]) weighted with the rule's weights (which sum to 0.45, q4); single=False:
+    ([n_int,M,3,3],[n_int,M]) (element.py:1127-1189)."""
+    return _stress(_ops.C3D10, coords, elements, displacement, E, nu, integral_point, single, device, dtype, True)
+
+
+def compute_c3d10_M_matrix(coords, elements, rho, integral_point=None, device="cuda:0", dtype=torch.float32):
+    """Consistent mass rho sum_q w_q |detJ_q| N^T N (x) I3, [M,30,30]; default rule = degree-5 14-point (exact for
+    straight-sided tets).  Not in the reference -- parity unpinned."""
+    return _solid_M(_ops.C3D10, coords, elements, rho, integral_point, device, dtype)
 
 
 # ------------------------------------------------------------------------------------------- hexahedra
@@ -320,6 +399,64 @@ def compute_c3d8_K_matrix(coords, elements, E, nu, integral_point=None, single=T
     return _solid_K(_ops.C3D8, coords, elements, E, nu, integral_point, single, device, dtype)
 
 
+def compute_c3d8_element_stress(coords, elements, displacement, E, nu, integral_point=None, single=True, device="cuda:0",
+                                dtype=torch.float32):
+    """single=True: ([M,3,3],[M]); single=False: ([M,n_int,3,3],[M,n_int]) (element.py:1696-1752)."""
+    return _stress(_ops.C3D8, coords, elements, displacement, E, nu, integral_point, single, device, dtype, False)
+
+
+def compute_c3d8_M_matrix(coords, elements, rho, integral_point=None, device="cuda:0", dtype=torch.float32):
+    """Consistent mass [M,24,24], default 3x3x3 Gauss.  Not in the reference -- parity unpinned."""
+    return _solid_M(_ops.C3D8, coords, elements, rho, integral_point, device, dtype)
+
+
+# ---- C3D20: the reference's implementation (element.py:1852-2188) cannot run -- compute_c3d20_Jacobian raises on an
+# einsum subscript mismatch (:1980) and its derivative table is not the serendipity gradient (rows sum to (0.89, 0.88,
+# 2.44) at a test point, SURVEY a12).  These functions keep the reference's names and signatures and compute the standard
+# 20-node serendipity hex in the node order of the reference's own table and vtk loader (0-7 corners, 8-11 bottom,
+# 12-15 top, 16-19 vertical mid-edges).  Parity unpinned; validated by invariants (tests/).
+
+def c3d20_to_c3d4(c3d20_elements, device="cuda:0"):
+    """The reference's 24-tet table as written (element.py:1852-1896)."""
+    return _ops.to_c3d4(_ops.C3D20, c3d20_elements, device)
+
+
+def c3d20_integration_points(device="cuda:0", dtype=torch.float32):
+    """3x3x3 Gauss, xi slowest, +-sqrt(3/5) rounded to fp32 (q1) (element.py:1898-1919)."""
+    return _points_out(_ops.C3D20, device, dtype)
+
+
+def compute_c3d20_Jacobian(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """[M,3,3] (signature of element.py:1921-1984)."""
+    return _solid(_ops.C3D20, 0, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d20_shape_gradients(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """[M,20,3] (signature of element.py:1986-2044)."""
+    return _solid(_ops.C3D20, 1, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d20_B_matrix(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    """[M,6,60] (signature of element.py:2046-2074)."""
+    return _solid(_ops.C3D20, 2, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d20_element_stress(coords, elements, displacement, E, nu, integral_point=None, single=True, device="cuda:0",
+                                 dtype=torch.float32):
+    """single=True: ([M,3,3],[M]); single=False: ([M,n_int,3,3],[M,n_int]) (signature of element.py:2076-2138)."""
+    return _stress(_ops.C3D20, coords, elements, displacement, E, nu, integral_point, single, device, dtype, False)
+
+
+def compute_c3d20_K_matrix(coords, elements, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32):
+    """[M,60,60]; single=False -> [n_int,M,60,60] unweighted (signature of element.py:2140-2188)."""
+    return _solid_K(_ops.C3D20, coords, elements, E, nu, integral_point, single, device, dtype)
+
+
+def compute_c3d20_M_matrix(coords, elements, rho, integral_point=None, device="cuda:0", dtype=torch.float32):
+    """Consistent mass [M,60,60], default 3x3x3 Gauss.  Not in the reference -- parity unpinned."""
+    return _solid_M(_ops.C3D20, coords, elements, rho, integral_point, device, dtype)
+
+
 # ------------------------------------------------------------------------------------------- wedges
 
 def compute_wedge_volumes(coords, elements, device="cuda:0", dtype=torch.float32):
@@ -372,6 +509,53 @@ def compute_c3d6_K_matrix(coords, elements, E, nu, integral_point=None, single=T
         centroid = _pts(_ops.C3D6, torch.tensor([[1 / 3, 1 / 3, 0.0, 1.0]], dtype=torch.float64), dtype)
         return _ops.solid(_ops.C3D6, 5, coords, elements, centroid, E, nu, device, dtype)
     return _solid(_ops.C3D6, 3, coords, elements, integral_point, device, dtype, E, nu, single_point=False)
+
+
+def compute_c3d6_element_stress(coords, elements, displacement, E, nu, integral_point=None, single=True, device="cuda:0",
+                                dtype=torch.float32):
+    """single=True: 6-point weighted sums ([M,3,3],[M]); single=False: ([M,n_int,3,3],[M,n_int]) (element.py:2570-2629)."""
+    return _stress(_ops.C3D6, coords, elements, displacement, E, nu, integral_point, single, device, dtype, False)
+
+
+def compute_c3d6_M_matrix(coords, elements, rho, integral_point=None, device="cuda:0", dtype=torch.float32):
+    """Consistent mass [M,18,18], default degree-4 triangle rule x 3-point Gauss.  Not in the reference -- parity unpinned."""
+    return _solid_M(_ops.C3D6, coords, elements, rho, integral_point, device, dtype)
+
+
+# ---- C3D15: a header only in the reference (element.py:2679); its dispatchers name compute_c3d15_* functions that do not
+# exist (:377-426 -> NameError).  Standard 15-node wedge: 0-2 bottom, 3-5 top corners, 6-8 bottom mid-edges (0,1),(1,2),(2,0),
+# 9-11 top mid-edges, 12-14 vertical mid-edges; natural coordinates as C3D6.  Parity unpinned; validated by invariants.
+
+def c3d15_integration_points(device="cuda:0", dtype=torch.float32):
+    """9 points: 3-point triangle rule x 3-point Gauss, weights sum to 1 (the wedge's natural volume)."""
+    return _points_out(_ops.C3D15, device, dtype)
+
+
+def compute_c3d15_Jacobian(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    return _solid(_ops.C3D15, 0, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d15_shape_gradients(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    return _solid(_ops.C3D15, 1, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d15_B_matrix(coords, elements, integral_point, device="cuda:0", dtype=torch.float32):
+    return _solid(_ops.C3D15, 2, coords, elements, integral_point, device, dtype)
+
+
+def compute_c3d15_element_stress(coords, elements, displacement, E, nu, integral_point=None, single=True, device="cuda:0",
+                                 dtype=torch.float32):
+    return _stress(_ops.C3D15, coords, elements, displacement, E, nu, integral_point, single, device, dtype, False)
+
+
+def compute_c3d15_K_matrix(coords, elements, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32):
+    """[M,45,45]; single=False -> [n_int,M,45,45] unweighted."""
+    return _solid_K(_ops.C3D15, coords, elements, E, nu, integral_point, single, device, dtype)
+
+
+def compute_c3d15_M_matrix(coords, elements, rho, integral_point=None, device="cuda:0", dtype=torch.float32):
+    """Consistent mass [M,45,45].  Not in the reference -- parity unpinned."""
+    return _solid_M(_ops.C3D15, coords, elements, rho, integral_point, device, dtype)
 
 
 # ------------------------------------------------------------------------------------------- misc topology

@@ -42,7 +42,7 @@ int femb_version(void);
  * ------------------------------------------------------------------------------------------- */
 
 /* element kinds */
-enum { FEMB_C3D4 = 4, FEMB_C3D6 = 6, FEMB_C3D8 = 8, FEMB_C3D10 = 10, FEMB_S3 = 103, FEMB_S4 = 104 };
+enum { FEMB_C3D4 = 4, FEMB_C3D6 = 6, FEMB_C3D8 = 8, FEMB_C3D10 = 10, FEMB_C3D15 = 15, FEMB_C3D20 = 20, FEMB_S3 = 103, FEMB_S4 = 104 };
 
 /* compute_tetrahedral_volumes :514-541, compute_hexahedral_volumes :1248-1291, compute_wedge_volumes :2198-2232.
  * vol[M] = sum of |det|/6 over the reference's sub-tet table of `kind`. */
@@ -56,21 +56,43 @@ int femb_elem_volumes(int kind, const void* coords, int fp, const void* conn, in
 int femb_c3d4(int what, const void* coords, int fp, const void* conn, int ib, int64_t M, double E, double nu, void* out,
               int32_t* flag, femb_stream stream);
 
-/* Isoparametric solids C3D10/C3D8/C3D6:
+/* Isoparametric solids C3D10/C3D8/C3D6/C3D20/C3D15:
  *   compute_c3d10_{Jacobian,shape_gradients,B_matrix,K_matrix} :1026-1125,:1191-1239
  *   compute_c3d8_*  :1601-1694,:1754-1803     compute_c3d6_* :2482-2568,:2631-2676
+ *   compute_c3d20_* :1921-2188 (the reference's Jacobian raises and its derivative table is wrong; this is the
+ *   standard 20-node serendipity hex in VTK/Abaqus node order) and C3D15 (dispatch targets :377-426 are undefined
+ *   in the reference; standard 15-node wedge) -- both "parity unpinned", validated by invariants.
  * `pts_host` = [nq,4] doubles (xi,eta,zeta,w) on the HOST (the caller resolves defaults; the library ships
  * the reference's rules through femb_default_points).
  * what = 0: J [M,3,3] at pts[0]; 1: gradients [M,nen,3] at pts[0]; 2: B [M,6,3nen] at pts[0];
  *        3: K [M,nd,nd] = sum_q w_q detJ_q B^T D B (signed detJ);
  *        4: per-point K [nq,M,nd,nd] = detJ_q B^T D B, unweighted (single=False);
- *        5: (C3D6 single=True) K = B^T D B at pts[0] times the 3-tet |volume|. */
+ *        5: (C3D6 single=True) K = B^T D B at pts[0] times the 3-tet |volume|;
+ *        6: consistent mass [M,nd,nd] = rho sum_q w_q |detJ_q| N^T N (x) I3 with rho passed in `E` (the reference only
+ *           calls an undefined compute_c3d4_M_matrix, solver_example.ipynb cell 13 -- parity unpinned). */
 int femb_solid(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* pts_host,
                int nq, double E, double nu, void* out, femb_stream stream);
 
 /* c3d10_integration_points :995-1024, c3d8_integration_points :1583-1599, c3d6_integration_points :2448-2480,
- * s4_integration_points shell.py:651-672.  Fills pts_host[nq*4] (shells: xi,eta,0,w), returns nq (or -1). */
+ * c3d20_integration_points :1898-1919, s4_integration_points shell.py:651-672; C3D15: 3-point triangle x 3-point Gauss
+ * (not in the reference).  Fills pts_host[nq*4] (shells: xi,eta,0,w), returns nq (or -1). */
 int femb_default_points(int kind, double* pts_host);
+
+/* Rules used by the consistent mass (what = 6) when the caller passes none: C3D10 degree-5 14-point, C3D8/C3D20
+ * 3x3x3 Gauss, C3D6/C3D15 degree-4 triangle x 3-point Gauss.  Fills pts_host[nq*4], returns nq <= 27 (or -1). */
+int femb_mass_points(int kind, double* pts_host);
+
+/* Host-only: the natural-coordinate tables the solid kernels consume, N_host[nq,nen] and dN_host[nq,nen,3] at the
+ * points pts_host[nq,4] (the host part of compute_*_Jacobian's dN_dnatural, e.g. element.py:1042-1055). */
+int femb_shape_tables(int kind, const double* pts_host, int nq, double* N_host, double* dN_host);
+
+/* Stress recovery: compute_c3d4_element_stress :905-939, compute_c3d10_element_stress :1127-1189,
+ * compute_c3d8_element_stress :1696-1752, compute_c3d6_element_stress :2570-2629 (+ C3D20 / C3D15).
+ * disp[N,3]; single != 0: stress[M,3,3] = sum_q w_q sigma_q and vm[M] = sum_q w_q vonMises(sigma_q);
+ * single == 0: stress[nq,M,3,3], vm[nq,M].  C3D4 takes one point with weight 1. */
+int femb_solid_stress(int kind, const void* coords, int fp, const void* conn, int ib, int64_t M, const void* disp,
+                      const double* pts_host, int nq, double E, double nu, int single, void* stress, void* vm,
+                      femb_stream stream);
 
 /* Shell elements (solver/shell.py): compute_s3_* :297-453, compute_s4_* :597-861.
  * what = 0: unit [M,3,3]; 1: J [M,2,2]; 2: gradients [M,nen,2]; 3: B [M,6,6nen]; 4: K [M,6nen,6nen];
@@ -78,8 +100,12 @@ int femb_default_points(int kind, double* pts_host);
 int femb_shell(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* pts_host,
                int nq, const double* D6_host, void* out, femb_stream stream);
 
-/* Fixed-table connectivity expansion: c3d10_to_c3d4 :963-993, c3d8_to_c3d4 :1555-1581, c3d6_to_c3d4 :2424-2446.
- * out[k*M,4] int64, k = 8/6/3. */
+/* compute_stress_tensor :308-330 (what = 0: Voigt [M,6] xx,yy,zz,xy,yz,zx -> [M,3,3]) and compute_von_mises_stress
+ * :332-353 (what = 1: [M,3,3] -> [M]). */
+int femb_stress_helper(int what, const void* in, int fp, int64_t M, void* out, femb_stream stream);
+
+/* Fixed-table connectivity expansion: c3d10_to_c3d4 :963-993, c3d8_to_c3d4 :1555-1581, c3d6_to_c3d4 :2424-2446,
+ * c3d20_to_c3d4 :1852-1896.  out[k*M,4] int64, k = 8/6/3/24. */
 int femb_to_c3d4(int kind, const void* conn, int ib, int64_t M, int64_t* out, femb_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -145,6 +171,10 @@ int femb_spmv(int64_t n_rows, int64_t nnz, const int32_t* crow, const int32_t* c
  * compute_shell_nodal_forces shell.py:58-102 when unit != NULL (ndof = 6, rotates into/out of the element frame). */
 int femb_ebe_apply(femb_csr_plan* plan, int ndof, const void* Ke, const void* u, const void* unit, int fp, void* y,
                    femb_stream stream);
+
+/* compute_node_vm_stress element.py:466-504: out[N] = mean over the elements containing the node of elem_values[M]
+ * (0 for nodes without elements); sums run in ascending element order (deterministic; the reference uses index_add). */
+int femb_node_average(femb_csr_plan* plan, const void* elem_values, int fp, void* out, femb_stream stream);
 
 typedef struct femb_cg_result {
   int32_t iterations; /* the count the reference prints: i+1 at exit, max_iter when not converged */

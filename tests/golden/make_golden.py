@@ -302,6 +302,13 @@ def gen_stress():
     save("stress", **{k: npy(v) for k, v in o.items()})
 
 
+def gen_quadratic():
+    """The two C3D20 functions of the reference that run: the 27-point rule and the 24-tet table."""
+    p, w = R.c3d20_integration_points(**KW)
+    h20 = torch.arange(40, dtype=torch.int64).reshape(2, 20) * 3 + 1
+    save("quadratic", p20=npy(p), w20=npy(w), h20=npy(h20), h20_tets=npy(R.c3d20_to_c3d4(h20, device="cpu")))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_units()
@@ -311,3 +318,4 @@ if __name__ == "__main__":
     gen_shells()
     gen_solve()
     gen_stress()
+    gen_quadratic()

@@ -70,3 +70,34 @@ def test_mirror_api_names():
     assert sig.parameters["tol"].default == 1e-10 and sig.parameters["eps"].default == 1e-30
     sig = inspect.signature(element.compute_K_matrix)
     assert list(sig.parameters) == ["coords", "elements", "element_type", "E", "nu", "integral_point", "single", "device", "dtype"]
+
+
+def test_host_tables_match_oracle():
+    """Host-side tables of the library (no GPU needed): default / mass rules and the natural-coordinate shape tables the
+    solid kernels consume, against the oracle's independent restatement."""
+    import numpy as np
+    from femb200 import _lib
+    from oracle import fem_oracle as O
+    kinds = {"c3d10": 10, "c3d8": 8, "c3d6": 6, "c3d20": 20, "c3d15": 15}
+    buf = (ctypes.c_double * 256)()
+    for name, k in kinds.items():
+        n = _lib.lib.femb_default_points(k, buf)
+        p, w = O._POINTS[name]()
+        got = np.array(buf[:4 * n]).reshape(n, 4)
+        assert n == len(w) and np.array_equal(got[:, :3], p) and np.abs(got[:, 3] - w).max() < 1e-16, name
+        n = _lib.lib.femb_mass_points(k, buf)
+        p, w = O.mass_points(name)
+        got = np.array(buf[:4 * n]).reshape(n, 4)
+        assert n == len(w) and np.abs(got[:, :3] - p).max() < 1e-16 and np.abs(got[:, 3] - w).max() < 1e-17, name
+    rng = np.random.default_rng(5)
+    for name, k in kinds.items():
+        nq = 7
+        pts = rng.uniform(-0.7, 0.7, (nq, 4)) if name in ("c3d8", "c3d20") else np.abs(rng.uniform(0.05, 0.3, (nq, 4)))
+        Nh = (ctypes.c_double * (nq * k))()
+        dNh = (ctypes.c_double * (nq * k * 3))()
+        rc = _lib.lib.femb_shape_tables(k, pts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), nq, Nh, dNh)
+        assert rc == 0
+        Ng, dNg = np.array(Nh[:]).reshape(nq, k), np.array(dNh[:]).reshape(nq, k, 3)
+        for q in range(nq):
+            assert np.abs(O._N[name](pts[q, :3]) - Ng[q]).max() < 1e-14, name
+            assert np.abs(O._DN[name][0](pts[q, :3]) - dNg[q]).max() < 1e-14, name

@@ -583,3 +583,153 @@ def test_mixed_family_topology(api, O):
     of, ox = O.hex_surface_faces(N(h))
     same(f, of); same(x, ox)
     same(el.identify_hexahedral_shared_faces(h20, device=DEV), O.hex_shared_faces(N(h)))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Quadratic hex / wedge, consistent mass, stress recovery (BASELINE config 3)
+# --------------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind,gen,nen", [("c3d20", "hex20_cube", 20), ("c3d15", "wedge15_cube", 15)])
+def test_quadratic_solids(api, O, kind, gen, nen):
+    """C3D20 / C3D15 have no runnable reference (parity unpinned): CUDA against the invariant-checked oracle."""
+    el = api[0]
+    from femb200 import meshgen
+    c, e = getattr(meshgen, gen)(3, jitter=0.2)
+    cn, en = c.numpy(), e.numpy()
+    ip = torch.tensor([0.21, 0.13, -0.37], dtype=torch.float64)
+    fn = lambda what: getattr(el, f"compute_{kind}_{what}")
+    close(fn("Jacobian")(c, e, ip, **KW), O.jacobian(kind, cn, en, ip.numpy()))
+    close(fn("shape_gradients")(c, e, ip, **KW), O.shape_gradients(kind, cn, en, ip.numpy()))
+    close(fn("B_matrix")(c, e, ip, **KW), O.B_matrix(kind, cn, en, ip.numpy()))
+    Kref = O.solid_K(kind, cn, en, E, NU)
+    K = fn("K_matrix")(c, e, E, NU, **KW)
+    assert K.shape == (e.shape[0], 3 * nen, 3 * nen)
+    close(K, Kref)
+    close(el.compute_K_matrix(c, e, kind.upper(), E, NU, **KW), Kref)
+    close(fn("K_matrix")(c, e[:3], E, NU, single=False, **KW), O.solid_K(kind, cn, en[:3], E, NU, single=False))
+    close(fn("K_matrix")(c, e.to(torch.int32), E, NU, **KW), Kref)
+    pts = torch.tensor([[0.1, 0.2, -0.3, 0.7], [0.3, 0.1, 0.5, 0.3]], dtype=torch.float64)
+    close(fn("K_matrix")(c, e, E, NU, integral_point=pts, **KW), O.solid_K(kind, cn, en, E, NU, points=pts.numpy()))
+    p, w = getattr(el, f"{kind}_integration_points")(**KW)
+    pr, wr = O._POINTS[kind]()
+    close(p, pr, 0); close(w, wr, 1e-16)
+    assert el.integral_points(kind, device=DEV)[0].dtype == torch.float32      # dispatcher drops dtype (q2)
+    k32 = fn("K_matrix")(c, e, E, NU, device=DEV)
+    assert k32.dtype == torch.float32
+    close(k32.double(), Kref, 5e-5)
+    # invariants on the device result itself: symmetry, rigid-body null space
+    Kd = N(K)
+    assert np.abs(Kd - Kd.transpose(0, 2, 1)).max() <= 1e-14 * np.abs(Kd).max()
+    r = np.zeros((cn.shape[0], 3)); r[:, 0], r[:, 1] = -cn[:, 1], cn[:, 0]
+    assert np.abs(np.einsum("mij,mj->mi", Kd, r[en].reshape(en.shape[0], -1))).max() < 1e-12 * np.abs(Kd).max()
+
+
+def test_c3d20_reference_tables(api):
+    el = api[0]
+    g = load_golden("quadratic")
+    same(el.c3d20_to_c3d4(T(g["h20"]), device=DEV), g["h20_tets"])
+    p, w = el.c3d20_integration_points(**KW)
+    close(p, g["p20"], 0); close(w, g["w20"], 1e-16)
+    f, x = el.compute_hexahedral_surface_faces_with_extra_node(T(g["h20"]), device=DEV)    # corner columns of [M,20]
+    assert f.shape == (12, 4)
+
+
+@pytest.mark.parametrize("kind,gen", [("c3d10", "tet10_cube"), ("c3d8", "hex_cube"), ("c3d6", "wedge_cube"), ("c3d20", "hex20_cube"),
+                                      ("c3d15", "wedge15_cube")])
+def test_consistent_mass(api, O, kind, gen):
+    el = api[0]
+    from femb200 import meshgen
+    c, e = getattr(meshgen, gen)(3, jitter=0.15)
+    Mref = O.solid_mass(kind, c.numpy(), e.numpy(), 2.5)
+    Mm = getattr(el, f"compute_{kind}_M_matrix")(c, e, 2.5, **KW)
+    close(Mm, Mref)
+    close(el.compute_M_matrix(c, e, kind, 2.5, **KW), Mref)
+    pts = torch.tensor([[0.1, 0.2, -0.3, 0.7], [0.3, 0.1, 0.5, 0.3]], dtype=torch.float64)
+    close(getattr(el, f"compute_{kind}_M_matrix")(c, e, 2.5, integral_point=pts, **KW),
+          O.solid_mass(kind, c.numpy(), e.numpy(), 2.5, points=pts.numpy()))
+    Md = N(Mm)
+    assert np.array_equal(Md, Md.transpose(0, 2, 1))           # mirrored stores: exactly symmetric
+    # assembled: total mass = rho * volume (the cube), per direction
+    A = el.assemble_csr(Mm, e, c.shape[0], device=DEV)
+    ones = torch.zeros(c.shape[0] * 3, dtype=torch.float64, device=DEV); ones[0::3] = 1
+    from femb200 import ops
+    y = ops.spmv(A.crow_indices(), A.col_indices(), A.values(), ones)
+    assert abs(float(y.sum()) - 2.5) < 1e-12
+
+
+def test_stress_recovery(api, O):
+    """Against the reference's own outputs (tests/golden/stress.npz)."""
+    el = api[0]
+    g = load_golden("stress")
+    c, t, u = T(g["c"]), T(g["t"]), T(g["u"])
+    s, v = el.compute_c3d4_element_stress(c, t, u, E, NU, **KW)
+    close(s, g["s4"]); close(v, g["v4"])
+    s2, v2 = el.compute_element_stress(c, t, u, E, NU, "C3D4", **KW)
+    close(s2, g["s4"])
+    close(el.compute_node_vm_stress(c, t, v, **KW), g["node_vm4"])
+    close(el.compute_von_mises_stress(s), g["v4"])
+    voigt = s.reshape(-1, 9)[:, [0, 4, 8, 1, 5, 2]].contiguous()
+    close(el.compute_stress_tensor(voigt), g["s4"])
+    c10, e10, u10 = T(g["c10"]), T(g["e10"]), T(g["u10"])
+    s, v = el.compute_c3d10_element_stress(c10, e10, u10, E, NU, **KW)
+    close(s, g["s10"]); close(v, g["v10"])
+    s, v = el.compute_c3d10_element_stress(c10, e10[:6], u10, E, NU, single=False, **KW)
+    close(s, g["s10m"]); close(v, g["v10m"])
+    ch, uh = T(g["ch"]), T(g["uh"])
+    for kind, conn in (("c3d8", T(g["h"])), ("c3d6", T(g["w6"]))):
+        tag = kind[-1]
+        fn = getattr(el, f"compute_{kind}_element_stress")
+        s, v = fn(ch, conn, uh, E, NU, **KW)
+        close(s, g["s" + tag]); close(v, g["v" + tag])
+        s, v = fn(ch, conn, uh, E, NU, single=False, **KW)
+        close(s, g["s" + tag + "m"]); close(v, g["v" + tag + "m"])
+        s, v = el.compute_element_stress(ch, conn, uh, E, NU, kind, **KW)
+        close(s, g["s" + tag])
+    # quadratic hex / wedge: oracle only (unpinned); float32 default dtype
+    from femb200 import meshgen
+    for kind, gen in (("c3d20", "hex20_cube"), ("c3d15", "wedge15_cube")):
+        cq, eq = getattr(meshgen, gen)(2, jitter=0.2)
+        uq = torch.randn(cq.shape[0], 3, dtype=torch.float64, generator=torch.Generator().manual_seed(4)) * 0.01
+        fn = getattr(el, f"compute_{kind}_element_stress")
+        for single in (True, False):
+            s, v = fn(cq, eq, uq, E, NU, single=single, **KW)
+            sr, vr = O.solid_element_stress(kind, cq.numpy(), eq.numpy(), uq.numpy(), E, NU, single=single)
+            close(s, sr); close(v, vr)
+        assert fn(cq, eq, uq, E, NU, device=DEV)[0].dtype == torch.float32
+    # isolated nodes average to 0
+    iso = el.compute_node_vm_stress(torch.zeros(c.shape[0] + 3, 3), t, T(g["v4"]), **KW)
+    assert iso.shape[0] == c.shape[0] + 3 and float(iso[-3:].abs().max()) == 0.0
+
+
+def test_mixed_quadratic_assembly(api, O):
+    """BASELINE config 3 in small: hex20 | wedge15 | tet10 slabs in one numbering; stiffness + mass per type -> CSR, summed operator
+    against the oracle's COO -> CSR; surface extraction of the whole box from corner columns."""
+    el = api[0]
+    from femb200 import meshgen, ops
+    c, parts = meshgen.mixed_box_quadratic(3, jitter=0.1)
+    Nn = c.shape[0]
+    x = torch.randn(Nn * 3, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    yK = np.zeros(Nn * 3); yM = np.zeros(Nn * 3)
+    dK = torch.zeros(Nn * 3, dtype=torch.float64, device=DEV); dM = torch.zeros_like(dK)
+    for kind, conn in parts.items():
+        K = el.compute_K_matrix(c, conn, kind, E, NU, **KW)
+        Mm = el.compute_M_matrix(c, conn, kind, 1.5, **KW)
+        A, B = el.assemble_csr(K, conn, Nn, device=DEV), el.assemble_csr(Mm, conn, Nn, device=DEV)
+        Kr, Mr = O.solid_K(kind, c.numpy(), conn.numpy(), E, NU), O.solid_mass(kind, c.numpy(), conn.numpy(), 1.5)
+        crow, col, val, _ = O.assemble_csr(Kr, conn.numpy(), 3, Nn)
+        same(A.crow_indices(), crow); same(A.col_indices(), col); close(A.values(), val)
+        crow, col, valm, _ = O.assemble_csr(Mr, conn.numpy(), 3, Nn)
+        same(B.col_indices(), col); close(B.values(), valm)
+        dK += ops.spmv(A.crow_indices(), A.col_indices(), A.values(), x.to(DEV))
+        dM += ops.spmv(B.crow_indices(), B.col_indices(), B.values(), x.to(DEV))
+        yK += O.csr_matvec(crow, col, val, x.numpy()); yM += O.csr_matvec(crow, col, valm, x.numpy())
+    close(dK, yK, 1e-12); close(dM, yM, 1e-12)
+    # surface of the box: every slab contributes its outer faces; interior slab interfaces are shared between different
+    # element types and so stay "surface" per type, exactly like the reference's per-type routines
+    f20, _ = el.compute_hexahedral_surface_faces_with_extra_node(parts["c3d20"], device=DEV)
+    same(f20, O.hex_surface_faces(parts["c3d20"].numpy()[:, :8])[0])
+    (q15, t15), _ = el.compute_wedge_surface_faces_with_extra_node(parts["c3d15"], device=DEV)
+    rq, rt = O.wedge_surface_faces(parts["c3d15"].numpy()[:, :6])[0]
+    same(q15, rq); same(t15, rt)
+    f10, _ = el.compute_tetrahedral_surface_faces_with_fourth_node(parts["c3d10"], device=DEV)
+    same(f10, O.tet_surface_faces(parts["c3d10"].numpy()[:, :4])[0])

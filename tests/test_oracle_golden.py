@@ -235,3 +235,115 @@ def test_stress_recovery():
         close(s, g["s" + tag]); close(v, g["v" + tag])
         s, v = O.solid_element_stress(kind, cc, conn, g["uh"], E, NU, single=False)
         close(s, g["s" + tag + "m"]); close(v, g["v" + tag + "m"])
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# C3D20 / C3D15 / consistent mass: not computable with the reference -- the oracle is pinned where
+# the reference runs (27-point rule, 24-tet table) and otherwise held to invariants.
+# --------------------------------------------------------------------------------------------------------------------
+
+def _rigid_modes(c):
+    n = c.shape[0]
+    R = np.zeros((6, n, 3))
+    R[0, :, 0] = R[1, :, 1] = R[2, :, 2] = 1
+    R[3, :, 0], R[3, :, 1] = -c[:, 1], c[:, 0]
+    R[4, :, 1], R[4, :, 2] = -c[:, 2], c[:, 1]
+    R[5, :, 0], R[5, :, 2] = c[:, 2], -c[:, 0]
+    return R
+
+
+def test_c3d20_reference_pins():
+    g = load_golden("quadratic")
+    p, w = O.c3d20_points()
+    assert np.array_equal(p, g["p20"]) and np.abs(w - g["w20"]).max() < 1e-16
+    assert np.array_equal(O.to_c3d4(g["h20"]), g["h20_tets"])
+
+
+@pytest.mark.parametrize("kind", ["c3d20", "c3d15"])
+def test_quadratic_shape_functions(kind):
+    shape = {"c3d20": O.c3d20_shape, "c3d15": O.c3d15_shape}[kind]
+    nodes = O.HEX20_NAT if kind == "c3d20" else np.array(
+        [(0, 0, -1), (1, 0, -1), (0, 1, -1), (0, 0, 1), (1, 0, 1), (0, 1, 1), (.5, 0, -1), (.5, .5, -1), (0, .5, -1), (.5, 0, 1),
+         (.5, .5, 1), (0, .5, 1), (0, 0, 0), (1, 0, 0), (0, 1, 0)], float)
+    for a, na in enumerate(nodes):                      # Kronecker property
+        N, _ = shape(na)
+        assert abs(N[a] - 1) < 1e-14 and np.abs(np.delete(N, a)).max() < 1e-14
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        p = rng.uniform(-0.6, 0.6, 3) if kind == "c3d20" else np.array([0.25, 0.3, 0.0]) + rng.uniform(-0.2, 0.2, 3)
+        N, dN = shape(p)
+        assert abs(N.sum() - 1) < 1e-14 and np.abs(dN.sum(axis=0)).max() < 1e-14
+        h = 1e-6
+        fd = np.stack([(shape(p + h * np.eye(3)[d])[0] - shape(p - h * np.eye(3)[d])[0]) / (2 * h) for d in range(3)], axis=1)
+        assert np.abs(fd - dN).max() < 1e-9
+        # isoparametric completeness: sum_a dN_a (x) x_a = I for the natural node coordinates themselves
+        assert np.abs(dN.T @ nodes - np.eye(3)).max() < 1e-13
+
+
+@pytest.mark.parametrize("kind,gen", [("c3d20", "hex20_cube"), ("c3d15", "wedge15_cube")])
+def test_quadratic_stiffness_invariants(kind, gen):
+    from femb200 import meshgen
+    c, e = getattr(meshgen, gen)(2, jitter=0.2)
+    c, e = c.numpy(), e.numpy()
+    K = O.solid_K(kind, c, e, E, NU)
+    scale = np.abs(K).max()
+    assert np.abs(K - K.transpose(0, 2, 1)).max() < 1e-14 * scale
+    for r in _rigid_modes(c):
+        assert np.abs(np.einsum("mij,mj->mi", K, r[e].reshape(e.shape[0], -1))).max() < 1e-13 * scale
+    ev = np.linalg.eigvalsh(K[0])
+    assert (ev > -1e-12 * scale).all() and (ev > 1e-8 * scale).sum() == K.shape[1] - 6     # exactly six zero-energy modes
+    p, w = O._POINTS[kind]()
+    vol = sum(w[q] * np.linalg.det(O.jacobian(kind, c, e, p[q])) for q in range(len(w)))
+    assert abs(vol.sum() - 1.0) < 1e-12
+    # patch test: a linear displacement field leaves no residual force on interior nodes
+    A = np.array([[0.01, 0.02, -0.01], [0.0, 0.03, 0.01], [0.02, -0.01, 0.015]])
+    u = c @ A.T
+    f = np.zeros_like(c)
+    fe = np.einsum("mij,mj->mi", K, u[e].reshape(e.shape[0], -1)).reshape(-1, 3)
+    np.add.at(f, e.reshape(-1), fe)
+    inner = ((c > 1e-9) & (c < 1 - 1e-9)).all(axis=1)
+    assert inner.any() and np.abs(f[inner]).max() < 1e-13 and np.abs(f).max() > 1e-4
+    # constant-strain stress: the recovered stress equals D eps everywhere
+    eps = 0.5 * (A + A.T)
+    voigt = np.array([eps[0, 0], eps[1, 1], eps[2, 2], 2 * eps[0, 1], 2 * eps[1, 2], 2 * eps[0, 2]])
+    S, _ = O.solid_element_stress(kind, c, e, u, E, NU, single=False)
+    close(S, np.broadcast_to(O.stress_tensor((O.elasticity_matrix(E, NU) @ voigt)[None])[0], S.shape), 1e-12)
+
+
+@pytest.mark.parametrize("kind,gen", [("c3d10", "tet10_cube"), ("c3d8", "hex_cube"), ("c3d6", "wedge_cube"), ("c3d20", "hex20_cube"),
+                                      ("c3d15", "wedge15_cube")])
+def test_consistent_mass_invariants(kind, gen):
+    from femb200 import meshgen
+    c, e = getattr(meshgen, gen)(2, jitter=0.15)
+    c, e = c.numpy(), e.numpy()
+    rho = 2.5
+    Mm = O.solid_mass(kind, c, e, rho)
+    assert np.abs(Mm - Mm.transpose(0, 2, 1)).max() < 1e-17 + 1e-15 * np.abs(Mm).max()
+    assert np.linalg.eigvalsh(Mm[0]).min() > 0
+    pm, wm = O.mass_points(kind)
+    vol = sum(wm[q] * np.abs(np.linalg.det(O.jacobian(kind, c, e, pm[q]))) for q in range(len(wm)))
+    assert abs(vol.sum() - 1.0) < 1e-12
+    for d in range(3):
+        close(Mm[:, d::3, d::3].sum(axis=(1, 2)), rho * vol, 1e-13)
+    assert np.abs(Mm[:, 0::3, 1::3]).max() == 0
+    if kind == "c3d10":   # straight-sided P2 tets: the degree-5 rule is exact -> closed form (V/420)[6 on corners, ...]
+        c0, e0 = meshgen.tet10_cube(1)
+        M0 = O.solid_mass(kind, c0.numpy(), e0.numpy(), 1.0)[0, 0::3, 0::3]
+        V = 1.0 / 6
+        assert abs(M0[0, 0] - 6 * V / 420) < 1e-15 and abs(M0[0, 1] - V / 420) < 1e-15 and abs(M0[4, 4] - 32 * V / 420) < 1e-15
+
+
+def test_mass_rules_are_exact():
+    from math import factorial
+    p, w = O.mass_points("c3d10")
+    for i in range(6):
+        for j in range(6 - i):
+            for k in range(6 - i - j):
+                exact = factorial(i) * factorial(j) * factorial(k) / factorial(i + j + k + 3)
+                assert abs((w * p[:, 0] ** i * p[:, 1] ** j * p[:, 2] ** k).sum() - exact) < 1e-16
+    p, w = O.mass_points("c3d15")
+    for i in range(5):
+        for j in range(5 - i):
+            for k in range(6):
+                exact = factorial(i) * factorial(j) / factorial(i + j + 2) * (0 if k % 2 else 2 / (k + 1))
+                assert abs((w * p[:, 0] ** i * p[:, 1] ** j * p[:, 2] ** k).sum() - exact) < 1e-15
