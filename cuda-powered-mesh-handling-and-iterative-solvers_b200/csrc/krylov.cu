@@ -117,6 +117,110 @@ __global__ void __launch_bounds__(TMA_THREADS) spmv_tma_kernel(long long n, long
   if (FUSED) cg_k1_epilogue_n<TMA_THREADS>(dot, partial, st, eps, guards & 1);
 }
 
+// block-CSR (3x3) variant for 3-dof operators: n = 3 nb scalar rows, crow/col are the node-level pattern, val the blocks
+template <int LR, bool FUSED>
+__global__ void __launch_bounds__(TMA_THREADS) spmv_bsr3_tma_kernel(long long nb, long long nnzb, const int* __restrict__ brow,
+                                                                    const int* __restrict__ bcol, const double* __restrict__ bval,
+                                                                    const double* __restrict__ x, double* __restrict__ y,
+                                                                    const unsigned char* __restrict__ mask, double* __restrict__ partial,
+                                                                    CGState* __restrict__ st, double eps, int guards) {
+  if (st && st->stop) return;
+  const double dot = spmv_bsr3_tma_rows<LR, true>(nb, nnzb, brow, bcol, bval, x, y, mask, (guards & 2) != 0, FUSED);
+  if (FUSED) cg_k1_epilogue_n<TMA_THREADS>(dot, partial, st, eps, guards & 1);
+}
+
+// Warp-per-block-row variant (default for 3x3 blocks).  ncu on the 2 M-tet P2 operator showed the TMA row-tile kernels
+// (scalar and block) latency-bound at 16 resident warps per SM (long-scoreboard 15 per issue, 32-35 % of DRAM peak): with
+// ~28 blocks per row a tile holds only 8 rows, so the x gathers of one tile are all that is in flight between two CTA
+// barriers, while the plain lanes-per-row kernel at 64 warps per SM reached 64 %.  Here every warp is independent and lean:
+// lanes 0..26 cover three consecutive blocks per step (lane = 9*block + position, fixed for the whole kernel, so no index
+// arithmetic in the loop), the 216 bytes of a step are one contiguous coalesced read, every lane keeps ONE accumulator
+// (its position's row of the block), the three x gathers of a block land in one sector, and four shuffles finish a row.
+constexpr int BSRV_THREADS = 256;
+template <bool FUSED, int U>
+__global__ void __launch_bounds__(BSRV_THREADS) spmv_bsr3_vec_kernel(long long nb, long long nnzb, const int* __restrict__ brow,
+                                                                     const int* __restrict__ bcol, const double* __restrict__ bval,
+                                                                     const double* __restrict__ x, double* __restrict__ y,
+                                                                     const unsigned char* __restrict__ mask, double* __restrict__ partial,
+                                                                     CGState* __restrict__ st, double eps, int guards) {
+  if (st && st->stop) return;
+  const bool accumulate = (guards & 2) != 0;
+  guards &= 1;
+  const int lane = threadIdx.x & 31;
+  const int boff = lane / 9, pos = lane - 9 * boff, cx = pos % 3;  // lanes 27..31: boff = 3 -> idle
+  const bool active = lane < 27;
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0;
+  for (long long r = gw; r < nb; r += nw) {
+    const int a = __ldg(brow + r), e = __ldg(brow + r + 1);
+    double acc = 0.0;
+    if (active) {
+      int b = a + boff;
+      for (; b + 3 * (U - 1) < e; b += 3 * U) {
+        double v[U], xv[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          v[q] = ld_stream(bval + (size_t)(b + 3 * q) * 9 + pos);
+          xv[q] = __ldg(x + 3ll * ld_stream(bcol + b + 3 * q) + cx);
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) acc += v[q] * xv[q];
+      }
+      for (; b < e; b += 3) acc += ld_stream(bval + (size_t)b * 9 + pos) * __ldg(x + 3ll * ld_stream(bcol + b) + cx);
+    }
+    // lanes p, p+9, p+18 hold the same position; then positions 3i..3i+2 form row i of the block
+    acc += __shfl_down_sync(0xffffffffu, acc, 9) + __shfl_down_sync(0xffffffffu, acc, 18);
+    acc += __shfl_down_sync(0xffffffffu, acc, 1) + __shfl_down_sync(0xffffffffu, acc, 2);
+    if (lane == 0 || lane == 3 || lane == 6) {
+      const long long i = 3 * r + lane / 3;
+      double sv = acc;
+      if (accumulate) sv += y[i];
+      if (FUSED) {
+        if (mask && !mask[i]) sv = 0.0;
+        dot += sv * __ldg(x + i);
+      }
+      y[i] = sv;
+    }
+  }
+  if (FUSED) cg_k1_epilogue_n<BSRV_THREADS>(dot, partial, st, eps, guards);
+}
+
+// CSR values of a 3-dof operator (rows 3i..3i+2 of node i stored one after the other) <-> 3x3 blocks: a permutation inside
+// each node's 9*len segment.  One warp per node row.
+template <bool TO_BSR>
+__global__ void csr_bsr3_permute_kernel(long long nb, const int* __restrict__ brow, const double* __restrict__ in, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = w0; i < nb; i += nw) {
+    const long long a = brow[i];
+    const int len = brow[i + 1] - (int)a, row = 3 * len;
+    for (int t = lane; t < 9 * len; t += 32) {
+      const int al = t / row, rem = t - al * row, slot = rem / 3, be = rem - 3 * slot;
+      const long long ci = 9 * a + t, bi = 9 * (a + slot) + 3 * al + be;
+      if (TO_BSR) out[bi] = in[ci];
+      else out[ci] = in[bi];
+    }
+  }
+}
+
+__global__ void bsr3_jacobi_kernel(long long nb, const int* __restrict__ brow, const int* __restrict__ bcol, const double* __restrict__ bval,
+                                   const unsigned char* __restrict__ mask, double* __restrict__ minv) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nb; r += (long long)gridDim.x * blockDim.x) {
+    int lo = brow[r], hi = brow[r + 1];
+    const int end = hi;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (bcol[mid] < r) lo = mid + 1;
+      else hi = mid;
+    }
+    const bool found = lo < end && bcol[lo] == r;
+    for (int i = 0; i < 3; ++i) {
+      const double d = found ? bval[(size_t)lo * 9 + 4 * i] : 0.0;
+      minv[3 * r + i] = (d != 0.0 && (!mask || mask[3 * r + i])) ? 1.0 / d : 0.0;
+    }
+  }
+}
+
 constexpr int VEC_THREADS = 256;
 
 // k2: u += alpha p ; r -= alpha Ap ; partial r.r or r.(minv r) ; last CTA: convergence / beta / bookkeeping
@@ -231,10 +335,17 @@ __global__ void jacobi_kernel(long long n, const int* __restrict__ crow, const i
 
 // Kernel selection, encoded in one int: 100+LR = TMA-pipelined (default), LR = LDG-streaming (FEMB_SPMV_STREAM=1),
 // -L = legacy L-lanes-per-row vector kernel (FEMB_SPMV_VECTOR=1).  The env switches exist for A/B profiling.
-static int pick_lanes(long long n, long long nnz) {
+static int pick_lanes(long long n, long long nnz, int block = 1) {
+  static const bool bsr_tma = getenv("FEMB_BSR_TMA") != nullptr;
+  static const int bsrv_unroll = getenv("FEMB_BSRV_UNROLL") ? atoi(getenv("FEMB_BSRV_UNROLL")) : 4;
+  if (block == 3) return bsr_tma ? 200 + bsr_pick_lr(n / 3, nnz) : (bsrv_unroll == 2 ? 301 : 300);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
   static const bool force_vector = getenv("FEMB_SPMV_VECTOR") != nullptr, force_stream = getenv("FEMB_SPMV_STREAM") != nullptr;
   if (force_vector) return -(avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 24 ? 8 : avg <= 48 ? 16 : 32);
+  // long rows (P2 / quadratic-hex elasticity kept in scalar CSR, 6-dof shell operators): a warp per row keeps 64 warps per
+  // SM busy on independent gathers and measured 0.64 of the HBM peak on the 2 M-tet P2 operator against 0.47 for row tiles
+  static const bool force_tma = getenv("FEMB_SPMV_TMA") != nullptr;
+  if (!force_stream && !force_tma && avg >= 64.0) return -32;
   if (!force_stream) return 100 + tma_pick_lr(n, nnz);
   for (int lr = 1; lr <= 32; lr *= 2)
     if ((SPMV_THREADS / lr) * avg * 1.25 <= STREAM_CAP) return lr;
@@ -252,7 +363,20 @@ static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const 
     cudaFuncSetAttribute(spmv_tma_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);                 \
     spmv_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, TMA_SMEM, s>>>(n, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); \
   }
+#define FEMB_BSR(LRV)                                                                                                              \
+  {                                                                                                                                \
+    cudaFuncSetAttribute(spmv_bsr3_tma_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSR_SMEM);            \
+    spmv_bsr3_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, BSR_SMEM, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); \
+  }
   switch (lanes) {
+    case 300: spmv_bsr3_vec_kernel<FUSED, 4><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+    case 301: spmv_bsr3_vec_kernel<FUSED, 2><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+    case 201: FEMB_BSR(1) break;
+    case 202: FEMB_BSR(2) break;
+    case 204: FEMB_BSR(4) break;
+    case 208: FEMB_BSR(8) break;
+    case 216: FEMB_BSR(16) break;
+    case 232: FEMB_BSR(32) break;
     case 101: FEMB_TMA(1) break;
     case 102: FEMB_TMA(2) break;
     case 104: FEMB_TMA(4) break;
@@ -272,10 +396,24 @@ static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const 
     default: spmv_kernel<32, FUSED><<<grid, SPMV_THREADS, 0, s>>>(FEMB_SPMV_ARGS); break;
   }
 #undef FEMB_TMA
+#undef FEMB_BSR
 #undef FEMB_SPMV_ARGS
 }
 
 static int spmv_grid(long long n, int lanes) {
+  if (lanes == 300 || lanes == 301) {  // warp per block row, persistent: every CTA that fits on the device
+    static int fit[2] = {0, 0};
+    if (!fit[0]) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit[0], spmv_bsr3_vec_kernel<true, 4>, BSRV_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit[1], spmv_bsr3_vec_kernel<true, 2>, BSRV_THREADS, 0);
+      if (fit[0] < 1) fit[0] = 1;
+      if (fit[1] < 1) fit[1] = 1;
+    }
+    const int per_sm = getenv("FEMB_BSRV_CTAS") ? atoi(getenv("FEMB_BSRV_CTAS")) : fit[lanes - 300];
+    const long long ctas = (n / 3 + BSRV_THREADS / 32 - 1) / (BSRV_THREADS / 32);
+    return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)SMS * per_sm));
+  }
+  if (lanes >= 200) return tma_grid(n / 3, lanes - 200);
   if (lanes >= 100) return tma_grid(n, lanes - 100);  // persistent: TMA_CTAS_PER_SM CTAs per SM
   const long long rows_per_block = SPMV_THREADS / (lanes < 0 ? -lanes : lanes);
   const long long tiles = std::max<long long>(1, (n + rows_per_block - 1) / rows_per_block);
@@ -325,9 +463,10 @@ static cudaStream_t solver_stream(cudaStream_t user) {
 }
 
 struct CsrRef {
-  long long nnz;
+  long long nnz;  // scalar nonzeros, or 3x3 blocks when block == 3
   const int *crow, *col;
   const double* val;
+  int block = 1;
 };
 
 static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* F, const uint8_t* mask, const double* minv, double* u,
@@ -342,7 +481,7 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   double *r = work, *p = work + n, *Ap = work + 2 * n;
   int lanes[8], g1[8], gmax = 1;
   for (int m = 0; m < nmat; ++m) {
-    lanes[m] = pick_lanes(n, mats[m].nnz);
+    lanes[m] = pick_lanes(n, mats[m].nnz, mats[m].block);
     g1[m] = spmv_grid(n, lanes[m]);
     gmax = std::max(gmax, g1[m]);
   }
@@ -431,8 +570,46 @@ extern "C" int femb_cg_solve(int64_t n, int64_t nnz, const int32_t* crow, const 
                              const uint8_t* mask, const double* minv, double* u, double* work, double tol, int max_iter, double eps,
                              int check_every, femb_cg_result* result_host, femb_stream stream) {
   FEMB_CHECK_ARG(crow && col && val, "null CSR pointer");
-  const CsrRef m{nnz, crow, col, val};
+  const CsrRef m{nnz, crow, col, val, 1};
   return cg_solve_impl(n, 1, &m, F, mask, minv, u, work, tol, max_iter, eps, check_every, result_host, stream);
+}
+
+extern "C" int femb_spmv_bsr3(int64_t nb, int64_t nnzb, const int32_t* brow, const int32_t* bcol, const double* bval, const double* x,
+                              double* y, femb_stream stream) {
+  FEMB_CHECK_ARG(nb >= 0 && nnzb >= 0, "nb >= 0, nnzb >= 0");
+  if (nb == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int lanes = pick_lanes(3 * nb, nnzb, 3);
+  nnz_hint = nnzb;
+  launch_spmv<false>(lanes, spmv_grid(3 * nb, lanes), s, 3 * nb, brow, bcol, bval, x, y, nullptr, nullptr, nullptr, 0.0, 0);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+extern "C" int femb_cg_solve_bsr3(int64_t nb, int64_t nnzb, const int32_t* brow, const int32_t* bcol, const double* bval, const double* F,
+                                  const uint8_t* mask, const double* minv, double* u, double* work, double tol, int max_iter, double eps,
+                                  int check_every, femb_cg_result* result_host, femb_stream stream) {
+  FEMB_CHECK_ARG(brow && bcol && bval, "null BSR pointer");
+  const CsrRef m{nnzb, brow, bcol, bval, 3};
+  return cg_solve_impl(3 * nb, 1, &m, F, mask, minv, u, work, tol, max_iter, eps, check_every, result_host, stream);
+}
+
+extern "C" int femb_csr_bsr3_convert(int to_bsr, int64_t nb, const int32_t* brow, const double* in, double* out, femb_stream stream) {
+  FEMB_CHECK_ARG(nb >= 0 && brow && in && out && in != out, "nb >= 0, non-null distinct buffers");
+  if (nb == 0) return FEMB_OK;
+  const int grid = grid_for(nb * 32, 256, 32);
+  if (to_bsr) csr_bsr3_permute_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(nb, brow, in, out);
+  else csr_bsr3_permute_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(nb, brow, in, out);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+extern "C" int femb_bsr3_jacobi(int64_t nb, const int32_t* brow, const int32_t* bcol, const double* bval, const uint8_t* mask, double* minv,
+                                femb_stream stream) {
+  if (nb == 0) return FEMB_OK;
+  bsr3_jacobi_kernel<<<grid_for(nb, 256), 256, 0, as_stream(stream)>>>(nb, brow, bcol, bval, mask, minv);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
 }
 
 extern "C" int femb_cg_solve_multi(int64_t n, int nmat, const int64_t* nnz_host, const int32_t* const* crow_host,
@@ -441,6 +618,6 @@ extern "C" int femb_cg_solve_multi(int64_t n, int nmat, const int64_t* nnz_host,
                                    femb_cg_result* result_host, femb_stream stream) {
   FEMB_CHECK_ARG(nmat >= 1 && nmat <= 8 && nnz_host && crow_host && col_host && val_host, "nmat in 1..8, non-null arrays");
   CsrRef m[8];
-  for (int k = 0; k < nmat; ++k) m[k] = CsrRef{nnz_host[k], crow_host[k], col_host[k], val_host[k]};
+  for (int k = 0; k < nmat; ++k) m[k] = CsrRef{nnz_host[k], crow_host[k], col_host[k], val_host[k], 1};
   return cg_solve_impl(n, nmat, m, F, mask, minv, u, work, tol, max_iter, eps, check_every, result_host, stream);
 }

@@ -274,4 +274,166 @@ inline int tma_grid(long long n, int lr) {
   return (int)std::max<long long>(1, std::min<long long>(tiles, (long long)SMS * TMA_CTAS_PER_SM));
 }
 
+// ---- TMA-pipelined block-CSR SpMV, 3x3 blocks (elasticity: 3 dofs per node) ---------------------------------------------------
+// The node-level pattern (brow/bcol) with one 72-byte row-major block per entry cuts the index stream 9x against scalar CSR
+// (12 -> 8.44 bytes per scalar nonzero) and fetches x[3c..3c+2] once per block instead of once per scalar row, i.e. a third
+// of the gathers.  Same pipeline as spmv_tma_rows: persistent CTAs, thread 0 stages the block and column slices of the next
+// row tile with cp.async.bulk while the CTA multiplies the current one; LR lanes share a block row, each lane walks its
+// blocks (stride 9 doubles between lanes => conflict-free LDS) and the three partial sums are reduced with shuffles.
+// Slices start at a multiple of 4 blocks so both copies are 16-byte aligned (4*72 and 4*4 bytes).
+constexpr int BSR_CAP = 352;  // blocks per stage: 2 stages x 352 x 76 B = 53.5 KB per CTA, 4 CTAs per SM
+constexpr size_t BSR_SMEM = (size_t)TMA_STAGES * BSR_CAP * 76;
+
+template <int LR, bool NC, int THREADS = TMA_THREADS, int STAGES = TMA_STAGES, int CAP = BSR_CAP>
+__device__ __forceinline__ double spmv_bsr3_tma_rows(long long nb, long long nnzb, const int* __restrict__ brow, const int* __restrict__ bcol,
+                                                     const double* __restrict__ bval, const double* __restrict__ x, double* __restrict__ y,
+                                                     const unsigned char* __restrict__ mask, bool accumulate, bool fused) {
+  constexpr int R = THREADS / LR;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  double* vbuf = reinterpret_cast<double*>(tma_smem);                                // [STAGES][CAP][9]
+  int* cbuf = reinterpret_cast<int*>(tma_smem + sizeof(double) * 9 * STAGES * CAP);  // [STAGES][CAP]
+  __shared__ unsigned long long full[STAGES];
+  __shared__ int base[STAGES];
+  const int tid = threadIdx.x, sub = tid % LR, lr = tid / LR;
+  const long long ntiles = (nb + R - 1) / R;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto bounds = [&](long long k, int& a, int& b) {
+    const long long t = blockIdx.x + k * gridDim.x;
+    a = b = 0;
+    if (t < ntiles) a = __ldg(brow + t * R), b = __ldg(brow + min(nb, t * R + R));
+  };
+  auto stage_tile = [&](long long k, int a, int b) {
+    if (blockIdx.x + k * gridDim.x >= ntiles) return;
+    const int s = (int)(k % STAGES);
+    const int a0 = a & ~3, cnt = (b - a0 + 3) & ~3;
+    if (cnt > CAP || (long long)a0 + cnt > nnzb || cnt == 0) {
+      base[s] = -1;
+      return;
+    }
+    base[s] = a0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&full[s], (unsigned)cnt * 76u);
+    bulk_g2s(vbuf + (size_t)s * CAP * 9, bval + (size_t)a0 * 9, (unsigned)cnt * 72u, &full[s]);
+    bulk_g2s(cbuf + (size_t)s * CAP, bcol + a0, (unsigned)cnt * 4u, &full[s]);
+  };
+  int na = 0, nbnd = 0;
+  if (tid == 0) {
+    for (int k = 0; k < STAGES - 1; ++k) {
+      bounds(k, na, nbnd);
+      stage_tile(k, na, nbnd);
+    }
+    bounds(STAGES - 1, na, nbnd);
+  }
+  double dot = 0.0;
+  unsigned phase_bits = 0;
+  for (long long k = 0;; ++k) {
+    const long long t = blockIdx.x + k * gridDim.x;
+    if (t >= ntiles) break;
+    const int s = (int)(k % STAGES);
+    if (tid == 0) {
+      stage_tile(k + STAGES - 1, na, nbnd);
+      bounds(k + STAGES, na, nbnd);
+    }
+    const long long r = t * R + lr;
+    int ra = 0, rb = 0;
+    double xo[3] = {0, 0, 0}, yp[3] = {0, 0, 0};
+    bool keep[3] = {true, true, true};
+    if (r < nb) {
+      ra = __ldg(brow + r), rb = __ldg(brow + r + 1);
+      if (sub == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (fused) {
+            xo[i] = ld_x<NC>(x + 3 * r + i);
+            if (mask) keep[i] = mask[3 * r + i] != 0;
+          }
+          if (accumulate) yp[i] = y[3 * r + i];
+        }
+      }
+    }
+    __syncthreads();
+    const int a0 = base[s];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    if (a0 >= 0) {
+      mbar_wait(&full[s], (phase_bits >> s) & 1u);
+      phase_bits ^= 1u << s;
+      const double* vs = vbuf + (size_t)s * CAP * 9 - (size_t)a0 * 9;
+      const int* cs = cbuf + (size_t)s * CAP - a0;
+      int j = ra + sub;
+      for (; j + 3 * LR < rb; j += 4 * LR) {  // four blocks = twelve independent x gathers in flight per lane
+        double xv[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double* xp = x + 3ll * cs[j + q * LR];
+          xv[q][0] = ld_x<NC>(xp), xv[q][1] = ld_x<NC>(xp + 1), xv[q][2] = ld_x<NC>(xp + 2);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double* b = vs + (size_t)(j + q * LR) * 9;
+          s0 += b[0] * xv[q][0] + b[1] * xv[q][1] + b[2] * xv[q][2];
+          s1 += b[3] * xv[q][0] + b[4] * xv[q][1] + b[5] * xv[q][2];
+          s2 += b[6] * xv[q][0] + b[7] * xv[q][1] + b[8] * xv[q][2];
+        }
+      }
+      {
+        double xv[3][3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const bool in = j + q * LR < rb;
+          const double* xp = x + 3ll * (in ? cs[j + q * LR] : 0);
+          xv[q][0] = in ? ld_x<NC>(xp) : 0.0, xv[q][1] = in ? ld_x<NC>(xp + 1) : 0.0, xv[q][2] = in ? ld_x<NC>(xp + 2) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (j + q * LR < rb) {
+            const double* b = vs + (size_t)(j + q * LR) * 9;
+            s0 += b[0] * xv[q][0] + b[1] * xv[q][1] + b[2] * xv[q][2];
+            s1 += b[3] * xv[q][0] + b[4] * xv[q][1] + b[5] * xv[q][2];
+            s2 += b[6] * xv[q][0] + b[7] * xv[q][1] + b[8] * xv[q][2];
+          }
+      }
+    } else {
+      for (int j = ra + sub; j < rb; j += LR) {
+        const double* b = bval + (size_t)j * 9;
+        const double* xp = x + 3ll * ld_stream(bcol + j);
+        const double x0 = ld_x<NC>(xp), x1 = ld_x<NC>(xp + 1), x2 = ld_x<NC>(xp + 2);
+        s0 += ld_stream(b) * x0 + ld_stream(b + 1) * x1 + ld_stream(b + 2) * x2;
+        s1 += ld_stream(b + 3) * x0 + ld_stream(b + 4) * x1 + ld_stream(b + 5) * x2;
+        s2 += ld_stream(b + 6) * x0 + ld_stream(b + 7) * x1 + ld_stream(b + 8) * x2;
+      }
+    }
+#pragma unroll
+    for (int o = LR / 2; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (r < nb && sub == 0) {
+      double sv[3] = {s0, s1, s2};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (accumulate) sv[i] += yp[i];
+        if (fused) {
+          if (!keep[i]) sv[i] = 0.0;
+          dot += sv[i] * xo[i];
+        }
+        y[3 * r + i] = sv[i];
+      }
+    }
+    __syncthreads();
+  }
+  return dot;
+}
+
+inline int bsr_pick_lr(long long nb, long long nnzb) {
+  const double avg = nb > 0 ? (double)nnzb / (double)nb : 1.0;
+  for (int lr = 1; lr <= 32; lr *= 2)
+    if ((TMA_THREADS / lr) * avg * 1.15 <= BSR_CAP) return lr;
+  return 32;
+}
+
 }  // namespace femb

@@ -47,6 +47,11 @@ SIGNATURES = {
     "femb_ebe_apply": [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp],
     "femb_cg_solve": [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_i32, c_f64, c_i32,
                       C.POINTER(CGResult), c_vp],
+    "femb_cg_solve_bsr3": [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_i32, c_f64, c_i32,
+                           C.POINTER(CGResult), c_vp],
+    "femb_spmv_bsr3": [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "femb_csr_bsr3_convert": [c_i32, c_i64, c_vp, c_vp, c_vp, c_vp],
+    "femb_bsr3_jacobi": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "femb_cg_solve_multi": [c_i64, c_i32, C.POINTER(c_i64), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_vp, c_vp, c_vp, c_vp,
                             c_vp, c_f64, c_i32, c_f64, c_i32, C.POINTER(CGResult), c_vp],
     "femb_csr_jacobi": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],

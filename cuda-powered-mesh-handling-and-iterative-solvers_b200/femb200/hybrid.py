@@ -16,6 +16,8 @@ of the reference CG loop on that level's assembled operator; repeat up to the fi
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -53,11 +55,17 @@ def hybrid_solve(coords, tets, levels, load_fn, fixed_fn, E=None, nu=None, kind=
     ndof = 3 if kind == "elasticity" else 1
     info = {"levels": [], "kind": kind}
 
+    plans = {}
+
     def operator(c, t):
-        plan = ops.CsrPlan(t, c.shape[0], dev)
+        plan = plans[t.data_ptr()] = ops.CsrPlan(t, c.shape[0], dev)
         crow, col = plan.pattern(ndof)
         vals = plan.assemble_c3d4(c, kind, E or 0.0, nu or 0.0)
         return crow, col, vals
+
+    def bsr_of(c, t, vals):
+        brow, bcol = plans[t.data_ptr()].pattern(1)
+        return ops.Bsr3.from_csr_values(brow, bcol, vals)
 
     # ---- level 0: direct solve of the constrained system (fixed dofs replaced by identity rows/columns)
     crow, col, vals = operator(coords, tets)
@@ -81,7 +89,11 @@ def hybrid_solve(coords, tets, levels, load_fn, fixed_fn, E=None, nu=None, kind=
         F = load_fn(coords, tets).to(dev, torch.float64)
         mask = torch.ones((coords.shape[0], ndof), dtype=torch.uint8, device=dev)
         mask[fixed_fn(coords).to(dev).long()] = 0
-        u, it = ops.cg_solve(crow, col, vals, F.reshape(-1, ndof), mask=mask.reshape(-1).contiguous(), u_init=u0, tol=tol, max_iter=max_iter)
+        kw = dict(mask=mask.reshape(-1).contiguous(), u_init=u0, tol=tol, max_iter=max_iter)
+        if ndof == 3 and not os.environ.get("FEMB_NO_BSR"):   # elasticity: 3x3 block-CSR inner CG
+            u, it = bsr_of(coords, tets, vals).cg_solve(F.reshape(-1, ndof), **kw)
+        else:
+            u, it = ops.cg_solve(crow, col, vals, F.reshape(-1, ndof), **kw)
         u = u.reshape(-1, ndof)
         info["levels"].append({"nodes": coords.shape[0], "tets": tets.shape[0], "solver": "CG (warm start from the coarser level)",
                                "iterations": it["iterations"], "status": it["status"]})

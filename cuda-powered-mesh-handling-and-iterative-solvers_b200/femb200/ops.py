@@ -385,3 +385,60 @@ def cg_solve_multi(mats, F, mask=None, minv=None, u_init=None, tol=1e-10, max_it
                                       float(eps), int(check_every), C.byref(res), _stream(dev)), "femb_cg_solve_multi")
     info = {"iterations": res.iterations, "status": STATUS.get(res.status, "?"), "rs": res.rs, "loop_ms": res.loop_ms}
     return u.reshape(F.shape), info
+
+
+# ----------------------------------------------------------------------------- 3x3 block-CSR (3-dof operators)
+
+class Bsr3:
+    """Operator with 3 dofs per node in block-CSR form: (brow int32 [nb+1], bcol int32 [nnzb], bval fp64 [nnzb,3,3])."""
+
+    def __init__(self, brow, bcol, bval):
+        self.brow, self.bcol, self.bval = brow, bcol, bval
+        self.nb, self.nnzb, self.dev = brow.numel() - 1, bcol.numel(), bval.device
+
+    @classmethod
+    def from_csr_values(cls, brow, bcol, csr_val):
+        """csr_val: values of the ndof=3 CSR generated from the node pattern (CsrPlan.pattern(3) / assemble(K, 3))."""
+        assert csr_val.numel() == 9 * bcol.numel(), (csr_val.numel(), bcol.numel())
+        bval = torch.empty((bcol.numel(), 3, 3), device=csr_val.device, dtype=torch.float64)
+        with torch.cuda.device(csr_val.device):
+            check(lib.femb_csr_bsr3_convert(1, brow.numel() - 1, _p(brow), _p(csr_val), _p(bval), _stream(csr_val.device)),
+                  "femb_csr_bsr3_convert")
+        return cls(brow, bcol, bval)
+
+    def to_csr_values(self):
+        out = torch.empty(9 * self.nnzb, device=self.dev, dtype=torch.float64)
+        with torch.cuda.device(self.dev):
+            check(lib.femb_csr_bsr3_convert(0, self.nb, _p(self.brow), _p(self.bval), _p(out), _stream(self.dev)), "femb_csr_bsr3_convert")
+        return out
+
+    def spmv(self, x):
+        xx = x.to(device=self.dev, dtype=torch.float64).reshape(-1).contiguous()
+        assert xx.numel() == 3 * self.nb
+        y = torch.empty(3 * self.nb, device=self.dev, dtype=torch.float64)
+        with torch.cuda.device(self.dev):
+            check(lib.femb_spmv_bsr3(self.nb, self.nnzb, _p(self.brow), _p(self.bcol), _p(self.bval), _p(xx), _p(y), _stream(self.dev)),
+                  "femb_spmv_bsr3")
+        return y.reshape(x.shape)
+
+    def jacobi(self, mask=None):
+        out = torch.empty(3 * self.nb, device=self.dev, dtype=torch.float64)
+        with torch.cuda.device(self.dev):
+            check(lib.femb_bsr3_jacobi(self.nb, _p(self.brow), _p(self.bcol), _p(self.bval), _p(mask), _p(out), _stream(self.dev)),
+                  "femb_bsr3_jacobi")
+        return out
+
+    def cg_solve(self, F, mask=None, minv=None, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, check_every=16):
+        n = 3 * self.nb
+        Ff = F.to(device=self.dev, dtype=torch.float64).reshape(-1).contiguous()
+        assert Ff.numel() == n, (Ff.numel(), n)
+        u = torch.zeros(n, device=self.dev, dtype=torch.float64) if u_init is None else \
+            u_init.to(device=self.dev, dtype=torch.float64).reshape(-1).clone().contiguous()
+        work = torch.empty(4 * n, device=self.dev, dtype=torch.float64)
+        res = CGResult()
+        with torch.cuda.device(self.dev):
+            check(lib.femb_cg_solve_bsr3(self.nb, self.nnzb, _p(self.brow), _p(self.bcol), _p(self.bval), _p(Ff), _p(mask), _p(minv), _p(u),
+                                         _p(work), float(tol), int(max_iter), float(eps), int(check_every), C.byref(res),
+                                         _stream(self.dev)), "femb_cg_solve_bsr3")
+        info = {"iterations": res.iterations, "status": STATUS.get(res.status, "?"), "rs": res.rs, "loop_ms": res.loop_ms}
+        return u.reshape(F.shape), info

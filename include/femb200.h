@@ -176,6 +176,18 @@ int femb_ebe_apply(femb_csr_plan* plan, int ndof, const void* Ke, const void* u,
  * (0 for nodes without elements); sums run in ascending element order (deterministic; the reference uses index_add). */
 int femb_node_average(femb_csr_plan* plan, const void* elem_values, int fp, void* out, femb_stream stream);
 
+/* Block-CSR with 3x3 blocks for 3-dof operators (every elasticity operator of the reference: dofs = node*3+{0,1,2},
+ * element.py:447-449).  brow[nb+1] / bcol[nnzb] = the node-level pattern (femb_csr_plan_pattern with ndof = 1),
+ * bval[nnzb][3][3] row-major.  8.44 instead of 12 bytes per scalar nonzero and a third of the x gathers.
+ *   femb_csr_bsr3_convert: permutes between the ndof=3 CSR values of femb_csr_assemble and the block layout (to_bsr != 0
+ *   CSR -> blocks, else blocks -> CSR); in and out must not alias.
+ *   femb_spmv_bsr3: y = A x, x/y [3 nb].   femb_bsr3_jacobi: minv[3 nb] = 1/diag (0 for masked or zero-diagonal rows). */
+int femb_csr_bsr3_convert(int to_bsr, int64_t nb, const int32_t* brow, const double* in, double* out, femb_stream stream);
+int femb_spmv_bsr3(int64_t nb, int64_t nnzb, const int32_t* brow, const int32_t* bcol, const double* bval, const double* x, double* y,
+                   femb_stream stream);
+int femb_bsr3_jacobi(int64_t nb, const int32_t* brow, const int32_t* bcol, const double* bval, const uint8_t* mask, double* minv,
+                     femb_stream stream);
+
 typedef struct femb_cg_result {
   int32_t iterations; /* the count the reference prints: i+1 at exit, max_iter when not converged */
   int32_t status;     /* 0 converged, 1 breakdown (pAp guard / NaN), 2 max_iter */
@@ -191,6 +203,11 @@ typedef struct femb_cg_result {
 int femb_cg_solve(int64_t n, int64_t nnz, const int32_t* crow, const int32_t* col, const double* val, const double* F,
                   const uint8_t* mask, const double* minv, double* u, double* work, double tol, int max_iter, double eps,
                   int check_every, femb_cg_result* result_host, femb_stream stream);
+
+/* Same loop on a 3x3 block-CSR operator (n = 3 nb unknowns; F, mask, minv, u, work sized as for femb_cg_solve). */
+int femb_cg_solve_bsr3(int64_t nb, int64_t nnzb, const int32_t* brow, const int32_t* bcol, const double* bval, const double* F,
+                       const uint8_t* mask, const double* minv, double* u, double* work, double tol, int max_iter, double eps,
+                       int check_every, femb_cg_result* result_host, femb_stream stream);
 
 /* Same loop with the operator given as a SUM of up to 8 CSR matrices over the same n rows (static_structure_solver
  * solver.py:11-135 sums one operator per element family: C3D4/C3D8/C3D6 on the translations, S3/S4 on all six dofs).

@@ -70,6 +70,15 @@ ms_S, _ = timed(lambda: ops.spmv(crow, col, vals, x), reps=5)
 bytes_S = nnz * 12 + 3 * N * 20
 out["spmv"] = {"ms": round(ms_S, 3), "GBps": round(bytes_S / ms_S / 1e6, 1), "hbm_frac": round(bytes_S / ms_S / 1e6 / HBM, 3)}
 
+brow, bcol = plan.pattern(1)
+t0 = time.perf_counter()
+A = ops.Bsr3.from_csr_values(brow, bcol, vals)
+torch.cuda.synchronize()
+ms_B, _ = timed(lambda: A.spmv(x), reps=5)
+bytes_B = nnz * 8 + (nnz // 9) * 4 + N * 4 + 3 * N * 16
+out["spmv_bsr3"] = {"ms": round(ms_B, 3), "GBps_own_bytes": round(bytes_B / ms_B / 1e6, 1), "hbm_frac_own_bytes": round(bytes_B / ms_B / 1e6 / HBM, 3),
+                    "hbm_frac_csr_bytes": round(bytes_S / ms_B / 1e6 / HBM, 3), "convert_s": round(time.perf_counter() - t0, 3)}
+
 fixed = torch.nonzero(coords[:, 2] == 0).reshape(-1)
 mask = torch.ones((N, 3), dtype=torch.uint8, device=dev)
 mask[fixed] = 0
@@ -81,6 +90,12 @@ u, info = ops.cg_solve(crow, col, vals, F, minv=minv, tol=0.0, max_iter=a.iters,
 bytes_it = bytes_S + 11 * 3 * N * 8
 out["jacobi_pcg"] = {"iters": info["iterations"], "ms_per_iter": round(info["loop_ms"] / a.iters, 3), "iters_per_s": round(a.iters / info["loop_ms"] * 1e3, 1),
                      "hbm_frac": round(bytes_it / (info["loop_ms"] / a.iters) / 1e6 / HBM, 3)}
+u3, info3 = A.cg_solve(F, minv=minv, tol=0.0, max_iter=a.iters, check_every=min(a.iters, 50))
+bytes_itb = bytes_B + 11 * 3 * N * 8
+out["jacobi_pcg_bsr3"] = {"ms_per_iter": round(info3["loop_ms"] / a.iters, 3), "iters_per_s": round(a.iters / info3["loop_ms"] * 1e3, 1),
+                          "hbm_frac_own_bytes": round(bytes_itb / (info3["loop_ms"] / a.iters) / 1e6 / HBM, 3),
+                          "hbm_frac_csr_bytes": round(bytes_it / (info3["loop_ms"] / a.iters) / 1e6 / HBM, 3),
+                          "max_abs_diff_vs_csr": float((u3 - u).abs().max())}
 u2, info2 = ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=a.iters, check_every=min(a.iters, 50))
 out["cg"] = {"ms_per_iter": round(info2["loop_ms"] / a.iters, 3), "iters_per_s": round(a.iters / info2["loop_ms"] * 1e3, 1)}
 print(json.dumps(out), flush=True)
