@@ -264,7 +264,7 @@ def run_gpu(args):
         "e2e": {"value": round(K / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(F_host.numel() * 8 / K),
                 "d2h_bytes_per_step": int(u_host.numel() * 8 / K),
                 "note": f"one solver-API call of {K} iterations: F pinned host -> device, CG, u -> pinned host; bytes are per call / K"},
-        "gpu_launches": 3 * K + 4,
+        "gpu_launches": (3 if os.environ.get("FEMB_CG_CLASSIC") else 2) * K + 4,
         "roofline": {"kernel": "spmv_tma_kernel<1,false> (TMA-pipelined CSR SpMV; its fused twin is CG step k1)", "bound": "hbm",
                      "achieved": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
                      "frac": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9 / hbm, 4), "traffic": ncu_traffic(n, "spmv_tma_kernel"), "peak_source": peak_src,
@@ -272,7 +272,10 @@ def run_gpu(args):
                      "ms_per_launch": round(ms_spmv, 4), "algorithmic_bytes": bytes_spmv},
         "cg_iteration": {"ms": round(ms_loop / K, 4), "algorithmic_bytes": bytes_iter,
                          "achieved_GBps": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9, 1),
-                         "frac": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9 / hbm, 4), "api_call_ms": round(ms_call, 2)},
+                         "frac": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9 / hbm, 4), "api_call_ms": round(ms_call, 2),
+                         "kernels": "spmv_tma_kernel<1,true> (SpMV + p.Ap, r.Ap, Ap.Ap -> alpha, rs_new, beta) + cg_merged_kernel "
+                                    "(u, r, p in one pass + exact r.r): 2 launches, 7 vector passes + r in the SpMV",
+                         "bytes_actually_moved": bytes_spmv + 8 * N * 8},
         "assembly": {"metric": "assembled_elems_per_s", "value": round(M / (ms_asm * 1e-3), 1), "ms": round(ms_asm, 3),
                      "kernel": "pad_coords + assemble_p1_poisson_tiles (coords -> CSR values; pattern and per-incidence records prebuilt)",
                      "algorithmic_bytes": bytes_asm, "achieved_GBps": round(bytes_asm / (ms_asm * 1e-3) / 1e9, 1),

@@ -33,7 +33,8 @@ struct SymHeader {
   volatile long long flagC[MAXP];  // r.r partial of rank q arrived
   volatile double redB[MAXP];
   volatile double redC[MAXP];
-  double pad[MAXP * 3];
+  volatile double red2[2][4][MAXP];  // merged-reduction CG: [epoch parity][p.Ap, r.Ap, Ap.Ap, r.r][rank]
+  double pad[MAXP];
 };
 static_assert(sizeof(SymHeader) % 256 == 0, "header keeps p 256-byte aligned");
 
@@ -298,6 +299,175 @@ __global__ void __launch_bounds__(DV_THREADS) dist_direction_kernel(Peers pe, lo
       for (int k = 0; k < pe.nnbr; ++k) pe.hdr[pe.nbr[k]]->flagA[pe.rank] = e;
     }
     trace_stamp(st, 10);
+  }
+}
+
+// =====================================================================================================================
+// Merged-reduction iteration (default): TWO kernels and ONE waited all-reduce per iteration.
+//   m1  SpMV as k1, but the CTA partials carry three sums: p.Ap, r.Ap and Ap.Ap (r is one more streamed vector)
+//   m2  waits for that all-reduce, then alpha = rs/(p.Ap+eps) and, without a second global sum,
+//         rs_new = rs - 2 alpha r.Ap + alpha^2 Ap.Ap        ( = |r - alpha Ap|^2 )
+//       -> convergence test, beta, and ONE pass over the vectors: u += alpha p, r -= alpha Ap, p = r + beta p (boundary rows
+//       are pushed to the neighbours' ghosts).  The same pass accumulates the TRUE r.r of the new residual; its all-reduce is
+//       only consumed by m2 of the NEXT iteration (one SpMV later, so nobody waits for it) as the `rs` the recurrence starts
+//       from -- rounding errors of the recurrence therefore never accumulate: each rs_new is one step away from an exact sum
+//       (relative error ~ eps * rs/rs_new), and iteration counts match the three-kernel loop (tests: +-1).
+// Against k1/k2/k3 this removes one launch boundary, one all-rank wait and two of the nine vector passes per iteration.
+// Reduction slots are double-buffered by epoch parity: with a single all-rank wait per iteration a fast rank could
+// otherwise overwrite a slot a slow rank has not read yet.
+// =====================================================================================================================
+template <int LR, bool NC>
+__global__ void __launch_bounds__(TMA_THREADS) dist_spmv3_kernel(Peers pe, long long n_owned, long long nnz, const int* __restrict__ crow,
+                                                                 const int* __restrict__ col, const double* __restrict__ val,
+                                                                 double* __restrict__ y, const unsigned char* __restrict__ mask,
+                                                                 const double* __restrict__ rvec, double* __restrict__ partial, DistState* st,
+                                                                 long long n_interior) {
+  if (st->stop) return;
+  SymHeader* me = pe.hdr[pe.rank];
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 2), trace_stamp(st, 3);
+  __shared__ int nbr[MAXP];
+  if (threadIdx.x < MAXP) nbr[threadIdx.x] = pe.nbr[threadIdx.x];
+  __syncthreads();
+  const double* x = sym_p(me);
+  const GraphHaloWaiter hw{me, nbr, pe.nnbr, st->epochA, st};
+  double extra[2] = {0.0, 0.0};
+  const double dot = spmv_tma_rows<LR, NC, TMA_THREADS, TMA_STAGES, TMA_CAP, GraphHaloWaiter>(
+      n_owned, nnz, crow, col, val, x, y, mask, false, true, pe.nnbr > 0 ? n_interior : 0x7fffffffffffffffll, hw, rvec, extra);
+  if (st->stop == 3) return;
+  const double t0 = block_sum<TMA_THREADS>(dot), t1 = block_sum<TMA_THREADS>(extra[0]), t2 = block_sum<TMA_THREADS>(extra[1]);
+  const int G = gridDim.x;
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = t0, partial[G + blockIdx.x] = t1, partial[2 * G + blockIdx.x] = t2;
+    __threadfence();
+    last = atomicAdd(&st->ticket1, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int k = threadIdx.x; k < G; k += TMA_THREADS)
+      a[0] += ((volatile double*)partial)[k], a[1] += ((volatile double*)partial)[G + k], a[2] += ((volatile double*)partial)[2 * G + k];
+    a[0] = block_sum<TMA_THREADS>(a[0]), a[1] = block_sum<TMA_THREADS>(a[1]), a[2] = block_sum<TMA_THREADS>(a[2]);
+    if (threadIdx.x == 0) {
+      st->ticket1 = 0;
+      const long long e = st->epochB + 1;
+      st->epochB = e;
+      const int par = (int)(e & 1);
+      for (int q = 0; q < pe.P; ++q) {
+        pe.hdr[q]->red2[par][0][pe.rank] = a[0];
+        pe.hdr[q]->red2[par][1][pe.rank] = a[1];
+        pe.hdr[q]->red2[par][2][pe.rank] = a[2];
+      }
+      __threadfence_system();
+      for (int q = 0; q < pe.P; ++q) pe.hdr[q]->flagB[pe.rank] = e;
+      trace_stamp(st, 4);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, long long n, double* __restrict__ u, double* __restrict__ r,
+                                                                     const double* __restrict__ Ap, double* __restrict__ partial,
+                                                                     DistState* st, double tol, double eps, int guards, int max_iter,
+                                                                     BoundaryPush bp) {
+  if (st->stop) return;
+  SymHeader* me = pe.hdr[pe.rank];
+  __shared__ int all[MAXP];
+  __shared__ double sc[4];
+  if (threadIdx.x < MAXP) all[threadIdx.x] = threadIdx.x;
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 5);
+  const long long eB = st->epochB, eC = st->epochC;
+  const int it = st->it;
+  wait_flags(me->flagB, all, pe.P, eB, st);
+  if (it > 0) wait_flags(me->flagC, all, pe.P, eC, st);  // true r.r of the previous update: arrived one SpMV ago
+  if (st->stop) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 6);
+  if (threadIdx.x == 0) {  // one thread reads the slots (rank order: identical sums on every rank)
+    const int pb = (int)(eB & 1), pc = (int)(eC & 1);
+    sc[0] = sum_slots_serial(me->red2[pb][0], pe.P);
+    sc[1] = sum_slots_serial(me->red2[pb][1], pe.P);
+    sc[2] = sum_slots_serial(me->red2[pb][2], pe.P);
+    sc[3] = it > 0 ? sum_slots_serial(me->red2[pc][3], pe.P) : st->rs_old;
+  }
+  __syncthreads();
+  const double pAp = sc[0], rAp = sc[1], ApAp = sc[2], rs_old = sc[3];
+  const double alpha = rs_old / (pAp + eps);
+  if (guards && (fabs(pAp) < eps || pAp < 0.0 || !isfinite(alpha))) {  // solver.py:187-198, same verdict on every rank/CTA
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->stop = 1, st->status = 1, st->iterations = it + 1, st->pAp = pAp;
+    return;
+  }
+  double rs_new = rs_old - 2.0 * alpha * rAp + alpha * alpha * ApAp;
+  if (!(rs_new > 0.0)) rs_new = 0.0;                      // cancellation at machine-precision convergence
+  const double beta = rs_new / (rs_old + eps);
+  const bool conv = sqrt(rs_new) < tol;                   // solver.py:210-212 (u and r are updated before the break)
+  const bool bad = guards && !isfinite(beta);             // solver.py:216-218
+  const bool move_p = !(conv || bad);
+  double* p = sym_p(me);
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  const long long n_plain = bp.ptr ? bp.n_interior : n;
+  double dot = 0.0;
+  if (bp.ptr) {  // boundary rows first: their new p has the longest way to go
+    for (long long b = gtid; b < n - bp.n_interior; b += gsz) {
+      const long long i = bp.n_interior + b;
+      const double pi = p[i], ri = r[i] - alpha * Ap[i];
+      u[i] += alpha * pi;
+      r[i] = ri;
+      dot += ri * ri;
+      if (move_p) {
+        const double v = ri + beta * pi;
+        p[i] = v;
+        for (int e = bp.ptr[b]; e < bp.ptr[b + 1]; ++e) {
+          const int k = bp.k[e];
+          (sym_p(pe.hdr[pe.nbr[k]]) + pe.ghost_off[k])[bp.off[e]] = v;
+        }
+      }
+    }
+    __threadfence_system();
+  }
+  for (long long i = gtid; i < n_plain; i += gsz) {
+    const double pi = p[i], ri = r[i] - alpha * Ap[i];
+    u[i] += alpha * pi;
+    r[i] = ri;
+    dot += ri * ri;
+    if (move_p) p[i] = ri + beta * pi;
+  }
+  const double t = block_sum<DV_THREADS>(dot);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(&st->ticket2, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += DV_THREADS) a += ((volatile double*)partial)[k];
+    a = block_sum<DV_THREADS>(a);
+    if (threadIdx.x == 0) {
+      trace_stamp(st, 7), trace_stamp(st, 8), trace_stamp(st, 9);
+      st->ticket2 = 0;
+      st->pAp = pAp, st->alpha = alpha, st->beta = beta, st->rs_new = rs_new, st->rs_old = rs_new;
+      if (!move_p) {
+        st->stop = 1, st->status = conv ? 0 : 1, st->iterations = it + 1;
+      } else {
+        st->it = it + 1;
+        if (it + 1 >= max_iter) st->stop = 2, st->status = 2, st->iterations = max_iter;
+        const long long e = eC + 1;
+        st->epochC = e;
+        const int par = (int)(e & 1);
+        for (int q = 0; q < pe.P; ++q) pe.hdr[q]->red2[par][3][pe.rank] = a;
+        __threadfence_system();
+        for (int q = 0; q < pe.P; ++q) pe.hdr[q]->flagC[pe.rank] = e;
+        if (bp.ptr) {
+          const long long ea = st->epochA + 1;
+          st->epochA = ea;
+          for (int k = 0; k < pe.nnbr; ++k) pe.hdr[pe.nbr[k]]->flagA[pe.rank] = ea;
+        }
+      }
+      trace_stamp(st, 10);
+    }
   }
 }
 
@@ -569,6 +739,25 @@ static void launch_dist_spmv(int lr, int grid, cudaStream_t s, const Peers& pe, 
 #undef FEMB_DSPMV
 }
 
+static void launch_dist_spmv3(int lr, int grid, cudaStream_t s, const Peers& pe, long long n, long long nnz, const int* crow, const int* col,
+                              const double* val, double* y, const unsigned char* mask, const double* rvec, double* partial, DistState* st,
+                              long long n_interior) {
+#define FEMB_DSPMV3(LRV)                                                                                                    \
+  {                                                                                                                         \
+    cudaFuncSetAttribute(dist_spmv3_kernel<LRV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);         \
+    dist_spmv3_kernel<LRV, true><<<grid, TMA_THREADS, TMA_SMEM, s>>>(pe, n, nnz, crow, col, val, y, mask, rvec, partial, st, n_interior); \
+  }
+  switch (lr) {
+    case 1: FEMB_DSPMV3(1) break;
+    case 2: FEMB_DSPMV3(2) break;
+    case 4: FEMB_DSPMV3(4) break;
+    case 8: FEMB_DSPMV3(8) break;
+    case 16: FEMB_DSPMV3(16) break;
+    default: FEMB_DSPMV3(32) break;
+  }
+#undef FEMB_DSPMV3
+}
+
 static cudaStream_t dist_stream(cudaStream_t user) {
   static thread_local cudaStream_t s = nullptr;
   static thread_local cudaEvent_t ev = nullptr;
@@ -629,6 +818,7 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   FEMB_CHECK_ARG(nranks >= 1 && nranks <= MAXP && rank >= 0 && rank < nranks && nnbr >= 0 && nnbr < MAXP, "rank/nranks/nnbr");
   FEMB_CHECK_ARG(n_owned > 0 && crow && col && val && F && u && work && sym_host && result_host, "null pointer / n_owned <= 0");
   if (check_every < 1) check_every = 16;
+  spmv_apply_env_once();
   cudaStream_t s = dist_stream(as_stream(stream));
   FEMB_CHECK_ARG(s != nullptr, "could not create the solver stream");
   Peers pe;
@@ -646,7 +836,7 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   Scratch scr(s);
   double* partial;
   DistState* st;
-  FEMB_CUDA(scr.alloc(&partial, (size_t)std::max(g1, g2)));
+  FEMB_CUDA(scr.alloc(&partial, (size_t)std::max(3 * g1, g2)));
   FEMB_CUDA(scr.alloc(&st, 1));
   FEMB_CUDA(cudaMemsetAsync(st, 0, sizeof(DistState), s));
   long long* trace = nullptr;
@@ -725,11 +915,18 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   FEMB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   const bool folded = bptr != nullptr && nnbr > 0 && n_interior > 0 && !getenv("FEMB_DIST_SEPARATE_PUSH");
   BoundaryPush bp{folded ? bptr : nullptr, bk, boff, n_interior};
+  // FEMB_DIST_CLASSIC=1: the three-kernel loop k1/k2/k3 (two waited all-reduces); default: merged reduction m1/m2
+  static const bool classic = getenv("FEMB_DIST_CLASSIC") != nullptr;
   for (int k = 0; k < check_every; ++k) {
-    if (!folded) dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
-    launch_dist_spmv<true>(lr, g1, s, pe, n, nnz, crow, col, val, Ap, mask, partial, st, n_interior);
-    dist_update_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, eps, guards);
-    dist_direction_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, r, st, tol, eps, guards, max_iter, bp);
+    if (!folded && nnbr > 0) dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
+    if (classic) {
+      launch_dist_spmv<true>(lr, g1, s, pe, n, nnz, crow, col, val, Ap, mask, partial, st, n_interior);
+      dist_update_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, eps, guards);
+      dist_direction_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, r, st, tol, eps, guards, max_iter, bp);
+    } else {
+      launch_dist_spmv3(lr, g1, s, pe, n, nnz, crow, col, val, Ap, mask, r, partial, st, n_interior);
+      dist_merged_vec_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, tol, eps, guards, max_iter, bp);
+    }
   }
   cudaError_t ce = cudaStreamEndCapture(s, &graph);
   if (ce != cudaSuccess) {

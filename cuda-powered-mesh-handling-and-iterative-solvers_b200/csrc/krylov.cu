@@ -16,7 +16,8 @@ namespace femb {
 struct CGState {
   double rs_old, rs_new, pAp, alpha, beta;
   int it, stop, status, iterations;
-  unsigned int ticket1, ticket2, pad0, pad1;
+  unsigned int ticket1, ticket2;
+  int fin, fin_status;  // merged loop: this iteration ends the solve after the u/r update (converged / bad beta)
 };
 
 // Last-CTA-done epilogue of CG step k1: per-CTA partial of p.Ap, then the last CTA to arrive sums the partials in index
@@ -54,15 +55,60 @@ __device__ __forceinline__ void cg_k1_epilogue(double dot, double* __restrict__ 
   cg_k1_epilogue_n<SPMV_THREADS>(dot, partial, st, eps, guards);
 }
 
+// Merged-reduction loop (default for CG without a preconditioner): the SpMV also sums r.Ap and Ap.Ap, so its last CTA knows
+// alpha AND  rs_new = rs - 2 alpha r.Ap + alpha^2 Ap.Ap = |r - alpha Ap|^2  and with it the convergence verdict and beta:
+// every scalar of the iteration is decided here, and ONE vector kernel (cg_merged_kernel) applies u += alpha p,
+// r -= alpha Ap, p = r + beta p in a single pass (7 vector passes instead of 9, 2 kernels instead of 3).  That pass also
+// accumulates the true r.r of the new residual, which becomes the `rs` of the next iteration, so the recurrence never runs
+// more than one step away from an exactly summed value (relative error ~ eps * rs/rs_new).
+template <int THREADS>
+__device__ __forceinline__ void cg_k1_epilogue3_n(double dot, double e0, double e1, double* __restrict__ partial, CGState* __restrict__ st,
+                                                  double eps, int guards, double tol) {
+  const double t0 = block_sum<THREADS>(dot), t1 = block_sum<THREADS>(e0), t2 = block_sum<THREADS>(e1);
+  const int G = gridDim.x;
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = t0, partial[G + blockIdx.x] = t1, partial[2 * G + blockIdx.x] = t2;
+    __threadfence();
+    last = atomicAdd(&st->ticket1, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int k = threadIdx.x; k < G; k += THREADS)
+      a += ((volatile double*)partial)[k], b += ((volatile double*)partial)[G + k], c += ((volatile double*)partial)[2 * G + k];
+    a = block_sum<THREADS>(a), b = block_sum<THREADS>(b), c = block_sum<THREADS>(c);
+    if (threadIdx.x == 0) {
+      st->ticket1 = 0;
+      st->pAp = a;
+      const double rs = st->rs_old, alpha = rs / (a + eps);
+      if (guards && (fabs(a) < eps || a < 0.0 || !isfinite(alpha))) {  // solver.py:187-198: break before any update
+        st->stop = 1, st->status = 1, st->iterations = st->it + 1;
+      } else {
+        double rs_new = rs - 2.0 * alpha * b + alpha * alpha * c;
+        if (!(rs_new > 0.0)) rs_new = 0.0;  // cancellation at machine-precision convergence
+        const double beta = rs_new / (rs + eps);
+        st->alpha = alpha, st->beta = beta, st->rs_new = rs_new;
+        st->fin = 0;
+        if (sqrt(rs_new) < tol) st->fin = 1, st->fin_status = 0;            // solver.py:210-212 (after the u/r update)
+        else if (guards && !isfinite(beta)) st->fin = 1, st->fin_status = 1;  // solver.py:216-218
+      }
+    }
+  }
+}
+
 // L lanes cooperate on one row.  FUSED adds the row mask, the p.Ap partial and the last-CTA scalar epilogue.
 template <int L, bool FUSED>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(long long n, const int* __restrict__ crow, const int* __restrict__ col,
                                                             const double* __restrict__ val, const double* __restrict__ x,
                                                             double* __restrict__ y, const unsigned char* __restrict__ mask,
-                                                            double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards) {
+                                                            double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards,
+                                                            const double* __restrict__ rvec, double tol) {
   if (st && st->stop) return;
   const bool accumulate = (guards & 2) != 0;  // y += A x (operator given as a sum of matrices)
   guards &= 1;
+  double e0 = 0.0, e1 = 0.0;
   const int sub = threadIdx.x % L;
   const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / L;
   const long long ngroups = ((long long)gridDim.x * blockDim.x) / L;
@@ -88,11 +134,15 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(long long n, const i
       if (FUSED) {
         if (mask && !mask[r]) sum = 0.0;
         dot += sum * __ldg(x + r);
+        if (rvec) e0 += sum * rvec[r], e1 += sum * sum;
       }
       y[r] = sum;
     }
   }
-  if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards);
+  if (FUSED) {
+    if (rvec) cg_k1_epilogue3_n<SPMV_THREADS>(dot, e0, e1, partial, st, eps, guards, tol);
+    else cg_k1_epilogue(dot, partial, st, eps, guards);
+  }
 }
 
 template <int LR, bool FUSED>
@@ -100,7 +150,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(long long n, 
                                                                    const double* __restrict__ val, const double* __restrict__ x,
                                                                    double* __restrict__ y, const unsigned char* __restrict__ mask,
                                                                    double* __restrict__ partial, CGState* __restrict__ st, double eps,
-                                                                   int guards) {
+                                                                   int guards, const double* __restrict__ rvec, double tol) {
   if (st && st->stop) return;
   const double dot = spmv_stream_rows<LR, true>(n, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED);
   if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards & 1);
@@ -111,10 +161,16 @@ template <int LR, bool FUSED>
 __global__ void __launch_bounds__(TMA_THREADS) spmv_tma_kernel(long long n, long long nnz, const int* __restrict__ crow, const int* __restrict__ col,
                                                                const double* __restrict__ val, const double* __restrict__ x,
                                                                double* __restrict__ y, const unsigned char* __restrict__ mask,
-                                                               double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards) {
+                                                               double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards,
+                                                               const double* __restrict__ rvec, double tol) {
   if (st && st->stop) return;
-  const double dot = spmv_tma_rows<LR, true>(n, nnz, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED);
-  if (FUSED) cg_k1_epilogue_n<TMA_THREADS>(dot, partial, st, eps, guards & 1);
+  double extra[2] = {0.0, 0.0};
+  const double dot = spmv_tma_rows<LR, true>(n, nnz, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED, 0x7fffffffffffffffll, NoHaloWait(),
+                                             rvec, rvec ? extra : nullptr);
+  if (FUSED) {
+    if (rvec) cg_k1_epilogue3_n<TMA_THREADS>(dot, extra[0], extra[1], partial, st, eps, guards & 1, tol);
+    else cg_k1_epilogue_n<TMA_THREADS>(dot, partial, st, eps, guards & 1);
+  }
 }
 
 // block-CSR (3x3) variant for 3-dof operators: n = 3 nb scalar rows, crow/col are the node-level pattern, val the blocks
@@ -123,7 +179,8 @@ __global__ void __launch_bounds__(TMA_THREADS) spmv_bsr3_tma_kernel(long long nb
                                                                     const int* __restrict__ bcol, const double* __restrict__ bval,
                                                                     const double* __restrict__ x, double* __restrict__ y,
                                                                     const unsigned char* __restrict__ mask, double* __restrict__ partial,
-                                                                    CGState* __restrict__ st, double eps, int guards) {
+                                                                    CGState* __restrict__ st, double eps, int guards,
+                                                                    const double* __restrict__ rvec, double tol) {
   if (st && st->stop) return;
   const double dot = spmv_bsr3_tma_rows<LR, true>(nb, nnzb, brow, bcol, bval, x, y, mask, (guards & 2) != 0, FUSED);
   if (FUSED) cg_k1_epilogue_n<TMA_THREADS>(dot, partial, st, eps, guards & 1);
@@ -142,10 +199,12 @@ __global__ void __launch_bounds__(BSRV_THREADS) spmv_bsr3_vec_kernel(long long n
                                                                      const int* __restrict__ bcol, const double* __restrict__ bval,
                                                                      const double* __restrict__ x, double* __restrict__ y,
                                                                      const unsigned char* __restrict__ mask, double* __restrict__ partial,
-                                                                     CGState* __restrict__ st, double eps, int guards) {
+                                                                     CGState* __restrict__ st, double eps, int guards,
+                                                                     const double* __restrict__ rvec, double tol) {
   if (st && st->stop) return;
   const bool accumulate = (guards & 2) != 0;
   guards &= 1;
+  double e0 = 0.0, e1 = 0.0;
   const int lane = threadIdx.x & 31;
   const int boff = lane / 9, pos = lane - 9 * boff, cx = pos % 3;  // lanes 27..31: boff = 3 -> idle
   const bool active = lane < 27;
@@ -178,11 +237,15 @@ __global__ void __launch_bounds__(BSRV_THREADS) spmv_bsr3_vec_kernel(long long n
       if (FUSED) {
         if (mask && !mask[i]) sv = 0.0;
         dot += sv * __ldg(x + i);
+        if (rvec) e0 += sv * rvec[i], e1 += sv * sv;
       }
       y[i] = sv;
     }
   }
-  if (FUSED) cg_k1_epilogue_n<BSRV_THREADS>(dot, partial, st, eps, guards);
+  if (FUSED) {
+    if (rvec) cg_k1_epilogue3_n<BSRV_THREADS>(dot, e0, e1, partial, st, eps, guards, tol);
+    else cg_k1_epilogue_n<BSRV_THREADS>(dot, partial, st, eps, guards);
+  }
 }
 
 // CSR values of a 3-dof operator (rows 3i..3i+2 of node i stored one after the other) <-> 3x3 blocks: a permutation inside
@@ -281,6 +344,47 @@ __global__ void __launch_bounds__(VEC_THREADS) cg_direction_kernel(long long n, 
   }
 }
 
+// merged loop, second kernel: all scalars were fixed by the SpMV's last CTA (cg_k1_epilogue3_n)
+__global__ void __launch_bounds__(VEC_THREADS) cg_merged_kernel(long long n, double* __restrict__ u, double* __restrict__ r, double* __restrict__ p,
+                                                                const double* __restrict__ Ap, double* __restrict__ partial,
+                                                                CGState* __restrict__ st, int max_iter) {
+  if (st->stop) return;
+  const double alpha = st->alpha, beta = st->beta;
+  const bool move_p = st->fin == 0;
+  double dot = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double pi = p[i], ri = r[i] - alpha * Ap[i];
+    u[i] += alpha * pi;
+    r[i] = ri;
+    dot += ri * ri;
+    if (move_p) p[i] = ri + beta * pi;
+  }
+  const double t = block_sum<VEC_THREADS>(dot);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(&st->ticket2, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += VEC_THREADS) a += ((volatile double*)partial)[k];
+    a = block_sum<VEC_THREADS>(a);
+    if (threadIdx.x == 0) {
+      st->ticket2 = 0;
+      if (!move_p) {
+        st->stop = 1, st->status = st->fin_status, st->iterations = st->it + 1;
+      } else {
+        st->rs_old = a;  // exactly summed r.r of the new residual: the next recurrence starts from it
+        st->it += 1;
+        if (st->it >= max_iter) st->stop = 2, st->status = 2, st->iterations = max_iter;
+      }
+    }
+  }
+}
+
 // setup: u <- mask.*u ; (after Ap = A u) r = mask.*(F - Ap), p = z, partial r.z -> rs_old
 __global__ void cg_mask_kernel(long long n, double* __restrict__ u, const unsigned char* __restrict__ mask) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -356,21 +460,22 @@ static thread_local long long nnz_hint = 0;  // set by the callers right before 
 
 template <bool FUSED>
 static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const int* crow, const int* col, const double* val, const double* x,
-                        double* y, const unsigned char* mask, double* partial, CGState* st, double eps, int guards) {
-#define FEMB_SPMV_ARGS n, crow, col, val, x, y, mask, partial, st, eps, guards
+                        double* y, const unsigned char* mask, double* partial, CGState* st, double eps, int guards,
+                        const double* rvec = nullptr, double tol = 0.0) {
+#define FEMB_SPMV_ARGS n, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol
 #define FEMB_TMA(LRV)                                                                                                              \
   {                                                                                                                                \
     cudaFuncSetAttribute(spmv_tma_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);                 \
-    spmv_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, TMA_SMEM, s>>>(n, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); \
+    spmv_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, TMA_SMEM, s>>>(n, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
   }
 #define FEMB_BSR(LRV)                                                                                                              \
   {                                                                                                                                \
     cudaFuncSetAttribute(spmv_bsr3_tma_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSR_SMEM);            \
-    spmv_bsr3_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, BSR_SMEM, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); \
+    spmv_bsr3_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, BSR_SMEM, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
   }
   switch (lanes) {
-    case 300: spmv_bsr3_vec_kernel<FUSED, 4><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); break;
-    case 301: spmv_bsr3_vec_kernel<FUSED, 2><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards); break;
+    case 300: spmv_bsr3_vec_kernel<FUSED, 4><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); break;
+    case 301: spmv_bsr3_vec_kernel<FUSED, 2><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); break;
     case 201: FEMB_BSR(1) break;
     case 202: FEMB_BSR(2) break;
     case 204: FEMB_BSR(4) break;
@@ -433,6 +538,7 @@ extern "C" int femb_spmv(int64_t n, int64_t nnz, const int32_t* crow, const int3
   FEMB_CHECK_ARG(n >= 0, "n >= 0");
   if (n == 0) return FEMB_OK;
   cudaStream_t s = as_stream(stream);
+  spmv_apply_env_once();
   const int lanes = pick_lanes(n, nnz);
   nnz_hint = nnz;
   launch_spmv<false>(lanes, spmv_grid(n, lanes), s, n, crow, col, val, x, y, nullptr, nullptr, nullptr, 0.0, 0);
@@ -474,6 +580,7 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
                          femb_stream stream) {
   FEMB_CHECK_ARG(n > 0 && nmat >= 1 && nmat <= 8 && F && u && work && result_host, "null pointer / n <= 0 / nmat not in 1..8");
   if (check_every < 1) check_every = 16;
+  spmv_apply_env_once();
   cudaStream_t s = solver_stream(as_stream(stream));
   FEMB_CHECK_ARG(s != nullptr, "could not create the solver stream");
   const int guards = minv ? 0 : 1;  // the reference's PCG loop carries no guards and no eps (solver.py:795-810)
@@ -489,7 +596,7 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   Scratch scr(s);
   double* partial;
   CGState* st;
-  FEMB_CUDA(scr.alloc(&partial, (size_t)std::max(gmax, g2)));
+  FEMB_CUDA(scr.alloc(&partial, (size_t)std::max(3 * gmax, g2)));
   FEMB_CUDA(scr.alloc(&st, 1));
   // ---- setup (solver.py:163-181)
   if (mask) cg_mask_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, mask);
@@ -498,6 +605,11 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   cg_init_kernel<<<g2, VEC_THREADS, 0, s>>>(n, F, Ap, mask, minv, r, p, partial);
   cg_init_finish<<<1, VEC_THREADS, 0, s>>>(g2, partial, st, max_iter);
   FEMB_LAUNCH_CHECK();
+  // merged-reduction loop (2 kernels, 7 vector passes per iteration) for plain CG on every SpMV kernel that sums the two extra
+  // dot products; PCG, the LDG-streaming / block-TMA A/B kernels and FEMB_CG_CLASSIC=1 take the three-kernel loop
+  static const bool classic_env = getenv("FEMB_CG_CLASSIC") != nullptr;
+  const int ll = lanes[nmat - 1];
+  const bool merged = !classic_env && !minv && (ll >= 300 || (ll >= 100 && ll < 200) || ll < 0);
   // ---- capture `check_every` iterations into one graph
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
@@ -507,10 +619,16 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
       nnz_hint = mats[m].nnz, launch_spmv<false>(lanes[m], g1[m], s, n, mats[m].crow, mats[m].col, mats[m].val, p, Ap, nullptr, nullptr, st, 0.0, m ? 2 : 0);
     const int last = nmat - 1;
     nnz_hint = mats[last].nnz;
-    launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
-                      guards | (last ? 2 : 0));
-    cg_update_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, r, p, Ap, minv, partial, st, tol, eps, guards, max_iter);
-    cg_direction_kernel<<<g2, VEC_THREADS, 0, s>>>(n, r, p, minv, st);
+    if (merged) {
+      launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
+                        guards | (last ? 2 : 0), r, tol);
+      cg_merged_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, r, p, Ap, partial, st, max_iter);
+    } else {
+      launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
+                        guards | (last ? 2 : 0));
+      cg_update_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, r, p, Ap, minv, partial, st, tol, eps, guards, max_iter);
+      cg_direction_kernel<<<g2, VEC_THREADS, 0, s>>>(n, r, p, minv, st);
+    }
   }
   cudaError_t ce = cudaStreamEndCapture(s, &graph);
   if (ce != cudaSuccess) {

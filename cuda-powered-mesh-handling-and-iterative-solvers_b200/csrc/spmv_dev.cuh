@@ -1,5 +1,7 @@
 // Device-side building blocks shared by the single-GPU solver (krylov.cu) and the multi-GPU solver (dist.cu).
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace femb {
@@ -140,6 +142,30 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                : "memory");
 }
 
+// Same copy with an L2 evict-first policy: the matrix stream is read once per SpMV, so it should not displace the CG vectors
+// (x gathers, and u/r/p/Ap of the vector kernels), which fit in the 126 MB L2 once the operator is split over several GPUs.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+static __device__ int g_spmv_l2_hint = 1;  // per translation unit; FEMB_SPMV_L2HINT=0 switches the hint off (A/B runs)
+static inline void spmv_apply_env_once() {  // call outside stream capture, before the first launch
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  done_for = dev;
+  if (const char* e = getenv("FEMB_SPMV_L2HINT")) {
+    const int v = atoi(e);
+    cudaMemcpyToSymbol(g_spmv_l2_hint, &v, sizeof(int));
+  }
+}
+
 constexpr int TMA_THREADS = 128, TMA_STAGES = 2, TMA_CAP = 2304, TMA_CTAS_PER_SM = 4;
 constexpr size_t TMA_SMEM = (size_t)TMA_STAGES * TMA_CAP * 12;
 
@@ -148,7 +174,9 @@ template <int LR, bool NC, int THREADS = TMA_THREADS, int STAGES = TMA_STAGES, i
 __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, const int* __restrict__ crow, const int* __restrict__ col,
                                                 const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
                                                 const unsigned char* __restrict__ mask, bool accumulate, bool fused,
-                                                long long halo_row = 0x7fffffffffffffffll, Wait wait = Wait()) {
+                                                long long halo_row = 0x7fffffffffffffffll, Wait wait = Wait(),
+                                                const double* __restrict__ rvec = nullptr, double* extra = nullptr) {
+  // rvec/extra (merged-reduction CG): extra[0] += y_r * rvec_r, extra[1] += y_r * y_r for the rows this thread finishes
   constexpr int R = THREADS / LR;
   extern __shared__ __align__(128) unsigned char tma_smem[];
   double* vbuf = reinterpret_cast<double*>(tma_smem);                           // [STAGES][CAP]
@@ -157,6 +185,8 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
   __shared__ int base[STAGES];  // first staged entry of the tile (aligned down), -1 = not staged (direct path)
   const int tid = threadIdx.x, sub = tid % LR, lr = tid / LR;
   const long long ntiles = (n + R - 1) / R;
+  const bool use_hint = g_spmv_l2_hint != 0;
+  const unsigned long long pol = l2_evict_first_policy();
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -180,8 +210,13 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
     base[s] = a0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&full[s], (unsigned)cnt * 12u);
-    bulk_g2s(vbuf + (size_t)s * CAP, val + a0, (unsigned)cnt * 8u, &full[s]);
-    bulk_g2s(cbuf + (size_t)s * CAP, col + a0, (unsigned)cnt * 4u, &full[s]);
+    if (use_hint) {
+      bulk_g2s_hint(vbuf + (size_t)s * CAP, val + a0, (unsigned)cnt * 8u, &full[s], pol);
+      bulk_g2s_hint(cbuf + (size_t)s * CAP, col + a0, (unsigned)cnt * 4u, &full[s], pol);
+    } else {
+      bulk_g2s(vbuf + (size_t)s * CAP, val + a0, (unsigned)cnt * 8u, &full[s]);
+      bulk_g2s(cbuf + (size_t)s * CAP, col + a0, (unsigned)cnt * 4u, &full[s]);
+    }
   };
   int na = 0, nb = 0;  // bounds of the next tile to stage (thread 0 only)
   if (tid == 0) {
@@ -208,7 +243,7 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
     }
     const long long r = t * R + lr;
     int ra = 0, rb = 0;
-    double x_own = 0.0, y_prev = 0.0;
+    double x_own = 0.0, y_prev = 0.0, r_own = 0.0;
     bool keep = true;
     if (r < n) {
       ra = __ldg(crow + r), rb = __ldg(crow + r + 1);
@@ -216,6 +251,7 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
         if (fused) {
           x_own = ld_x<NC>(x + r);
           if (mask) keep = mask[r] != 0;
+          if (rvec) r_own = rvec[r];
         }
         if (accumulate) y_prev = y[r];
       }
@@ -254,6 +290,7 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
       if (fused) {
         if (!keep) sum = 0.0;
         dot += sum * x_own;
+        if (extra) extra[0] += sum * r_own, extra[1] += sum * sum;
       }
       y[r] = sum;
     }

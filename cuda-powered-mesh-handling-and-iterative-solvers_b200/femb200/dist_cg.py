@@ -189,8 +189,8 @@ def bench(args, dev, rank, world, metric, unit):
             "e2e": {"value": round(K / (float(ms2.item()) * 1e-3), 2), "unit": unit, "h2d_bytes_per_step": int(N * 8 / K),
                     "d2h_bytes_per_step": int(N * 8 / K),
                     "note": f"one solve call of {K} iterations per rank: F pinned host -> device, CG, owned u -> pinned host; bytes are whole-job per call / K"},
-            "gpu_launches": 4 * K + 5,
-            "roofline": {"kernel": "whole CG iteration (dist_push + dist_spmv + dist_update + dist_direction), aggregate over ranks",
+            "gpu_launches": (3 if os.environ.get("FEMB_DIST_CLASSIC") else 2) * K + 5,
+            "roofline": {"kernel": "whole CG iteration (dist_spmv3 + dist_merged_vec: merged-reduction loop, halo push folded in), aggregate over ranks",
                          "bound": "hbm", "achieved": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9, 1), "peak": hbm * world, "unit": "GB/s",
                          "frac": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9 / (hbm * world), 4), "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes": bytes_iter},
