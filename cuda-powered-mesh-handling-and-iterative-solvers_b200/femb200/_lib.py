@@ -55,6 +55,8 @@ SIGNATURES = {
     "femb_cg_solve_multi": [c_i64, c_i32, C.POINTER(c_i64), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_vp, c_vp, c_vp, c_vp,
                             c_vp, c_f64, c_i32, c_f64, c_i32, C.POINTER(CGResult), c_vp],
     "femb_csr_jacobi": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "femb_graph_from_pairs": [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
+    "femb_graph_bfs": [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, C.POINTER(c_i32), c_vp],
     "femb_dist_header_bytes": [],
     "femb_dist_alloc": [c_i64, C.POINTER(c_vp), c_vp],
     "femb_dist_open": [c_vp, C.POINTER(c_vp)],

@@ -54,16 +54,31 @@ def _operator(K, elements, N, dev):
     return crow, col, plan.assemble(K, ndof), plan
 
 
-def _cg(K, elements, F, dev, **kw):
-    """Assemble once and run the device loop.  3-dof operators (every elasticity operator of the reference,
+class _Assembled:
+    """The assembled operator of one solve.  3-dof operators (every elasticity operator of the reference,
     dofs = node*3+{0,1,2}) are stored as 3x3 block-CSR: 8.44 instead of 12 bytes per nonzero and a third of the x gathers
     per SpMV; everything else (and FEMB_NO_BSR=1, for A/B runs) takes scalar CSR."""
+
+    def __init__(self, K, elements, N, ndof, dev):
+        crow, col, val, plan = _operator(K, elements, N, dev)
+        self.bsr = None
+        if plan is not None and ndof == 3 and not os.environ.get("FEMB_NO_BSR"):
+            brow, bcol = plan.pattern(1)
+            self.bsr = _ops.Bsr3.from_csr_values(brow, bcol, val)
+        else:
+            self.csr = (crow, col, val)
+
+    def spmv(self, x):
+        return self.bsr.spmv(x) if self.bsr is not None else _ops.spmv(*self.csr, x)
+
+    def cg_solve(self, F, **kw):
+        return self.bsr.cg_solve(F, **kw) if self.bsr is not None else _ops.cg_solve(*self.csr, F, **kw)
+
+
+def _cg(K, elements, F, dev, **kw):
+    """Assemble once and run the device loop."""
     N, ndof = F.shape
-    crow, col, val, plan = _operator(K, elements, N, dev)
-    if plan is not None and ndof == 3 and not os.environ.get("FEMB_NO_BSR"):
-        brow, bcol = plan.pattern(1)
-        return _ops.Bsr3.from_csr_values(brow, bcol, val).cg_solve(F, **kw)
-    return _ops.cg_solve(crow, col, val, F, **kw)
+    return _Assembled(K, elements, N, ndof, dev).cg_solve(F, **kw)
 
 
 def stable_conjugate_gradient_solver(K, elements, F, rbe2, u_init=None, tol=1e-10, max_iter=1000, device="cuda:0", dtype=torch.float64,
@@ -112,6 +127,152 @@ def stable_conjugate_gradient_shell_solver(K, elements, F, rbe2, coords=None, un
         _report("CG", info, max_iter)
     u = u.to(dtype)
     return (u, info) if return_info else u
+
+
+# ------------------------------------------------------------------------------------------- SPC / RBE2 / RBE3 constraints
+
+def parse_spc_list(spc_list, device="cuda:0", dtype=torch.float64):
+    """[{'node','dofs','value'}] -> (nodes int32 [S], dofs int32 [S], values [S]), one entry per constrained dof
+    (solver.py:396-435).  Host loop over the dict list, as in the reference."""
+    n, d, v = [], [], []
+    for spc in spc_list:
+        for dof in spc["dofs"]:
+            n.append(spc["node"]); d.append(dof); v.append(spc["value"])
+    return (torch.tensor(n, device=device, dtype=torch.int32), torch.tensor(d, device=device, dtype=torch.int32),
+            torch.tensor(v, device=device, dtype=dtype))
+
+
+def parse_rbe2_list(rbe2_list, device="cuda:0"):
+    """[{'master','slaves','dofs'}] -> (slaves, masters, dofs) int32 [R] (solver.py:437-476)."""
+    s, m, d = [], [], []
+    for rb in rbe2_list:
+        for slave in rb["slaves"]:
+            for dof in rb["dofs"]:
+                s.append(slave); m.append(rb["master"]); d.append(dof)
+    t = lambda a: torch.tensor(a, device=device, dtype=torch.int32)  # noqa: E731
+    return t(s), t(m), t(d)
+
+
+def parse_rbe3_list(rbe3_list, device="cuda:0", dtype=torch.float64):
+    """[{'master','slaves','dofs','weights'}] -> (masters, slaves, dofs, weights, offsets int64 [n+1], weight_sums [n])
+    (solver.py:603-651)."""
+    m, s, d, w, ws, off = [], [], [], [], [], [0]
+    for rb in rbe3_list:
+        for i, slave in enumerate(rb["slaves"]):
+            for dof in rb["dofs"]:
+                m.append(rb["master"]); s.append(slave); d.append(dof); w.append(rb["weights"][i])
+        ws.append(sum(rb["weights"]))
+        off.append(len(m))
+    t = lambda a: torch.tensor(a, device=device, dtype=torch.int32)  # noqa: E731
+    return (t(m), t(s), t(d), torch.tensor(w, device=device, dtype=dtype), torch.tensor(off, device=device, dtype=torch.int64),
+            torch.tensor(ws, device=device, dtype=dtype))
+
+
+def apply_loads_to_F(F, load_list):
+    """F[node] += force for every {'node','force':[fx,fy,fz]} (solver.py:653-663), in place; one index_put instead of a host
+    loop of three element writes per load."""
+    if not load_list:
+        return
+    nodes = torch.tensor([ld["node"] for ld in load_list], device=F.device, dtype=torch.long)
+    f = torch.tensor([list(ld["force"]) for ld in load_list], device=F.device, dtype=F.dtype)
+    F.index_put_((nodes,), f, accumulate=True)
+
+
+def enforce_constraints(u, r, spc_nodes, spc_dofs, spc_values, rbe2_slaves, rbe2_masters, rbe2_dofs):
+    """RBE2 then SPC, in place (solver.py:478-510)."""
+    if rbe2_slaves.numel() > 0:
+        s, m, d = rbe2_slaves.long(), rbe2_masters.long(), rbe2_dofs.long()
+        u[s, d] = u[m, d]
+        r[s, d] = 0.0
+    if spc_nodes.numel() > 0:
+        n, d = spc_nodes.long(), spc_dofs.long()
+        u[n, d] = spc_values.to(u.dtype)
+        r[n, d] = 0.0
+
+
+def new_enforce_constraints(u, r, spc_nodes, spc_dofs, spc_values, rbe2_slaves, rbe2_masters, rbe2_dofs, rbe3_master, rbe3_slaves,
+                            rbe3_dofs, rbe3_weights, rbe3_inds, weight_sums):
+    """SPC, RBE2, then every RBE3 master dof <- weighted mean of its slaves; r is not touched on RBE3 masters
+    (solver.py:665-700).  The reference walks the RBE3 list with `.item()` host syncs per constraint and dof; here the
+    weighted sums of all (constraint, dof) pairs are formed by one index_add and written with one index_put."""
+    if spc_nodes.numel() > 0:
+        n, d = spc_nodes.long(), spc_dofs.long()
+        u[n, d] = spc_values.to(u.dtype)
+        r[n, d] = 0.0
+    if rbe2_slaves.numel() > 0:
+        s, m, d = rbe2_slaves.long(), rbe2_masters.long(), rbe2_dofs.long()
+        u[s, d] = u[m, d]
+        r[s, d] = 0.0
+    k = rbe3_inds.numel() - 1
+    if k > 0 and rbe3_master.numel() > 0:
+        nd = u.shape[1]
+        cid = torch.repeat_interleave(torch.arange(k, device=u.device), (rbe3_inds[1:] - rbe3_inds[:-1]).to(u.device))
+        key = cid * nd + rbe3_dofs.long()
+        sums = torch.zeros(k * nd, device=u.device, dtype=u.dtype).index_add_(0, key, rbe3_weights.to(u.dtype) * u[rbe3_slaves.long(), rbe3_dofs.long()])
+        # one RBE3 after the other in the reference: a later master may read an earlier master's fresh value only if it is
+        # one of its slaves -- not supported by the vectorised form and rejected here
+        uk = torch.unique(key)
+        masters = rbe3_master.long()[rbe3_inds[:-1].long().to(u.device)][uk // nd]
+        if bool(torch.isin(rbe3_slaves.long(), masters).any()):
+            raise ValueError("an RBE3 master is also an RBE3 slave: chained RBE3 constraints are not supported")
+        u[masters, uk % nd] = sums[uk] / (weight_sums.to(u.dtype)[uk // nd] + 1e-30)
+
+
+def _constrained_solve(K, elements, F, spc, rbe2, rbe3, u_init, tol, max_iter, dev, dtype, eps, return_info, verbose):
+    """Both constrained CG loops of the reference.  On SPC and RBE2-slave dofs r is zeroed before p = r, so p stays zero there
+    and the loop is the dof-masked CG on the remaining dofs; the values written into u on constrained dofs (SPC values,
+    RBE2 copies, RBE3 means) never feed back into r.  The device loop therefore solves the masked problem for the
+    increment u - u_init and the constraints are written once, in the reference's order, on the final iterate."""
+    F = torch.as_tensor(F).to(dev, torch.float64)
+    N, nd = F.shape
+    A = _Assembled(K, elements, N, nd, dev)
+    mask = torch.ones((N, nd), device=dev, dtype=torch.uint8)
+    if spc[0].numel():
+        mask[spc[0].long(), spc[1].long()] = 0
+    if rbe2[0].numel():
+        mask[rbe2[0].long(), rbe2[2].long()] = 0
+    if u_init is None:
+        u0, rhs = torch.zeros_like(F), F
+    else:
+        u0 = torch.as_tensor(u_init).to(dev, torch.float64).clone()
+        rhs = F - A.spmv(u0.reshape(-1)).reshape(N, nd)
+    du, info = A.cg_solve(rhs, mask=mask.reshape(-1).contiguous(), tol=tol, max_iter=max_iter, eps=eps)
+    u = u0 + du
+    scratch = torch.zeros_like(u)
+    for _ in range(2):  # the reference enforces after every update: a second pass lets values set late in a pass (an SPC value on
+        # an RBE2 master, an RBE2 copy feeding an RBE3 mean) reach their dependants exactly as they do there
+        if rbe3 is None:
+            enforce_constraints(u, scratch, *spc, *rbe2)
+        else:
+            new_enforce_constraints(u, scratch, *spc, *rbe2, *rbe3)
+    if verbose:
+        if info["status"] == "converged":
+            print(f"[CG] Converged @ iter {info['iterations']}, residual norm = {info['rs']:.3e}")
+        elif info["status"] == "breakdown":
+            print(f"[CG] Early terminate @ iter {info['iterations']}: p^T K p not valid for SPD / NaN step.")
+        else:
+            print("[CG] Did not converge within max_iter.")
+    u = u.to(dtype)
+    return (u, info) if return_info else u
+
+
+def constrained_conjugate_gradient_solver(K, elements, F, rbe2_list, spc_list, u_init=None, tol=1e-10, max_iter=1000, device="cuda:0",
+                                          dtype=torch.float64, eps=1e-30, return_info=False, verbose=True):
+    """CG with SPC and RBE2 constraints given as dict lists (solver.py:512-596)."""
+    dev = _ops.cuda_device(device)
+    return _constrained_solve(K, elements, F, parse_spc_list(spc_list, dev, torch.float64), parse_rbe2_list(rbe2_list, dev), None, u_init,
+                              tol, max_iter, dev, dtype, eps, return_info, verbose)
+
+
+def new_constrained_conjugate_gradient_solver(K, elements, N, rbe2_list, rbe3_list, spc_list, load_list, u_init=None, tol=1e-10,
+                                              max_iter=1000, device="cuda:0", dtype=torch.float64, eps=1e-30, return_info=False,
+                                              verbose=True):
+    """Builds F [N,3] from the load list, then CG with SPC, RBE2 and RBE3 constraints (solver.py:702-759)."""
+    dev = _ops.cuda_device(device)
+    F = torch.zeros((N, 3), device=dev, dtype=torch.float64)
+    apply_loads_to_F(F, load_list)
+    return _constrained_solve(K, elements, F, parse_spc_list(spc_list, dev, torch.float64), parse_rbe2_list(rbe2_list, dev),
+                              parse_rbe3_list(rbe3_list, dev, torch.float64), u_init, tol, max_iter, dev, dtype, eps, return_info, verbose)
 
 
 def compute_diagonal_preconditioner(K, elements, N, device="cuda:0", dtype=torch.float32, fixed=None, reference_bug=False):

@@ -223,6 +223,21 @@ int femb_csr_jacobi(int64_t n, const int32_t* crow, const int32_t* col, const do
                     double* minv, femb_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Element-graph partition (subdivision.ipynb cells 8-9: build_adjacency_matrix, pick_distant_seeds,
+ * region_growing_partition)
+ * ------------------------------------------------------------------------------------------- */
+/* Symmetric CSR adjacency of M vertices from S undirected pairs.  pairs: int64, vertex ids at [t*pair_stride] and
+ * [t*pair_stride + pair_stride/2] -- pair_stride = 4 reads the [S,2,2] output of femb_entities_shared directly (element
+ * ids at 0 and 2), pair_stride = 2 a plain [S,2] list.  crow[M+1], col[2S], neighbours ascending.  Synchronises. */
+int femb_graph_from_pairs(const int64_t* pairs, int64_t S, int pair_stride, int64_t M, int32_t* crow, int32_t* col,
+                          femb_stream stream);
+/* Level-synchronous multi-source BFS: dist[M] (hops to the nearest source, -1 unreachable) and, when label != NULL,
+ * label[M] = index (into sources) of the region that reached the vertex first, highest index on ties.  One kernel per
+ * level; the host reads one flag per level.  levels_host (optional) receives the number of levels.  Synchronises. */
+int femb_graph_bfs(const int32_t* crow, const int32_t* col, int64_t M, const int64_t* sources, int n_sources, int32_t* dist,
+                   int32_t* label, int32_t* levels_host, femb_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU CG over NVLink peer memory (one process per GPU; nothing to match in the reference)
  * ------------------------------------------------------------------------------------------- */
 /* Each rank allocates one "symmetric" buffer = header (femb_dist_header_bytes) + p[n_owned+n_ghost] doubles with

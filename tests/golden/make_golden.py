@@ -12,6 +12,7 @@ because the reference iterates an undefined name (solver/element.py:824).
 """
 import contextlib
 import io
+import json
 import os
 import re
 import sys
@@ -62,7 +63,7 @@ def quiet(fn, *a, **k):
 
 
 def iters_of(text):
-    m = re.search(r"Converged after (\d+) iterations", text)
+    m = re.search(r"Converged after (\d+) iterations", text) or re.search(r"Converged @ iter (\d+)", text)
     return int(m.group(1)) if m else -1
 
 
@@ -302,6 +303,69 @@ def gen_stress():
     save("stress", **{k: npy(v) for k, v in o.items()})
 
 
+CONSTRAINTS = dict(
+    spc=[{"node": 0, "dofs": [0, 1, 2], "value": 0.0}, {"node": 4, "dofs": [0, 1, 2], "value": 0.0},
+         {"node": 20, "dofs": [0, 1, 2], "value": 0.0}, {"node": 24, "dofs": [0, 1, 2], "value": 0.0},
+         {"node": 12, "dofs": [2], "value": 0.002}, {"node": 2, "dofs": [0, 2], "value": 0.0}],
+    rbe2=[{"master": 124, "slaves": [123, 119, 118], "dofs": [0, 1, 2]}, {"master": 104, "slaves": [103], "dofs": [2]}],
+    rbe3=[{"master": 62, "slaves": [61, 63, 57, 67], "dofs": [0, 1, 2], "weights": [1.0, 2.0, 1.0, 0.5]},
+          {"master": 112, "slaves": [111, 113], "dofs": [2], "weights": [1.0, 3.0]}],
+    loads=[{"node": 124, "force": [0.0, 0.0, -0.01]}, {"node": 100, "force": [0.002, 0.0, -0.005]},
+           {"node": 62, "force": [0.0, 0.003, 0.0]}])
+
+
+def gen_constrained():
+    """SPC / RBE2 / RBE3 constrained CG (SURVEY 8f next #2) on the n=4 Kuhn cube (125 nodes)."""
+    coords, tets = meshgen.kuhn_cube(4, jitter=0.1)
+    N = coords.shape[0]
+    K = R.compute_c3d4_K_matrix(coords, tets, E, NU, **KW)
+    C = CONSTRAINTS
+    F = torch.zeros(N, 3, dtype=torch.float64)
+    RV.apply_loads_to_F(F, C["loads"])
+    u1, t1 = quiet(RV.constrained_conjugate_gradient_solver, K, tets, F, C["rbe2"], C["spc"], tol=1e-9, max_iter=2000, **KW)
+    u2, t2 = quiet(RV.new_constrained_conjugate_gradient_solver, K, tets, N, C["rbe2"], C["rbe3"], C["spc"], C["loads"], tol=1e-9,
+                   max_iter=2000, **KW)
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.randn(N, 3, dtype=torch.float64, generator=g) * 1e-3
+    u3, t3 = quiet(RV.constrained_conjugate_gradient_solver, K, tets, F, C["rbe2"], C["spc"], u_init=u0, tol=1e-9, max_iter=2000, **KW)
+    sp = RV.parse_spc_list(C["spc"], device="cpu")
+    r2 = RV.parse_rbe2_list(C["rbe2"], device="cpu")
+    r3 = RV.parse_rbe3_list(C["rbe3"], device="cpu")
+    save("constrained", coords=npy(coords), tets=npy(tets), F=npy(F), u_c=npy(u1), it_c=iters_of(t1), u_n=npy(u2), it_n=iters_of(t2),
+         u0=npy(u0), u_c0=npy(u3), it_c0=iters_of(t3), spc_n=npy(sp[0]), spc_d=npy(sp[1]), spc_v=npy(sp[2]), r2_s=npy(r2[0]),
+         r2_m=npy(r2[1]), r2_d=npy(r2[2]), r3_m=npy(r3[0]), r3_s=npy(r3[1]), r3_d=npy(r3[2]), r3_w=npy(r3[3]), r3_i=npy(r3[4]),
+         r3_ws=npy(r3[5]), constraints_json=np.array(json.dumps(C)))
+
+
+def gen_partition():
+    """subdivision.ipynb cells 7-9 executed as written (CPU), with torch.randint pinned so the first seed is reproducible."""
+    import math
+    nb = json.load(open("/root/reference/subdivision.ipynb"))
+    ns = {"torch": torch, "math": math}
+    exec("".join(nb["cells"][7]["source"]).split("\nprint(")[0], ns)
+    exec("".join(nb["cells"][9]["source"]), ns)
+    coords, tets = meshgen.kuhn_cube(4, jitter=0.1)
+    M = tets.shape[0]
+    K = R.compute_c3d4_K_matrix(coords, tets, E, NU, **KW)
+    sh = R.identify_tetrahedral_shared_faces(tets, device="cpu")
+    edge = torch.cat([sh[:, 0, 0].unsqueeze(0), sh[:, 1, 0].unsqueeze(0)], dim=0)
+    first = 37
+    real_randint = torch.randint
+    torch.randint = lambda *a, **k: torch.tensor([first])
+    try:
+        groups, seeds = ns["region_growing_partition"](edge, 5, M, device="cpu")
+    finally:
+        torch.randint = real_randint
+    labels = torch.full((M,), -1, dtype=torch.long)
+    for i, g in enumerate(groups):
+        labels[g] = i
+    Kl, gn = ns["build_sparse_K_local"](K, tets, groups[2], device="cpu")
+    csr = Kl.coalesce().to_sparse_csr()
+    save("partition", coords=npy(coords), tets=npy(tets), edge=npy(edge), first=first, labels=npy(labels), seeds=npy(seeds),
+         group2=npy(groups[2]), nodes2=npy(gn), crow2=npy(csr.crow_indices()), col2=npy(csr.col_indices()), val2=npy(csr.values()),
+         subdiv=np.array([ns["compute_subdivisions"](338619, 10), ns["compute_subdivisions"](1000, 1), ns["compute_subdivisions"](3000000, 4)]))
+
+
 def gen_quadratic():
     """The two C3D20 functions of the reference that run: the 27-point rule and the 24-tet table."""
     p, w = R.c3d20_integration_points(**KW)
@@ -319,3 +383,5 @@ if __name__ == "__main__":
     gen_solve()
     gen_stress()
     gen_quadratic()
+    gen_constrained()
+    gen_partition()

@@ -782,3 +782,66 @@ def test_bsr3_operator(api, O, mesh):
     u4, i4 = ops.cg_solve(crow, col, val, F, minv=minv, tol=1e-9, max_iter=5000)
     assert i3["status"] == "converged" and abs(i3["iterations"] - i4["iterations"]) <= (1 if mesh != "hex20" else 3)
     close(u3, N(u4), 1e-8)
+
+
+def test_constrained_cg(api):
+    """SPC / RBE2 / RBE3 constrained CG (solver.py:512-596, 702-759) against the reference's own outputs."""
+    import json
+    _, _, sv = api
+    el = api[0]
+    g = load_golden("constrained")
+    C = json.loads(str(g["constraints_json"]))
+    c, t, F = T(g["coords"]), T(g["tets"]), T(g["F"])
+    K = el.compute_c3d4_K_matrix(c, t, E, NU, **KW)
+    u, info = sv.constrained_conjugate_gradient_solver(K, t, F, C["rbe2"], C["spc"], tol=1e-9, max_iter=2000, device=DEV, return_info=True,
+                                                       verbose=False)
+    assert info["status"] == "converged" and abs(info["iterations"] - int(g["it_c"])) <= 1
+    close(u, g["u_c"], 1e-8)
+    u, info = sv.new_constrained_conjugate_gradient_solver(K, t, c.shape[0], C["rbe2"], C["rbe3"], C["spc"], C["loads"], tol=1e-9,
+                                                           max_iter=2000, device=DEV, return_info=True, verbose=False)
+    assert info["status"] == "converged" and abs(info["iterations"] - int(g["it_n"])) <= 1
+    close(u, g["u_n"], 1e-8)
+    u, info = sv.constrained_conjugate_gradient_solver(K, t, F, C["rbe2"], C["spc"], u_init=T(g["u0"]), tol=1e-9, max_iter=2000, device=DEV,
+                                                       return_info=True, verbose=False)
+    assert info["status"] == "converged" and abs(info["iterations"] - int(g["it_c0"])) <= 1
+    close(u, g["u_c0"], 1e-8)
+    # constrained dofs carry exactly the prescribed values / copies
+    un = N(sv.constrained_conjugate_gradient_solver(K, t, F, C["rbe2"], C["spc"], tol=1e-9, max_iter=2000, device=DEV, verbose=False))
+    assert un[12, 2] == 0.002 and np.array_equal(un[123], un[124]) and un[103, 2] == un[104, 2]
+    Fz = torch.zeros_like(F).to(DEV)
+    sv.apply_loads_to_F(Fz, C["loads"])
+    close(Fz, g["F"], 0)
+
+
+def test_region_growing_partition(api, O):
+    """subdivision.ipynb cells 8-9 against the notebook's own code run on the CPU (tests/golden/partition.npz)."""
+    import subdivision as sd
+    el = api[0]
+    g = load_golden("partition")
+    t = T(g["tets"])
+    M = t.shape[0]
+    sh = el.identify_tetrahedral_shared_faces(t, device=DEV)
+    edge = torch.cat([sh[:, 0, 0].unsqueeze(0), sh[:, 1, 0].unsqueeze(0)], dim=0)            # cell 8
+    adj = sd.build_adjacency_matrix(edge, M, DEV)
+    nbr = O._adjacency_lists(g["edge"], M)
+    crow, col = N(adj.crow), N(adj.col)
+    assert all(sorted(nbr[v]) == col[crow[v]:crow[v + 1]].tolist() for v in range(M))
+    adj2 = sd.build_adjacency_matrix(sh, M, DEV)                                             # [S,2,2] accepted directly
+    assert torch.equal(adj2.crow, adj.crow) and torch.equal(adj2.col, adj.col)
+    groups, seeds = sd.region_growing_partition(edge, 5, M, device=DEV, first_seed=int(g["first"]))
+    same(seeds, g["seeds"])
+    lab = np.full(M, -1)
+    for i, grp in enumerate(groups):
+        lab[N(grp)] = i
+    assert np.array_equal(lab, g["labels"])
+    K = el.compute_c3d4_K_matrix(T(g["coords"]), t, E, NU, **KW)
+    Kl, gn = sd.build_sparse_K_local(K, t, groups[2], device=DEV)
+    same(gn, g["nodes2"]); same(Kl.crow_indices(), g["crow2"]); same(Kl.col_indices(), g["col2"]); close(Kl.values(), g["val2"])
+    Kp, maps, grp2, sd2 = sd.partition_and_build_sparse_K(K, t, edge, 5, device=DEV, first_seed=int(g["first"]))
+    assert len(Kp) == 5 and sum(x.numel() for x in grp2) == M
+    iface = sd.build_ordered_subdomain_map(maps)
+    assert all(len(k) >= 2 for k in iface) and len(iface) > 0
+    # disconnected graph: two components, one seed -> the other component stays unassigned instead of looping forever
+    e2 = torch.tensor([[0, 2], [1, 3]])
+    gr, _ = sd.region_growing_partition(e2, 1, 4, device=DEV, first_seed=0)
+    assert N(gr[0]).tolist() == [0, 1]

@@ -1,5 +1,7 @@
 """Pin the CPU oracle (oracle/fem_oracle.py) against outputs of the reference itself
 (tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -347,3 +349,50 @@ def test_mass_rules_are_exact():
             for k in range(6):
                 exact = factorial(i) * factorial(j) / factorial(i + j + 2) * (0 if k % 2 else 2 / (k + 1))
                 assert abs((w * p[:, 0] ** i * p[:, 1] ** j * p[:, 2] ** k).sum() - exact) < 1e-15
+
+
+def test_constrained_cg():
+    """SURVEY 8f next #2: SPC / RBE2 / RBE3 constrained CG loops against the reference's outputs."""
+    import json
+    g = load_golden("constrained")
+    C = json.loads(str(g["constraints_json"]))
+    sp, r2, r3 = O.parse_spc(C["spc"]), O.parse_rbe2(C["rbe2"]), O.parse_rbe3(C["rbe3"])
+    for a, b in zip(sp + r2 + r3, [g[k] for k in ("spc_n", "spc_d", "spc_v", "r2_s", "r2_m", "r2_d", "r3_m", "r3_s", "r3_d", "r3_w", "r3_i", "r3_ws")]):
+        assert np.array_equal(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64))
+    K = O.c3d4_K(g["coords"], g["tets"], E, NU)
+    ap = lambda v: O.nodal_forces(K, g["tets"], v)  # noqa: E731
+    u, it, st = O.constrained_cg(ap, g["F"], C["rbe2"], C["spc"], tol=1e-9, max_iter=2000)
+    assert st == "converged" and abs(it - int(g["it_c"])) <= 1
+    close(u, g["u_c"], 1e-8)
+    u, it, st = O.constrained_cg(ap, g["F"], C["rbe2"], C["spc"], rbe3_list=C["rbe3"], tol=1e-9, max_iter=2000)
+    assert st == "converged" and abs(it - int(g["it_n"])) <= 1
+    close(u, g["u_n"], 1e-8)
+    u, it, st = O.constrained_cg(ap, g["F"], C["rbe2"], C["spc"], u_init=g["u0"], tol=1e-9, max_iter=2000)
+    assert st == "converged" and abs(it - int(g["it_c0"])) <= 1
+    close(u, g["u_c0"], 1e-8)
+    # the product's host-side parsers (no GPU needed) produce the reference's tensors
+    import sys
+    from conftest import PKG
+    sys.path.insert(0, os.path.join(PKG, "solver"))
+    import solver as sv
+    got = sv.parse_spc_list(C["spc"], device="cpu") + sv.parse_rbe2_list(C["rbe2"], device="cpu") + sv.parse_rbe3_list(C["rbe3"], device="cpu")
+    keys = ("spc_n", "spc_d", "spc_v", "r2_s", "r2_m", "r2_d", "r3_m", "r3_s", "r3_d", "r3_w", "r3_i", "r3_ws")
+    for t, k in zip(got, keys):
+        assert np.array_equal(t.numpy().astype(np.float64), g[k].astype(np.float64)), k
+    assert got[0].dtype.is_floating_point is False and str(got[0].dtype) == "torch.int32" and str(got[10].dtype) == "torch.int64"
+
+
+def test_partition_oracle():
+    """subdivision.ipynb cells 7-9 (SURVEY a25): the oracle reproduces the notebook code's partition exactly."""
+    g = load_golden("partition")
+    lab, seeds = O.region_growing_partition(g["edge"], 5, g["tets"].shape[0], int(g["first"]))
+    assert np.array_equal(seeds, g["seeds"]) and np.array_equal(lab, g["labels"])
+    assert [O.compute_subdivisions(338619, 10), O.compute_subdivisions(1000, 1), O.compute_subdivisions(3000000, 4)] == g["subdiv"].tolist()
+    from conftest import PKG
+    import sys
+    sys.path.insert(0, os.path.join(PKG, "solver"))
+    import subdivision as sd
+    assert sd.compute_subdivisions(338619, 10) == int(g["subdiv"][0])
+    nm = [np.array([0, 1, 2, 5]), np.array([2, 3, 5]), np.array([5, 6])]
+    import torch
+    assert sd.build_ordered_subdomain_map([torch.tensor(a) for a in nm]) == {(0, 1): [2], (0, 1, 2): [5]}
