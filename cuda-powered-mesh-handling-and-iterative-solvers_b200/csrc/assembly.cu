@@ -969,3 +969,107 @@ extern "C" int femb_ebe_apply(femb_csr_plan* p, int ndof, const void* Ke, const 
   FEMB_LAUNCH_CHECK();
   return FEMB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// shell_extrude (shell.py:885-983): per-node normals of a mid-surface mesh of triangles and quads, then bottom / top layers.
+// The reference scatters unit face normals with index_add_ (triangles, then each quad's triangle (0,1,2), then its
+// triangle (0,2,3)); here every node walks its incidence lists in that same order, so the sums are deterministic.
+namespace femb {
+
+template <typename T>
+__device__ __forceinline__ void add_unit_normal(const T* __restrict__ X, int n0, int n1, int n2, T eps, T* s) {
+  T a[3], b[3];
+  for (int c = 0; c < 3; ++c) {
+    const T x0 = __ldg(X + 3ll * n0 + c);
+    a[c] = __ldg(X + 3ll * n1 + c) - x0;
+    b[c] = __ldg(X + 3ll * n2 + c) - x0;
+  }
+  const T n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+  const T len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) + eps;
+  for (int c = 0; c < 3; ++c) s[c] += n[c] / len;
+}
+
+template <typename T>
+__global__ void extrude_nodes_kernel(const int* __restrict__ tconn, const int* __restrict__ tptr, const int* __restrict__ tinc,
+                                     const int* __restrict__ qconn, const int* __restrict__ qptr, const int* __restrict__ qinc,
+                                     const T* __restrict__ X, long long N, T eps, T half_t, T* __restrict__ out) {
+  for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    T s[3] = {0, 0, 0};
+    T cnt = 0;
+    if (tptr) {
+      for (int k = tptr[n]; k < tptr[n + 1]; ++k) {
+        const int e = tinc[k] / 3;
+        add_unit_normal(X, tconn[3 * e], tconn[3 * e + 1], tconn[3 * e + 2], eps, s);
+        cnt += 1;
+      }
+    }
+    if (qptr) {
+      const int b = qptr[n], e1 = qptr[n + 1];
+      for (int k = b; k < e1; ++k) {  // quad[:, :3]
+        const int e = qinc[k] >> 2, a = qinc[k] & 3;
+        if (a == 3) continue;
+        add_unit_normal(X, qconn[4 * e], qconn[4 * e + 1], qconn[4 * e + 2], eps, s);
+        cnt += 1;
+      }
+      for (int k = b; k < e1; ++k) {  // quad[:, [0,2,3]]
+        const int e = qinc[k] >> 2, a = qinc[k] & 3;
+        if (a == 1) continue;
+        add_unit_normal(X, qconn[4 * e], qconn[4 * e + 2], qconn[4 * e + 3], eps, s);
+        cnt += 1;
+      }
+    }
+    T len = 0;
+    for (int c = 0; c < 3; ++c) {
+      s[c] = s[c] / (cnt + eps);
+      len += s[c] * s[c];
+    }
+    len = sqrt(len) + eps;
+    for (int c = 0; c < 3; ++c) {
+      const T x = X[3 * n + c], d = half_t * (s[c] / len);
+      out[3 * n + c] = x - d;
+      out[3 * (n + N) + c] = x + d;
+    }
+  }
+}
+
+template <typename I>
+__global__ void extrude_conn_kernel(const I* __restrict__ conn, long long M, int nen, long long N, I* __restrict__ out) {
+  const long long total = M * 2 * nen;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = t / (2 * nen);
+    const int a = (int)(t - e * 2 * nen);
+    out[t] = a < nen ? conn[e * nen + a] : (I)(conn[e * nen + a - nen] + N);
+  }
+}
+
+}  // namespace femb
+
+extern "C" int femb_shell_extrude(femb_csr_plan* tri, femb_csr_plan* quad, const void* coords, int fp, int64_t N, double thickness, double eps,
+                                  void* coords3d, femb_stream stream) {
+  FEMB_CHECK_ARG((fp == 4 || fp == 8) && N >= 0 && coords && coords3d, "fp in {4,8}, N >= 0, non-null buffers");
+  FEMB_CHECK_ARG(!tri || (tri->nen == 3 && tri->N == N), "triangle plan: nen = 3 and n_nodes = N");
+  FEMB_CHECK_ARG(!quad || (quad->nen == 4 && quad->N == N), "quad plan: nen = 4 and n_nodes = N");
+  if (N == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int grid = grid_for(N, 128);
+  const int *tc = tri ? tri->conn32 : nullptr, *tp = tri ? tri->inc_ptr : nullptr, *ti = tri ? tri->inc : nullptr;
+  const int *qc = quad ? quad->conn32 : nullptr, *qp = quad ? quad->inc_ptr : nullptr, *qi = quad ? quad->inc : nullptr;
+  if (fp == 8)
+    extrude_nodes_kernel<double><<<grid, 128, 0, s>>>(tc, tp, ti, qc, qp, qi, (const double*)coords, N, eps, 0.5 * thickness, (double*)coords3d);
+  else
+    extrude_nodes_kernel<float><<<grid, 128, 0, s>>>(tc, tp, ti, qc, qp, qi, (const float*)coords, N, (float)eps, (float)(0.5 * thickness),
+                                                     (float*)coords3d);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+extern "C" int femb_extrude_connectivity(const void* conn, int ib, int64_t M, int nen, int64_t N, void* out, femb_stream stream) {
+  FEMB_CHECK_ARG((ib == 4 || ib == 8) && M >= 0 && nen >= 1, "ib in {4,8}, M >= 0, nen >= 1");
+  if (M == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int grid = grid_for(M * 2 * nen, 256);
+  if (ib == 8) extrude_conn_kernel<long long><<<grid, 256, 0, s>>>((const long long*)conn, M, nen, N, (long long*)out);
+  else extrude_conn_kernel<int><<<grid, 256, 0, s>>>((const int*)conn, M, nen, N, (int*)out);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}

@@ -37,26 +37,49 @@ __device__ __forceinline__ void shell_frame(const T (*x)[3], T* u) {
   u[8] = a[0] * b[1] - a[1] * b[0];
 }
 
+// f = (1-xi, 1+xi, 1-eta, 1+eta): the four bilinear factors arrive evaluated by the host, because the reference forms them in
+// the dtype of whatever it was handed -- python doubles on the K path (`.item()`, shell.py:841-842), 0-dim fp32 tensors when
+// compute_s4_B_matrix iterates over its fp32 rule (shell.py:813-814 -> :683-695)
 template <int NEN>
-__device__ __forceinline__ void shell_dparam(double xi, double eta, double* dxi, double* deta) {
+__device__ __forceinline__ void shell_dparam(const double* f, double* dxi, double* deta) {
   if (NEN == 3) {
     dxi[0] = -1, dxi[1] = 1, dxi[2] = 0;
     deta[0] = -1, deta[1] = 0, deta[2] = 1;
   } else {
-    dxi[0] = 0.25 * -(1 - eta), dxi[1] = 0.25 * (1 - eta), dxi[2] = 0.25 * (1 + eta), dxi[3] = 0.25 * -(1 + eta);
-    deta[0] = 0.25 * -(1 - xi), deta[1] = 0.25 * -(1 + xi), deta[2] = 0.25 * (1 + xi), deta[3] = 0.25 * (1 - xi);
+    dxi[0] = 0.25 * -f[2], dxi[1] = 0.25 * f[2], dxi[2] = 0.25 * f[3], dxi[3] = 0.25 * -f[3];
+    deta[0] = 0.25 * -f[0], deta[1] = 0.25 * -f[1], deta[2] = 0.25 * f[1], deta[3] = 0.25 * f[0];
   }
 }
 
 struct ShellPts {
-  double p[16][4];
+  double f[16][4];  // 1-xi, 1+xi, 1-eta, 1+eta
+  double w[16];
   double D[36];
 };
 
-// what 0 unit [M,3,3]; 1 J [M,2,2]; 2 grads [M,NEN,2]; 3 B [M,6,6NEN]; 4 K [M,ND,ND]; 5 per-point K [M,ND,ND,nq]
+// B [6, 6 NEN] from the nodal gradients (shell.py:417-437, :772-798); `stride` > 1 writes one point of a [.., nq] layout
+template <typename T, int NEN>
+__device__ __forceinline__ void shell_store_B(T* __restrict__ B, int stride, const T* gx, const T* gy) {
+  constexpr int ND = 6 * NEN;
+  for (int k = 0; k < 6 * ND; ++k) B[(size_t)k * stride] = 0;
+  for (int a = 0; a < NEN; ++a) {
+    B[(size_t)(0 * ND + 6 * a + 0) * stride] = gx[a];
+    B[(size_t)(1 * ND + 6 * a + 1) * stride] = gy[a];
+    B[(size_t)(2 * ND + 6 * a + 0) * stride] = gy[a];
+    B[(size_t)(2 * ND + 6 * a + 1) * stride] = gx[a];
+    B[(size_t)(3 * ND + 6 * a + 4) * stride] = -gx[a];
+    B[(size_t)(4 * ND + 6 * a + 3) * stride] = gy[a];
+    B[(size_t)(5 * ND + 6 * a + 3) * stride] = gy[a];
+    B[(size_t)(5 * ND + 6 * a + 4) * stride] = gx[a];
+  }
+}
+
+// what 0 unit [M,3,3]; 1 J [M,2,2]; 2 grads [M,NEN,2]; 3 B [M,6,6NEN]; 4 K [M,ND,ND]; 5 per-point K [M,ND,ND,nq];
+//      7 sum_q w_q B_q [M,6,ND]; 8 per-point w_q B_q [M,6,ND,nq];
+//      9 stress resultants [M,6] = D (sum_q w_q B_q) u_e with u_e = disp[conn] taken in GLOBAL axes as the reference does
 template <typename T, typename I, int NEN>
 __global__ void __launch_bounds__(64) shell_kernel(const T* __restrict__ coords, const I* __restrict__ conn, long long M, ShellPts sp, int nq,
-                                                   int what, T* __restrict__ out) {
+                                                   int what, const T* __restrict__ disp, T* __restrict__ out) {
   constexpr int ND = 6 * NEN;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < M; e += (long long)gridDim.x * blockDim.x) {
     T x[NEN][3];
@@ -78,9 +101,11 @@ __global__ void __launch_bounds__(64) shell_kernel(const T* __restrict__ coords,
     }
     T* Ko = out + e * (size_t)ND * ND * (what == 5 ? nq : 1);
     const int npts = (what >= 4) ? nq : 1;
+    T Gx[NEN], Gy[NEN];  // what 7 / 9: weighted sums of the gradients over the rule
+    for (int a = 0; a < NEN; ++a) Gx[a] = 0, Gy[a] = 0;
     for (int q = 0; q < npts; ++q) {
       double dxi_d[4], deta_d[4];
-      shell_dparam<NEN>(sp.p[q][0], sp.p[q][1], dxi_d, deta_d);
+      shell_dparam<NEN>(sp.f[q], dxi_d, deta_d);
       T dxi[NEN], deta[NEN];
       for (int a = 0; a < NEN; ++a) dxi[a] = (T)dxi_d[a], deta[a] = (T)deta_d[a];
       T J[4] = {0, 0, 0, 0};
@@ -106,22 +131,22 @@ __global__ void __launch_bounds__(64) shell_kernel(const T* __restrict__ coords,
         break;
       }
       if (what == 3) {
-        T* B = out + e * 6 * ND;
-        for (int k = 0; k < 6 * ND; ++k) B[k] = 0;
-        for (int a = 0; a < NEN; ++a) {
-          B[0 * ND + 6 * a + 0] = gx[a];
-          B[1 * ND + 6 * a + 1] = gy[a];
-          B[2 * ND + 6 * a + 0] = gy[a];
-          B[2 * ND + 6 * a + 1] = gx[a];
-          B[3 * ND + 6 * a + 4] = -gx[a];
-          B[4 * ND + 6 * a + 3] = gy[a];
-          B[5 * ND + 6 * a + 3] = gy[a];
-          B[5 * ND + 6 * a + 4] = gx[a];
-        }
+        shell_store_B<T, NEN>(out + e * 6 * ND, 1, gx, gy);
         break;
       }
+      if (what >= 7) {
+        const T wq = NEN == 3 ? T(1) : (T)sp.w[q];
+        if (what == 8) {
+          T wx[NEN], wy[NEN];
+          for (int a = 0; a < NEN; ++a) wx[a] = gx[a] * wq, wy[a] = gy[a] * wq;
+          shell_store_B<T, NEN>(out + e * 6 * ND * nq + q, nq, wx, wy);
+        } else {
+          for (int a = 0; a < NEN; ++a) Gx[a] += gx[a] * wq, Gy[a] += gy[a] * wq;
+        }
+        continue;
+      }
       // K_ab = B_a^T D B_b * detJ * w ; only dof rows/cols {0,1,3,4} are populated
-      const T wt = det * (NEN == 3 ? T(0.5) : (T)sp.p[q][3]);
+      const T wt = det * (NEN == 3 ? T(0.5) : (T)sp.w[q]);
       for (int a = 0; a < NEN; ++a) {
         // Ba columns for dofs 0,1,3,4 as 6-vectors
         const T Ba[4][6] = {{gx[a], 0, gy[a], 0, 0, 0}, {0, gy[a], gx[a], 0, 0, 0}, {0, 0, 0, 0, gy[a], gy[a]}, {0, 0, 0, -gx[a], 0, gx[a]}};
@@ -151,37 +176,77 @@ __global__ void __launch_bounds__(64) shell_kernel(const T* __restrict__ coords,
         }
       }
     }
+    if (what == 7) shell_store_B<T, NEN>(out + e * 6 * ND, 1, Gx, Gy);
+    if (what == 9) {
+      // strain = B u_e (rows: exx, eyy, gxy from u,v; kx, ky, kxy from thx, thy), stress = D strain (shell.py:455-481, :863-879)
+      T st[6] = {0, 0, 0, 0, 0, 0};
+      for (int a = 0; a < NEN; ++a) {
+        const long long n = ldidx(conn + e * NEN + a);
+        const T ux = __ldg(disp + 6 * n), uy = __ldg(disp + 6 * n + 1), tx = __ldg(disp + 6 * n + 3), ty = __ldg(disp + 6 * n + 4);
+        st[0] += Gx[a] * ux;
+        st[1] += Gy[a] * uy;
+        st[2] += Gy[a] * ux + Gx[a] * uy;
+        st[3] += -Gx[a] * ty;
+        st[4] += Gy[a] * tx;
+        st[5] += Gy[a] * tx + Gx[a] * ty;
+      }
+      for (int r = 0; r < 6; ++r) {
+        T sg = 0;
+        for (int c = 0; c < 6; ++c) sg += st[c] * (T)sp.D[r * 6 + c];
+        out[e * 6 + r] = sg;
+      }
+    }
   }
 }
 
+// fac = [nq,5] rows (1-xi, 1+xi, 1-eta, 1+eta, w) on the host
 template <typename T, typename I>
-static int shell_dispatch(int kind, int what, const void* coords, const void* conn, long long M, const double* pts, int nq, const double* D6,
-                          void* out, cudaStream_t s) {
+static int shell_dispatch(int kind, int what, const void* coords, const void* conn, long long M, const double* fac, int nq, const double* D6,
+                          const void* disp, void* out, cudaStream_t s) {
+  FEMB_CHECK_ARG(what >= 0 && what <= 9 && what != 6, "femb_shell: what in 0..5, 7..9");
+  FEMB_CHECK_ARG(kind == FEMB_S3 || kind == FEMB_S4, "femb_shell: kind must be S3/S4");
   if (M == 0) return FEMB_OK;
-  FEMB_CHECK_ARG(what >= 0 && what <= 5, "femb_shell: what in 0..5");
   ShellPts sp;
   memset(&sp, 0, sizeof(sp));
   if (kind == FEMB_S4) {
-    FEMB_CHECK_ARG(pts != nullptr && nq >= 1 && nq <= 16, "S4 needs 1..16 points");
-    memcpy(sp.p, pts, sizeof(double) * 4 * nq);
+    FEMB_CHECK_ARG(fac != nullptr && nq >= 1 && nq <= 16, "S4 needs 1..16 points");
+    for (int q = 0; q < nq; ++q) {
+      for (int k = 0; k < 4; ++k) sp.f[q][k] = fac[5 * q + k];
+      sp.w[q] = fac[5 * q + 4];
+    }
   } else {
     nq = 1;
+    sp.w[0] = 1.0;
   }
-  if (what >= 4) {
+  if (what == 4 || what == 5 || what == 9) {
     FEMB_CHECK_ARG(D6 != nullptr, "D6_host");
     memcpy(sp.D, D6, sizeof(sp.D));
   }
+  FEMB_CHECK_ARG(what != 9 || disp != nullptr, "what = 9 needs the displacement [N,6]");
   const int grid = grid_for(M, 64);
   const T* X = static_cast<const T*>(coords);
   const I* C = static_cast<const I*>(conn);
-  if (kind == FEMB_S3) shell_kernel<T, I, 3><<<grid, 64, 0, s>>>(X, C, M, sp, nq, what == 5 ? 4 : what, (T*)out);
-  else if (kind == FEMB_S4) shell_kernel<T, I, 4><<<grid, 64, 0, s>>>(X, C, M, sp, nq, what, (T*)out);
-  else {
-    set_error("femb_shell: kind must be S3/S4");
-    return FEMB_ERR_ARG;
+  const T* U = static_cast<const T*>(disp);
+  if (kind == FEMB_S3) {
+    const int w3 = what == 5 ? 4 : what == 8 ? 7 : what;  // one point: the per-point layouts coincide with the summed ones
+    shell_kernel<T, I, 3><<<grid, 64, 0, s>>>(X, C, M, sp, nq, w3, U, (T*)out);
+  } else {
+    shell_kernel<T, I, 4><<<grid, 64, 0, s>>>(X, C, M, sp, nq, what, U, (T*)out);
   }
   FEMB_LAUNCH_CHECK();
   return FEMB_OK;
+}
+
+static int shell_entry(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* fac, int nq,
+                       const double* D6_host, const void* disp, void* out, femb_stream stream) {
+  FEMB_CHECK_ARG((fp == 4 || fp == 8) && (ib == 4 || ib == 8), "fp in {4,8}, ib in {4,8}");
+  cudaStream_t s = as_stream(stream);
+  if (fp == 8) {
+    if (ib == 8) return shell_dispatch<double, long long>(kind, what, coords, conn, M, fac, nq, D6_host, disp, out, s);
+    return shell_dispatch<double, int>(kind, what, coords, conn, M, fac, nq, D6_host, disp, out, s);
+  }
+  if (ib == 8) return shell_dispatch<float, long long>(kind, what, coords, conn, M, fac, nq, D6_host, disp, out, s);
+  return shell_dispatch<float, int>(kind, what, coords, conn, M, fac, nq, D6_host, disp, out, s);
 }
 
 }  // namespace femb
@@ -190,12 +255,19 @@ using namespace femb;
 
 extern "C" int femb_shell(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* pts_host, int nq,
                           const double* D6_host, void* out, femb_stream stream) {
-  FEMB_CHECK_ARG((fp == 4 || fp == 8) && (ib == 4 || ib == 8), "fp in {4,8}, ib in {4,8}");
-  cudaStream_t s = as_stream(stream);
-  if (fp == 8) {
-    if (ib == 8) return shell_dispatch<double, long long>(kind, what, coords, conn, M, pts_host, nq, D6_host, out, s);
-    return shell_dispatch<double, int>(kind, what, coords, conn, M, pts_host, nq, D6_host, out, s);
+  FEMB_CHECK_ARG(what >= 0 && what <= 5, "femb_shell: what in 0..5 (7..9 go through femb_shell_ex)");
+  double fac[16 * 5];
+  if (kind == FEMB_S4) {
+    FEMB_CHECK_ARG(pts_host != nullptr && nq >= 1 && nq <= 16, "S4 needs 1..16 points");
+    for (int q = 0; q < nq; ++q) {
+      const double xi = pts_host[4 * q], eta = pts_host[4 * q + 1];
+      fac[5 * q] = 1 - xi, fac[5 * q + 1] = 1 + xi, fac[5 * q + 2] = 1 - eta, fac[5 * q + 3] = 1 + eta, fac[5 * q + 4] = pts_host[4 * q + 3];
+    }
   }
-  if (ib == 8) return shell_dispatch<float, long long>(kind, what, coords, conn, M, pts_host, nq, D6_host, out, s);
-  return shell_dispatch<float, int>(kind, what, coords, conn, M, pts_host, nq, D6_host, out, s);
+  return shell_entry(kind, what, coords, fp, conn, ib, M, fac, nq, D6_host, nullptr, out, stream);
+}
+
+extern "C" int femb_shell_ex(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* fac_host,
+                             int nq, const double* D6_host, const void* disp, void* out, femb_stream stream) {
+  return shell_entry(kind, what, coords, fp, conn, ib, M, fac_host, nq, D6_host, disp, out, stream);
 }

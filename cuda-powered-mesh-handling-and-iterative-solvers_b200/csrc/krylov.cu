@@ -739,3 +739,88 @@ extern "C" int femb_cg_solve_multi(int64_t n, int nmat, const int64_t* nnz_host,
   for (int k = 0; k < nmat; ++k) m[k] = CsrRef{nnz_host[k], crow_host[k], col_host[k], val_host[k], 1};
   return cg_solve_impl(n, nmat, m, F, mask, minv, u, work, tol, max_iter, eps, check_every, result_host, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// conjugate_gradient_solver_Ku (solver.py:1029-1065): CG on an operator the caller supplies as a function.  The reference
+// loop carries no guards, no eps and no node fixing; delta_u starts at zero.  The callback runs on the caller's stream between
+// the fused vector kernels (it cannot be captured in a graph), scalars stay on the device, and the host reads the stop
+// flag every `check_every` iterations (kernels after the stop are no-ops, so the state is the one at the reference's break).
+namespace femb {
+
+__global__ void __launch_bounds__(VEC_THREADS) cg_dot_kernel(long long n, const double* __restrict__ p, const double* __restrict__ Ap,
+                                                             double* __restrict__ partial, CGState* __restrict__ st) {
+  if (st->stop) return;
+  double dot = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dot += p[i] * Ap[i];
+  cg_k1_epilogue_n<VEC_THREADS>(dot, partial, st, 0.0, 0);
+}
+
+}  // namespace femb
+
+extern "C" int femb_cg_solve_operator(int64_t n, femb_apply_fn apply, void* ctx, const double* R, double* u, double* work, double tol,
+                                      int max_iter, int check_every, femb_cg_result* result_host, femb_stream stream) {
+  FEMB_CHECK_ARG(n > 0 && apply && R && u && work && result_host, "null pointer / n <= 0");
+  if (check_every < 1) check_every = 8;
+  cudaStream_t s = as_stream(stream);
+  double *r = work, *p = work + n, *Ap = work + 2 * n;
+  const int g2 = grid_for(n, VEC_THREADS, 8);
+  Scratch scr(s);
+  double* partial;
+  CGState* st;
+  FEMB_CUDA(scr.alloc(&partial, (size_t)g2));
+  FEMB_CUDA(scr.alloc(&st, 1));
+  cudaEvent_t t0, t1;
+  FEMB_CUDA(cudaEventCreate(&t0));
+  FEMB_CUDA(cudaEventCreate(&t1));
+  int rc = FEMB_OK;
+  CGState h;
+  memset(&h, 0, sizeof(h));
+  auto fail = [&](const char* what) {
+    set_error(what);
+    rc = FEMB_ERR_ARG;
+  };
+  // r = R - K(u), p = r, rs_old = r.r   (solver.py:1047-1049)
+  if (apply(ctx, u, Ap, stream) != 0) fail("femb_cg_solve_operator: the operator callback failed");
+  if (rc == FEMB_OK) {
+    cg_init_kernel<<<g2, VEC_THREADS, 0, s>>>(n, R, Ap, nullptr, nullptr, r, p, partial);
+    cg_init_finish<<<1, VEC_THREADS, 0, s>>>(g2, partial, st, max_iter);
+    cudaEventRecord(t0, s);
+    for (int it = 0; it < max_iter && rc == FEMB_OK; ++it) {
+      if (apply(ctx, p, Ap, stream) != 0) {
+        fail("femb_cg_solve_operator: the operator callback failed");
+        break;
+      }
+      cg_dot_kernel<<<g2, VEC_THREADS, 0, s>>>(n, p, Ap, partial, st);
+      cg_update_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, r, p, Ap, nullptr, partial, st, tol, 0.0, 0, max_iter);
+      cg_direction_kernel<<<g2, VEC_THREADS, 0, s>>>(n, r, p, nullptr, st);
+      if ((it + 1) % check_every == 0 || it + 1 == max_iter) {
+        if (cudaMemcpyAsync(&h, st, sizeof(CGState), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+          set_error(std::string("femb_cg_solve_operator: ") + cudaGetErrorString(cudaGetLastError()));
+          rc = FEMB_ERR_CUDA;
+          break;
+        }
+        if (h.stop) break;
+      }
+    }
+    cudaEventRecord(t1, s);
+  }
+  if (rc == FEMB_OK) {
+    if (cudaMemcpyAsync(&h, st, sizeof(CGState), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error(std::string("femb_cg_solve_operator: ") + cudaGetErrorString(cudaGetLastError()));
+      rc = FEMB_ERR_CUDA;
+    }
+  }
+  float ms = 0.f;
+  if (rc == FEMB_OK) cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  if (rc != FEMB_OK) {
+    cudaStreamSynchronize(s);  // the scratch below is released stream-ordered; nothing of this solve may still be queued on error paths
+    return rc;
+  }
+  result_host->iterations = h.stop ? h.iterations : max_iter;
+  result_host->status = h.stop ? h.status : 2;
+  result_host->rs = h.rs_new;
+  result_host->loop_ms = ms;
+  return FEMB_OK;
+}

@@ -18,6 +18,9 @@ class CGResult(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("status", C.c_int32), ("rs", C.c_double), ("loop_ms", C.c_double)]
 
 
+# int (*femb_apply_fn)(void* ctx, const double* x, double* y, femb_stream stream)
+APPLY_FN = C.CFUNCTYPE(C.c_int, c_vp, c_vp, c_vp, c_vp)
+
 # name -> argtypes; every function returns int (status) unless listed in _RESTYPES
 SIGNATURES = {
     "femb_version": [],
@@ -31,6 +34,15 @@ SIGNATURES = {
     "femb_stress_helper": [c_i32, c_vp, c_i32, c_i64, c_vp, c_vp],
     "femb_node_average": [c_vp, c_vp, c_i32, c_vp, c_vp],
     "femb_shell": [c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, C.POINTER(c_f64), c_i32, C.POINTER(c_f64), c_vp, c_vp],
+    "femb_shell_ex": [c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, C.POINTER(c_f64), c_i32, C.POINTER(c_f64), c_vp, c_vp, c_vp],
+    "femb_shell_local_coordinates": [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp],
+    "femb_shell_local_displacement": [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp],
+    "femb_shell_postprocess": [c_vp, c_i32, c_i64, c_i32, c_f64, c_f64, c_vp, c_vp],
+    "femb_face_forces": [c_vp, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp],
+    "femb_shared_face_forces_sum": [c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_vp],
+    "femb_wedge_face_normals": [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp],
+    "femb_shell_extrude": [c_vp, c_vp, c_vp, c_i32, c_i64, c_f64, c_f64, c_vp, c_vp],
+    "femb_extrude_connectivity": [c_vp, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp],
     "femb_to_c3d4": [c_i32, c_vp, c_i32, c_i64, c_vp, c_vp],
     "femb_entities_create": [c_i32, c_vp, c_i32, c_i64, c_i32, c_vp, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_i64)],
     "femb_entities_surface": [c_vp, c_vp, c_vp, c_vp],
@@ -54,6 +66,10 @@ SIGNATURES = {
     "femb_bsr3_jacobi": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "femb_cg_solve_multi": [c_i64, c_i32, C.POINTER(c_i64), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_vp, c_vp, c_vp, c_vp,
                             c_vp, c_f64, c_i32, c_f64, c_i32, C.POINTER(CGResult), c_vp],
+    "femb_cg_solve_operator": [c_i64, APPLY_FN, c_vp, c_vp, c_vp, c_vp, c_f64, c_i32, c_i32, C.POINTER(CGResult), c_vp],
+    "femb_vtk_open": [C.c_char_p, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(C.c_int32)],
+    "femb_vtk_read": [c_vp, c_vp, c_vp, c_vp],
+    "femb_vtk_close": [c_vp],
     "femb_csr_jacobi": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "femb_graph_from_pairs": [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
     "femb_graph_bfs": [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, C.POINTER(c_i32), c_vp],

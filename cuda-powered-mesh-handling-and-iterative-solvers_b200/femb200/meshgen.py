@@ -117,6 +117,15 @@ def quad_sheet(n, device="cpu", dtype=torch.float64, warp=0.0):
     return c, q.reshape(-1, 4).to(torch.int64).contiguous()
 
 
+def mixed_sheet(n, device="cpu", dtype=torch.float64, warp=0.0):
+    """The warped n x n sheet with every second quad split into triangles (0,1,2), (0,2,3): (coords [N,3], tri [T,3], quad [S,4]),
+    the mid-surface input of shell_extrude."""
+    c, q = quad_sheet(n, device, dtype, warp)
+    odd = (torch.arange(q.shape[0], device=device) % 2) == 1
+    t = torch.tensor(((0, 1, 2), (0, 2, 3)), device=device)
+    return c, q[odd][:, t].reshape(-1, 3).contiguous(), q[~odd].contiguous()
+
+
 # ---- quadratic (mid-edge) versions on the (2n+1)^3 lattice -----------------------------------------------------------
 HEX20_EDGES = ((0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7))   # VTK / Abaqus order
 WEDGE15_EDGES = ((0, 1), (1, 2), (2, 0), (3, 4), (4, 5), (5, 3), (0, 3), (1, 4), (2, 5))

@@ -170,6 +170,154 @@ def shell(kind, what, coords, elements, points=None, D=None, device="cuda:0", dt
     return out
 
 
+def shell_ex(kind, what, coords, elements, factors=None, D=None, disp=None, device="cuda:0", dtype=torch.float32):
+    """femb_shell_ex: factors = [[1-xi, 1+xi, 1-eta, 1+eta, w], ...] (host; S3 ignores them).  what 7: sum_q w_q B_q [M,6,nd]; 8: per-point [M,6,nd,nq]; 9: stress resultants [M,6] from disp [N,6]."""
+    dev = cuda_device(device)
+    x, conn = real(coords, dev, dtype), index(elements, dev)
+    nen = _NEN[kind]
+    M, nd = conn.shape[0], 6 * nen
+    factors = factors if factors is not None else [[1.0, 1.0, 1.0, 1.0, 1.0]]
+    nq = len(factors)
+    shape = {0: (M, 3, 3), 1: (M, 2, 2), 2: (M, nen, 2), 3: (M, 6, nd), 4: (M, nd, nd), 5: (M, nd, nd, nq), 7: (M, 6, nd),
+             8: (M, 6, nd, nq), 9: (M, 6)}[what]
+    out = torch.empty(shape, device=dev, dtype=dtype)
+    u = real(disp, dev, dtype) if disp is not None else None
+    if what == 9 and (u is None or u.dim() != 2 or u.shape[1] != 6 or u.shape[0] != x.shape[0]):
+        raise ValueError("shell stress needs the displacement as [N,6] (one row per node of coords)")
+    flat = [v for row in factors for v in row]
+    Dh = _host_doubles([float(v) for v in D.reshape(-1).tolist()]) if D is not None else None
+    with torch.cuda.device(dev):
+        check(lib.femb_shell_ex(kind, what, _p(x), _fp(x), _p(conn), _fp(conn), M, _host_doubles(flat), nq, Dh, _p(u), _p(out), _stream(dev)),
+              "femb_shell_ex")
+    return out
+
+
+def shell_local_coordinates(coords, elements, unit, device="cuda:0", dtype=torch.float32):
+    """[M,nen,3]: node coordinates relative to node 0 of each element, expressed in the frame `unit` [M,3,3]."""
+    dev = cuda_device(device)
+    x, conn = real(coords, dev, dtype), index(elements, dev)
+    R = real(unit, dev, dtype)
+    M, nen = conn.shape
+    if tuple(R.shape) != (M, 3, 3):
+        raise ValueError(f"unit must be [M,3,3], got {tuple(R.shape)}")
+    out = torch.empty((M, nen, 3), device=dev, dtype=dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_shell_local_coordinates(_p(x), _fp(x), _p(conn), _fp(conn), M, nen, _p(R), _p(out), _stream(dev)),
+              "femb_shell_local_coordinates")
+    return out
+
+
+def shell_local_displacement(elements, displacement, unit, device="cuda:0"):
+    """[M,nen,6]: nodal translations and rotations of every element in its own frame (dtype of `displacement`)."""
+    dev = cuda_device(device)
+    conn = index(elements, dev)
+    u = torch.as_tensor(displacement)
+    u = real(u, dev, u.dtype if u.dtype in (torch.float32, torch.float64) else torch.float32)
+    R = real(unit, dev, u.dtype)
+    M, nen = conn.shape
+    if u.dim() != 2 or u.shape[1] != 6 or tuple(R.shape) != (M, 3, 3):
+        raise ValueError(f"expected displacement [N,6] and unit [M,3,3], got {tuple(u.shape)} and {tuple(R.shape)}")
+    out = torch.empty((M, nen, 6), device=dev, dtype=u.dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_shell_local_displacement(_p(conn), _fp(conn), M, nen, _p(u), _p(R), _fp(u), _p(out), _stream(dev)),
+              "femb_shell_local_displacement")
+    return out
+
+
+def shell_postprocess(NMQ, t, z, device="cuda:0", dtype=torch.float32):
+    """[8,M]: sx, sy, txy, s1, s2, theta_p, tau_max, vm."""
+    dev = cuda_device(device)
+    v = real(NMQ, dev, dtype)
+    if v.dim() != 2 or v.shape[1] < 6:
+        raise ValueError(f"NMQ must be [M,6] or [M,8], got {tuple(v.shape)}")
+    M = v.shape[0]
+    out = torch.empty((8, M), device=dev, dtype=dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_shell_postprocess(_p(v), _fp(v), M, v.shape[1], float(t), float(z), _p(out), _stream(dev)), "femb_shell_postprocess")
+    return out
+
+
+def face_forces(normals, stress, device="cuda:0"):
+    dev = cuda_device(device)
+    s = torch.as_tensor(stress)
+    dt = s.dtype if s.dtype in (torch.float32, torch.float64) else torch.float32
+    s, n = real(s, dev, dt), real(normals, dev, dt)
+    M, nf = n.shape[0], n.shape[1]
+    if tuple(s.shape) != (M, 3, 3) or n.shape[2] != 3:
+        raise ValueError(f"expected normals [M,nf,3] and stress [M,3,3], got {tuple(n.shape)} and {tuple(s.shape)}")
+    out = torch.empty((M, nf, 3), device=dev, dtype=dt)
+    with torch.cuda.device(dev):
+        check(lib.femb_face_forces(_p(n), _p(s), _fp(s), M, nf, _p(out), _stream(dev)), "femb_face_forces")
+    return out
+
+
+def shared_face_forces_sum(pairs, forces, device="cuda:0"):
+    dev = cuda_device(device)
+    pr = torch.as_tensor(pairs).to(device=dev, dtype=torch.int64).contiguous()
+    f = torch.as_tensor(forces)
+    f = real(f, dev, f.dtype if f.dtype in (torch.float32, torch.float64) else torch.float32)
+    S = pr.shape[0]
+    if tuple(pr.shape[1:]) != (2, 2) or f.dim() != 3 or f.shape[2] != 3:
+        raise ValueError(f"expected pairs [S,2,2] and forces [M,nf,3], got {tuple(pr.shape)} and {tuple(f.shape)}")
+    if S and (int(pr[:, :, 0].max()) >= f.shape[0] or int(pr[:, :, 1].max()) >= f.shape[1] or int(pr.min()) < 0):
+        raise IndexError("shared-face pair refers to an element / local face outside element_forces")
+    out = torch.empty((S, 3), device=dev, dtype=f.dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_shared_face_forces_sum(_p(pr), S, _p(f), _fp(f), f.shape[1], _p(out), _stream(dev)), "femb_shared_face_forces_sum")
+    return out
+
+
+def wedge_face_normals(coords, elements, device="cuda:0", dtype=torch.float32):
+    dev = cuda_device(device)
+    x, conn = real(coords, dev, dtype), index(elements, dev)
+    out = torch.empty((conn.shape[0], 5, 3), device=dev, dtype=dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_wedge_face_normals(_p(x), _fp(x), _p(conn), _fp(conn), conn.shape[0], conn.shape[1], _p(out), _stream(dev)),
+              "femb_wedge_face_normals")
+    return out
+
+
+def shell_extrude(coords, tri, quad, thickness, eps=1e-8, device="cuda:0", dtype=torch.float32):
+    """(coords3d [2N,3], wedges [T,6], hexahedra [S,8]) from a mid-surface mesh; connectivity keeps its integer dtype."""
+    dev = cuda_device(device)
+    x = real(coords, dev, dtype)
+    N = x.shape[0]
+    conns, plans, outs = [], [], []
+    for c, nen in ((tri, 3), (quad, 4)):
+        c = index(c if c is not None else torch.empty((0, nen), dtype=torch.int64), dev).reshape(-1, nen)
+        if c.numel() and (int(c.max()) >= N or int(c.min()) < 0):
+            raise IndexError("shell connectivity refers to a node outside coords")
+        conns.append(c)
+        plans.append(cached_plan(c, N, dev) if c.shape[0] else None)
+        outs.append(torch.empty((c.shape[0], 2 * nen), device=dev, dtype=c.dtype))
+    x3 = torch.empty((2 * N, 3), device=dev, dtype=dtype)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        check(lib.femb_shell_extrude(plans[0].handle if plans[0] else None, plans[1].handle if plans[1] else None, _p(x), _fp(x), N,
+                                     float(thickness), float(eps), _p(x3), st), "femb_shell_extrude")
+        for c, o, nen in zip(conns, outs, (3, 4)):
+            check(lib.femb_extrude_connectivity(_p(c), _fp(c), c.shape[0], nen, N, _p(o), st), "femb_extrude_connectivity")
+    return x3, outs[0], outs[1]
+
+
+def vtk_read(file_path):
+    """Host parse of a legacy .vtk unstructured grid -> (points float64 [n,3] (numpy), flat cells int64 (pyvista's mesh.cells
+    layout), cell types int32 or None, points_are_float)."""
+    import numpy as np
+    h, npnt, ncell, csize, isf = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+    check(lib.femb_vtk_open(str(file_path).encode(), C.byref(h), C.byref(npnt), C.byref(ncell), C.byref(csize), C.byref(isf)), "femb_vtk_open")
+    try:
+        pts = np.empty((npnt.value, 3), dtype=np.float64)
+        cells = np.empty(csize.value, dtype=np.int64)
+        types = np.empty(ncell.value, dtype=np.int32)
+        check(lib.femb_vtk_read(h, pts.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p), None), "femb_vtk_read")
+        if lib.femb_vtk_read(h, None, None, types.ctypes.data_as(C.c_void_p)) != 0:
+            types = None
+    finally:
+        lib.femb_vtk_close(h)
+    return pts, cells, types, bool(isf.value)
+
+
 def to_c3d4(kind, elements, device="cuda:0"):
     dev = cuda_device(device)
     conn = index(elements, dev)
@@ -385,6 +533,41 @@ def cg_solve_multi(mats, F, mask=None, minv=None, u_init=None, tol=1e-10, max_it
                                       float(eps), int(check_every), C.byref(res), _stream(dev)), "femb_cg_solve_multi")
     info = {"iterations": res.iterations, "status": STATUS.get(res.status, "?"), "rs": res.rs, "loop_ms": res.loop_ms}
     return u.reshape(F.shape), info
+
+
+def cg_solve_operator(apply, R, tol=1e-8, max_iter=1000, check_every=8, device="cuda:0"):
+    """CG on y = apply(x) (torch fp64 vectors of R's shape in, same shape out) -- the reference's conjugate_gradient_solver_Ku loop.
+    The library drives the loop and calls back for the operator; exceptions raised by `apply` are re-raised here."""
+    dev = cuda_device(device)
+    Rf = R.to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+    n = Rf.numel()
+    u = torch.zeros(n, device=dev, dtype=torch.float64)
+    work = torch.empty(3 * n, device=dev, dtype=torch.float64)
+    views = {u.data_ptr(): u, (work.data_ptr() + 8 * n): work[n:2 * n]}   # the two vectors the loop ever applies the operator to
+    Ap = work[2 * n:]
+    raised = []
+
+    def _cb(_ctx, xptr, yptr, _stream_):
+        try:
+            x = views[int(xptr)]
+            assert int(yptr) == Ap.data_ptr()
+            y = apply(x.reshape(R.shape))
+            Ap.copy_(torch.as_tensor(y).to(device=dev, dtype=torch.float64).reshape(-1))
+            return 0
+        except BaseException as exc:   # noqa: BLE001  (must not propagate through the C frame)
+            raised.append(exc)
+            return 1
+
+    cb = _lib.APPLY_FN(_cb)
+    res = CGResult()
+    with torch.cuda.device(dev):
+        rc = lib.femb_cg_solve_operator(n, cb, None, _p(Rf), _p(u), _p(work), float(tol), int(max_iter), int(check_every), C.byref(res),
+                                        _stream(dev))
+    if raised:
+        raise raised[0]
+    check(rc, "femb_cg_solve_operator")
+    info = {"iterations": res.iterations, "status": STATUS.get(res.status, "?"), "rs": res.rs, "loop_ms": res.loop_ms}
+    return u.reshape(R.shape), info
 
 
 # ----------------------------------------------------------------------------- 3x3 block-CSR (3-dof operators)

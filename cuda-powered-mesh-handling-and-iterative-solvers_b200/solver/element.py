@@ -477,6 +477,12 @@ def compute_wedge_surface_normals(coords, elements, device="cuda:0", dtype=torch
     return [_ops.surface_normals(coords, q, qe, 3, device, dtype), _ops.surface_normals(coords, t, te, 2, device, dtype)]
 
 
+def compute_wedge_normals_and_area(coords, elements, device="cuda:0", dtype=torch.float32):
+    """[M,5,3] UNIT normals of the faces (0,1,4,3) (1,2,5,4) (2,0,3,5) (0,2,1) (3,4,5), not re-oriented -- despite its name the
+    reference neither area-weights nor orients them (element.py:2377-2420)."""
+    return _ops.wedge_face_normals(coords, elements, device, dtype)
+
+
 def c3d6_to_c3d4(element, device="cuda:0"):
     """element.py:2424-2446"""
     return _ops.to_c3d4(_ops.C3D6, element, device)
@@ -556,6 +562,47 @@ def compute_c3d15_K_matrix(coords, elements, E, nu, integral_point=None, single=
 def compute_c3d15_M_matrix(coords, elements, rho, integral_point=None, device="cuda:0", dtype=torch.float32):
     """Consistent mass [M,45,45].  Not in the reference -- parity unpinned."""
     return _solid_M(_ops.C3D15, coords, elements, rho, integral_point, device, dtype)
+
+
+# ------------------------------------------------------------------------------------------- face force balance
+
+def compute_c3d4_surface_forces(normal_vectors, stress_tensors, device="cuda:0"):
+    """[M,4,3] = element stress [M,3,3] applied to the area-weighted face normals [M,4,3] (element.py:3343-3360)."""
+    return _ops.face_forces(normal_vectors, stress_tensors, device)
+
+
+def compute_c3d4_shared_face_forces_sum(shared_face_indices, element_forces, device="cuda:0"):
+    """[S,3] = sum of the two face forces meeting on every shared face (pairs [S,2,2] from identify_tetrahedral_shared_faces;
+    zero everywhere at equilibrium) (element.py:3362-3384)."""
+    return _ops.shared_face_forces_sum(shared_face_indices, element_forces, device)
+
+
+# ------------------------------------------------------------------------------------------- mesh input
+
+_VTK_NEN = {"c3d4": 4, "c3d10": 10, "c3d8": 8, "c3d20": 20, "c3d6": 6, "c3d15": 15, "s3": 3, "s6": 6, "s4": 4, "s8": 8}
+
+
+def vtk_loader_to_torch(file_path, element_type, device="cuda:0", dtype=torch.float32):
+    """(points [N,3] in `dtype`, connectivity [M,nen] int64) of a VTK file whose cells are all of `element_type`
+    (element.py:39-90).  The reference reads through pyvista and reshapes the flat `mesh.cells` array
+    `[nen, ids.., nen, ids..]` to `[-1, nen+1]`; here libfemb200's own host parser produces that array from legacy `.vtk`
+    unstructured grids (ASCII or BINARY, classic or 5.x cell layout).  Like the reference's reshape this raises when the flat
+    array is not a whole number of `nen+1` rows, and additionally when a row's count is not `nen` (the reference would return
+    garbage there).  Files storing 32-bit coordinates go through float32 exactly as pyvista's `mesh.points` does."""
+    if element_type not in _VTK_NEN:
+        raise ValueError("Invalid element type.")
+    dev = _ops.cuda_device(device)
+    nen = _VTK_NEN[element_type]
+    pts, cells, _types, is_float = _ops.vtk_read(file_path)
+    if cells.size % (nen + 1):
+        raise ValueError(f"cannot reshape the cell array of size {cells.size} into rows of {nen + 1}")
+    rows = cells.reshape(-1, nen + 1)
+    if rows.shape[0] and not (rows[:, 0] == nen).all():
+        raise ValueError(f"the file holds cells that are not {element_type} ({nen} nodes per cell)")
+    p = torch.from_numpy(pts)
+    if is_float:
+        p = p.to(torch.float32)
+    return p.to(device=dev, dtype=dtype), torch.from_numpy(rows[:, 1:].copy()).to(device=dev, dtype=torch.long)
 
 
 # ------------------------------------------------------------------------------------------- misc topology

@@ -40,6 +40,22 @@ def compute_shell_nodal_forces(K, shell, displacement, unit, device="cuda:0", dt
     return plan.ebe_apply(K, u, 6, unit, dtype)
 
 
+def compute_global_to_local_displacement(shell, displacement, unit, device="cuda:0"):
+    """[M,nen,6]: translations and rotations of every element's nodes rotated into the element frame (shell.py:41-56)."""
+    return _ops.shell_local_displacement(shell, displacement, unit, device=device)
+
+
+_POST_KEYS = ("sx", "sy", "txy", "s1", "s2", "theta_p", "tau_max", "vm_stress")
+
+
+def compute_shell_postprocess_values(NMQ, t, z=0, device="cuda:0", dtype=torch.float32):
+    """Stresses at through-thickness coordinate z from the resultants N, M: sx, sy, txy, principal stresses, principal angle,
+    maximum in-plane shear and the plane-stress von Mises value, each [M] (shell.py:104-160; the dict keys are the
+    reference's, including 'vm_stress').  One kernel writes all eight rows."""
+    out = _ops.shell_postprocess(NMQ, t, z, device=device, dtype=dtype)
+    return {k: out[i] for i, k in enumerate(_POST_KEYS)}
+
+
 # ------------------------------------------------------------------------------------------- S3
 
 def compute_s3_normal(coords, shell, device="cuda:0"):
@@ -73,6 +89,12 @@ def compute_s3_local_unitvector(coords, shell, device="cuda:0"):
     return _ops.shell(_ops.S3, 0, coords, shell, device=device, dtype=_coords_dtype(coords))
 
 
+def compute_s3_global_to_local_coordinates(coords, shell, unit, device="cuda:0", dtype=torch.float32):
+    """[M,3,3] node coordinates relative to node 0 in the element frame (shell.py:323-347).  The reference ignores `dtype`
+    here and works in the dtype of `coords`; so does this."""
+    return _ops.shell_local_coordinates(coords, shell, unit, device=device, dtype=_coords_dtype(coords))
+
+
 def compute_s3_jacobian(coords, shell, device="cuda:0", dtype=torch.float32):
     """[M,2,2] in the element frame (shell.py:349-384)."""
     return _ops.shell(_ops.S3, 1, coords, shell, device=device, dtype=dtype)
@@ -91,6 +113,12 @@ def compute_s3_B_matrix(coords, shell, device="cuda:0", dtype=torch.float32):
 def compute_s3_K_matrix(coords, shell, membrane, bending, device="cuda:0", dtype=torch.float32):
     """K = B^T D B detJ / 2, [M,18,18] (shell.py:440-453)."""
     return _ops.shell(_ops.S3, 4, coords, shell, D=_D_host(membrane, bending, dtype), device=device, dtype=dtype)
+
+
+def compute_s3_shell_stress(coords, shell, membrane, bending, displacement, device="cuda:0", dtype=torch.float32):
+    """Stress resultants [M,6] = D B u_e with u_e = displacement[shell] ([N,6], taken in global axes as the reference does)
+    (shell.py:455-481)."""
+    return _ops.shell_ex(_ops.S3, 9, coords, shell, D=_D_host(membrane, bending, dtype), disp=displacement, device=device, dtype=dtype)
 
 
 # ------------------------------------------------------------------------------------------- S4
@@ -120,6 +148,11 @@ def compute_s4_local_unitvector(coords, shell, device="cuda:0"):
     return _ops.shell(_ops.S4, 0, coords, shell, device=device, dtype=_coords_dtype(coords))
 
 
+def compute_s4_global_to_local_coordinates(coords, shell, unit, device="cuda:0", dtype=torch.float32):
+    """[M,4,3] node coordinates relative to node 0 in the element frame, in `dtype` (shell.py:625-649)."""
+    return _ops.shell_local_coordinates(coords, shell, unit, device=device, dtype=dtype)
+
+
 def s4_integration_points(device="cuda:0"):
     """2x2 rule, ALWAYS float32 (shell.py:651-672, quirk q1)."""
     rows = torch.tensor(_ops.default_points(_ops.S4), dtype=torch.float64)
@@ -135,19 +168,56 @@ def _s4_pts(points, weights=None):
     return [[float(p[q, 0]), float(p[q, 1]), 0.0, float(w[q])] for q in range(p.shape[0])]
 
 
+def _s4_factor_row(xi, eta, w=1.0):
+    """(1-xi, 1+xi, 1-eta, 1+eta, w).  The reference evaluates 1 -/+ xi in the type it was handed: python floats on the K path
+    (`.item()`, shell.py:841-842) but 0-dim float32 tensors when compute_s4_B_matrix iterates over the rows of its float32
+    rule (shell.py:813-814, :683-695) -- the fp32 rounding of the sums is part of its numbers."""
+    def pm(v):
+        if torch.is_tensor(v):
+            v = v.detach().to("cpu")
+            return float(1 - v), float(1 + v)
+        return 1 - float(v), 1 + float(v)
+
+    return [*pm(xi), *pm(eta), float(w)]
+
+
+def _s4_rule_rows(integration_points):
+    """Factor rows of a user rule given as (points [n,2], weights [n]) -- or of the default rule iterated as tensors."""
+    if integration_points is None:
+        pts, wts = s4_integration_points(device="cpu")
+    else:
+        pts, wts = integration_points
+        pts, wts = torch.as_tensor(pts), torch.as_tensor(wts)
+    return [_s4_factor_row(pts[q, 0], pts[q, 1], wts[q]) for q in range(pts.shape[0])]
+
+
+def compute_s4_B_matrix(coords, shell, integration_points=None, single=True, device="cuda:0", dtype=torch.float32):
+    """sum_q w_q B(xi_q, eta_q) [M,6,24], or the weighted per-point matrices [M,6,24,4] when single=False (shell.py:802-823).
+    `integration_points`, if given, is (points [n,2], weights [n]) as for compute_s4_K_matrix -- the reference only runs with
+    the default (its `weights` is unbound otherwise, shell.py:810-816)."""
+    return _ops.shell_ex(_ops.S4, 7 if single else 8, coords, shell, factors=_s4_rule_rows(integration_points), device=device, dtype=dtype)
+
+
+def compute_s4_shell_stress(coords, shell, membrane, bending, displacement, device="cuda:0", dtype=torch.float32):
+    """Stress resultants [M,6] = D (sum_q B_q) u_e over the default 2x2 rule, u_e = displacement[shell] ([N,6], global axes)
+    (shell.py:863-879)."""
+    return _ops.shell_ex(_ops.S4, 9, coords, shell, factors=_s4_rule_rows(None), D=_D_host(membrane, bending, dtype), disp=displacement,
+                         device=device, dtype=dtype)
+
+
 def compute_s4_jacobian(coords, shell, xi, eta, device="cuda:0", dtype=torch.float32):
     """shell.py:674-721"""
-    return _ops.shell(_ops.S4, 1, coords, shell, points=_s4_pts([[float(xi), float(eta)]]), device=device, dtype=dtype)
+    return _ops.shell_ex(_ops.S4, 1, coords, shell, factors=[_s4_factor_row(xi, eta)], device=device, dtype=dtype)
 
 
 def compute_s4_shape_gradient(coords, shell, xi, eta, device="cuda:0", dtype=torch.float32):
     """shell.py:723-746"""
-    return _ops.shell(_ops.S4, 2, coords, shell, points=_s4_pts([[float(xi), float(eta)]]), device=device, dtype=dtype)
+    return _ops.shell_ex(_ops.S4, 2, coords, shell, factors=[_s4_factor_row(xi, eta)], device=device, dtype=dtype)
 
 
 def compute_s4_B_matrix_single(coords, shell, xi, eta, device="cuda:0", dtype=torch.float32):
     """shell.py:748-800"""
-    return _ops.shell(_ops.S4, 3, coords, shell, points=_s4_pts([[float(xi), float(eta)]]), device=device, dtype=dtype)
+    return _ops.shell_ex(_ops.S4, 3, coords, shell, factors=[_s4_factor_row(xi, eta)], device=device, dtype=dtype)
 
 
 def compute_s4_K_matrix(coords, shell, membrane, bending, integration_points=None, single=True, device="cuda:0", dtype=torch.float32):
@@ -157,3 +227,13 @@ def compute_s4_K_matrix(coords, shell, membrane, bending, integration_points=Non
     else:
         pts = _s4_pts(integration_points[0], integration_points[1])
     return _ops.shell(_ops.S4, 4 if single else 5, coords, shell, points=pts, D=_D_host(membrane, bending, dtype), device=device, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------- shell -> wedge / hexahedron
+
+def shell_extrude(coords, tri, quad, thickness, device="cuda:0", dtype=torch.float32):
+    """Extrudes a mid-surface mesh along its node normals: (coords_3d [2N,3] = bottom layer then top layer, wedges [T,6] =
+    (tri | tri+N), hexahedra [S,8] = (quad | quad+N)) (shell.py:885-983).  Node normals are the normalised mean of the unit
+    normals of the incident triangles and of both halves (0,1,2), (0,2,3) of the incident quads; every node sums them over
+    its incidence list in the reference's order instead of scattering with atomics."""
+    return _ops.shell_extrude(coords, tri, quad, thickness, device=device, dtype=dtype)

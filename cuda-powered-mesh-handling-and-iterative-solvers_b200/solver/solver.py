@@ -314,6 +314,24 @@ def preconditioned_conjugate_gradient_solver(K, elements, F, M_inv, u_init=None,
     return (u, info) if return_info else u
 
 
+def conjugate_gradient_solver_Ku(compute_Ku, R, tol=1e-8, max_iter=1000, device="cuda:0", dtype=torch.float32, return_info=False):
+    """CG on an operator given as a function, K(u) delta_u = R (solver.py:1029-1065): no node fixing, no guards, start from
+    zero, converged iff sqrt(r.r) < tol.  `compute_Ku` receives and returns [N,3] tensors of `dtype` on `device`, as in the
+    reference; the loop itself (dot products, updates, convergence test) runs in fp64 inside libfemb200, which calls back
+    for the operator once per iteration, and the result is cast to `dtype`."""
+    dev = _ops.cuda_device(device)
+    R = torch.as_tensor(R).to(dev)
+
+    def apply(x):
+        return compute_Ku(x.to(dtype))
+
+    du, info = _ops.cg_solve_operator(apply, R, tol=tol, max_iter=max_iter, device=dev)
+    if info["status"] != "converged":
+        print("CG did not converge within the maximum number of iterations.")
+    du = du.to(dtype)
+    return (du, info) if return_info else du
+
+
 def static_structure_solver(coords, force, fixed, c3d4=None, c3d6=None, c3d8=None, s3=None, s4=None, material=None, u_init=None,
                             tol=1e-10, max_iter=1000, device="cuda:0", dtype=torch.float64, eps=1e-30, return_info=False, verbose=True):
     """Mixed-element static solve on [N,6] (solver.py:11-135): solids act on the translations, shells on all six dofs

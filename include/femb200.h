@@ -100,6 +100,34 @@ int femb_solid_stress(int kind, const void* coords, int fp, const void* conn, in
 int femb_shell(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* pts_host,
                int nq, const double* D6_host, void* out, femb_stream stream);
 
+/* Extended shell entry.  fac_host[nq,5] = (1-xi, 1+xi, 1-eta, 1+eta, w): the four bilinear factors are passed evaluated
+ * because the reference forms them in the dtype of what it was handed -- python doubles on the K path (shell.py:841-842),
+ * 0-dim fp32 tensors when compute_s4_B_matrix iterates over its fp32 rule (:813-814 -> :683-695).  S3 ignores fac_host.
+ * what 0..5 as femb_shell, plus
+ *   7: sum_q w_q B_q [M,6,6nen]   8: per-point w_q B_q [M,6,6nen,nq]   (compute_s4_B_matrix :802-823)
+ *   9: stress resultants [M,6] = D (sum_q w_q B_q) disp[conn] with disp [N,6] in GLOBAL axes exactly as the reference takes it
+ *      (compute_s3_shell_stress :455-481, compute_s4_shell_stress :863-879) */
+int femb_shell_ex(int kind, int what, const void* coords, int fp, const void* conn, int ib, int64_t M, const double* fac_host,
+                  int nq, const double* D6_host, const void* disp, void* out, femb_stream stream);
+
+/* compute_s3_global_to_local_coordinates shell.py:323-347, compute_s4_global_to_local_coordinates :625-649:
+ * out[M,nen,3] = coordinates relative to node 0 of each element expressed in the frame unit[M,3,3] (rows = axes) */
+int femb_shell_local_coordinates(const void* coords, int fp, const void* conn, int ib, int64_t M, int nen, const void* unit, void* out,
+                                 femb_stream stream);
+
+/* compute_global_to_local_displacement shell.py:41-56: out[M,nen,6] = (unit g_trans, unit g_rot), g = disp[conn] ([N,6]) */
+int femb_shell_local_displacement(const void* conn, int ib, int64_t M, int nen, const void* disp, const void* unit, int fp,
+                                  void* out, femb_stream stream);
+
+/* compute_shell_postprocess_values shell.py:104-160: nmq[M,ncol] (N, M resultants in columns 0..5) -> out[8,M] =
+ * sx, sy, txy, s1, s2, theta_p, tau_max, vm at through-thickness coordinate z of a shell of thickness t */
+int femb_shell_postprocess(const void* nmq, int fp, int64_t M, int ncol, double t, double z, void* out, femb_stream stream);
+
+/* compute_c3d4_surface_forces element.py:3343-3360: out[M,nf,3] = stress[M,3,3] normals[M,nf,3] */
+int femb_face_forces(const void* normals, const void* stress, int fp, int64_t M, int nf, void* out, femb_stream stream);
+/* compute_c3d4_shared_face_forces_sum element.py:3362-3384: out[S,3] = forces[e1,f1] + forces[e2,f2], pairs[S,2,2] int64 */
+int femb_shared_face_forces_sum(const int64_t* pairs, int64_t S, const void* forces, int fp, int nf, void* out, femb_stream stream);
+
 /* compute_stress_tensor :308-330 (what = 0: Voigt [M,6] xx,yy,zz,xy,yz,zx -> [M,3,3]) and compute_von_mises_stress
  * :332-353 (what = 1: [M,3,3] -> [M]). */
 int femb_stress_helper(int what, const void* in, int fp, int64_t M, void* out, femb_stream stream);
@@ -141,6 +169,11 @@ int femb_surface_normals(const void* coords, int fp, const int64_t* faces, const
 int femb_face_normals_area(int kind, const void* coords, int fp, const void* conn, int ib, int64_t M, int conn_stride,
                            void* out, femb_stream stream);
 
+/* compute_wedge_normals_and_area :2377-2420: UNIT normals [M,5,3] of the faces (0,1,4,3) (1,2,5,4) (2,0,3,5) (0,2,1) (3,4,5),
+ * not re-oriented (the reference neither orients nor area-weights them, despite the name) */
+int femb_wedge_face_normals(const void* coords, int fp, const void* conn, int ib, int64_t M, int conn_stride, void* out,
+                            femb_stream stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Global assembly: COO (subdivision.ipynb cell 6) -> CSR, deterministic
  * ------------------------------------------------------------------------------------------- */
@@ -171,6 +204,15 @@ int femb_spmv(int64_t n_rows, int64_t nnz, const int32_t* crow, const int32_t* c
  * compute_shell_nodal_forces shell.py:58-102 when unit != NULL (ndof = 6, rotates into/out of the element frame). */
 int femb_ebe_apply(femb_csr_plan* plan, int ndof, const void* Ke, const void* u, const void* unit, int fp, void* y,
                    femb_stream stream);
+
+/* shell_extrude shell.py:885-983: per-node unit normals of a mid-surface mesh (mean of the unit normals of the incident
+ * triangles and of both triangles (0,1,2), (0,2,3) of the incident quads, eps = 1e-8 in every denominator), then
+ * coords3d[2N,3] = (x - t/2 n | x + t/2 n).  tri / quad = plans of the [T,3] / [S,4] connectivity built with n_nodes = N
+ * (either may be NULL); sums run over the incidence lists in the reference's order (deterministic). */
+int femb_shell_extrude(femb_csr_plan* tri, femb_csr_plan* quad, const void* coords, int fp, int64_t N, double thickness, double eps,
+                       void* coords3d, femb_stream stream);
+/* out[M,2nen] = (conn | conn + N): wedges from triangles, hexahedra from quads (shell.py:957-973); same index type */
+int femb_extrude_connectivity(const void* conn, int ib, int64_t M, int nen, int64_t N, void* out, femb_stream stream);
 
 /* compute_node_vm_stress element.py:466-504: out[N] = mean over the elements containing the node of elem_values[M]
  * (0 for nodes without elements); sums run in ascending element order (deterministic; the reference uses index_add). */
@@ -217,6 +259,13 @@ int femb_cg_solve_multi(int64_t n, int nmat, const int64_t* nnz_host, const int3
                         const double* minv, double* u, double* work, double tol, int max_iter, double eps, int check_every,
                         femb_cg_result* result_host, femb_stream stream);
 
+/* conjugate_gradient_solver_Ku solver.py:1029-1065: CG on an operator supplied as a function (no node fixing, no guards, no
+ * eps; u must hold the start vector -- zeros in the reference -- and returns the solution).  `apply(ctx, x, y, stream)` must
+ * enqueue y = K x on `stream` and return 0.  work = 3*n doubles.  The host reads the stop flag every check_every iterations. */
+typedef int (*femb_apply_fn)(void* ctx, const double* x, double* y, femb_stream stream);
+int femb_cg_solve_operator(int64_t n, femb_apply_fn apply, void* ctx, const double* R, double* u, double* work, double tol,
+                           int max_iter, int check_every, femb_cg_result* result_host, femb_stream stream);
+
 /* Jacobi diagonal of a CSR matrix: minv[i] = mask[i] ? 1/A_ii : 0 (the documented replacement for the
  * reference's broken compute_diagonal_preconditioner solver.py:814-833) */
 int femb_csr_jacobi(int64_t n, const int32_t* crow, const int32_t* col, const double* val, const uint8_t* mask,
@@ -236,6 +285,18 @@ int femb_graph_from_pairs(const int64_t* pairs, int64_t S, int pair_stride, int6
  * level; the host reads one flag per level.  levels_host (optional) receives the number of levels.  Synchronises. */
 int femb_graph_bfs(const int32_t* crow, const int32_t* col, int64_t M, const int64_t* sources, int n_sources, int32_t* dist,
                    int32_t* label, int32_t* levels_host, femb_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mesh input: legacy .vtk unstructured grids (vtk_loader_to_torch element.py:39-90 reads them through pyvista)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct femb_vtk_mesh femb_vtk_mesh;
+/* Parses the file on the host (ASCII or BINARY; classic CELLS and the 5.x OFFSETS/CONNECTIVITY layout).  cells_size = length
+ * of the flat `[nen, id0, .., nen, id0, ..]` array (= pyvista's mesh.cells); points_are_float = file stores 32-bit reals. */
+int femb_vtk_open(const char* path, femb_vtk_mesh** mesh, int64_t* n_points, int64_t* n_cells, int64_t* cells_size,
+                  int32_t* points_are_float);
+/* Copies into caller-owned HOST arrays: points_host[n_points*3], cells_host[cells_size], types_host[n_cells] (any may be NULL) */
+int femb_vtk_read(femb_vtk_mesh* mesh, double* points_host, int64_t* cells_host, int32_t* types_host);
+int femb_vtk_close(femb_vtk_mesh* mesh);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU CG over NVLink peer memory (one process per GPU; nothing to match in the reference)

@@ -373,6 +373,74 @@ def gen_quadratic():
     save("quadratic", p20=npy(p), w20=npy(w), h20=npy(h20), h20_tets=npy(R.c3d20_to_c3d4(h20, device="cpu")))
 
 
+def gen_widen():
+    """Functions either side of the element path: shell frames / stress / post-processing, shell extrusion, wedge face normals,
+    tet face-force balance and the operator-callback CG."""
+    o = {}
+    c3, s3 = meshgen.tri_sheet(3, warp=0.15)
+    c4, s4 = meshgen.quad_sheet(3, warp=0.15)
+    unit3 = RS.compute_s3_local_unitvector(c3, s3, device="cpu")
+    unit4 = RS.compute_s4_local_unitvector(c4, s4, device="cpu")
+    o["loc3"] = RS.compute_s3_global_to_local_coordinates(c3, s3, unit3, **KW)
+    o["loc4"] = RS.compute_s4_global_to_local_coordinates(c4, s4, unit4, **KW)
+    g = torch.Generator().manual_seed(11)
+    u3 = torch.randn(c3.shape[0], 6, dtype=torch.float64, generator=g)
+    u4 = torch.randn(c4.shape[0], 6, dtype=torch.float64, generator=g)
+    o["u3"], o["u4"] = u3, u4
+    o["ul3"] = RS.compute_global_to_local_displacement(s3, u3, unit3, device="cpu")
+    o["ul4"] = RS.compute_global_to_local_displacement(s4, u4, unit4, device="cpu")
+    o["B4_sum"] = RS.compute_s4_B_matrix(c4, s4, single=True, **KW)
+    o["B4_all"] = RS.compute_s4_B_matrix(c4, s4, single=False, **KW)
+    # the same single-point functions handed 0-dim float32 tensors (what compute_s4_B_matrix passes down, shell.py:813-814)
+    p4, _ = RS.s4_integration_points(device="cpu")
+    o["J4_t"] = RS.compute_s4_jacobian(c4, s4, p4[0, 0], p4[0, 1], **KW)
+    o["g4_t"] = RS.compute_s4_shape_gradient(c4, s4, p4[0, 0], p4[0, 1], **KW)
+    o["stress3"] = RS.compute_s3_shell_stress(c3, s3, MEMB, BEND, u3, **KW)
+    o["stress4"] = RS.compute_s4_shell_stress(c4, s4, MEMB, BEND, u4, **KW)
+    tz = (0.1, 0.03)
+    o["post_tz"] = np.array(tz)
+    post = RS.compute_shell_postprocess_values(o["stress4"], tz[0], z=tz[1], **KW)
+    o["post_keys"] = np.array(list(post.keys()))
+    o["post"] = torch.stack([post[k] for k in post])
+    post32 = RS.compute_shell_postprocess_values(o["stress4"], tz[0], z=tz[1], device="cpu")
+    o["post32"] = torch.stack([post32[k] for k in post32])
+    # extrusion of a mixed tri / quad mid-surface (fp64 and the default fp32)
+    cm, tri, quad = meshgen.mixed_sheet(4, warp=0.2)
+    o["cm"], o["tri"], o["quad"], o["thickness"] = cm, tri, quad, np.array(0.07)
+    x3, w6, h8 = RS.shell_extrude(cm, tri, quad, 0.07, **KW)
+    o["ext_x"], o["ext_w"], o["ext_h"] = x3, w6, h8
+    o["ext_x32"] = RS.shell_extrude(cm, tri, quad, 0.07, device="cpu")[0]
+    o["ext_x_tri_only"] = RS.shell_extrude(cm, tri, quad[:0], 0.07, **KW)[0]
+    o["ext_x_quad_only"] = RS.shell_extrude(cm, tri[:0], quad, 0.07, **KW)[0]
+    # wedge face normals
+    cw, w = meshgen.wedge_cube(2, jitter=0.2)
+    o["cw"], o["w"] = cw, w
+    try:   # the reference takes torch.cross(..., dim=3) of 3-d tensors (element.py:2409): IndexError on every input
+        R.compute_wedge_normals_and_area(cw, w, **KW)
+        o["wedge_normals_raises"] = np.array(0)
+    except IndexError:
+        o["wedge_normals_raises"] = np.array(1)
+    # tet face forces and their balance over shared faces
+    ct, tets = meshgen.kuhn_cube(2, jitter=0.2)
+    o["ct"], o["tets"] = ct, tets
+    nrm = R.compute_tetrahedral_normals_and_area(ct, tets, **KW)
+    sig = torch.randn(tets.shape[0], 3, 3, dtype=torch.float64, generator=g)
+    sig = sig + sig.transpose(1, 2)
+    o["sigma"] = sig
+    o["face_forces"] = R.compute_c3d4_surface_forces(nrm, sig, device="cpu")
+    shared = R.identify_tetrahedral_shared_faces(tets, device="cpu")
+    o["shared"] = shared
+    o["shared_sum"] = R.compute_c3d4_shared_face_forces_sum(shared, o["face_forces"], device="cpu")
+    # conjugate_gradient_solver_Ku on the SPD operator u -> K u + 0.1 u (no boundary conditions in that loop)
+    K = R.compute_c3d4_K_matrix(ct, tets, E, NU, **KW)
+    Rv = torch.randn(ct.shape[0], 3, dtype=torch.float64, generator=g)
+    o["ku_R"] = Rv
+    o["ku_shift"] = np.array(0.1)
+    o["ku_u"], _ = quiet(RV.conjugate_gradient_solver_Ku, lambda v: R.compute_nodal_forces(K, tets, v, **KW) + 0.1 * v, Rv, tol=1e-10,
+                         max_iter=500, **KW)
+    save("widen", **{k: npy(v) for k, v in o.items()})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_units()
@@ -385,3 +453,4 @@ if __name__ == "__main__":
     gen_quadratic()
     gen_constrained()
     gen_partition()
+    gen_widen()

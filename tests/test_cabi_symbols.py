@@ -53,14 +53,19 @@ def test_mirror_api_names():
                   "compute_c3d8_Jacobian", "compute_c3d8_shape_gradients", "compute_c3d8_B_matrix", "compute_c3d8_K_matrix",
                   "compute_wedge_volumes", "compute_wedge_surface_faces_with_extra_node", "compute_wedge_surface_normals", "c3d6_to_c3d4",
                   "c3d6_integration_points", "compute_c3d6_Jacobian", "compute_c3d6_shape_gradients", "compute_c3d6_B_matrix",
-                  "compute_c3d6_K_matrix", "element_to_edge"],
+                  "compute_c3d6_K_matrix", "element_to_edge", "compute_wedge_normals_and_area", "compute_c3d4_surface_forces",
+                  "compute_c3d4_shared_face_forces_sum", "vtk_loader_to_torch", "compute_element_stress", "compute_node_vm_stress"],
         shell: ["compute_kirchoff_D_matrix", "compute_shell_nodal_forces", "identify_s3_shared_edges",
                 "compute_triangle_surface_faces_with_third_node", "compute_s3_local_unitvector", "compute_s3_jacobian",
                 "compute_s3_shape_gradient", "compute_s3_B_matrix", "compute_s3_K_matrix", "identify_s4_shared_edges",
                 "compute_square_surface_faces_with_fourth_node", "compute_s4_local_unitvector", "s4_integration_points",
-                "compute_s4_jacobian", "compute_s4_shape_gradient", "compute_s4_B_matrix_single", "compute_s4_K_matrix"],
+                "compute_s4_jacobian", "compute_s4_shape_gradient", "compute_s4_B_matrix_single", "compute_s4_K_matrix",
+                "compute_global_to_local_displacement", "compute_shell_postprocess_values", "compute_s3_global_to_local_coordinates",
+                "compute_s4_global_to_local_coordinates", "compute_s4_B_matrix", "compute_s3_shell_stress", "compute_s4_shell_stress",
+                "shell_extrude"],
         solver: ["static_structure_solver", "stable_conjugate_gradient_solver", "final_solver", "stable_conjugate_gradient_shell_solver",
-                 "preconditioned_conjugate_gradient_solver", "compute_diagonal_preconditioner", "compute_K_matrix"],
+                 "preconditioned_conjugate_gradient_solver", "compute_diagonal_preconditioner", "compute_K_matrix",
+                 "conjugate_gradient_solver_Ku", "constrained_conjugate_gradient_solver", "new_constrained_conjugate_gradient_solver"],
     }
     for mod, names in expect.items():
         for n in names:
@@ -68,6 +73,11 @@ def test_mirror_api_names():
     sig = inspect.signature(solver.stable_conjugate_gradient_solver)
     assert list(sig.parameters)[:10] == ["K", "elements", "F", "rbe2", "u_init", "tol", "max_iter", "device", "dtype", "eps"]
     assert sig.parameters["tol"].default == 1e-10 and sig.parameters["eps"].default == 1e-30
+    sig = inspect.signature(solver.conjugate_gradient_solver_Ku)
+    assert list(sig.parameters)[:6] == ["compute_Ku", "R", "tol", "max_iter", "device", "dtype"] and sig.parameters["tol"].default == 1e-8
+    assert list(inspect.signature(shell.shell_extrude).parameters) == ["coords", "tri", "quad", "thickness", "device", "dtype"]
+    assert list(inspect.signature(shell.compute_shell_postprocess_values).parameters) == ["NMQ", "t", "z", "device", "dtype"]
+    assert list(inspect.signature(element.vtk_loader_to_torch).parameters) == ["file_path", "element_type", "device", "dtype"]
     sig = inspect.signature(element.compute_K_matrix)
     assert list(sig.parameters) == ["coords", "elements", "element_type", "E", "nu", "integral_point", "single", "device", "dtype"]
 

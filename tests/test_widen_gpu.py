@@ -1,0 +1,231 @@
+"""GPU parity tests for the rows either side of the element path (SURVEY section 8a complements a14/a15/a18/a23, 8f #1/#3):
+shell frames / stress / post-processing, shell extrusion, wedge face normals, tet face-force balance, the operator-callback
+CG and the VTK loader -- through the reference-shaped Python API -> ctypes -> libfemb200, against outputs of the reference
+itself (tests/golden/widen.npz) and the CPU oracle on larger seeded inputs.  fp64 bars: 1e-12 relative (CG 1e-8)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(PKG, "solver"))
+
+TOL = 1e-12
+DEV = "cuda:0"
+KW = dict(device=DEV, dtype=torch.float64)
+MB = torch.tensor([1.0, 0.3, 0.1], dtype=torch.float64)
+
+
+@pytest.fixture(scope="module")
+def api():
+    import element
+    import shell
+    import solver
+    return element, shell, solver
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import fem_oracle
+    return fem_oracle
+
+
+def T(a, dtype=None):
+    t = torch.as_tensor(np.asarray(a))
+    return t.to(dtype) if dtype is not None else t
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, tol=TOL):
+    a, b = N(a) if torch.is_tensor(a) else np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert rel_err(a, b) <= tol, rel_err(a, b)
+
+
+def test_shell_frames_and_displacements(api):
+    sh = api[1]
+    d, g = load_golden("widen"), load_golden("shells")
+    c3, s3, c4, s4 = T(g["c3"]), T(g["s3"]), T(g["c4"]), T(g["s4"])
+    unit3, unit4 = T(g["unit3"]), T(g["unit4"])
+    close(sh.compute_s3_global_to_local_coordinates(c3, s3, unit3, **KW), d["loc3"])
+    close(sh.compute_s4_global_to_local_coordinates(c4, s4, unit4, **KW), d["loc4"])
+    close(sh.compute_s4_global_to_local_coordinates(c4, s4.to(torch.int32), unit4, **KW), d["loc4"])
+    out = sh.compute_s4_global_to_local_coordinates(c4, s4, unit4, device=DEV)
+    assert out.dtype == torch.float32 and out.is_cuda
+    close(out.double(), d["loc4"], 1e-6)
+    close(sh.compute_global_to_local_displacement(s3, T(d["u3"]), unit3, device=DEV), d["ul3"])
+    close(sh.compute_global_to_local_displacement(s4, T(d["u4"]), unit4, device=DEV), d["ul4"])
+    close(sh.compute_global_to_local_displacement(s4.to(torch.int32), T(d["u4"]).float(), unit4, device=DEV).double(), d["ul4"], 1e-6)
+    # a frame other than the element's own is honoured (the reference just contracts with what it is given)
+    rot = torch.tensor([[0.0, 1.0, 0.0], [-1.0, 0.0, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    other = (rot @ unit4).contiguous()
+    close(sh.compute_s4_global_to_local_coordinates(c4, s4, other, **KW), np.einsum("mnd,ed->mne", d["loc4"], rot.numpy()))
+    assert sh.compute_s3_global_to_local_coordinates(c3, s3[:0], unit3[:0], **KW).shape == (0, 3, 3)
+
+
+def test_shell_B_stress_postprocess(api, O):
+    sh = api[1]
+    d, g = load_golden("widen"), load_golden("shells")
+    c3, s3, c4, s4 = T(g["c3"]), T(g["s3"]), T(g["c4"]), T(g["s4"])
+    close(sh.compute_s4_B_matrix(c4, s4, **KW), d["B4_sum"])
+    close(sh.compute_s4_B_matrix(c4, s4, single=False, **KW), d["B4_all"])
+    p, w = sh.s4_integration_points(device=DEV)
+    close(sh.compute_s4_B_matrix(c4, s4, integration_points=(p, w), **KW), d["B4_sum"])
+    close(sh.compute_s4_jacobian(c4, s4, p[0, 0], p[0, 1], **KW), d["J4_t"])          # 0-dim float32 tensors, as the reference passes
+    close(sh.compute_s4_shape_gradient(c4, s4, p[0, 0], p[0, 1], **KW), d["g4_t"])
+    close(sh.compute_s3_shell_stress(c3, s3, MB, MB, T(d["u3"]), **KW), d["stress3"])
+    close(sh.compute_s4_shell_stress(c4, s4, MB, MB, T(d["u4"]), **KW), d["stress4"])
+    close(sh.compute_s4_shell_stress(c4, s4.to(torch.int32), MB, MB, T(d["u4"]), device=DEV).double(), d["stress4"], 1e-5)
+    with pytest.raises(ValueError):
+        sh.compute_s4_shell_stress(c4, s4, MB, MB, T(d["u4"])[:, :3], **KW)
+    t, z = (float(v) for v in d["post_tz"])
+    post = sh.compute_shell_postprocess_values(T(d["stress4"]), t, z=z, **KW)
+    assert list(post.keys()) == [str(k) for k in d["post_keys"]]
+    close(torch.stack([post[k] for k in post]), d["post"])
+    post32 = sh.compute_shell_postprocess_values(T(d["stress4"]), t, z=z, device=DEV)
+    assert post32["sx"].dtype == torch.float32
+    close(torch.stack([post32[k] for k in post32]).double(), d["post32"].astype(np.float64), 2e-6)
+    # larger seeded case against the oracle, 8-column [N, M, Q] input
+    rng = np.random.default_rng(7)
+    nmq = rng.standard_normal((5000, 8))
+    post = sh.compute_shell_postprocess_values(T(nmq), 0.2, z=-0.05, **KW)
+    close(torch.stack([post[k] for k in post]), O.shell_postprocess(nmq, 0.2, -0.05))
+
+
+def test_shell_stress_large_vs_oracle(api, O):
+    sh = api[1]
+    from femb200 import meshgen
+    c4, s4 = meshgen.quad_sheet(40, warp=0.2)
+    c3, s3 = meshgen.tri_sheet(40, warp=0.2)
+    g = torch.Generator().manual_seed(3)
+    u = torch.randn(c4.shape[0], 6, dtype=torch.float64, generator=g)
+    close(sh.compute_s4_shell_stress(c4, s4, MB, MB, u, **KW), O.s4_shell_stress(N(c4), N(s4), N(MB), N(MB), N(u)))
+    close(sh.compute_s3_shell_stress(c3, s3, MB, MB, u, **KW), O.s3_shell_stress(N(c3), N(s3), N(MB), N(MB), N(u)))
+    close(sh.compute_s4_B_matrix(c4, s4, single=False, **KW), O.s4_B(N(c4), N(s4), single=False))
+
+
+def test_shell_extrude(api, O):
+    el, sh = api[0], api[1]
+    d = load_golden("widen")
+    cm, tri, quad, th = T(d["cm"]), T(d["tri"]), T(d["quad"]), float(d["thickness"])
+    x, w6, h8 = sh.shell_extrude(cm, tri, quad, th, **KW)
+    close(x, d["ext_x"])
+    assert w6.dtype == torch.int64 and np.array_equal(N(w6), d["ext_w"]) and np.array_equal(N(h8), d["ext_h"])
+    x32, w32, _ = sh.shell_extrude(cm, tri.to(torch.int32), quad.to(torch.int32), th, device=DEV)
+    assert x32.dtype == torch.float32 and w32.dtype == torch.int32 and np.array_equal(N(w32), d["ext_w"])
+    close(x32.double(), d["ext_x32"].astype(np.float64), 1e-6)
+    close(sh.shell_extrude(cm, tri, quad[:0], th, **KW)[0], d["ext_x_tri_only"])
+    xq, wq, hq = sh.shell_extrude(cm, tri[:0], quad, th, **KW)
+    close(xq, d["ext_x_quad_only"])
+    assert wq.shape == (0, 6) and hq.shape == (quad.shape[0], 8)
+    with pytest.raises(IndexError):
+        sh.shell_extrude(cm[:10], tri, quad, th, **KW)
+    # larger seeded sheet against the oracle; the solids it makes are positively oriented for the wedge / hex kernels
+    from femb200 import meshgen
+    cm, tri, quad = meshgen.mixed_sheet(60, warp=0.25)
+    x, w6, h8 = sh.shell_extrude(cm, tri, quad, 0.01, **KW)
+    xo, wo, ho = O.shell_extrude(N(cm), N(tri), N(quad), 0.01)
+    close(x, xo)
+    assert np.array_equal(N(w6), wo) and np.array_equal(N(h8), ho)
+    Jw = el.compute_c3d6_Jacobian(x, w6, torch.tensor([1 / 3, 1 / 3, 0.0], dtype=torch.float64), **KW)
+    Jh = el.compute_c3d8_Jacobian(x, h8, torch.zeros(3, dtype=torch.float64), **KW)
+    assert float(torch.linalg.det(Jw).min()) > 0 and float(torch.linalg.det(Jh).min()) > 0
+    # run-to-run determinism (incidence-ordered sums, no atomics)
+    x2 = sh.shell_extrude(cm, tri, quad, 0.01, **KW)[0]
+    assert torch.equal(x, x2)
+
+
+def test_wedge_normals_and_face_forces(api, O):
+    el = api[0]
+    d = load_golden("widen")
+    cw, w = T(d["cw"]), T(d["w"])
+    close(el.compute_wedge_normals_and_area(cw, w, **KW), O.wedge_face_normals(d["cw"], d["w"]))
+    close(el.compute_wedge_normals_and_area(cw, w.to(torch.int32), device=DEV).double(), O.wedge_face_normals(d["cw"], d["w"]), 1e-6)
+    ct, tets = T(d["ct"]), T(d["tets"])
+    nrm = el.compute_tetrahedral_normals_and_area(ct, tets, **KW)
+    ff = el.compute_c3d4_surface_forces(nrm, T(d["sigma"]), device=DEV)
+    close(ff, d["face_forces"])
+    close(el.compute_c3d4_shared_face_forces_sum(T(d["shared"]), ff, device=DEV), d["shared_sum"])
+    # with this library's own pairs (lower element first) the sums are the same set of rows
+    pairs = el.identify_tetrahedral_shared_faces(tets, device=DEV)
+    close(el.compute_c3d4_shared_face_forces_sum(pairs, ff, device=DEV), O.c3d4_shared_face_forces_sum(N(pairs), d["face_forces"]))
+    with pytest.raises(IndexError):
+        el.compute_c3d4_shared_face_forces_sum(T(d["shared"]) + 100, ff, device=DEV)
+    assert el.compute_c3d4_shared_face_forces_sum(T(d["shared"])[:0], ff, device=DEV).shape == (0, 3)
+
+
+def test_cg_operator_callback(api, O, capsys):
+    el, sv = api[0], api[2]
+    d = load_golden("widen")
+    ct, tets, R = T(d["ct"]), T(d["tets"]), T(d["ku_R"])
+    K = el.compute_c3d4_K_matrix(ct, tets, 1.0, 0.3, **KW)
+    shift = float(d["ku_shift"])
+    calls = []
+
+    def Ku(v):
+        assert v.dtype == torch.float64 and v.is_cuda and v.shape == (ct.shape[0], 3)
+        calls.append(1)
+        return el.compute_nodal_forces(K, tets, v, **KW) + shift * v
+
+    u, info = sv.conjugate_gradient_solver_Ku(Ku, R, tol=1e-10, max_iter=500, return_info=True, **KW)
+    Ko = O.c3d4_K(d["ct"], d["tets"], 1.0, 0.3)
+    uo, ito = O.cg_solve_Ku(lambda v: O.nodal_forces(Ko, d["tets"], v) + shift * v, d["ku_R"], tol=1e-10, max_iter=500)
+    assert info["status"] == "converged" and abs(info["iterations"] - ito) <= 1, (info, ito)
+    assert len(calls) >= info["iterations"] + 1
+    close(u, d["ku_u"], 1e-8)
+    close(u, uo, 1e-8)
+    # the same loop on an assembled operator (callback = this library's SpMV)
+    A = sv.assemble_csr(K, tets)
+    from femb200 import ops
+    crow, col, val = A.crow_indices().to(torch.int32), A.col_indices().to(torch.int32), A.values()
+    u2 = sv.conjugate_gradient_solver_Ku(lambda v: ops.spmv(crow, col, val, v) + shift * v, R, tol=1e-10, max_iter=500, **KW)
+    close(u2, d["ku_u"], 1e-8)
+    # default dtype float32: operator sees float32, result is float32
+    seen = []
+    u32 = sv.conjugate_gradient_solver_Ku(lambda v: (seen.append(v.dtype), Ku(v.double()).float())[1], R, tol=1e-5, max_iter=500, device=DEV)
+    assert u32.dtype == torch.float32 and seen[0] == torch.float32
+    close(u32.double(), d["ku_u"], 1e-4)
+    # not converged: the reference's message, max_iter reported
+    capsys.readouterr()
+    _, info = sv.conjugate_gradient_solver_Ku(Ku, R, tol=1e-30, max_iter=3, return_info=True, **KW)
+    assert info["status"] == "maxiter" and info["iterations"] == 3
+    assert "did not converge" in capsys.readouterr().out
+    # exceptions raised inside the operator surface unchanged
+    def boom(v):
+        raise KeyError("operator failed")
+    with pytest.raises(KeyError):
+        sv.conjugate_gradient_solver_Ku(boom, R, **KW)
+
+
+def test_vtk_loader(api, tmp_path):
+    el = api[0]
+    from test_widen_cpu import _mesh, _write_ascii, _write_binary
+    pts, tets = _mesh()
+    a = str(tmp_path / "a.vtk")
+    _write_ascii(a, pts, tets, 10)
+    p, e = el.vtk_loader_to_torch(a, "c3d4", **KW)
+    assert p.is_cuda and p.dtype == torch.float64 and e.dtype == torch.long and np.array_equal(N(p), pts) and np.array_equal(N(e), tets)
+    b = str(tmp_path / "b.vtk")
+    hexes = np.array([[0, 1, 2, 3, 4, 5, 6, 7], [1, 2, 3, 4, 5, 6, 7, 8]], dtype=np.int64)
+    _write_binary(b, pts, hexes, 12, real="float", v5=True)
+    p, e = el.vtk_loader_to_torch(b, "c3d8", device=DEV)
+    assert p.dtype == torch.float32 and np.array_equal(N(p), pts.astype(np.float32)) and np.array_equal(N(e), hexes)
+    p64, _ = el.vtk_loader_to_torch(b, "c3d8", **KW)
+    assert np.array_equal(N(p64), pts.astype(np.float32).astype(np.float64))     # float file -> float32 -> dtype, as through pyvista
+    with pytest.raises(ValueError, match="Invalid element type"):
+        el.vtk_loader_to_torch(a, "c3d99", **KW)
+    with pytest.raises(ValueError):
+        el.vtk_loader_to_torch(a, "c3d10", **KW)     # 4 cells x 5 entries do not reshape to rows of 11
+    with pytest.raises(ValueError):
+        el.vtk_loader_to_torch(a, "s3", **KW)        # 20 entries reshape to rows of 4, but the per-cell counts are not 3
+    # the loaded mesh feeds the element path directly
+    K = el.compute_c3d4_K_matrix(*el.vtk_loader_to_torch(a, "c3d4", **KW), 1.0, 0.3, **KW)
+    assert K.shape == (4, 12, 12)
