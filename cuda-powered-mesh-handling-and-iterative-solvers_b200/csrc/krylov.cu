@@ -193,8 +193,11 @@ __global__ void __launch_bounds__(TMA_THREADS) spmv_bsr3_tma_kernel(long long nb
 // lanes 0..26 cover three consecutive blocks per step (lane = 9*block + position, fixed for the whole kernel, so no index
 // arithmetic in the loop), the 216 bytes of a step are one contiguous coalesced read, every lane keeps ONE accumulator
 // (its position's row of the block), the three x gathers of a block land in one sector, and four shuffles finish a row.
+// MERGED (the two extra dot products of the merged-reduction loop) is a template parameter: compiled into the plain and the
+// classic-fused kernels it costs them 8 registers, i.e. 48 instead of 64 resident warps per SM (measured: 1.30 -> 1.52 ms on
+// the 2 M-tet P2 operator).
 constexpr int BSRV_THREADS = 256;
-template <bool FUSED, int U>
+template <bool FUSED, int U, bool MERGED>
 __global__ void __launch_bounds__(BSRV_THREADS) spmv_bsr3_vec_kernel(long long nb, long long nnzb, const int* __restrict__ brow,
                                                                      const int* __restrict__ bcol, const double* __restrict__ bval,
                                                                      const double* __restrict__ x, double* __restrict__ y,
@@ -237,13 +240,13 @@ __global__ void __launch_bounds__(BSRV_THREADS) spmv_bsr3_vec_kernel(long long n
       if (FUSED) {
         if (mask && !mask[i]) sv = 0.0;
         dot += sv * __ldg(x + i);
-        if (rvec) e0 += sv * rvec[i], e1 += sv * sv;
+        if (MERGED) e0 += sv * rvec[i], e1 += sv * sv;
       }
       y[i] = sv;
     }
   }
   if (FUSED) {
-    if (rvec) cg_k1_epilogue3_n<BSRV_THREADS>(dot, e0, e1, partial, st, eps, guards, tol);
+    if (MERGED) cg_k1_epilogue3_n<BSRV_THREADS>(dot, e0, e1, partial, st, eps, guards, tol);
     else cg_k1_epilogue_n<BSRV_THREADS>(dot, partial, st, eps, guards);
   }
 }
@@ -474,8 +477,15 @@ static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const 
     spmv_bsr3_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, BSR_SMEM, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
   }
   switch (lanes) {
-    case 300: spmv_bsr3_vec_kernel<FUSED, 4><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); break;
-    case 301: spmv_bsr3_vec_kernel<FUSED, 2><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); break;
+#define FEMB_BSRV(UV)                                                                                                              \
+  {                                                                                                                                \
+    if (FUSED && rvec)                                                                                                             \
+      spmv_bsr3_vec_kernel<FUSED, UV, FUSED><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
+    else                                                                                                                           \
+      spmv_bsr3_vec_kernel<FUSED, UV, false><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
+  }
+    case 300: FEMB_BSRV(4) break;
+    case 301: FEMB_BSRV(2) break;
     case 201: FEMB_BSR(1) break;
     case 202: FEMB_BSR(2) break;
     case 204: FEMB_BSR(4) break;
@@ -502,19 +512,23 @@ static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const 
   }
 #undef FEMB_TMA
 #undef FEMB_BSR
+#undef FEMB_BSRV
 #undef FEMB_SPMV_ARGS
 }
 
-static int spmv_grid(long long n, int lanes) {
+static int spmv_grid(long long n, int lanes, bool merged = false) {
   if (lanes == 300 || lanes == 301) {  // warp per block row, persistent: every CTA that fits on the device
-    static int fit[2] = {0, 0};
-    if (!fit[0]) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit[0], spmv_bsr3_vec_kernel<true, 4>, BSRV_THREADS, 0);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit[1], spmv_bsr3_vec_kernel<true, 2>, BSRV_THREADS, 0);
-      if (fit[0] < 1) fit[0] = 1;
-      if (fit[1] < 1) fit[1] = 1;
+    static int fit[2][2] = {{0, 0}, {0, 0}};  // [U = 4 / 2][classic (also bounds the plain kernel) / merged]
+    if (!fit[0][0]) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit[0][0], spmv_bsr3_vec_kernel<true, 4, false>, BSRV_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit[1][0], spmv_bsr3_vec_kernel<true, 2, false>, BSRV_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit[0][1], spmv_bsr3_vec_kernel<true, 4, true>, BSRV_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit[1][1], spmv_bsr3_vec_kernel<true, 2, true>, BSRV_THREADS, 0);
+      for (auto& f : fit)
+        for (int& v : f)
+          if (v < 1) v = 1;
     }
-    const int per_sm = getenv("FEMB_BSRV_CTAS") ? atoi(getenv("FEMB_BSRV_CTAS")) : fit[lanes - 300];
+    const int per_sm = getenv("FEMB_BSRV_CTAS") ? atoi(getenv("FEMB_BSRV_CTAS")) : fit[lanes - 300][merged ? 1 : 0];
     const long long ctas = (n / 3 + BSRV_THREADS / 32 - 1) / (BSRV_THREADS / 32);
     return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)SMS * per_sm));
   }
@@ -587,9 +601,14 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   if (minv) eps = 0.0;
   double *r = work, *p = work + n, *Ap = work + 2 * n;
   int lanes[8], g1[8], gmax = 1;
+  for (int m = 0; m < nmat; ++m) lanes[m] = pick_lanes(n, mats[m].nnz, mats[m].block);
+  // merged-reduction loop (2 kernels, 7 vector passes per iteration) for plain CG on every SpMV kernel that sums the two extra
+  // dot products; PCG, the LDG-streaming / block-TMA A/B kernels and FEMB_CG_CLASSIC=1 take the three-kernel loop
+  static const bool classic_env = getenv("FEMB_CG_CLASSIC") != nullptr;
+  const int ll = lanes[nmat - 1];
+  const bool merged = !classic_env && !minv && (ll >= 300 || (ll >= 100 && ll < 200) || ll < 0);
   for (int m = 0; m < nmat; ++m) {
-    lanes[m] = pick_lanes(n, mats[m].nnz, mats[m].block);
-    g1[m] = spmv_grid(n, lanes[m]);
+    g1[m] = spmv_grid(n, lanes[m], merged && m == nmat - 1);  // one grid per matrix: setup (plain) and loop (fused) launches share it
     gmax = std::max(gmax, g1[m]);
   }
   const int g2 = grid_for(n, VEC_THREADS, 8);
@@ -605,11 +624,6 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   cg_init_kernel<<<g2, VEC_THREADS, 0, s>>>(n, F, Ap, mask, minv, r, p, partial);
   cg_init_finish<<<1, VEC_THREADS, 0, s>>>(g2, partial, st, max_iter);
   FEMB_LAUNCH_CHECK();
-  // merged-reduction loop (2 kernels, 7 vector passes per iteration) for plain CG on every SpMV kernel that sums the two extra
-  // dot products; PCG, the LDG-streaming / block-TMA A/B kernels and FEMB_CG_CLASSIC=1 take the three-kernel loop
-  static const bool classic_env = getenv("FEMB_CG_CLASSIC") != nullptr;
-  const int ll = lanes[nmat - 1];
-  const bool merged = !classic_env && !minv && (ll >= 300 || (ll >= 100 && ll < 200) || ll < 0);
   // ---- capture `check_every` iterations into one graph
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;

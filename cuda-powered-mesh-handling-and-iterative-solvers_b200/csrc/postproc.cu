@@ -97,9 +97,53 @@ __global__ void wedge_normals_kernel(const T* __restrict__ coords, const I* __re
   }
 }
 
+// subdivision.ipynb cell 15: every subdomain starts from the global load vector ...
+template <typename T>
+__global__ void subdomain_broadcast_kernel(const T* __restrict__ F, long long len, int n_sub, T* __restrict__ out) {
+  const long long total = len * n_sub;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) out[t] = F[t % len];
+}
+// ... and every (subdomain, interface node) target receives its interface-force unknowns: + the one it shares with the next
+// subdomain of the node's group, - the one it shares with the previous (targets are unique, so no two threads write one entry)
+template <typename T>
+__global__ void subdomain_interface_kernel(const T* __restrict__ F, long long N, const T* __restrict__ fv, long long ntgt,
+                                           const long long* __restrict__ tgt, const int* __restrict__ plus, const int* __restrict__ minus,
+                                           T* __restrict__ out) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ntgt; t += (long long)gridDim.x * blockDim.x) {
+    const long long o = tgt[t], node = o % N;
+    const int a = plus[t], b = minus[t];
+    for (int c = 0; c < 3; ++c) {
+      const T f = F[3 * node + c];
+      T v;
+      if (a >= 0 && b >= 0) v = f + (fv[3ll * a + c] - fv[3ll * b + c]);
+      else if (a >= 0) v = f + fv[3ll * a + c];
+      else if (b >= 0) v = f - fv[3ll * b + c];
+      else v = f;
+      out[3 * o + c] = v;
+    }
+  }
+}
+
 }  // namespace femb
 
 using namespace femb;
+
+extern "C" int femb_subdomain_forces(const void* F, int fp, int64_t N, int n_sub, const void* free_vars, int64_t ntgt, const int64_t* tgt,
+                                     const int32_t* plus, const int32_t* minus, void* out, femb_stream stream) {
+  FEMB_CHECK_ARG((fp == 4 || fp == 8) && N >= 0 && n_sub >= 1 && ntgt >= 0, "fp in {4,8}, N >= 0, n_sub >= 1, ntgt >= 0");
+  if (N == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int g1 = grid_for(3 * N * n_sub, 256), g2 = grid_for(ntgt, 128);
+  if (fp == 8) {
+    subdomain_broadcast_kernel<double><<<g1, 256, 0, s>>>((const double*)F, 3 * N, n_sub, (double*)out);
+    if (ntgt) subdomain_interface_kernel<double><<<g2, 128, 0, s>>>((const double*)F, N, (const double*)free_vars, ntgt, (const long long*)tgt, plus, minus, (double*)out);
+  } else {
+    subdomain_broadcast_kernel<float><<<g1, 256, 0, s>>>((const float*)F, 3 * N, n_sub, (float*)out);
+    if (ntgt) subdomain_interface_kernel<float><<<g2, 128, 0, s>>>((const float*)F, N, (const float*)free_vars, ntgt, (const long long*)tgt, plus, minus, (float*)out);
+  }
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
 
 extern "C" int femb_shell_local_displacement(const void* conn, int ib, int64_t M, int nen, const void* disp, const void* unit, int fp, void* out,
                                              femb_stream stream) {

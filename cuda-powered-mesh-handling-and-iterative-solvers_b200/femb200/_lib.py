@@ -72,6 +72,7 @@ SIGNATURES = {
     "femb_vtk_close": [c_vp],
     "femb_csr_jacobi": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "femb_graph_from_pairs": [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
+    "femb_subdomain_forces": [c_vp, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
     "femb_graph_bfs": [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, C.POINTER(c_i32), c_vp],
     "femb_dist_header_bytes": [],
     "femb_dist_alloc": [c_i64, C.POINTER(c_vp), c_vp],

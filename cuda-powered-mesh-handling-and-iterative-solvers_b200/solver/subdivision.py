@@ -1,5 +1,6 @@
 """Drop-in for the helper functions the reference defines inside `subdivision.ipynb` (cells 6-9, 13): memory-driven
-subdivision count, element face-adjacency graph, farthest-seed region-growing partition and per-part local operators.
+subdivision count, element face-adjacency graph, farthest-seed region-growing partition and per-part local operators, and of
+its closing fragments (cells 12, 14, 15): dense subdomain inverses, interface-force unknowns and per-subdomain load vectors.
 
 Same names and argument order as the notebook cells.  The notebook runs every BFS level as a `torch.sparse.mm` with a dense
 [n_parts, M] frontier and renumbers nodes through a Python dict; here the adjacency is a CSR built by one radix sort
@@ -137,3 +138,76 @@ def build_ordered_subdomain_map(node_maps):
             out[tuple(parts[i:j])].append(nodes[i])
         i = j
     return dict(out)
+
+
+# ------------------------------------------------------------------------------------------- cells 12, 14, 15 (fragments)
+
+def invert_K_parts(K_parts):
+    """cell 12: dense inverse of every subdomain operator (a library call in the notebook too: torch.linalg.inv of
+    K.to_dense()).  Floating subdomains are singular -- the notebook inverts them regardless, and so does this."""
+    return [torch.linalg.inv(K.to_dense()) for K in K_parts]
+
+
+def count_free_variables(group_to_nodes):
+    """Number of interface-force unknowns: (parts sharing the node - 1) per interface node (cell 14)."""
+    return sum((len(k) - 1) * len(v) for k, v in group_to_nodes.items())
+
+
+def make_free_variables(group_to_nodes, device="cuda:0", dtype=torch.float64):
+    """cell 14: zero-initialised interface-force unknowns [n_free, 3] (the notebook builds them from a Python list of
+    [0,0,0] rows, which makes an int64 tensor; pass the dtype of the load vector instead)."""
+    return torch.zeros((count_free_variables(group_to_nodes), 3), device=device, dtype=dtype)
+
+
+class SubdomainForcePlan:
+    """Index form of cell 15's double loop over (group, node): for every (subdomain, interface node) the unknown it gains and
+    the one it loses.  Built once per partition on the host (the notebook walks the dict on every call)."""
+
+    def __init__(self, group_to_nodes, rbe2, N, n_sub, device):
+        fixed = set(int(v) for v in (rbe2.reshape(-1).tolist() if torch.is_tensor(rbe2) else (rbe2 if rbe2 is not None else ())))
+        tgt, plus, minus = [], [], []
+        off = 0
+        for k, v in group_to_nodes.items():
+            m = len(k) - 1
+            sd = sorted(k)
+            idx = off
+            for nd in v:
+                if nd not in fixed:
+                    for j in range(m + 1):
+                        tgt.append(sd[j] * N + nd)
+                        plus.append(idx + j if j < m else -1)
+                        minus.append(idx + j - 1 if j > 0 else -1)
+                idx += m
+            off += m * len(v)
+        if len(set(tgt)) != len(tgt):
+            raise ValueError("a node appears in more than one interface group")
+        if tgt and (max(tgt) >= n_sub * N or min(tgt) < 0):
+            raise IndexError("interface group refers to a subdomain / node outside (n_sub, N)")
+        self.n_free, self.N, self.n_sub, self.dev = off, N, n_sub, device
+        self.tgt = torch.tensor(tgt, device=device, dtype=torch.int64)
+        self.plus = torch.tensor(plus, device=device, dtype=torch.int32)
+        self.minus = torch.tensor(minus, device=device, dtype=torch.int32)
+
+    def apply(self, free_vars, F):
+        F = _ops.real(F, self.dev, F.dtype if F.dtype in (torch.float32, torch.float64) else torch.float64)
+        fv = _ops.real(free_vars, self.dev, F.dtype).reshape(-1, 3)
+        if fv.shape[0] < self.n_free or tuple(F.shape) != (self.N, 3):
+            raise ValueError(f"expected free_vars [>={self.n_free},3] and F [{self.N},3], got {tuple(fv.shape)} and {tuple(F.shape)}")
+        out = torch.empty((self.n_sub, self.N, 3), device=self.dev, dtype=F.dtype)
+        with torch.cuda.device(self.dev):
+            check(lib.femb_subdomain_forces(_ops._p(F), F.element_size(), self.N, self.n_sub, _ops._p(fv), self.tgt.numel(), _ops._p(self.tgt),
+                                            _ops._p(self.plus), _ops._p(self.minus), _ops._p(out), _ops._stream(self.dev)),
+                  "femb_subdomain_forces")
+        return list(out.unbind(0))
+
+
+def make_sub_domain_forces(free_vars, group_to_nodes, rbe2, F, n_sub, device="cuda", plan=None):
+    """cell 15: the load vector of every subdomain = F plus the interface forces it exchanges with the other subdomains that
+    share its interface nodes (chained +f_j / -f_j so that they cancel in the sum over subdomains); nodes in `rbe2` carry
+    none.  Returns n_sub tensors [N,3] in the global node numbering, as the notebook does.  Pass `plan`
+    (a SubdomainForcePlan) to reuse the index arrays across calls of an interface iteration."""
+    dev = _ops.cuda_device("cuda:0" if str(device) == "cuda" else device)
+    F = torch.as_tensor(F).to(dev)
+    if plan is None:
+        plan = SubdomainForcePlan(group_to_nodes, rbe2, F.shape[0], n_sub, dev)
+    return plan.apply(free_vars, F)

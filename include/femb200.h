@@ -286,6 +286,12 @@ int femb_graph_from_pairs(const int64_t* pairs, int64_t S, int pair_stride, int6
 int femb_graph_bfs(const int32_t* crow, const int32_t* col, int64_t M, const int64_t* sources, int n_sources, int32_t* dist,
                    int32_t* label, int32_t* levels_host, femb_stream stream);
 
+/* subdivision.ipynb cell 15 (make_sub_domain_forces): out[n_sub,N,3] = F[N,3] copied to every subdomain, then for each of the
+ * ntgt interface targets o = tgt[t] = sub*N + node (unique): out[o] = F[node] + (fv[plus[t]] - fv[minus[t]]), an index of -1
+ * meaning "absent" (first / last subdomain of the node's group).  free_vars [n_free,3] in the dtype of F. */
+int femb_subdomain_forces(const void* F, int fp, int64_t N, int n_sub, const void* free_vars, int64_t ntgt, const int64_t* tgt,
+                          const int32_t* plus, const int32_t* minus, void* out, femb_stream stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Mesh input: legacy .vtk unstructured grids (vtk_loader_to_torch element.py:39-90 reads them through pyvista)
  * ------------------------------------------------------------------------------------------- */
