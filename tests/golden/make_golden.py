@@ -373,6 +373,34 @@ def gen_quadratic():
     save("quadratic", p20=npy(p), w20=npy(w), h20=npy(h20), h20_tets=npy(R.c3d20_to_c3d4(h20, device="cpu")))
 
 
+def gen_subdomain_forces():
+    """subdivision.ipynb cells 13 and 15 executed as written (CPU) on a 5-part partition of a small cube."""
+    from collections import defaultdict
+    nb = json.load(open("/root/reference/subdivision.ipynb"))
+    ns = {"torch": torch, "defaultdict": defaultdict, "print": lambda *a, **k: None}
+    exec("".join(nb["cells"][13]["source"]).split("\ngroup_to_nodes =")[0], ns)
+    exec("".join(nb["cells"][15]["source"]), ns)
+    g = np.load(os.path.join(HERE, "partition.npz"))
+    tets, labels = torch.tensor(g["tets"]), torch.tensor(g["labels"])
+    node_maps = [torch.unique(tets[labels == p]) for p in range(5)]
+    g2n = ns["build_ordered_subdomain_map"](node_maps)
+    keys = sorted(g2n)                                   # a fixed group order for the fixture
+    g2n = {k: sorted(g2n[k]) for k in keys}
+    n_free = sum((len(k) - 1) * len(v) for k, v in g2n.items())
+    gen = torch.Generator().manual_seed(21)
+    fv = torch.randn(n_free, 3, dtype=torch.float64, generator=gen)
+    N = int(tets.max()) + 1
+    F = torch.randn(N, 3, dtype=torch.float64, generator=gen)
+    iface = sorted(n for v in g2n.values() for n in v)
+    rbe2 = iface[::7]                                    # some interface nodes are fixed: they consume unknowns, receive nothing
+    out = ns["make_sub_domain_forces"](fv, g2n, rbe2, F, 5, device="cpu")
+    flat_keys = np.array([list(k) + [-1] * (5 - len(k)) for k in keys])
+    flat_nodes = np.concatenate([np.array(g2n[k]) for k in keys])
+    counts = np.array([len(g2n[k]) for k in keys])
+    save("subdomain_forces", keys=flat_keys, nodes=flat_nodes, counts=counts, fv=npy(fv), F=npy(F), rbe2=np.array(rbe2),
+         out=npy(torch.stack(out)), node_maps_flat=np.concatenate([npy(m) for m in node_maps]), node_maps_len=np.array([m.numel() for m in node_maps]))
+
+
 def gen_widen():
     """Functions either side of the element path: shell frames / stress / post-processing, shell extrusion, wedge face normals,
     tet face-force balance and the operator-callback CG."""
@@ -454,3 +482,4 @@ if __name__ == "__main__":
     gen_constrained()
     gen_partition()
     gen_widen()
+    gen_subdomain_forces()

@@ -88,6 +88,51 @@ def test_wedge_face_normals_invariants():
         assert ((np.cross(e1, e2) * n[:, f]).sum(-1) > 0).all()
 
 
+def load_groups(d):
+    """{sorted tuple of parts: [nodes]} in the fixture's order."""
+    out, off = {}, 0
+    for row, c in zip(d["keys"], d["counts"]):
+        out[tuple(int(v) for v in row if v >= 0)] = [int(v) for v in d["nodes"][off:off + c]]
+        off += c
+    return out
+
+
+def test_subdomain_forces_oracle():
+    """subdivision.ipynb cell 15 run as written (fixture) against the oracle, bit for bit (only additions and subtractions)."""
+    d = load_golden("subdomain_forces")
+    g2n = load_groups(d)
+    s = O.sub_domain_forces(d["fv"], g2n, d["rbe2"], d["F"], 5)
+    assert np.array_equal(np.stack(s), d["out"])
+    # interface forces cancel in the sum over subdomains; fixed interface nodes and interior nodes keep F everywhere
+    assert np.abs(np.stack(s).sum(0) - 5 * d["F"]).max() < 1e-13
+    for nd in d["rbe2"]:
+        assert all(np.array_equal(si[nd], d["F"][nd]) for si in s)
+    # the index form the product builds on the host addresses every (subdomain, interface node) once
+    import sys
+    from conftest import PKG
+    sys.path.insert(0, os.path.join(PKG, "solver"))
+    import subdivision as sd
+    plan = sd.SubdomainForcePlan(g2n, d["rbe2"], d["F"].shape[0], 5, "cpu")
+    assert plan.n_free == d["fv"].shape[0] == sd.count_free_variables(g2n)
+    free_nodes = [n for v in g2n.values() for n in v if n not in set(d["rbe2"].tolist())]
+    assert plan.tgt.numel() == sum(len(k) for k, v in g2n.items() for n in v if n in free_nodes)
+    ref = np.broadcast_to(d["F"], (5,) + d["F"].shape).copy().reshape(-1, 3)
+    tgt, plus, minus = plan.tgt.numpy(), plan.plus.numpy(), plan.minus.numpy()
+    for t, a, b in zip(tgt, plus, minus):
+        f = d["F"][t % d["F"].shape[0]]
+        ref[t] = f + (d["fv"][a] - d["fv"][b]) if a >= 0 and b >= 0 else (f + d["fv"][a] if a >= 0 else f - d["fv"][b])
+    assert np.array_equal(ref.reshape(5, -1, 3), d["out"])
+    maps, off = [], 0
+    import torch
+    for n in d["node_maps_len"]:
+        maps.append(torch.tensor(d["node_maps_flat"][off:off + n]))
+        off += n
+    got = sd.build_ordered_subdomain_map(maps)
+    assert {k: sorted(v) for k, v in got.items()} == g2n
+    with pytest.raises(ValueError):
+        sd.SubdomainForcePlan({(0, 1): [3], (1, 2): [3]}, [], 10, 3, "cpu")
+
+
 # ------------------------------------------------------------------------------------------------ legacy VTK files
 
 def _mesh():

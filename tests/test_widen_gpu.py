@@ -229,3 +229,37 @@ def test_vtk_loader(api, tmp_path):
     # the loaded mesh feeds the element path directly
     K = el.compute_c3d4_K_matrix(*el.vtk_loader_to_torch(a, "c3d4", **KW), 1.0, 0.3, **KW)
     assert K.shape == (4, 12, 12)
+
+
+def test_subdomain_forces(api):
+    """subdivision.ipynb cells 12, 14, 15 against the notebook's own code run on the CPU (tests/golden/subdomain_forces.npz)."""
+    import subdivision as sd
+    from test_widen_cpu import load_groups
+    d = load_golden("subdomain_forces")
+    g2n = load_groups(d)
+    F, fv = T(d["F"]), T(d["fv"])
+    out = sd.make_sub_domain_forces(fv, g2n, d["rbe2"].tolist(), F, 5, device="cuda")
+    assert len(out) == 5 and out[0].shape == F.shape and out[0].is_cuda
+    assert np.array_equal(N(torch.stack(out)), d["out"])                      # additions / subtractions only: bit-exact
+    plan = sd.SubdomainForcePlan(g2n, T(d["rbe2"]), F.shape[0], 5, torch.device(DEV))
+    out2 = sd.make_sub_domain_forces(fv.to(DEV), g2n, None, F.to(DEV), 5, device=DEV, plan=plan)
+    assert np.array_equal(N(torch.stack(out2)), d["out"])
+    out32 = sd.make_sub_domain_forces(fv, g2n, d["rbe2"].tolist(), F.float(), 5, device=DEV)
+    assert out32[0].dtype == torch.float32
+    close(torch.stack(out32).double(), d["out"], 1e-6)
+    z = sd.make_free_variables(g2n, device=DEV)
+    assert tuple(z.shape) == (d["fv"].shape[0], 3) and float(z.abs().max()) == 0
+    same_as_F = sd.make_sub_domain_forces(z, g2n, [], F, 5, device=DEV)
+    assert all(np.array_equal(N(s), d["F"]) for s in same_as_F)
+    with pytest.raises(ValueError):
+        sd.make_sub_domain_forces(fv[:5], g2n, [], F, 5, device=DEV)
+    # cell 12 on subdomain operators made non-singular by a mass-like shift
+    el = api[0]
+    ct, tets = T(load_golden("partition")["coords"]), T(load_golden("partition")["tets"])
+    K = el.compute_c3d4_K_matrix(ct, tets, 1.0, 0.3, **KW)
+    sh = el.identify_tetrahedral_shared_faces(tets, device=DEV)
+    Kp, maps, _, _ = sd.partition_and_build_sparse_K(K, tets, sh, 3, device=DEV, first_seed=0)
+    Kp = [(k.to_dense() + 0.5 * torch.eye(k.shape[0], device=DEV, dtype=torch.float64)).to_sparse_csr() for k in Kp]
+    inv = sd.invert_K_parts(Kp)
+    for k, ki in zip(Kp, inv):
+        close(ki @ k.to_dense(), np.eye(k.shape[0]), 1e-10)
