@@ -501,6 +501,75 @@ __global__ void __launch_bounds__(WARPS * 32) assemble_gather(const int* __restr
   }
 }
 
+// Same ownership and summation order, batched: ncu on the 2 M-tet P2 operator showed the kernel above waiting ~5 us per
+// incidence on one dependent chain (inc -> conn -> binary search over the row's columns -> Ke), 23 % of the HBM peak.  Here the
+// positions come from the plan's slot table (one coalesced byte load per batch instead of a search), the per-lane index
+// arithmetic (alpha, b, beta of entry t) is hoisted out of the loops, and the Ke rows of U consecutive incidences are all in
+// flight before the first is accumulated.  The adds into acc[] still happen incidence by incidence in ascending element
+// order, so the values are bit-identical to the kernel above.  R = ceil(d*nd/32) entries per lane and incidence.
+template <int WARPS, int R, int U>
+__global__ void __launch_bounds__(WARPS * 32) assemble_gather_batched(const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                                                      const unsigned char* __restrict__ slots, const int* __restrict__ node_ptr,
+                                                                      long long N, int nen, int d, int max_row, const double* __restrict__ Ke,
+                                                                      double* __restrict__ vals) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nd = nen * d, per = d * nd;  // entries of the d consecutive Ke rows of one incidence
+  double* acc = sm + (size_t)w * max_row * d * d;
+  unsigned char* spos = reinterpret_cast<unsigned char*>(sm + (size_t)WARPS * max_row * d * d) + (size_t)w * 256;  // [U][nen] <= 256
+  int bq[R], off[R];  // entry t = q*32+lane of an incidence: local column node b, and alpha*len*d + beta filled per row
+  int al[R], be[R];
+  bool valid[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    const int t = q * 32 + lane;
+    valid[q] = t < per;
+    const int tt = valid[q] ? t : 0;
+    al[q] = tt / nd;
+    const int c = tt - al[q] * nd;
+    bq[q] = c / d;
+    be[q] = c - bq[q] * d;
+  }
+  const long long warp = (long long)blockIdx.x * WARPS + w, nwarps = (long long)gridDim.x * WARPS;
+  for (long long i = warp; i < N; i += nwarps) {
+    const int s = node_ptr[i], len = node_ptr[i + 1] - s;
+    const int nacc = len * d * d;
+    for (int t = lane; t < nacc; t += 32) acc[t] = 0.0;
+#pragma unroll
+    for (int q = 0; q < R; ++q) off[q] = al[q] * len * d + be[q];
+    const int k0 = inc_ptr[i], k1 = inc_ptr[i + 1];
+    for (int kb = k0; kb < k1; kb += U) {
+      const int nb = min(U, k1 - kb);
+      __syncwarp();  // acc zeroing / the previous batch's use of spos
+      const int myslot = lane < nb ? __ldg(inc + kb + lane) : 0;
+      for (int t = lane; t < nb * nen; t += 32) spos[t] = __ldg(slots + (long long)kb * nen + t);
+      double v[U][R];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int slot = __shfl_sync(0xffffffffu, myslot, j);
+        const int e = slot / nen, a = slot - e * nen;
+        const double* src = Ke + ((long long)e * nd + (long long)a * d) * nd;
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[j][q] = (j < nb && valid[q]) ? __ldg(src + q * 32 + lane) : 0.0;
+      }
+      __syncwarp();  // spos visible
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (j < nb) {
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+            if (valid[q]) acc[off[q] + (int)spos[j * nen + bq[q]] * d] += v[j][q];
+        }
+        __syncwarp();  // the next incidence may touch the same entries from other lanes
+      }
+    }
+    __syncwarp();
+    double* dst = vals + (long long)d * d * s;
+    for (int t = lane; t < nacc; t += 32) dst[t] = acc[t];
+    __syncwarp();
+  }
+}
+
 // ---- fused P1 tet assembly -------------------------------------------------------------------------
 // warp per node, one lane per incident element (batches of 32).  Each lane rebuilds the element's cofactor vectors from
 // the coordinates and produces row `a` of Ke; off-diagonal columns are merged in lane (= element) order through
@@ -853,6 +922,29 @@ extern "C" int femb_csr_assemble(femb_csr_plan* p, int ndof, const double* Ke, d
     FEMB_CUDA(cudaFuncSetAttribute(assemble_gather<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * W))); \
     assemble_gather<W><<<grid_for(p->N, W, 16), W * 32, per_warp * W, s>>>(p->conn32, p->inc_ptr, p->inc, p->node_ptr, p->node_col, p->N, \
                                                                           p->nen, ndof, p->max_row, Ke, vals);      \
+  }
+  // batched variant: needs the slot table, at most 6 entries per lane and incidence, U*nen <= 256 position bytes
+  static const bool gather_old = getenv("FEMB_GATHER_OLD") != nullptr;  // A/B switch
+  const int R = (ndof * ndof * p->nen + 31) / 32;
+  if (p->inc_slots && R <= 6 && p->nen <= 32 && per_warp * 8 + 8 * 256 <= 96 * 1024 && !gather_old) {
+    const size_t smem = per_warp * 8 + 8 * 256;
+#define LAUNCH_BATCHED(RV, UV)                                                                                                   \
+  {                                                                                                                              \
+    FEMB_CUDA(cudaFuncSetAttribute(assemble_gather_batched<8, RV, UV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    assemble_gather_batched<8, RV, UV><<<grid_for(p->N, 8, 16), 256, smem, s>>>(p->inc_ptr, p->inc, p->inc_slots, p->node_ptr, p->N, p->nen, \
+                                                                             ndof, p->max_row, Ke, vals);                       \
+  }
+    switch (R) {
+      case 1: LAUNCH_BATCHED(1, 8) break;
+      case 2: LAUNCH_BATCHED(2, 6) break;
+      case 3: LAUNCH_BATCHED(3, 4) break;
+      case 4: LAUNCH_BATCHED(4, 3) break;
+      case 5: LAUNCH_BATCHED(5, 2) break;
+      default: LAUNCH_BATCHED(6, 2) break;
+    }
+#undef LAUNCH_BATCHED
+    FEMB_LAUNCH_CHECK();
+    return FEMB_OK;
   }
   if (per_warp * 8 <= 96 * 1024) LAUNCH_GATHER(8)
   else if (per_warp * 4 <= 200 * 1024) LAUNCH_GATHER(4)

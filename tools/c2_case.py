@@ -33,7 +33,9 @@ def timed(fn, reps=3):
     torch.cuda.synchronize()
     e0, e1 = ev(), ev()
     e0.record()
+    out = None
     for _ in range(reps):
+        out = None   # release the previous result first: a second multi-GB output block would be cudaMalloc'ed inside the timed region
         out = fn()
     e1.record()
     torch.cuda.synchronize()
