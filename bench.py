@@ -11,6 +11,7 @@ Prints ONE JSON line (rank 0).  `value` = CG iterations/s with everything reside
 graph-captured loop), `e2e` = the same through the public solver API with the load vector in pinned host memory and the
 solution read back to the host inside the timed region.  `roofline` is for the dominant kernel (the CSR SpMV).
 `assembly` reports the second half of the metric (assembled elems/s, fused coords->CSR values) with its own roofline.
+`config2` (1 GPU only) reports BASELINE config 2 beside it: P2 elasticity element K, assembly, block-CSR SpMV, Jacobi-PCG.
 `--impl reference` times the CPU restatement of the reference (oracle/, the numpy port or its C/OpenMP build) on a
 bounded sample of the same workload.
 """
@@ -133,6 +134,73 @@ def cpu_cg_rate(n_sample, iters, full_nnz):
     return rate_full, desc, threads, kind
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE config 2 (secondary)
+def config2(dev, hbm, n=69, iters=100):
+    """P2 tet linear elasticity (BASELINE config 2: ~2 M C3D10 tets, fp64): element K, CSR assembly from Ke, block-CSR SpMV and
+    Jacobi-PCG, each with its SURVEY 8d byte count against the measured HBM peak.  Reported beside the headline workload."""
+    import torch
+    import element as el
+    from femb200 import meshgen, ops
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        out = None
+        for _ in range(reps):
+            out = None          # release the previous multi-GB result before the next call allocates
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    c1, t1 = meshgen.kuhn_cube(n, device=dev)
+    coords, e10 = meshgen.p1_to_p2_lattice(n, meshgen.swap01(t1), device=dev)
+    del c1, t1
+    M, N = e10.shape[0], coords.shape[0]
+    ms_K, K = timed(lambda: el.compute_c3d10_K_matrix(coords, e10, 1.0, 0.3, device=dev, dtype=torch.float64))
+    plan = el.CsrPlan(e10, N, dev)
+    plan.pattern(3)
+    vals = torch.empty(plan.nnz_nodes * 9, device=dev, dtype=torch.float64)
+    ms_A, _ = timed(lambda: plan.assemble(K, 3, out=vals))
+    del K
+    nnz = vals.numel()
+    brow, bcol = plan.pattern(1)
+    A = ops.Bsr3.from_csr_values(brow, bcol, vals)
+    x = torch.randn(3 * N, dtype=torch.float64, device=dev)
+    ms_S, _ = timed(lambda: A.spmv(x), reps=10)
+    mask = torch.ones((N, 3), dtype=torch.uint8, device=dev)
+    mask[coords[:, 2] == 0] = 0
+    mask = mask.reshape(-1).contiguous()
+    F = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+    F[coords[:, 2] == 1, 2] = 1.0 / float((coords[:, 2] == 1).sum())
+    minv = A.jacobi(mask)
+    A.cg_solve(F, minv=minv, tol=0.0, max_iter=10, check_every=10)
+    _, info = A.cg_solve(F, minv=minv, tol=0.0, max_iter=iters, check_every=min(iters, 50))
+    ms_it = info["loop_ms"] / iters
+    bytes_K = M * (10 * 8 + 900 * 8) + N * 24                  # SURVEY 8d: Ke materialised
+    bytes_A = M * 900 * (8 + 4) + nnz * 8                       # SURVEY 8d: two-step assembly
+    bytes_S_csr = nnz * 12 + 3 * N * 20                         # SURVEY 8d: scalar-CSR SpMV
+    bytes_S_own = nnz * 8 + (nnz // 9) * 4 + N * 4 + 3 * N * 16  # what the 3x3 block layout moves
+    frac = lambda b, ms: round(b / (ms * 1e-3) / 1e9 / hbm, 4)  # noqa: E731
+    return {
+        "workload": f"P2 tet linear elasticity, Kuhn n={n}: {M} C3D10 tets, {N} nodes, {3 * N} dofs, CSR nnz {nnz} (BASELINE config 2)",
+        "element_K": {"ms": round(ms_K, 3), "elems_per_s": round(M / ms_K * 1e3), "algorithmic_bytes": bytes_K, "frac": frac(bytes_K, ms_K)},
+        "assemble_from_Ke": {"ms": round(ms_A, 3), "elems_per_s": round(M / ms_A * 1e3), "algorithmic_bytes": bytes_A, "frac": frac(bytes_A, ms_A),
+                             "kernel": "assemble_gather_batched<8,3,4>"},
+        "assembled_elems_per_s": round(M / (ms_K + ms_A) * 1e3),
+        "spmv_bsr3": {"ms": round(ms_S, 4), "bytes_moved": bytes_S_own, "frac_bytes_moved": frac(bytes_S_own, ms_S),
+                      "algorithmic_bytes_scalar_csr": bytes_S_csr, "frac_scalar_csr_bytes": frac(bytes_S_csr, ms_S),
+                      "kernel": "spmv_bsr3_vec_kernel (3x3 block-CSR, warp per block row)"},
+        "jacobi_pcg": {"iters_per_s": round(1e3 / ms_it, 1), "ms_per_iter": round(ms_it, 4),
+                       "algorithmic_bytes_scalar_csr": bytes_S_csr + 11 * 3 * N * 8, "frac_scalar_csr_bytes": frac(bytes_S_csr + 11 * 3 * N * 8, ms_it),
+                       "frac_bytes_moved": frac(bytes_S_own + 11 * 3 * N * 8, ms_it)},
+    }
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -251,6 +319,14 @@ def run_gpu(args):
     while time.perf_counter() - t_soak < 0.5:
         ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=200, check_every=50)
     clocks = sampler.stop()
+    c2 = None
+    if not args.no_c2:
+        del A, u, u2, x, vals, crow, col, plan, coords, tets
+        torch.cuda.empty_cache()
+        try:
+            c2 = config2(dev, hbm)
+        except Exception as exc:  # noqa: BLE001  (the headline line must print regardless)
+            c2 = {"error": f"{type(exc).__name__}: {exc}"}
 
     value = K / (ms_loop * 1e-3)
     out = {
@@ -289,6 +365,8 @@ def run_gpu(args):
                      "element_K_frac": round(bytes_ke / (ms_ke * 1e-3) / 1e9 / hbm, 4),
                      "two_step_gather_ms": round(ms_gather, 3)},
     }
+    if c2 is not None:
+        out["config2"] = c2
     if not args.no_cpu:
         rate, desc, cores, kind = cpu_cg_rate(args.cpu_n, args.cpu_iters, nnz)
         out["cpu_baseline"] = {"value": round(rate, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
@@ -329,6 +407,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=96, help="cube size of the CPU sample")
     ap.add_argument("--cpu-iters", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-c2", action="store_true", help="skip the secondary BASELINE config 2 (P2 elasticity) measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
