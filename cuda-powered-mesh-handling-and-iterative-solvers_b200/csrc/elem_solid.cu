@@ -231,6 +231,16 @@ __global__ void volumes_kernel(const T* __restrict__ coords, const I* __restrict
 //             into a shared K tile
 //   phase C : the whole CTA streams the tile to global memory with coalesced stores
 // ------------------------------------------------------------------------------------------------
+// shared -> global bulk copy (TMA engine, 1-D): the finished K tile drains to HBM while the CTA already works on its next
+// elements.  Source and destination 16-byte aligned, size a multiple of 16 bytes.
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 struct SolidTab {
   const double* dN;  // [nq][nen][3]
   const double* w;   // [nq]
@@ -253,6 +263,8 @@ __global__ void __launch_bounds__(512) solid_K_kernel(const T* __restrict__ coor
   T* wsh = nsh + (size_t)nq * NEN;                // [nq]
   const int tid = threadIdx.x;
   const int nslice = mode == 4 ? nq : 1;
+  // element tiles whose byte size is a multiple of 16 leave through the TMA engine (all but C3D15: 45*45 entries)
+  constexpr bool BULK = (ND * ND * sizeof(T)) % 16 == 0;
   for (int t = tid; t < nq * NEN * 3; t += blockDim.x) dns[t] = (T)tab.dN[t];
   for (int t = tid; t < nq * NEN; t += blockDim.x) nsh[t] = (T)tab.N[t];
   for (int t = tid; t < nq; t += blockDim.x) wsh[t] = (T)tab.w[t];
@@ -320,6 +332,10 @@ __global__ void __launch_bounds__(512) solid_K_kernel(const T* __restrict__ coor
       }
     __syncthreads();
     for (int slice = 0; slice < nslice; ++slice) {
+      if (BULK) {  // the previous tile must have been read out of shared memory before phase B overwrites it
+        if (tid == 0) bulk_wait_read();
+        __syncthreads();
+      }
       // ---- phase B
       for (int t = tid; t < ne * NPAIR; t += blockDim.x) {
         const int el = t / NPAIR;
@@ -337,21 +353,24 @@ __global__ void __launch_bounds__(512) solid_K_kernel(const T* __restrict__ coor
           for (int q = 0; q < nq; ++q) m += wd[el * nq + q] * (nsh[q * NEN + a] * nsh[q * NEN + b]);
           acc[0] = acc[4] = acc[8] = m;
         } else {
+          // S[i][j] = sum_q w g_a[i] g_b[j]; the block is lam S + mu S^T + mu tr(S) I -- 12 FMAs per point instead of forming
+          // lam g_a[i] g_b[j] + mu g_a[j] g_b[i] + mu delta_ij g_a.g_b point by point (33 operations)
+          T S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
           for (int q = q0; q < q1; ++q) {
             const T* g = gs + ((size_t)el * nq + q) * NEN * 3;
             const T w = wd[el * nq + q];
-            const T ga[3] = {g[a * 3], g[a * 3 + 1], g[a * 3 + 2]};
+            const T wa[3] = {w * g[a * 3], w * g[a * 3 + 1], w * g[a * 3 + 2]};
             const T gb[3] = {g[b * 3], g[b * 3 + 1], g[b * 3 + 2]};
-            const T dot = mu * (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]);
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                T k = lam * ga[i] * gb[j] + mu * ga[j] * gb[i];
-                if (i == j) k += dot;
-                acc[i * 3 + j] += k * w;
-              }
+              for (int j = 0; j < 3; ++j) S[i * 3 + j] += wa[i] * gb[j];
           }
+          const T tr = mu * (S[0] + S[4] + S[8]);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[i * 3 + j] = lam * S[i * 3 + j] + mu * S[j * 3 + i] + (i == j ? tr : T(0));
         }
         T* K = kt + (size_t)el * ND * ND;
 #pragma unroll
@@ -366,6 +385,13 @@ __global__ void __launch_bounds__(512) solid_K_kernel(const T* __restrict__ coor
       // ---- phase C
       T* dst = out + ((size_t)slice * M + e0) * ND * ND;
       const int total = ne * ND * ND;
+      if (BULK) {
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy writes of phase B, ordered by the barrier above
+          bulk_s2g(dst, kt, (unsigned)(total * sizeof(T)));
+        }
+        continue;  // no barrier here: the wait + barrier before the next phase B protects the tile
+      }
       if (sizeof(T) == 8 && (ND * ND) % 2 == 0) {  // even tiles: every element starts 16-byte aligned
         for (int t = 2 * tid; t < total; t += 2 * blockDim.x)
           st128(reinterpret_cast<double*>(dst) + t, (double)kt[t], (double)kt[t + 1]);
@@ -375,6 +401,7 @@ __global__ void __launch_bounds__(512) solid_K_kernel(const T* __restrict__ coor
       __syncthreads();
     }
   }
+  if (BULK && tid == 0) bulk_wait_all();  // shared memory must outlive the last copy
 }
 
 // what 0: J [M,3,3]; 1: gradients [M,NEN,3]; 2: B [M,6,3*NEN] -- single point, one thread per element
