@@ -1174,3 +1174,38 @@ extern "C" int femb_extrude_connectivity(const void* conn, int ib, int64_t M, in
   FEMB_LAUNCH_CHECK();
   return FEMB_OK;
 }
+
+// Diagonal of sum_e K_e without assembling: out[node*d + alpha] = sum over the node's incidences (ascending element id) of
+// Ke[e][a*d+alpha][a*d+alpha].  The lumped mass of vectorized_modal_solver (solver.py:1126-1131) and the Jacobi diagonal of
+// compute_diagonal_preconditioner (solver.py:814-833) -- both index_add_ scatters in the reference.  col0 != 0 reproduces the
+// reference preconditioner's strided-view bug, which sums column 0 of every row instead of the diagonal (solver.py:828).
+namespace femb {
+template <typename T>
+__global__ void ebe_diag_kernel(const int* __restrict__ inc_ptr, const int* __restrict__ inc, long long N, int nen, int d, int col0,
+                                const T* __restrict__ Ke, T* __restrict__ out) {
+  const long long total = N * d;
+  const int nd = nen * d;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long node = t / d;
+    const int alpha = (int)(t - node * d);
+    T sum = 0;
+    for (int k = inc_ptr[node]; k < inc_ptr[node + 1]; ++k) {
+      const int slot = inc[k], e = slot / nen, a = slot - e * nen;
+      const int row = a * d + alpha;
+      sum += __ldg(Ke + ((long long)e * nd + row) * nd + (col0 ? 0 : row));
+    }
+    out[t] = sum;
+  }
+}
+}  // namespace femb
+
+extern "C" int femb_ebe_diag(femb_csr_plan* p, int ndof, const void* Ke, int fp, int col0, void* out, femb_stream stream) {
+  FEMB_CHECK_ARG(p && (fp == 4 || fp == 8) && ndof >= 1 && ndof <= 6 && Ke && out, "plan, fp in {4,8}, 1 <= ndof <= 6, non-null buffers");
+  if (p->N == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int grid = grid_for(p->N * ndof, 128);
+  if (fp == 8) ebe_diag_kernel<double><<<grid, 128, 0, s>>>(p->inc_ptr, p->inc, p->N, p->nen, ndof, col0, (const double*)Ke, (double*)out);
+  else ebe_diag_kernel<float><<<grid, 128, 0, s>>>(p->inc_ptr, p->inc, p->N, p->nen, ndof, col0, (const float*)Ke, (float*)out);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}

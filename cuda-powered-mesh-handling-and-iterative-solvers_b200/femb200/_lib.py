@@ -70,6 +70,10 @@ SIGNATURES = {
     "femb_vtk_open": [C.c_char_p, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(C.c_int32)],
     "femb_vtk_read": [c_vp, c_vp, c_vp, c_vp],
     "femb_vtk_close": [c_vp],
+    "femb_ebe_diag": [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp],
+    "femb_mv_gram": [c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, C.POINTER(c_f64), c_vp],
+    "femb_mv_update": [c_i64, c_i32, c_vp, c_i64, c_i32, C.POINTER(c_f64), c_f64, c_vp, c_i64, c_vp],
+    "femb_mv_scale_mask": [c_i64, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "femb_csr_jacobi": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "femb_graph_from_pairs": [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
     "femb_subdomain_forces": [c_vp, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],

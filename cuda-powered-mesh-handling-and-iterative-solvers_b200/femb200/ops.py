@@ -440,6 +440,15 @@ class CsrPlan:
             check(lib.femb_ebe_apply(self.handle, ndof, _p(Ke), _p(u), _p(un), _fp(u), _p(y), _stream(self.dev)), "femb_ebe_apply")
         return y
 
+    def ebe_diag(self, Ke, ndof, dtype=torch.float64, col0=False):
+        """[N, ndof] diagonal of sum_e K_e (element-ascending sums); col0=True sums column 0 of every row instead."""
+        Ke = real(Ke, self.dev, dtype)
+        assert Ke.shape == (self.M, self.nen * ndof, self.nen * ndof), (Ke.shape, self.M, self.nen, ndof)
+        out = torch.empty((self.n_nodes, ndof), device=self.dev, dtype=dtype)
+        with torch.cuda.device(self.dev):
+            check(lib.femb_ebe_diag(self.handle, ndof, _p(Ke), _fp(Ke), 1 if col0 else 0, _p(out), _stream(self.dev)), "femb_ebe_diag")
+        return out
+
     def node_average(self, elem_values, dtype=None):
         """[N] mean over the elements containing each node (0 for isolated nodes), ascending element order."""
         v = torch.as_tensor(elem_values)
@@ -568,6 +577,49 @@ def cg_solve_operator(apply, R, tol=1e-8, max_iter=1000, check_every=8, device="
     check(rc, "femb_cg_solve_operator")
     info = {"iterations": res.iterations, "status": STATUS.get(res.status, "?"), "rs": res.rs, "loop_ms": res.loop_ms}
     return u.reshape(R.shape), info
+
+
+# ----------------------------------------------------------------------------- tall-skinny vectors (modal solver)
+
+class MultiVec:
+    """k vectors of length n stored one after the other (fp64): `data` is [k, n] contiguous, column j = data[j]."""
+
+    def __init__(self, data):
+        assert data.dim() == 2 and data.dtype == torch.float64 and data.is_contiguous() and data.shape[0] <= 8
+        self.data, self.k, self.n, self.dev = data, data.shape[0], data.shape[1], data.device
+
+    @classmethod
+    def from_columns(cls, X, dev):
+        """From the reference's layout [n, k] (any float dtype)."""
+        return cls(torch.as_tensor(X).to(device=dev, dtype=torch.float64).t().contiguous())
+
+    def columns(self):
+        return self.data.t().contiguous()
+
+    def cols(self, a, b):
+        return MultiVec(self.data[a:b])
+
+    def gram(self, other, w=None):
+        """[k_self, k_other] host tensor: sum_r self_i[r] w[r] other_j[r] (deterministic)."""
+        G = (C.c_double * (self.k * other.k))()
+        with torch.cuda.device(self.dev):
+            check(lib.femb_mv_gram(self.n, self.k, _p(self.data), self.n, other.k, _p(other.data), other.n, _p(w), G, _stream(self.dev)),
+                  "femb_mv_gram")
+        return torch.tensor(list(G), dtype=torch.float64).reshape(self.k, other.k)
+
+    def update_into(self, coef, out, beta=0.0):
+        """out_j = beta out_j + sum_i self_i coef[i][j]; `out` may be this object (in-place rotation / scaling)."""
+        coef = torch.as_tensor(coef, dtype=torch.float64).reshape(self.k, out.k)
+        Ch = _host_doubles(coef.reshape(-1).tolist())
+        with torch.cuda.device(self.dev):
+            check(lib.femb_mv_update(self.n, self.k, _p(self.data), self.n, out.k, Ch, float(beta), _p(out.data), out.n, _stream(self.dev)),
+                  "femb_mv_update")
+        return out
+
+    def scale_mask(self, scale=None, mask=None):
+        with torch.cuda.device(self.dev):
+            check(lib.femb_mv_scale_mask(self.n, self.k, _p(self.data), self.n, _p(scale), _p(mask), _stream(self.dev)), "femb_mv_scale_mask")
+        return self
 
 
 # ----------------------------------------------------------------------------- 3x3 block-CSR (3-dof operators)

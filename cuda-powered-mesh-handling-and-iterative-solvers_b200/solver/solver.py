@@ -282,16 +282,12 @@ def compute_diagonal_preconditioner(K, elements, N, device="cuda:0", dtype=torch
     every row, not the diagonal, and yields a useless preconditioner.  The default here is the correct Jacobi diagonal
     (rows of `fixed` nodes set to 0); `reference_bug=True` reproduces the reference's numbers."""
     dev = _ops.cuda_device(device)
-    K = torch.as_tensor(K).to(dev)
-    e = torch.as_tensor(elements).to(dev).long()
-    nd = K.shape[-1]
-    ndof = nd // e.shape[1]
-    dofs = (e.unsqueeze(-1) * ndof + torch.arange(ndof, device=dev)).reshape(-1)
-    entries = K[:, :, 0].reshape(-1) if reference_bug else K.diagonal(dim1=1, dim2=2).reshape(-1)
-    diag = torch.zeros(N * ndof, device=dev, dtype=dtype).index_add_(0, dofs, entries.to(dtype))
+    K = torch.as_tensor(K)
+    ndof = K.shape[-1] // torch.as_tensor(elements).shape[1]
+    # one kernel over the node -> element incidence lists (ascending element order) instead of an index_add_ scatter
+    diag = _ops.cached_plan(elements, N, dev).ebe_diag(K, ndof, dtype, col0=reference_bug)
     m = 1.0 / diag
     m[m == float("inf")] = 0.0
-    m = m.view(N, ndof)
     if fixed is not None and not reference_bug:
         m[torch.as_tensor(fixed).to(dev).long()] = 0.0
     return m
@@ -330,6 +326,174 @@ def conjugate_gradient_solver_Ku(compute_Ku, R, tol=1e-8, max_iter=1000, device=
         print("CG did not converge within the maximum number of iterations.")
     du = du.to(dtype)
     return (du, info) if return_info else du
+
+
+# ------------------------------------------------------------------------------------------- modal solver
+
+def _np_dtype(dtype):
+    import numpy as np
+    return np.float32 if dtype == torch.float32 else np.float64
+
+
+def _invert_small_matrix(MM):
+    """Gauss-Jordan without pivoting, pivots below 1e-14 replaced by 1e-14 (solver.py:1225-1243)."""
+    import numpy as np
+    n = MM.shape[0]
+    aug = np.concatenate([MM, np.eye(n, dtype=MM.dtype)], axis=1)
+    for i in range(n):
+        row_i = aug[i].copy()
+        pivot = row_i[i]
+        if abs(pivot) < 1e-14:
+            pivot = MM.dtype.type(1e-14)
+        row_i = row_i / pivot
+        aug[i] = row_i
+        for r in range(n):
+            if r != i:
+                aug[r] = aug[r] - aug[r, i] * row_i
+    return aug[:, n:]
+
+
+def _naive_jacobi(AA, max_sweeps=30, tol=1e-10):
+    """The reference's Jacobi rotations (solver.py:1245-1283) on a matrix it treats as symmetric (B^-1 A is not): largest
+    off-diagonal entry, one rotation per sweep, rows rotated and then copied onto the columns.  Eigenvalues = the diagonal,
+    ascending; restated step by step because the result on a non-symmetric input depends on the exact sequence."""
+    import numpy as np
+    n = AA.shape[0]
+    ty = AA.dtype.type
+    V = np.eye(n, dtype=AA.dtype)
+    for _ in range(max_sweeps):
+        off = AA - np.diag(np.diagonal(AA))
+        idx = int(np.argmax(np.abs(off)))
+        i, j = idx // n, idx % n
+        if i == j:
+            break
+        if i > j:
+            i, j = j, i
+        val = AA[i, j]
+        if abs(val) < tol:
+            break
+        theta = ty(0.5) * (AA[j, j] - AA[i, i]) / val
+        t = np.sign(theta) / (abs(theta) + np.sqrt(ty(1) + theta * theta))
+        c = ty(1.0) / np.sqrt(ty(1) + t * t)
+        sn = t * c
+        aii, aij, ajj = AA[i, i], AA[i, j], AA[j, j]
+        AA[i, i] = aii - t * aij
+        AA[j, j] = ajj + t * aij
+        AA[i, j] = 0
+        AA[j, i] = 0
+        rowi, rowj = AA[i].copy(), AA[j].copy()
+        AA[i] = c * rowi - sn * rowj
+        AA[j] = sn * rowi + c * rowj
+        AA[:, i] = AA[i].copy()
+        AA[:, j] = AA[j].copy()
+        Vi, Vj = V[:, i].copy(), V[:, j].copy()
+        V[:, i] = c * Vi - sn * Vj
+        V[:, j] = sn * Vi + c * Vj
+    ev = np.diagonal(AA).copy()
+    order = np.argsort(ev, kind="stable")
+    return ev[order], V[:, order]
+
+
+def _solve_small_gevp(A_k, B_k, npdt):
+    """lam, Z of B^-1 A (solver.py:1285-1290); k x k host arithmetic in the solver's dtype."""
+    A = A_k.numpy().astype(npdt)
+    B = B_k.numpy().astype(npdt)
+    A_ = (_invert_small_matrix(B) @ A).astype(npdt)
+    return _naive_jacobi(A_.copy())
+
+
+def _solve_small_gevp_sym(A_k, B_k):
+    """Ritz pairs of the symmetric-definite pencil (A, B): B = L L^T, eigh(L^-1 A L^-T), Z = L^-T Q; lam ascending."""
+    import numpy as np
+    A = A_k.numpy().astype(np.float64)
+    B = B_k.numpy().astype(np.float64)
+    L = np.linalg.cholesky(0.5 * (B + B.T))
+    Li = np.linalg.inv(L)
+    Cm = Li @ (0.5 * (A + A.T)) @ Li.T
+    lam, Q = np.linalg.eigh(0.5 * (Cm + Cm.T))
+    return lam, Li.T @ Q
+
+
+def _gram_schmidt_euclid(X):
+    """Column-by-column Euclidean orthonormalisation exactly as the reference orders it (solver.py:1176-1199): normalise,
+    subtract the projections on all previous columns at once (classical Gram-Schmidt), normalise again; columns shorter
+    than 1e-14 are replaced by a unit vector."""
+    for j in range(X.k):
+        col = X.cols(j, j + 1)
+        for stage in range(2):
+            if stage == 1 and j > 0:
+                prev = X.cols(0, j)
+                dots = prev.gram(col)                        # [j, 1]
+                prev.update_into(-dots, col, beta=1.0)      # col -= prev @ dots
+            nrm = float(col.gram(col)[0, 0]) ** 0.5
+            if nrm < 1e-14:
+                col.data.zero_()
+                if j < X.n:
+                    col.data[0, j] = 1.0
+            else:
+                col.update_into([[1.0 / nrm]], col)
+    return X
+
+
+def vectorized_modal_solver(K_local, M_local, elements, rbe2_node_ids, num_nodes, num_eigs=5, max_iter=20, device="cuda:0",
+                            dtype=torch.float32, X0=None, reference_gevp=False):
+    """Subspace iteration on M^-1 K with a lumped mass, Euclidean Gram-Schmidt and a small generalised eigenproblem per sweep
+    (solver.py:1084-1312; as written it is a block power iteration, i.e. it drifts towards the LARGEST eigenvalues of
+    K u = lambda M u).  Returns (lam [num_eigs] ascending, modes [3*num_nodes, num_eigs]).
+
+    PARITY UNPINNED: the reference raises on every input (`row_i /= pivot` divides a row by a view of itself,
+    solver.py:1232-1234), and its k x k step -- Jacobi rotations for symmetric matrices applied to the non-symmetric
+    B^-1 A -- does not produce eigenpairs even when that line is repaired (the restated sequence yields negative
+    "eigenvalues" of an SPD pencil).  Default here: the same outer iteration with the small pencil solved as what it is,
+    symmetric-definite (Cholesky of B, eigh), so lam / modes are genuine Ritz pairs; `reference_gevp=True` follows the
+    reference's Gauss-Jordan + Jacobi steps literally (in `dtype`).
+
+    The n_dof-long work runs on the device in fp64: K is assembled once (3x3 block-CSR) and applied column by column, the lumped
+    mass comes from one pass over the incidence lists, and norms / projections / X^T K X / X Z are three tall-skinny kernels
+    (femb_mv_*); the k x k problems follow the reference's Gauss-Jordan and Jacobi steps on the host in `dtype`.  The reference
+    draws its start subspace from an unseeded torch.randn; pass `X0` [3*num_nodes, num_eigs] (additive) for a reproducible run."""
+    dev = _ops.cuda_device(device)
+    if not 1 <= num_eigs <= 8:
+        raise ValueError("num_eigs must be between 1 and 8")
+    n = num_nodes * 3
+    npdt = _np_dtype(dtype)
+    A = _Assembled(K_local, elements, num_nodes, 3, dev)
+    plan = _ops.cached_plan(elements, num_nodes, dev)
+    Mdiag = plan.ebe_diag(M_local, 3, torch.float64).reshape(-1).clamp_(min=1e-12)
+    Minv = (1.0 / Mdiag).contiguous()
+    mask = _dof_mask(num_nodes, 3, rbe2_node_ids, dev)
+    if X0 is None:
+        X0 = torch.randn(n, num_eigs, device=dev, dtype=dtype)
+    X = _ops.MultiVec.from_columns(X0, dev)
+    if X.n != n or X.k != num_eigs:
+        raise ValueError(f"X0 must be [{n}, {num_eigs}]")
+
+    def apply_K(V):
+        out = _ops.MultiVec(torch.empty_like(V.data))
+        for i in range(V.k):
+            out.data[i] = A.spmv(V.data[i])
+        return out
+
+    def build_Ak_Bk(V):
+        return V.gram(apply_K(V)), V.gram(V, w=Mdiag)
+
+    def gevp(V):
+        A_k, B_k = build_Ak_Bk(V)
+        return _solve_small_gevp(A_k, B_k, npdt) if reference_gevp else _solve_small_gevp_sym(A_k, B_k)
+
+    X.scale_mask(mask=mask)
+    _gram_schmidt_euclid(X)
+    for _ in range(max_iter):
+        Y = apply_K(X).scale_mask(scale=Minv, mask=mask)
+        _gram_schmidt_euclid(Y)
+        lam, Z = gevp(Y)
+        Y.update_into(torch.from_numpy(Z.astype("float64")), Y)
+        Y.scale_mask(mask=mask)
+        _gram_schmidt_euclid(Y)
+        X = Y
+    lam, Z = gevp(X)
+    X.update_into(torch.from_numpy(Z.astype("float64")), X)
+    return torch.from_numpy(lam.copy()).to(device=dev, dtype=dtype), X.columns().to(dtype)
 
 
 def static_structure_solver(coords, force, fixed, c3d4=None, c3d6=None, c3d8=None, s3=None, s4=None, material=None, u_init=None,

@@ -214,6 +214,11 @@ int femb_shell_extrude(femb_csr_plan* tri, femb_csr_plan* quad, const void* coor
 /* out[M,2nen] = (conn | conn + N): wedges from triangles, hexahedra from quads (shell.py:957-973); same index type */
 int femb_extrude_connectivity(const void* conn, int ib, int64_t M, int nen, int64_t N, void* out, femb_stream stream);
 
+/* Diagonal of sum_e K_e without assembling: out[N*ndof], element-ascending sums.  Lumped mass of vectorized_modal_solver
+ * (solver.py:1126-1131) and the Jacobi diagonal behind compute_diagonal_preconditioner (solver.py:814-833); col0 != 0 sums
+ * column 0 of every element row instead (the reference preconditioner's strided-view bug, solver.py:828). */
+int femb_ebe_diag(femb_csr_plan* plan, int ndof, const void* Ke, int fp, int col0, void* out, femb_stream stream);
+
 /* compute_node_vm_stress element.py:466-504: out[N] = mean over the elements containing the node of elem_values[M]
  * (0 for nodes without elements); sums run in ascending element order (deterministic; the reference uses index_add). */
 int femb_node_average(femb_csr_plan* plan, const void* elem_values, int fp, void* out, femb_stream stream);
@@ -265,6 +270,17 @@ int femb_cg_solve_multi(int64_t n, int nmat, const int64_t* nnz_host, const int3
 typedef int (*femb_apply_fn)(void* ctx, const double* x, double* y, femb_stream stream);
 int femb_cg_solve_operator(int64_t n, femb_apply_fn apply, void* ctx, const double* R, double* u, double* work, double tol,
                            int max_iter, int check_every, femb_cg_result* result_host, femb_stream stream);
+
+/* Tall-skinny kernels of the subspace-iteration modal solver (vectorized_modal_solver solver.py:1084-1312).  Vectors are stored
+ * one after the other: column i of X at X + i*ldx (ldx >= n), 1 <= ki, kj <= 8.
+ *   femb_mv_gram:   G_host[i*kj+j] = sum_r X_i[r] w[r] Y_j[r] (w = NULL: 1); deterministic two-stage sums; synchronises.
+ *   femb_mv_update: Y_j = beta Y_j + sum_i X_i C_host[i*kj+j]; Y may alias X (in-place scaling / basis rotation).
+ *   femb_mv_scale_mask: X_j[r] *= scale[r] (NULL: 1), set to 0 where mask[r] == 0 (NULL: nowhere). */
+int femb_mv_gram(int64_t n, int ki, const double* X, int64_t ldx, int kj, const double* Y, int64_t ldy, const double* w, double* G_host,
+                 femb_stream stream);
+int femb_mv_update(int64_t n, int ki, const double* X, int64_t ldx, int kj, const double* C_host, double beta, double* Y, int64_t ldy,
+                   femb_stream stream);
+int femb_mv_scale_mask(int64_t n, int k, double* X, int64_t ldx, const double* scale, const uint8_t* mask, femb_stream stream);
 
 /* Jacobi diagonal of a CSR matrix: minv[i] = mask[i] ? 1/A_ii : 0 (the documented replacement for the
  * reference's broken compute_diagonal_preconditioner solver.py:814-833) */

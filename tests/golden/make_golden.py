@@ -24,6 +24,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "cuda-powered-mesh-handling-and-iterative-solvers_b200"))
+sys.path.insert(0, ROOT)
 from femb200 import meshgen  # noqa: E402
 
 for name in ("plotly", "plotly.graph_objects", "pyvista"):
@@ -401,6 +402,30 @@ def gen_subdomain_forces():
          out=npy(torch.stack(out)), node_maps_flat=np.concatenate([npy(m) for m in node_maps]), node_maps_len=np.array([m.numel() for m in node_maps]))
 
 
+def gen_modal():
+    """vectorized_modal_solver (solver.py:1084-1312) on CPU / fp64 with its torch.randn start pinned to a stored X0.  The
+    reference cannot finish: its Gauss-Jordan helper divides a row in place by a view of one of its own entries
+    (`row_i /= pivot`, solver.py:1232-1234), which torch rejects -- recorded here; the oracle restates the evident intent."""
+    from oracle import fem_oracle as O
+    coords, tets = meshgen.kuhn_cube(3, jitter=0.15)
+    K = R.compute_c3d4_K_matrix(coords, tets, E, NU, **KW)
+    Mloc = torch.tensor(O.c3d4_mass(coords.numpy(), tets.numpy(), 2.5))      # the reference has no mass routine: M_local is an input
+    N = coords.shape[0]
+    fixed = torch.nonzero(coords[:, 2] == 0).reshape(-1)
+    gen = torch.Generator().manual_seed(8)
+    X0 = torch.randn(3 * N, 4, dtype=torch.float64, generator=gen)
+    real_randn = torch.randn
+    torch.randn = lambda *a, **k: X0.clone()
+    raised = ""
+    try:
+        RV.vectorized_modal_solver(K, Mloc, tets, fixed, N, num_eigs=4, max_iter=2, **KW)
+    except RuntimeError as exc:
+        raised = str(exc)[:120]
+    finally:
+        torch.randn = real_randn
+    save("modal", coords=npy(coords), tets=npy(tets), Mloc=npy(Mloc), fixed=npy(fixed), X0=npy(X0), reference_raises=np.array(raised))
+
+
 def gen_widen():
     """Functions either side of the element path: shell frames / stress / post-processing, shell extrusion, wedge face normals,
     tet face-force balance and the operator-callback CG."""
@@ -483,3 +508,4 @@ if __name__ == "__main__":
     gen_partition()
     gen_widen()
     gen_subdomain_forces()
+    gen_modal()

@@ -65,7 +65,7 @@ def test_mirror_api_names():
                 "shell_extrude"],
         solver: ["static_structure_solver", "stable_conjugate_gradient_solver", "final_solver", "stable_conjugate_gradient_shell_solver",
                  "preconditioned_conjugate_gradient_solver", "compute_diagonal_preconditioner", "compute_K_matrix",
-                 "conjugate_gradient_solver_Ku", "constrained_conjugate_gradient_solver", "new_constrained_conjugate_gradient_solver"],
+                 "conjugate_gradient_solver_Ku", "vectorized_modal_solver", "constrained_conjugate_gradient_solver", "new_constrained_conjugate_gradient_solver"],
     }
     for mod, names in expect.items():
         for n in names:

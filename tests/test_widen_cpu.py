@@ -133,6 +133,56 @@ def test_subdomain_forces_oracle():
         sd.SubdomainForcePlan({(0, 1): [3], (1, 2): [3]}, [], 10, 3, "cpu")
 
 
+def test_modal_solver_oracle_and_host_steps():
+    """The reference's vectorized_modal_solver raises on every input (recorded in the fixture).  The oracle restates its steps;
+    with the small pencil solved as a symmetric-definite one the iteration converges to the largest eigenvalues of the
+    constrained problem (dense scipy solve), and the product's host-side k x k routines agree with the oracle's."""
+    import scipy.linalg as sl
+    d = load_golden("modal")
+    assert "single memory location" in str(d["reference_raises"])
+    N = d["coords"].shape[0]
+    K = O.c3d4_K(d["coords"], d["tets"], 1.0, 0.3)
+    lam, modes = O.modal_solver(K, d["Mloc"], d["tets"], d["fixed"], N, d["X0"], max_iter=300, as_written=False)
+    e = d["tets"]
+    dofs = (e[:, :, None] * 3 + np.arange(3)).reshape(-1)
+    Md = np.bincount(dofs, weights=np.diagonal(d["Mloc"], axis1=1, axis2=2).reshape(-1), minlength=3 * N)
+    A = np.stack([O.nodal_forces(K, e, np.eye(3 * N)[c].reshape(N, 3)).reshape(-1) for c in range(3 * N)], axis=1)
+    fix = (d["fixed"].reshape(-1, 1) * 3 + np.arange(3)).reshape(-1)
+    free = np.setdiff1d(np.arange(3 * N), fix)
+    exact = sl.eigh(A[np.ix_(free, free)], np.diag(Md[free]), eigvals_only=True)
+    assert np.abs(lam - exact[-4:]).max() < 1e-4 * exact[-1]
+    v = modes[:, -1]
+    Kv = A @ v
+    Kv[fix] = 0
+    assert np.linalg.norm(Kv - lam[-1] * Md * v) < 1e-3 * np.linalg.norm(Kv) and np.abs(modes[fix]).max() == 0
+    # host-side small-matrix routines of the product against the oracle's restatement
+    import sys
+    import torch
+    from conftest import PKG
+    sys.path.insert(0, os.path.join(PKG, "solver"))
+    import solver as sv
+    rng = np.random.default_rng(4)
+    for k in (2, 4, 5):
+        B = rng.standard_normal((k, k))
+        B = B @ B.T + k * np.eye(k)
+        Am = rng.standard_normal((k, k))
+        Am = Am + Am.T
+        close(sv._invert_small_matrix(B.copy()), O._gj_inverse(B))
+        close(sv._invert_small_matrix(B.copy()), np.linalg.inv(B), 1e-10)
+        l1, Z1 = sv._solve_small_gevp(torch.tensor(Am), torch.tensor(B), np.float64)
+        l2, Z2 = O._jacobi_as_written(O._gj_inverse(B) @ Am)
+        close(l1, l2)
+        close(Z1, Z2)
+        l3, Z3 = sv._solve_small_gevp_sym(torch.tensor(Am), torch.tensor(B))
+        close(l3, sl.eigh(Am, B, eigvals_only=True), 1e-10)
+        close(Z3.T @ B @ Z3, np.eye(k), 1e-10)
+    # the reference's rotation formulas are not a valid Jacobi method even for symmetric input (2x2: one "sweep" does not
+    # diagonalise), which is why the product's default solves the small pencil with a proper symmetric eigen-solver
+    S2 = np.array([[2.0, 1.0], [1.0, -1.0]])
+    ls, _ = sv._naive_jacobi(S2.copy(), max_sweeps=200, tol=1e-14)
+    assert np.abs(ls - np.linalg.eigvalsh(S2)).max() > 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ legacy VTK files
 
 def _mesh():

@@ -263,3 +263,63 @@ def test_subdomain_forces(api):
     inv = sd.invert_K_parts(Kp)
     for k, ki in zip(Kp, inv):
         close(ki @ k.to_dense(), np.eye(k.shape[0]), 1e-10)
+
+
+def test_modal_solver_and_lumped_diagonals(api, O):
+    """vectorized_modal_solver: the reference raises (fixture), so the product is checked against the oracle's restatement --
+    literal k x k steps for two sweeps, the symmetric-definite variant for twenty -- and against the dense eigenvalues."""
+    import scipy.linalg as sl
+    el, sv = api[0], api[2]
+    d = load_golden("modal")
+    ct, tets, X0 = T(d["coords"]), T(d["tets"]), T(d["X0"])
+    Nn = ct.shape[0]
+    K = el.compute_c3d4_K_matrix(ct, tets, 1.0, 0.3, **KW)
+    Ko = O.c3d4_K(d["coords"], d["tets"], 1.0, 0.3)
+    Mloc = el.compute_c3d4_M_matrix(ct, tets, 2.5, **KW)
+    close(Mloc, d["Mloc"])
+    fixed = T(d["fixed"])
+
+    def same_up_to_sign(a, b, tol):
+        a, b = N(a), np.asarray(b)
+        sg = np.sign((a * b).sum(0))
+        close(a * sg, b, tol)
+
+    lam, modes = sv.vectorized_modal_solver(K, Mloc, tets, fixed, Nn, num_eigs=4, max_iter=2, X0=X0, reference_gevp=True, **KW)
+    lo, mo = O.modal_solver(Ko, d["Mloc"], d["tets"], d["fixed"], Nn, d["X0"], max_iter=2, as_written=True)
+    assert lam.is_cuda and lam.dtype == torch.float64 and modes.shape == (3 * Nn, 4)
+    close(lam, lo, 1e-8)
+    same_up_to_sign(modes, mo, 1e-8)
+    lam, modes = sv.vectorized_modal_solver(K, Mloc, tets, fixed, Nn, num_eigs=4, max_iter=20, X0=X0, **KW)
+    lo, mo = O.modal_solver(Ko, d["Mloc"], d["tets"], d["fixed"], Nn, d["X0"], max_iter=20, as_written=False)
+    close(lam, lo, 1e-8)
+    same_up_to_sign(modes, mo, 1e-6)
+    # convergence to the largest eigenvalues of K u = lambda M_lumped u on the free dofs
+    lam, modes = sv.vectorized_modal_solver(K, Mloc, tets, fixed, Nn, num_eigs=4, max_iter=300, X0=X0, **KW)
+    e = d["tets"]
+    dofs = (e[:, :, None] * 3 + np.arange(3)).reshape(-1)
+    Md = np.bincount(dofs, weights=np.diagonal(d["Mloc"], axis1=1, axis2=2).reshape(-1), minlength=3 * Nn)
+    A = N(sv.assemble_csr(K, tets).to_dense())
+    fix = (d["fixed"].reshape(-1, 1) * 3 + np.arange(3)).reshape(-1)
+    free = np.setdiff1d(np.arange(3 * Nn), fix)
+    exact = sl.eigh(A[np.ix_(free, free)], np.diag(Md[free]), eigvals_only=True)
+    assert np.abs(N(lam) - exact[-4:]).max() < 1e-4 * exact[-1]
+    assert float(modes[torch.as_tensor(fix, device=DEV)].abs().max()) == 0
+    # default dtype (float32 in, float32 out) and an unseeded start run through
+    lam32, modes32 = sv.vectorized_modal_solver(K, Mloc, tets, fixed, Nn, num_eigs=3, max_iter=3, device=DEV)
+    assert lam32.dtype == torch.float32 and modes32.shape == (3 * Nn, 3) and bool(torch.isfinite(modes32).all())
+    # the lumped diagonals behind it and behind compute_diagonal_preconditioner
+    minv = sv.compute_diagonal_preconditioner(K, tets, Nn, **KW)
+    diag = np.bincount(dofs, weights=np.diagonal(Ko, axis1=1, axis2=2).reshape(-1), minlength=3 * Nn).reshape(Nn, 3)
+    close(minv, 1.0 / diag)
+    # the reference's strided-view bug (column-0 sums): compare the sums themselves -- where they cancel to rounding noise the
+    # reciprocal is arbitrary in any summation order
+    col0 = np.bincount(dofs, weights=Ko[:, :, 0].reshape(-1), minlength=3 * Nn).reshape(Nn, 3)
+    bug = N(sv.compute_diagonal_preconditioner(K, tets, Nn, reference_bug=True, **KW))
+    big = np.abs(col0) > 1e-9 * np.abs(col0).max()
+    close(1.0 / bug[big], col0[big])
+    ref = O.reference_diagonal_preconditioner(Ko, d["tets"], Nn)
+    close(bug[big], ref[big])
+    from femb200 import ops
+    Xm = ops.MultiVec.from_columns(X0, torch.device(DEV))
+    G = Xm.gram(Xm, w=T(Md).to(DEV))
+    close(G, d["X0"].T @ (d["X0"] * Md[:, None]))
