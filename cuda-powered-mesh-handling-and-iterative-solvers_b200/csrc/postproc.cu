@@ -97,6 +97,48 @@ __global__ void wedge_normals_kernel(const T* __restrict__ coords, const I* __re
   }
 }
 
+// compute_s3_normal shell.py:184-203 (cross(x1-x0, x2-x0)/2) and compute_s4_normal :483-502 (cross(x1-x0, x3-x0))
+template <typename T, typename I>
+__global__ void shell_normal_kernel(const T* __restrict__ coords, const I* __restrict__ conn, long long M, int nen, T* __restrict__ out) {
+  const int second = nen == 3 ? 2 : 3;
+  const T sc = nen == 3 ? T(0.5) : T(1);
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const long long n0 = ldidx(conn + m * nen), n1 = ldidx(conn + m * nen + 1), n2 = ldidx(conn + m * nen + second);
+    T a[3], b[3];
+    for (int c = 0; c < 3; ++c) {
+      const T x0 = coords[3 * n0 + c];
+      a[c] = coords[3 * n1 + c] - x0;
+      b[c] = coords[3 * n2 + c] - x0;
+    }
+    out[3 * m] = (a[1] * b[2] - a[2] * b[1]) * sc;
+    out[3 * m + 1] = (a[2] * b[0] - a[0] * b[2]) * sc;
+    out[3 * m + 2] = (a[0] * b[1] - a[1] * b[0]) * sc;
+  }
+}
+
+// Element operator of a shell in global axes: Kg = T^T K T with T = blockdiag(R, R, ...) (R = unit, rows = local axes), i.e.
+// every 3x3 block (p,q) of K becomes R^T K_pq R -- what compute_shell_nodal_forces (shell.py:58-102) applies implicitly by
+// rotating the nodal vectors into the element frame and the forces back.  One thread per block.
+template <typename T>
+__global__ void shell_rotate_K_kernel(const T* __restrict__ K, const T* __restrict__ unit, long long M, int nb, T* __restrict__ out) {
+  const long long total = M * nb * nb;
+  const int nd = 3 * nb;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / (nb * nb);
+    const int pq = (int)(t - m * nb * nb), p = pq / nb, q = pq - p * nb;
+    T R[9], B[9], W[9];
+    for (int k = 0; k < 9; ++k) R[k] = __ldg(unit + 9 * m + k);
+    const T* src = K + (m * nd + 3 * p) * nd + 3 * q;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) B[3 * i + j] = src[i * nd + j];
+    for (int i = 0; i < 3; ++i)  // W = B R
+      for (int b = 0; b < 3; ++b) W[3 * i + b] = B[3 * i] * R[b] + B[3 * i + 1] * R[3 + b] + B[3 * i + 2] * R[6 + b];
+    T* dst = out + (m * nd + 3 * p) * nd + 3 * q;
+    for (int a = 0; a < 3; ++a)  // out = R^T W
+      for (int b = 0; b < 3; ++b) dst[a * nd + b] = R[a] * W[b] + R[3 + a] * W[3 + b] + R[6 + a] * W[6 + b];
+  }
+}
+
 // subdivision.ipynb cell 15: every subdomain starts from the global load vector ...
 template <typename T>
 __global__ void subdomain_broadcast_kernel(const T* __restrict__ F, long long len, int n_sub, T* __restrict__ out) {
@@ -127,6 +169,36 @@ __global__ void subdomain_interface_kernel(const T* __restrict__ F, long long N,
 }  // namespace femb
 
 using namespace femb;
+
+extern "C" int femb_shell_normal(const void* coords, int fp, const void* conn, int ib, int64_t M, int nen, void* out, femb_stream stream) {
+  FEMB_CHECK_ARG((fp == 4 || fp == 8) && (ib == 4 || ib == 8) && M >= 0 && (nen == 3 || nen == 4), "fp in {4,8}, ib in {4,8}, nen in {3,4}");
+  if (M == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int grid = grid_for(M, 128);
+#define SN(T, I) shell_normal_kernel<T, I><<<grid, 128, 0, s>>>((const T*)coords, (const I*)conn, M, nen, (T*)out)
+  if (fp == 8) {
+    if (ib == 8) SN(double, long long);
+    else SN(double, int);
+  } else {
+    if (ib == 8) SN(float, long long);
+    else SN(float, int);
+  }
+#undef SN
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
+extern "C" int femb_shell_rotate_operator(const void* K, const void* unit, int fp, int64_t M, int nd, void* out, femb_stream stream) {
+  FEMB_CHECK_ARG((fp == 4 || fp == 8) && M >= 0 && nd >= 3 && nd % 3 == 0 && K != out, "fp in {4,8}, nd a multiple of 3, distinct buffers");
+  if (M == 0) return FEMB_OK;
+  cudaStream_t s = as_stream(stream);
+  const int nb = nd / 3;
+  const int grid = grid_for(M * nb * nb, 128);
+  if (fp == 8) shell_rotate_K_kernel<double><<<grid, 128, 0, s>>>((const double*)K, (const double*)unit, M, nb, (double*)out);
+  else shell_rotate_K_kernel<float><<<grid, 128, 0, s>>>((const float*)K, (const float*)unit, M, nb, (float*)out);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
 
 extern "C" int femb_subdomain_forces(const void* F, int fp, int64_t N, int n_sub, const void* free_vars, int64_t ntgt, const int64_t* tgt,
                                      const int32_t* plus, const int32_t* minus, void* out, femb_stream stream) {

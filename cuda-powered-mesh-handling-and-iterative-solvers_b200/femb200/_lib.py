@@ -35,6 +35,8 @@ SIGNATURES = {
     "femb_node_average": [c_vp, c_vp, c_i32, c_vp, c_vp],
     "femb_shell": [c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, C.POINTER(c_f64), c_i32, C.POINTER(c_f64), c_vp, c_vp],
     "femb_shell_ex": [c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, C.POINTER(c_f64), c_i32, C.POINTER(c_f64), c_vp, c_vp, c_vp],
+    "femb_shell_normal": [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp],
+    "femb_shell_rotate_operator": [c_vp, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp],
     "femb_shell_local_coordinates": [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp],
     "femb_shell_local_displacement": [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp],
     "femb_shell_postprocess": [c_vp, c_i32, c_i64, c_i32, c_f64, c_f64, c_vp, c_vp],

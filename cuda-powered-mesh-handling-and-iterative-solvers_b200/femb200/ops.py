@@ -192,6 +192,32 @@ def shell_ex(kind, what, coords, elements, factors=None, D=None, disp=None, devi
     return out
 
 
+def shell_normal(coords, elements, device="cuda:0"):
+    """[M,3]: S3 cross(x1-x0, x2-x0)/2, S4 cross(x1-x0, x3-x0), in the dtype of `coords`."""
+    dev = cuda_device(device)
+    x = torch.as_tensor(coords)
+    x = real(x, dev, x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32)
+    conn = index(elements, dev)
+    out = torch.empty((conn.shape[0], 3), device=dev, dtype=x.dtype)
+    with torch.cuda.device(dev):
+        check(lib.femb_shell_normal(_p(x), _fp(x), _p(conn), _fp(conn), conn.shape[0], conn.shape[1], _p(out), _stream(dev)), "femb_shell_normal")
+    return out
+
+
+def shell_rotate_K(K, unit):
+    """[M,nd,nd] = T^T K T with T = blockdiag(unit, ...): the shell element operator in global axes (fp64)."""
+    dev = K.device
+    K = real(K, dev, torch.float64)
+    R = real(unit, dev, torch.float64)
+    M, nd, _ = K.shape
+    if tuple(R.shape) != (M, 3, 3):
+        raise ValueError(f"unit must be [M,3,3], got {tuple(R.shape)}")
+    out = torch.empty_like(K)
+    with torch.cuda.device(dev):
+        check(lib.femb_shell_rotate_operator(_p(K), _p(R), 8, M, nd, _p(out), _stream(dev)), "femb_shell_rotate_operator")
+    return out
+
+
 def shell_local_coordinates(coords, elements, unit, device="cuda:0", dtype=torch.float32):
     """[M,nen,3]: node coordinates relative to node 0 of each element, expressed in the frame `unit` [M,3,3]."""
     dev = cuda_device(device)

@@ -59,13 +59,8 @@ def compute_shell_postprocess_values(NMQ, t, z=0, device="cuda:0", dtype=torch.f
 # ------------------------------------------------------------------------------------------- S3
 
 def compute_s3_normal(coords, shell, device="cuda:0"):
-    """cross(x1-x0, x2-x0)/2 (shell.py:184-203) = area * third row of the local frame."""
-    dev = _ops.cuda_device(device)
-    x = torch.as_tensor(coords).to(dev)
-    dt = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
-    unit = _ops.shell(_ops.S3, 0, x, shell, device=dev, dtype=dt)
-    J = _ops.shell(_ops.S3, 1, x, shell, device=dev, dtype=dt)
-    return unit[:, 2, :] * (0.5 * (J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0])).unsqueeze(1)
+    """cross(x1-x0, x2-x0)/2 (shell.py:184-203)."""
+    return _ops.shell_normal(coords, shell, device)
 
 
 def identify_s3_shared_edges(shell, device="cuda:0"):
@@ -125,11 +120,7 @@ def compute_s3_shell_stress(coords, shell, membrane, bending, displacement, devi
 
 def compute_s4_normal(coords, shell, device="cuda:0"):
     """cross(x1-x0, x3-x0) (shell.py:483-502)."""
-    dev = _ops.cuda_device(device)
-    x = torch.as_tensor(coords).to(dev)
-    s = _ops.index(shell, dev).long()
-    a, b = x[s[:, 1]] - x[s[:, 0]], x[s[:, 3]] - x[s[:, 0]]
-    return torch.linalg.cross(a, b, dim=1)
+    return _ops.shell_normal(coords, shell, device)
 
 
 def identify_s4_shared_edges(shell, device="cuda:0"):

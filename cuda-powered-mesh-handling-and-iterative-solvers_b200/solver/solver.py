@@ -103,11 +103,8 @@ def final_solver(K, elements, F, rbe2, u_init=None, tol=1e-10, max_iter=1000, de
 
 
 def _shell_global_K(K, unit):
-    """T^T K T with T = blockdiag(R,R,...) per node: the element operator of shell.py:58-102 in global axes."""
-    M, nd, _ = K.shape
-    nb = nd // 3
-    Kb = K.reshape(M, nb, 3, nb, 3)
-    return torch.einsum("mia,mpiqj,mjb->mpaqb", unit, Kb, unit).reshape(M, nd, nd).contiguous()
+    """T^T K T with T = blockdiag(R,R,...) per node: the element operator of shell.py:58-102 in global axes (one kernel)."""
+    return _ops.shell_rotate_K(K, unit)
 
 
 def stable_conjugate_gradient_shell_solver(K, elements, F, rbe2, coords=None, unit=None, u_init=None, tol=1e-10, max_iter=1000,

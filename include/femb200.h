@@ -115,6 +115,14 @@ int femb_shell_ex(int kind, int what, const void* coords, int fp, const void* co
 int femb_shell_local_coordinates(const void* coords, int fp, const void* conn, int ib, int64_t M, int nen, const void* unit, void* out,
                                  femb_stream stream);
 
+/* compute_s3_normal shell.py:184-203 (nen = 3: cross(x1-x0, x2-x0)/2) and compute_s4_normal :483-502 (nen = 4:
+ * cross(x1-x0, x3-x0)): out[M,3] */
+int femb_shell_normal(const void* coords, int fp, const void* conn, int ib, int64_t M, int nen, void* out, femb_stream stream);
+/* Shell element operator in global axes: out[M,nd,nd] = T^T K T, T = blockdiag(unit, unit, ...) per 3 dofs -- the operator
+ * compute_shell_nodal_forces (shell.py:58-102) applies by rotating in and out of the element frame; assembled once for the
+ * shell CG (solver.py:297-389) and the shell families of static_structure_solver (:11-135). */
+int femb_shell_rotate_operator(const void* K, const void* unit, int fp, int64_t M, int nd, void* out, femb_stream stream);
+
 /* compute_global_to_local_displacement shell.py:41-56: out[M,nen,6] = (unit g_trans, unit g_rot), g = disp[conn] ([N,6]) */
 int femb_shell_local_displacement(const void* conn, int ib, int64_t M, int nen, const void* disp, const void* unit, int fp,
                                   void* out, femb_stream stream);

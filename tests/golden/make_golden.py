@@ -434,6 +434,8 @@ def gen_widen():
     c4, s4 = meshgen.quad_sheet(3, warp=0.15)
     unit3 = RS.compute_s3_local_unitvector(c3, s3, device="cpu")
     unit4 = RS.compute_s4_local_unitvector(c4, s4, device="cpu")
+    o["normal3"] = RS.compute_s3_normal(c3, s3, device="cpu")
+    o["normal4"] = RS.compute_s4_normal(c4, s4, device="cpu")
     o["loc3"] = RS.compute_s3_global_to_local_coordinates(c3, s3, unit3, **KW)
     o["loc4"] = RS.compute_s4_global_to_local_coordinates(c4, s4, unit4, **KW)
     g = torch.Generator().manual_seed(11)

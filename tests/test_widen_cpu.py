@@ -22,6 +22,13 @@ def close(a, b, tol=TOL):
 def test_shell_frames_stress_postprocess_oracle():
     d, g = load_golden("widen"), load_golden("shells")
     c3, s3, c4, s4 = g["c3"], g["s3"], g["c4"], g["s4"]
+    close(O.shell_normal(c3, s3), d["normal3"])
+    close(O.shell_normal(c4, s4), d["normal4"])
+    # the global-axes element operator reproduces the reference's rotate / apply / rotate-back force routine
+    Kg = O.shell_global_K(g["K3"], g["unit3"])
+    dofs = (s3[:, :, None] * 6 + np.arange(6)).reshape(s3.shape[0], -1)
+    f = np.bincount(dofs.reshape(-1), weights=np.einsum("mij,mj->mi", Kg, g["u3"].reshape(-1)[dofs]).reshape(-1), minlength=g["u3"].size)
+    close(f.reshape(-1, 6), g["f3"])
     close(O.shell_local_coords(c3, s3, O.s3_unit(c3, s3)), d["loc3"])
     close(O.shell_local_coords(c4, s4, O.s4_unit(c4, s4)), d["loc4"])
     close(O.shell_local_displacement(s3, d["u3"], O.s3_unit(c3, s3)), d["ul3"])

@@ -55,6 +55,13 @@ def test_shell_frames_and_displacements(api):
     d, g = load_golden("widen"), load_golden("shells")
     c3, s3, c4, s4 = T(g["c3"]), T(g["s3"]), T(g["c4"]), T(g["s4"])
     unit3, unit4 = T(g["unit3"]), T(g["unit4"])
+    close(sh.compute_s3_normal(c3, s3, device=DEV), d["normal3"])
+    close(sh.compute_s4_normal(c4, s4, device=DEV), d["normal4"])
+    assert sh.compute_s4_normal(c4.float(), s4.to(torch.int32), device=DEV).dtype == torch.float32
+    from femb200 import ops
+    from oracle import fem_oracle as O
+    close(ops.shell_rotate_K(T(g["K3"]).to(DEV), unit3.to(DEV)), O.shell_global_K(g["K3"], g["unit3"]))
+    close(ops.shell_rotate_K(T(g["K4"]).to(DEV), unit4.to(DEV)), O.shell_global_K(g["K4"], g["unit4"]))
     close(sh.compute_s3_global_to_local_coordinates(c3, s3, unit3, **KW), d["loc3"])
     close(sh.compute_s4_global_to_local_coordinates(c4, s4, unit4, **KW), d["loc4"])
     close(sh.compute_s4_global_to_local_coordinates(c4, s4.to(torch.int32), unit4, **KW), d["loc4"])
