@@ -291,7 +291,7 @@ __global__ void pad_coords(const double* __restrict__ coords, long long N, doubl
 }
 
 __device__ __forceinline__ void ld_xyz(const double* __restrict__ c4, int node, double* x) {
-  double w;
+  [[maybe_unused]] double w;  // fourth lane of the padded record
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(w) : "l"(c4 + 4ll * node));
 }
 
