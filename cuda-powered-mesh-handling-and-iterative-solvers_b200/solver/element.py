@@ -37,6 +37,14 @@ def _pts(kind, integral_point, dtype, single_point=False):
     return rows.to(dtype).to(torch.float64).tolist()
 
 
+def human_readable_number(num):
+    """'12.3M'-style counts for the notebooks' prints (element.py:23-37): one decimal, suffix K / M / B / T / Quad / Quint."""
+    for power, suffix in ((18, "Quint"), (15, "Quad"), (12, "T"), (9, "B"), (6, "M"), (3, "K")):
+        if abs(num) >= 10 ** power:
+            return f"{num / 10 ** power:.1f}{suffix}"
+    return f"{num:.1f}"
+
+
 # ------------------------------------------------------------------------------------------- constants
 
 def compute_elasticity_matrix(E, nu, device="cuda:0", dtype=torch.float32):

@@ -73,6 +73,8 @@ def test_mirror_api_names():
     sig = inspect.signature(solver.stable_conjugate_gradient_solver)
     assert list(sig.parameters)[:10] == ["K", "elements", "F", "rbe2", "u_init", "tol", "max_iter", "device", "dtype", "eps"]
     assert sig.parameters["tol"].default == 1e-10 and sig.parameters["eps"].default == 1e-30
+    assert [element.human_readable_number(v) for v in (5, 1000, 63888000, -2.5e9, 1.6e13, 3e15, 7e18)] == \
+        ["5.0", "1.0K", "63.9M", "-2.5B", "16.0T", "3.0Quad", "7.0Quint"]
     sig = inspect.signature(solver.conjugate_gradient_solver_Ku)
     assert list(sig.parameters)[:6] == ["compute_Ku", "R", "tol", "max_iter", "device", "dtype"] and sig.parameters["tol"].default == 1e-8
     assert list(inspect.signature(shell.shell_extrude).parameters) == ["coords", "tri", "quad", "thickness", "device", "dtype"]
