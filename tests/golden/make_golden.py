@@ -426,6 +426,24 @@ def gen_modal():
     save("modal", coords=npy(coords), tets=npy(tets), Mloc=npy(Mloc), fixed=npy(fixed), X0=npy(X0), reference_raises=np.array(raised))
 
 
+def gen_notebook_calls():
+    """Names the reference's two notebooks call that its own solver modules define: what a drop-in has to offer."""
+    import builtins
+    called = set()
+    for nbf in ("/root/reference/solver_example.ipynb", "/root/reference/subdivision.ipynb"):
+        for c in json.load(open(nbf))["cells"]:
+            if c["cell_type"] == "code":
+                called |= set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", "".join(c["source"])))
+    defined = set(dir(R)) | set(dir(RS)) | set(dir(RV))
+    nb_defs = set()
+    for c in json.load(open("/root/reference/subdivision.ipynb"))["cells"]:
+        nb_defs |= set(re.findall(r"^def ([A-Za-z_][A-Za-z0-9_]*)", "".join(c["source"]), flags=re.M))
+    names = sorted(n for n in called if (n in defined or n in nb_defs) and not hasattr(builtins, n) and not hasattr(torch, n))
+    with open(os.path.join(HERE, "notebook_calls.json"), "w") as f:
+        json.dump({"module_functions": [n for n in names if n in defined], "notebook_functions": [n for n in names if n in nb_defs]}, f, indent=1)
+    print("notebook_calls:", len(names), "names")
+
+
 def gen_widen():
     """Functions either side of the element path: shell frames / stress / post-processing, shell extrusion, wedge face normals,
     tet face-force balance and the operator-callback CG."""
@@ -511,3 +529,4 @@ if __name__ == "__main__":
     gen_widen()
     gen_subdomain_forces()
     gen_modal()
+    gen_notebook_calls()

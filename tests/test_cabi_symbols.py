@@ -113,3 +113,18 @@ def test_host_tables_match_oracle():
         for q in range(nq):
             assert np.abs(O._N[name](pts[q, :3]) - Ng[q]).max() < 1e-14, name
             assert np.abs(O._DN[name][0](pts[q, :3]) - dNg[q]).max() < 1e-14, name
+
+
+def test_notebook_call_sites_are_covered():
+    """Every function of its own modules / cells that the reference's two notebooks call (fixture written by
+    tests/golden/make_golden.py from the notebooks) exists in the mirror."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(PKG, "solver"))
+    import element, shell, solver, subdivision   # noqa: E401
+    calls = json.load(open(os.path.join(ROOT, "tests", "golden", "notebook_calls.json")))
+    for n in calls["module_functions"]:
+        assert callable(getattr(solver, n, None)), n      # solver re-exports element and shell, as the reference's does
+    for n in calls["notebook_functions"]:
+        assert callable(getattr(subdivision, n, None)), n
+    assert len(calls["module_functions"]) >= 7 and len(calls["notebook_functions"]) >= 9
