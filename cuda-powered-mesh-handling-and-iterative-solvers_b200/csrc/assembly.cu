@@ -983,16 +983,9 @@ extern "C" int femb_csr_assemble_c3d4(femb_csr_plan* p, int kind, const double* 
     assemble_p1_poisson_tiles<BD, 4, V><<<grid_for(p->ntiles, BD / 32, 16), BD, smem, s>>>(p->rec, p->tile_ptr, p->node_ptr, p->pdiag, p->N, \
                                                                                         p->ntiles, c4, vals, flag);             \
   }
-    static const int occ_ctas = getenv("FEMB_ASM_OCC") ? atoi(getenv("FEMB_ASM_OCC")) : 4;  // resident CTAs per SM the register budget is cut for
-#define LAUNCH_TILES_OCC(O)                                                                                                      \
-  {                                                                                                                              \
-    FEMB_CUDA(cudaFuncSetAttribute(assemble_p1_poisson_tiles<BD, O, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    assemble_p1_poisson_tiles<BD, O, 2><<<grid_for(p->ntiles, BD / 32, 16), BD, smem, s>>>(p->rec, p->tile_ptr, p->node_ptr, p->pdiag, p->N, \
-                                                                                        p->ntiles, c4, vals, flag);             \
-  }
-    if (occ_ctas == 5) LAUNCH_TILES_OCC(5) else if (occ_ctas == 6) LAUNCH_TILES_OCC(6) else if (occ_ctas == 8) LAUNCH_TILES_OCC(8)
-    else if (occ == 1) LAUNCH_TILES(1) else if (occ == 2) LAUNCH_TILES(2) else if (occ == 3) LAUNCH_TILES(3) else LAUNCH_TILES(0)
-#undef LAUNCH_TILES_OCC
+    // register budget: the five-deep record pipeline needs all 128 registers; cutting it for 5 / 6 / 8 resident CTAs spills and
+    // measured 3.4 / 6.1 / 8.2 ms against 2.55 ms
+    if (occ == 1) LAUNCH_TILES(1) else if (occ == 2) LAUNCH_TILES(2) else if (occ == 3) LAUNCH_TILES(3) else LAUNCH_TILES(0)
 #undef LAUNCH_TILES
   } else if (kind == 0 && p->inc_slots && (size_t)p->max_row * 8 * 128 <= 160 * 1024) {
     constexpr int BD = 128;
