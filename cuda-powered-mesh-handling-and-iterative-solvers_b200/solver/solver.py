@@ -447,7 +447,7 @@ def vectorized_modal_solver(K_local, M_local, elements, rbe2_node_ids, num_nodes
 
     The n_dof-long work runs on the device in fp64: K is assembled once (3x3 block-CSR) and applied column by column, the lumped
     mass comes from one pass over the incidence lists, and norms / projections / X^T K X / X Z are three tall-skinny kernels
-    (femb_mv_*); the k x k problems follow the reference's Gauss-Jordan and Jacobi steps on the host in `dtype`.  The reference
+    (femb_mv_*); only the k x k problems are solved on the host.  The reference
     draws its start subspace from an unseeded torch.randn; pass `X0` [3*num_nodes, num_eigs] (additive) for a reproducible run."""
     dev = _ops.cuda_device(device)
     if not 1 <= num_eigs <= 8:
