@@ -95,6 +95,31 @@ def test_wedge_face_normals_invariants():
         assert ((np.cross(e1, e2) * n[:, f]).sum(-1) > 0).all()
 
 
+def test_s4_factor_rows_follow_the_argument_type():
+    """Host logic of the S4 wrappers: python floats give 1 -/+ x in double, 0-dim float32 tensors give it rounded to float32
+    first (what the reference's own arithmetic does when compute_s4_B_matrix walks its float32 rule)."""
+    import sys
+    import torch
+    from conftest import PKG
+    sys.path.insert(0, os.path.join(PKG, "solver"))
+    import shell as sh
+    g32 = np.float32(1.0) / np.sqrt(np.float32(3.0))
+    row = sh._s4_factor_row(torch.tensor(g32), torch.tensor(-g32), torch.tensor(1.0))
+    one = np.float32(1.0)
+    assert row == [float(one - g32), float(one + g32), float(one + g32), float(one - g32), 1.0]
+    row = sh._s4_factor_row(0.3, -0.6)
+    assert row == [1 - 0.3, 1 + 0.3, 1 + 0.6, 1 - 0.6, 1.0]
+    x = 0.1234567891234
+    assert sh._s4_factor_row(torch.tensor(x, dtype=torch.float32), 0.0)[1] == float(np.float32(1) + np.float32(x)) != 1 + x
+    rows = sh._s4_rule_rows(None)
+    p, w = O.s4_points()
+    assert len(rows) == 4 and [r[4] for r in rows] == [1.0] * 4
+    for q in range(4):
+        dxi, deta = O._s4_d32(p[q, 0], p[q, 1])
+        assert np.array_equal(0.25 * np.array([-rows[q][2], rows[q][2], rows[q][3], -rows[q][3]]), dxi)
+        assert np.array_equal(0.25 * np.array([-rows[q][0], -rows[q][1], rows[q][1], rows[q][0]]), deta)
+
+
 def load_groups(d):
     """{sorted tuple of parts: [nodes]} in the fixture's order."""
     out, off = {}, 0
