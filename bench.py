@@ -99,7 +99,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU side (oracle)
-def cpu_cg_rate(n_sample, iters, full_nnz):
+def cpu_cg_rate(n_sample, iters, full_nnz, scale=True):
     """Times the oracle's CSR CG loop (the reference's loop, solver.py:144-229) on a Kuhn-cube Poisson operator of size
     n_sample built on the CPU, and scales the measured rate by nnz_sample/nnz_full to the benchmark workload (CG is
     memory-bound and linear in nnz far beyond the last-level cache).  Returns (iters/s at full size, description, cores)."""
@@ -128,9 +128,12 @@ def cpu_cg_rate(n_sample, iters, full_nnz):
     solve(iters)
     dt = time.perf_counter() - t0
     rate_sample = iters / dt
-    rate_full = rate_sample * (val.size / full_nnz)
     desc = (f"{impl}; sample = {iters} CG iterations on the n={n_sample} Kuhn-cube Poisson operator ({t.shape[0]} tets, nnz {val.size}), "
-            f"{rate_sample:.1f} it/s measured, scaled by nnz ratio {val.size / full_nnz:.4f} to the full workload")
+            f"{rate_sample:.1f} it/s measured")
+    if not scale:
+        return rate_sample, desc + " (not extrapolated)", threads, kind
+    rate_full = rate_sample * (val.size / full_nnz)
+    desc += f", scaled by nnz ratio {val.size / full_nnz:.4f} to the full workload"
     return rate_full, desc, threads, kind
 
 
@@ -354,9 +357,8 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": round(ms_loop / K, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"P1 tet Poisson, Kuhn cube n={n}: {M} C3D4 tets, {N} nodes, CSR nnz {nnz} (BASELINE config 4); "
-                               "step = one CG iteration of the reference loop", "index_dtype": "int32 CSR / int64 API connectivity",
-                   "l2": "inputs larger than L2 (CSR operator %.2f GB)" % (nnz * 12 / 1e9), "tol": 0.0, "partition": "none (1 GPU)"},
+        "config": workload_config(n, M, N, nnz),
+        "impl_details": {"index_dtype": "int32 CSR / int64 API connectivity", "partition": "none (1 GPU)"},
         "clocks": clocks,
         "e2e": {"value": round(K / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(F_host.numel() * 8 / K),
                 "d2h_bytes_per_step": int(u_host.numel() * 8 / K),
@@ -391,33 +393,115 @@ def run_gpu(args):
     if c2 is not None:
         out["config2"] = c2
     if not args.no_cpu:
-        rate, desc, cores, kind = cpu_cg_rate(args.cpu_n, args.cpu_iters, nnz)
-        out["cpu_baseline"] = {"value": round(rate, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+        out["cpu_baseline"] = cpu_baseline_leg(args, nnz)
     print(json.dumps(out), flush=True)
 
 
+def cpu_baseline_leg(args, nnz):
+    """cpu_baseline of the GPU arm (rank 0, N=1): the reference itself on a bounded sample (kind "reference", measured, not
+    extrapolated), with the compiled C port of the same loop on the same sample beside it as a second, labelled line."""
+    n_s, iters = args.cpu_base_n, args.cpu_base_iters
+    ref = None
+    try:
+        ref = reference_sample(n_s, iters)
+    except Exception as exc:  # noqa: BLE001
+        ref_err = f"{type(exc).__name__}: {exc}"
+    port_rate, port_desc, port_cores, _ = cpu_cg_rate(n_s, max(iters, 20), nnz, scale=False)
+    port = {"value": round(port_rate, 3), "unit": UNIT, "cores": port_cores, "kind": "port", "sample": port_desc}
+    if ref is None:
+        port["note"] = "reference not installed on this box (baseline/_ref missing): this is the C port, not the reference" if "ref_err" not in locals() else ref_err
+        return port
+    return {"value": round(ref["rate"], 3), "unit": UNIT, "cores": ref["threads"], "kind": "reference",
+            "sample": (f"UNMODIFIED reference (baseline/_ref/solver: stable_conjugate_gradient_solver, torch CPU {ref['threads']} threads, fp64): "
+                       f"{iters} CG iterations on the n={n_s} Kuhn-cube Poisson sample ({ref['tets']} tets), measured, not extrapolated; "
+                       "the full-size reference arm is `bench.py --impl reference`"),
+            "ms_per_iter": round(ref["ms_per_iter"], 2), "port": port}
+
+
+def workload_config(n, M, N, nnz):
+    """The `config` object, identical on both arms (the driver compares them)."""
+    return {"workload": f"P1 tet Poisson, Kuhn cube n={n}: {M} C3D4 tets, {N} nodes, CSR nnz {nnz} (BASELINE config 4); "
+                        "step = one CG iteration of the reference loop (solver.py:144-229)",
+            "tol": 0.0,
+            "l2": "inputs larger than the last-level cache on both arms (GPU arm: CSR operator %.2f GB vs 126 MB L2, never flushed "
+                  "artificially; reference arm: per-element matrices of the sample, GBs vs tens of MB of L3)" % (nnz * 12 / 1e9)}
+
+
+def kuhn_counts(n):
+    N = (n + 1) ** 3
+    M = 6 * n ** 3
+    edges = 3 * n * (n + 1) ** 2 + 3 * n * n * (n + 1) + n ** 3  # axis + face-diagonal + body-diagonal edges of the Kuhn cube
+    return M, N, N + 2 * edges
+
+
+def reference_sample(n_sample, iters, c1=False, timeout=1500):
+    """Times the UNMODIFIED reference (baseline/_ref/solver, torch CPU, all host threads) in a subprocess: its
+    `stable_conjugate_gradient_solver` on the n_sample Kuhn-cube Poisson problem (baseline/ref_arm.py).  None if the
+    reference is not installed on this box."""
+    arm = os.path.join(ROOT, "baseline", "ref_arm.py")
+    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "solver", "solver.py")):
+        return None
+    cmd = [sys.executable, arm, "--n", str(n_sample), "--iters", str(iters)] + (["--c1"] if c1 else [])
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):   # torchrun pins OMP_NUM_THREADS=1
+        env.pop(k, None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference arm failed: {r.stderr[-400:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's own torch-CPU CG (solver.py:144-229 driving element.py:429-464) on the box's host
+    cores.  `value` is the MEASURED rate on the bounded sample (n = --cpu-n), never extrapolated; a second, smaller sample and
+    BASELINE config 1 (run exactly) are printed beside it so the size dependence is visible."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = args.n
-    N = (n + 1) ** 3
-    M = 6 * n ** 3
-    edges = 3 * n * (n + 1) ** 2 + 3 * n * n * (n + 1) + n ** 3 + 0  # axis + face-diagonal + body-diagonal edges of the Kuhn cube
-    nnz = N + 2 * edges
+    M, N, nnz = kuhn_counts(n)
     K, W = args.steps, max(args.warmup, 3)
     iters = max(3, min(K, args.cpu_iters))
     t0 = time.perf_counter()
-    rate, desc, cores, kind = cpu_cg_rate(args.cpu_n, iters, nnz)
+    big = reference_sample(args.cpu_n, iters, c1=True)
+    if big is None:      # reference not installed on this box: fall back to the labelled C port (never silently)
+        rate, desc, cores, kind = cpu_cg_rate(args.cpu_n, iters, nnz, scale=False)
+        extra = {"note": "baseline/_ref missing on this box: value is the C port of the reference loop on the sample, NOT the reference"}
+    else:
+        small_n = max(20, args.cpu_n // 2)
+        small = reference_sample(small_n, iters)
+        rate, cores, kind = big["rate"], big["threads"], "reference"
+        Ms = big["tets"]
+        desc = (f"UNMODIFIED reference (baseline/_ref/solver: stable_conjugate_gradient_solver -> compute_nodal_forces, torch {cores} threads, "
+                f"fp64): {iters} CG iterations (after 1 warm-up) on the n={args.cpu_n} Kuhn-cube Poisson sample = {Ms} tets "
+                f"({Ms / M:.4f} of the workload's {M}), measured {rate:.3f} it/s; value is NOT extrapolated to the full mesh")
+        per_tet = [big["ms_per_iter"] * 1e6 / big["tets"], small["ms_per_iter"] * 1e6 / small["tets"]]
+        extra = {"reference_measurements": {
+            "sample": {k: big[k] for k in ("n", "tets", "nodes", "iters", "rate", "ms_per_iter", "setup_s", "threads")},
+            "half_sample": {k: small[k] for k in ("n", "tets", "nodes", "iters", "rate", "ms_per_iter", "setup_s", "threads")},
+            "ns_per_tet_iteration": [round(v, 2) for v in per_tet],
+            "config1_exact": big.get("c1"),
+            "full_size_estimate": {"iters_per_s": round(1e3 / (per_tet[0] * 1e-6 * M), 4),
+                                   "how": "linear in tets from the larger sample (ns per tet-iteration above); an ESTIMATE, not `value`"}}}
     out = {"impl": "reference", "metric": METRIC, "value": round(rate, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
            "ms_per_step": round(1e3 / rate, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic",
-           "config": {"workload": f"P1 tet Poisson, Kuhn cube n={n}: {M} C3D4 tets, {N} nodes, CSR nnz {nnz} (BASELINE config 4); "
-                                  "step = one CG iteration of the reference loop"},
+           "data": "synthetic", "config": workload_config(n, M, N, nnz),
            "cpu_baseline": {"value": round(rate, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
            "e2e": {"value": round(rate, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "host": {"cpu_count": os.cpu_count(), "cpu_model": cpu_model()},
            "wall_s": round(time.perf_counter() - t0, 1)}
+    out.update(extra)
     print(json.dumps(out), flush=True)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def main():
@@ -428,7 +512,9 @@ def main():
     ap.add_argument("--n", type=int, default=220, help="Kuhn cube cells per edge (220 -> 63.9M tets)")
     ap.add_argument("--impl", default="femb200", choices=["femb200", "reference"])
     ap.add_argument("--cpu-n", type=int, default=96, help="cube size of the CPU sample")
-    ap.add_argument("--cpu-iters", type=int, default=30)
+    ap.add_argument("--cpu-iters", type=int, default=20)
+    ap.add_argument("--cpu-base-n", type=int, default=64, help="cube size of the cpu_baseline sample inside the GPU arm (~10 s of CPU work)")
+    ap.add_argument("--cpu-base-iters", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-topo", action="store_true", help="skip the face-connectivity timing on the headline mesh")
     ap.add_argument("--no-c2", action="store_true", help="skip the secondary BASELINE config 2 (P2 elasticity) measurements")

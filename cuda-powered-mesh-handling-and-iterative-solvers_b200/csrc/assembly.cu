@@ -32,11 +32,16 @@ struct femb_csr_plan {
 namespace femb {
 
 template <typename I>
-__global__ void conn_to_i32(const I* __restrict__ conn, long long L, int* __restrict__ out, int* __restrict__ iota) {
+__global__ void conn_to_i32(const I* __restrict__ conn, long long L, long long N, int* __restrict__ out, int* __restrict__ iota,
+                            int* __restrict__ bad) {
+  bool oob = false;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L; t += (long long)gridDim.x * blockDim.x) {
-    out[t] = (int)ldidx(conn + t);
+    const long long v = ldidx(conn + t);
+    oob |= v < 0 || v >= N;  // the reference raises an index error here; the sorts below would index out of bounds
+    out[t] = (int)v;
     iota[t] = (int)t;
   }
+  if (oob) *bad = 1;
 }
 
 // inc_ptr from the sorted node keys (handles nodes without elements)
@@ -799,8 +804,15 @@ static int plan_build(const I* conn, femb_csr_plan* p, cudaStream_t s) {
   int *iota, *keys_sorted, *cand, *cand_sorted, *off, *cnt;
   FEMB_CUDA(scr.alloc(&iota, L));
   FEMB_CUDA(scr.alloc(&keys_sorted, L));
-  conn_to_i32<I><<<grid_for(L, 256), 256, 0, s>>>(conn, L, p->conn32, iota);
+  int* bad;
+  FEMB_CUDA(scr.alloc(&bad, 1));
+  FEMB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
+  conn_to_i32<I><<<grid_for(L, 256), 256, 0, s>>>(conn, L, N, p->conn32, iota, bad);
   FEMB_LAUNCH_CHECK();
+  int hbad = 0;
+  FEMB_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaStreamSynchronize(s));
+  FEMB_CHECK_ARG(hbad == 0, "connectivity holds a node index outside [0, n_nodes)");
   int bits = 1;
   while ((1ll << bits) < N) ++bits;
   size_t tb = 0;

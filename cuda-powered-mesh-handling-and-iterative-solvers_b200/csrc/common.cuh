@@ -70,6 +70,21 @@ struct Scratch {
 
 int num_sms();
 
+// ---- per-(thread, device) solver context --------------------------------------------------------
+// Stream capture is illegal on the legacy default stream (torch's default current stream), so the graph-captured solves run
+// on a private non-blocking stream ordered after the caller's stream by an event.  Streams, events and the pinned status
+// buffer belong to ONE device: they are kept in a table indexed by the current device (a solve on cuda:1 after one on
+// cuda:0 in the same thread must not reuse device 0's stream).
+struct SolveCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t order_ev = nullptr;
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr}, time_ev[2] = {nullptr, nullptr};
+  void* pinned = nullptr;  // SOLVE_PINNED_BYTES of page-locked host memory (two status structs)
+};
+constexpr size_t SOLVE_PINNED_BYTES = 1024;
+// context of the CURRENT device with its stream ordered after `user`; nullptr (and set_error) on any CUDA failure
+SolveCtx* solve_ctx(cudaStream_t user);
+
 // ---- device helpers --------------------------------------------------------------------------
 constexpr int SMS = 148;  // B200
 

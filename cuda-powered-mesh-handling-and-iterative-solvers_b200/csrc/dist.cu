@@ -33,8 +33,13 @@ struct SymHeader {
   volatile long long flagC[MAXP];  // r.r partial of rank q arrived
   volatile double redB[MAXP];
   volatile double redC[MAXP];
-  volatile double red2[2][4][MAXP];  // merged-reduction CG: [epoch parity][p.Ap, r.Ap, Ap.Ap, r.r][rank]
+  volatile double red2[2][4][MAXP];  // (previous layout of the merged loop's slots; kept so the header size is unchanged)
   double pad[MAXP];
+  // merged-reduction CG all-reduce, "LL" style: ll[epoch parity][source rank][word].  A word is (epoch << 32) | half of a
+  // double, written with ONE 8-byte store, so data and flag arrive together: no fence, no separate flag store, and the
+  // receiver knows a value is complete the moment it sees the epoch.  Words 0..5 = lo/hi of p.Ap, r.Ap, Ap.Ap (epoch B),
+  // words 6..7 = lo/hi of the exactly summed r.r (epoch C).
+  volatile unsigned long long ll[2][MAXP][8];
 };
 static_assert(sizeof(SymHeader) % 256 == 0, "header keeps p 256-byte aligned");
 
@@ -182,6 +187,24 @@ __device__ __forceinline__ double sum_slots(volatile double* red, int P) {
   return v;
 }
 
+__device__ __forceinline__ void ll_store(volatile unsigned long long* w, double v, int half, long long epoch) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long part = half ? (bits >> 32) : (bits & 0xffffffffull);
+  *w = ((unsigned long long)(unsigned)epoch << 32) | part;
+}
+// spin until the word carries `epoch`; returns its 32 data bits
+__device__ __forceinline__ unsigned ll_wait(volatile unsigned long long* w, long long epoch, DistState* st) {
+  const long long t0 = clock64();
+  unsigned long long v;
+  while ((unsigned)((v = *w) >> 32) != (unsigned)epoch) {
+    if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+      st->stop = 3, st->status = 3;
+      break;
+    }
+  }
+  return (unsigned)v;
+}
+
 // ---- k2: u += alpha p ; r -= alpha Ap ; r.r partial -> everyone -------------------------------------------------------
 __global__ void __launch_bounds__(DV_THREADS) dist_update_kernel(Peers pe, long long n, double* __restrict__ u, double* __restrict__ r,
                                                                  const double* __restrict__ Ap, double* __restrict__ partial, DistState* st,
@@ -321,19 +344,28 @@ __global__ void __launch_bounds__(TMA_THREADS) dist_spmv3_kernel(Peers pe, long 
                                                                  const int* __restrict__ col, const double* __restrict__ val,
                                                                  double* __restrict__ y, const unsigned char* __restrict__ mask,
                                                                  const double* __restrict__ rvec, double* __restrict__ partial, DistState* st,
-                                                                 long long n_interior) {
-  if (st->stop) return;
+                                                                 long long n_interior, long long pin) {
+  pdl_launch_dependents();
   SymHeader* me = pe.hdr[pe.rank];
-  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 2), trace_stamp(st, 3);
   __shared__ int nbr[MAXP];
   if (threadIdx.x < MAXP) nbr[threadIdx.x] = pe.nbr[threadIdx.x];
   __syncthreads();
   const double* x = sym_p(me);
-  const GraphHaloWaiter hw{me, nbr, pe.nnbr, st->epochA, st};
+  // the halo epoch is read lazily (after the PDL wait inside spmv_tma_rows): st belongs to the previous kernel until then
+  struct LazyHalo {
+    SymHeader* me;
+    const int* nbr;
+    int nnbr;
+    DistState* st;
+    __device__ __forceinline__ void operator()() const { wait_flags(me->flagA, nbr, nnbr, st->epochA, st); }
+  };
+  const LazyHalo hw{me, nbr, pe.nnbr, st};
   double extra[2] = {0.0, 0.0};
-  const double dot = spmv_tma_rows<LR, NC, TMA_THREADS, TMA_STAGES, TMA_CAP, GraphHaloWaiter>(
-      n_owned, nnz, crow, col, val, x, y, mask, false, true, pe.nnbr > 0 ? n_interior : 0x7fffffffffffffffll, hw, rvec, extra);
-  if (st->stop == 3) return;
+  const double dot = spmv_tma_rows<LR, NC, TMA_THREADS, TMA_STAGES, TMA_CAP, LazyHalo, PdlWait>(
+      n_owned, nnz, crow, col, val, x, y, mask, false, true, pe.nnbr > 0 ? n_interior : 0x7fffffffffffffffll, hw, rvec, extra, PdlWait(), &st->stop,
+      pin);
+  if (st->stop) return;  // set before this kernel (block-uniform) or by a spin timeout (status 3: the solve is lost anyway)
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 3);
   const double t0 = block_sum<TMA_THREADS>(dot), t1 = block_sum<TMA_THREADS>(extra[0]), t2 = block_sum<TMA_THREADS>(extra[1]);
   const int G = gridDim.x;
   __shared__ bool last;
@@ -349,20 +381,22 @@ __global__ void __launch_bounds__(TMA_THREADS) dist_spmv3_kernel(Peers pe, long 
     for (int k = threadIdx.x; k < G; k += TMA_THREADS)
       a[0] += ((volatile double*)partial)[k], a[1] += ((volatile double*)partial)[G + k], a[2] += ((volatile double*)partial)[2 * G + k];
     a[0] = block_sum<TMA_THREADS>(a[0]), a[1] = block_sum<TMA_THREADS>(a[1]), a[2] = block_sum<TMA_THREADS>(a[2]);
+    __shared__ double sums[3];
+    __shared__ long long eB;
     if (threadIdx.x == 0) {
       st->ticket1 = 0;
-      const long long e = st->epochB + 1;
-      st->epochB = e;
-      const int par = (int)(e & 1);
-      for (int q = 0; q < pe.P; ++q) {
-        pe.hdr[q]->red2[par][0][pe.rank] = a[0];
-        pe.hdr[q]->red2[par][1][pe.rank] = a[1];
-        pe.hdr[q]->red2[par][2][pe.rank] = a[2];
-      }
-      __threadfence_system();
-      for (int q = 0; q < pe.P; ++q) pe.hdr[q]->flagB[pe.rank] = e;
-      trace_stamp(st, 4);
+      eB = st->epochB + 1;
+      st->epochB = eB;
+      sums[0] = a[0], sums[1] = a[1], sums[2] = a[2];
     }
+    __syncthreads();
+    // 6 words to each of the P ranks (own included), one thread per word: data and epoch travel in the same 8-byte store
+    const int par = (int)(eB & 1);
+    for (int t = threadIdx.x; t < 6 * pe.P; t += TMA_THREADS) {
+      const int q = t / 6, w = t - 6 * q;
+      ll_store(&pe.hdr[q]->ll[par][pe.rank][w], sums[w >> 1], w & 1, eB);
+    }
+    if (threadIdx.x == 0) trace_stamp(st, 4);
   }
 }
 
@@ -370,39 +404,51 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
                                                                      const double* __restrict__ Ap, double* __restrict__ partial,
                                                                      DistState* st, double tol, double eps, int guards, int max_iter,
                                                                      BoundaryPush bp) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->stop) return;
   SymHeader* me = pe.hdr[pe.rank];
-  __shared__ int all[MAXP];
+  __shared__ unsigned halves[MAXP * 8];
   __shared__ double sc[4];
-  if (threadIdx.x < MAXP) all[threadIdx.x] = threadIdx.x;
-  __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 5);
   const long long eB = st->epochB, eC = st->epochC;
   const int it = st->it;
-  wait_flags(me->flagB, all, pe.P, eB, st);
-  if (it > 0) wait_flags(me->flagC, all, pe.P, eC, st);  // true r.r of the previous update: arrived one SpMV ago
+  {  // all-reduce: wait for the 6 (+2 from the previous update, it > 0) words of every rank; one thread per word
+    const int pb = (int)(eB & 1), pc = (int)(eC & 1);
+    for (int t = threadIdx.x; t < 8 * pe.P; t += DV_THREADS) {
+      const int q = t >> 3, w = t & 7;
+      if (w < 6) halves[t] = ll_wait(&me->ll[pb][q][w], eB, st);
+      else halves[t] = it > 0 ? ll_wait(&me->ll[pc][q][w], eC, st) : 0u;
+    }
+  }
+  __syncthreads();
   if (st->stop) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 6);
-  if (threadIdx.x == 0) {  // one thread reads the slots (rank order: identical sums on every rank)
-    const int pb = (int)(eB & 1), pc = (int)(eC & 1);
-    sc[0] = sum_slots_serial(me->red2[pb][0], pe.P);
-    sc[1] = sum_slots_serial(me->red2[pb][1], pe.P);
-    sc[2] = sum_slots_serial(me->red2[pb][2], pe.P);
-    sc[3] = it > 0 ? sum_slots_serial(me->red2[pc][3], pe.P) : st->rs_old;
+  if (threadIdx.x < 4) {  // sums in rank order: identical on every rank and CTA
+    double a = 0.0;
+    for (int q = 0; q < pe.P; ++q)
+      a += __longlong_as_double((long long)(((unsigned long long)halves[q * 8 + 2 * threadIdx.x + 1] << 32) | halves[q * 8 + 2 * threadIdx.x]));
+    sc[threadIdx.x] = (threadIdx.x == 3 && it == 0) ? st->rs_old : a;
   }
   __syncthreads();
   const double pAp = sc[0], rAp = sc[1], ApAp = sc[2], rs_old = sc[3];
+  // rs_old is the exactly summed r.r of the previous update (it arrived one SpMV ago): the reference's convergence test
+  // (solver.py:208-212) is applied to IT, one SpMV late, before anything of this iteration is applied -- u and r are then
+  // exactly the reference's state at its break.  The recurrence value below only feeds beta.
+  if (it > 0 && sqrt(rs_old) < tol) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->stop = 1, st->status = 0, st->iterations = it, st->rs_new = rs_old;
+    return;
+  }
   const double alpha = rs_old / (pAp + eps);
   if (guards && (fabs(pAp) < eps || pAp < 0.0 || !isfinite(alpha))) {  // solver.py:187-198, same verdict on every rank/CTA
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->stop = 1, st->status = 1, st->iterations = it + 1, st->pAp = pAp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->stop = 1, st->status = 1, st->iterations = it + 1, st->pAp = pAp, st->rs_new = rs_old;
     return;
   }
   double rs_new = rs_old - 2.0 * alpha * rAp + alpha * alpha * ApAp;
-  if (!(rs_new > 0.0)) rs_new = 0.0;                      // cancellation at machine-precision convergence
+  if (!(rs_new > 0.0)) rs_new = 0.0;                      // cancellation: beta = 0 restarts the direction, never a false "converged"
   const double beta = rs_new / (rs_old + eps);
-  const bool conv = sqrt(rs_new) < tol;                   // solver.py:210-212 (u and r are updated before the break)
   const bool bad = guards && !isfinite(beta);             // solver.py:216-218
-  const bool move_p = !(conv || bad);
+  const bool move_p = !bad;
   double* p = sym_p(me);
   const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
   const long long n_plain = bp.ptr ? bp.n_interior : n;
@@ -445,29 +491,53 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
     double a = 0.0;
     for (int k = threadIdx.x; k < (int)gridDim.x; k += DV_THREADS) a += ((volatile double*)partial)[k];
     a = block_sum<DV_THREADS>(a);
+    __shared__ double rr;
+    __shared__ long long eCn;
     if (threadIdx.x == 0) {
       trace_stamp(st, 7), trace_stamp(st, 8), trace_stamp(st, 9);
       st->ticket2 = 0;
       st->pAp = pAp, st->alpha = alpha, st->beta = beta, st->rs_new = rs_new, st->rs_old = rs_new;
+      eCn = eC + 1;
+      st->epochC = eCn;
+      rr = a;
       if (!move_p) {
-        st->stop = 1, st->status = conv ? 0 : 1, st->iterations = it + 1;
+        st->stop = 1, st->status = 1, st->iterations = it + 1;
       } else {
         st->it = it + 1;
         if (it + 1 >= max_iter) st->stop = 2, st->status = 2, st->iterations = max_iter;
-        const long long e = eC + 1;
-        st->epochC = e;
-        const int par = (int)(e & 1);
-        for (int q = 0; q < pe.P; ++q) pe.hdr[q]->red2[par][3][pe.rank] = a;
-        __threadfence_system();
-        for (int q = 0; q < pe.P; ++q) pe.hdr[q]->flagC[pe.rank] = e;
-        if (bp.ptr) {
+        if (bp.ptr) {  // every CTA fenced its pushes before taking a ticket: the halo is complete on the neighbours
           const long long ea = st->epochA + 1;
           st->epochA = ea;
           for (int k = 0; k < pe.nnbr; ++k) pe.hdr[pe.nbr[k]]->flagA[pe.rank] = ea;
         }
       }
-      trace_stamp(st, 10);
     }
+    __syncthreads();
+    // exactly summed r.r of this update -> everyone (consumed by the next iteration's vector kernel / the final check)
+    const int par = (int)(eCn & 1);
+    for (int t2 = threadIdx.x; t2 < 2 * pe.P; t2 += DV_THREADS) {
+      const int q = t2 >> 1, w = 6 + (t2 & 1);
+      ll_store(&pe.hdr[q]->ll[par][pe.rank][w], rr, w & 1, eCn);
+    }
+    if (threadIdx.x == 0) trace_stamp(st, 10);
+  }
+}
+
+// after the last graph: the loop tests convergence one SpMV late, so an update that converged in the very last iteration
+// (status "maxiter") or right before a breakdown verdict is settled here from the r.r all-reduce that is still in flight
+__global__ void dist_final_check(Peers pe, DistState* st, double tol) {
+  SymHeader* me = pe.hdr[pe.rank];
+  __shared__ unsigned halves[MAXP * 2];
+  if (st->status == 3 || st->it == 0 || (st->stop == 1 && st->status == 0)) return;
+  const long long eC = st->epochC;
+  const int pc = (int)(eC & 1);
+  for (int t = threadIdx.x; t < 2 * pe.P; t += blockDim.x) halves[t] = ll_wait(&me->ll[pc][t >> 1][6 + (t & 1)], eC, st);
+  __syncthreads();
+  if (threadIdx.x == 0 && st->status != 3) {
+    double a = 0.0;
+    for (int q = 0; q < pe.P; ++q) a += __longlong_as_double((long long)(((unsigned long long)halves[2 * q + 1] << 32) | halves[2 * q]));
+    st->rs_new = a;  // the reported residual is the exactly summed one
+    if (sqrt(a) < tol && st->status == 2) st->stop = 1, st->status = 0, st->iterations = st->it;
   }
 }
 
@@ -739,13 +809,14 @@ static void launch_dist_spmv(int lr, int grid, cudaStream_t s, const Peers& pe, 
 #undef FEMB_DSPMV
 }
 
-static void launch_dist_spmv3(int lr, int grid, cudaStream_t s, const Peers& pe, long long n, long long nnz, const int* crow, const int* col,
-                              const double* val, double* y, const unsigned char* mask, const double* rvec, double* partial, DistState* st,
-                              long long n_interior) {
+static void launch_dist_spmv3(int lr, int grid, cudaStream_t s, bool pdl, const Peers& pe, long long n, long long nnz, const int* crow,
+                              const int* col, const double* val, double* y, const unsigned char* mask, const double* rvec, double* partial,
+                              DistState* st, long long n_interior, long long pin) {
 #define FEMB_DSPMV3(LRV)                                                                                                    \
   {                                                                                                                         \
     cudaFuncSetAttribute(dist_spmv3_kernel<LRV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);         \
-    dist_spmv3_kernel<LRV, true><<<grid, TMA_THREADS, TMA_SMEM, s>>>(pe, n, nnz, crow, col, val, y, mask, rvec, partial, st, n_interior); \
+    launch_pdl(dist_spmv3_kernel<LRV, true>, grid, TMA_THREADS, TMA_SMEM, s, pdl, pe, n, nnz, crow, col, val, y, mask, rvec, partial, st, \
+               n_interior, pin);                                                                                            \
   }
   switch (lr) {
     case 1: FEMB_DSPMV3(1) break;
@@ -756,18 +827,6 @@ static void launch_dist_spmv3(int lr, int grid, cudaStream_t s, const Peers& pe,
     default: FEMB_DSPMV3(32) break;
   }
 #undef FEMB_DSPMV3
-}
-
-static cudaStream_t dist_stream(cudaStream_t user) {
-  static thread_local cudaStream_t s = nullptr;
-  static thread_local cudaEvent_t ev = nullptr;
-  if (!s) {
-    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-  }
-  cudaEventRecord(ev, user);
-  cudaStreamWaitEvent(s, ev, 0);
-  return s;
 }
 
 }  // namespace femb
@@ -819,8 +878,9 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   FEMB_CHECK_ARG(n_owned > 0 && crow && col && val && F && u && work && sym_host && result_host, "null pointer / n_owned <= 0");
   if (check_every < 1) check_every = 16;
   spmv_apply_env_once();
-  cudaStream_t s = dist_stream(as_stream(stream));
-  FEMB_CHECK_ARG(s != nullptr, "could not create the solver stream");
+  SolveCtx* ctx = solve_ctx(as_stream(stream));  // private capture-capable stream of the current device, ordered after the caller's
+  if (!ctx) return FEMB_ERR_CUDA;
+  cudaStream_t s = ctx->stream;
   Peers pe;
   memset(&pe, 0, sizeof(pe));
   pe.rank = rank, pe.P = nranks, pe.nnbr = nnbr;
@@ -883,13 +943,9 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
     FEMB_CUDA(scr.alloc(&counters, 4));
     FEMB_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), s));
     pa.counters = counters;
-    static thread_local DistState* hfin = nullptr;
-    static thread_local cudaEvent_t pev[2] = {nullptr, nullptr};
-    if (!hfin) {
-      FEMB_CUDA(cudaMallocHost(&hfin, sizeof(DistState)));
-      FEMB_CUDA(cudaEventCreate(&pev[0]));
-      FEMB_CUDA(cudaEventCreate(&pev[1]));
-    }
+    static_assert(2 * sizeof(DistState) <= SOLVE_PINNED_BYTES, "pinned status buffer");
+    DistState* hfin = static_cast<DistState*>(ctx->pinned);
+    cudaEvent_t* pev = ctx->time_ev;
     void* kargs[] = {(void*)&pa};
     FEMB_CUDA(cudaEventRecord(pev[0], s));
     FEMB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(SPMV_THREADS), kargs, 0, s));
@@ -917,6 +973,11 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   BoundaryPush bp{folded ? bptr : nullptr, bk, boff, n_interior};
   // FEMB_DIST_CLASSIC=1: the three-kernel loop k1/k2/k3 (two waited all-reduces); default: merged reduction m1/m2
   static const bool classic = getenv("FEMB_DIST_CLASSIC") != nullptr;
+  const bool pdl = pdl_enabled() && !classic;
+  const long long pin = classic ? 0 : spmv_pin_entries(nnz);
+  // with PDL the next SpMV's CTAs (4 x 128 threads per SM) become resident beside the vector kernel: leave them room
+  static const int vec_waves = getenv("FEMB_DIST_VEC_WAVES") ? atoi(getenv("FEMB_DIST_VEC_WAVES")) : 6;
+  const int g2m = pdl ? grid_for(n, DV_THREADS, vec_waves) : g2;
   for (int k = 0; k < check_every; ++k) {
     if (!folded && nnbr > 0) dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
     if (classic) {
@@ -924,8 +985,8 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
       dist_update_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, eps, guards);
       dist_direction_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, r, st, tol, eps, guards, max_iter, bp);
     } else {
-      launch_dist_spmv3(lr, g1, s, pe, n, nnz, crow, col, val, Ap, mask, r, partial, st, n_interior);
-      dist_merged_vec_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, tol, eps, guards, max_iter, bp);
+      launch_dist_spmv3(lr, g1, s, pdl && k > 0, pe, n, nnz, crow, col, val, Ap, mask, r, partial, st, n_interior, pin);
+      launch_pdl(dist_merged_vec_kernel, g2m, DV_THREADS, 0, s, pdl, pe, n, u, r, Ap, partial, st, tol, eps, guards, max_iter, bp);
     }
   }
   cudaError_t ce = cudaStreamEndCapture(s, &graph);
@@ -934,15 +995,9 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
     return FEMB_ERR_CUDA;
   }
   FEMB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-  static thread_local DistState* hst = nullptr;
-  static thread_local cudaEvent_t ev[2] = {nullptr, nullptr}, tev[2] = {nullptr, nullptr};
-  if (!hst) {
-    FEMB_CUDA(cudaMallocHost(&hst, 2 * sizeof(DistState)));
-    for (int k = 0; k < 2; ++k) {
-      FEMB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
-      FEMB_CUDA(cudaEventCreate(&tev[k]));
-    }
-  }
+  DistState* hst = static_cast<DistState*>(ctx->pinned);  // [2] pinned
+  cudaEvent_t* ev = ctx->poll_ev;
+  cudaEvent_t* tev = ctx->time_ev;
   int rc = FEMB_OK;
   const int launches = (max_iter + check_every - 1) / check_every;
   hst[0].stop = hst[1].stop = 0;
@@ -961,6 +1016,7 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
     }
   }
   cudaEventRecord(tev[1], s);
+  if (!classic) dist_final_check<<<1, 64, 0, s>>>(pe, st, tol);
   DistState* fin = &hst[0];
   if (rc == FEMB_OK && (cudaMemcpyAsync(fin, st, sizeof(DistState), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)) {
     set_error(std::string("distributed CG final state: ") + cudaGetErrorString(cudaGetLastError()));
@@ -986,18 +1042,32 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 10; i < i1; ++i) {
       const long long* t = h + i * 12;
-      acc[0] += t[1] - t[0];                 // push
-      acc[1] += t[3] - t[2];                 // k1 wait for halo
-      acc[2] += t[4] - t[3];                 // k1 body + reduction + remote stores
-      acc[3] += t[6] - t[5];                 // k2 wait for all-reduce B
-      acc[4] += t[7] - t[6];                 // k2 body
-      acc[5] += t[9] - t[8];                 // k3 wait for all-reduce C
-      acc[6] += t[10] - t[9];                // k3 body
-      acc[7] += (h + (i + 1) * 12)[0] - t[0];  // whole iteration
+      if (classic) {
+        acc[0] += t[1] - t[0];                 // push
+        acc[1] += t[3] - t[2];                 // k1 wait for halo
+        acc[2] += t[4] - t[3];                 // k1 body + reduction + remote stores
+        acc[3] += t[6] - t[5];                 // k2 wait for all-reduce B
+        acc[4] += t[7] - t[6];                 // k2 body
+        acc[5] += t[9] - t[8];                 // k3 wait for all-reduce C
+        acc[6] += t[10] - t[9];                // k3 body
+        acc[7] += (h + (i + 1) * 12)[0] - t[0];  // whole iteration
+      } else {
+        const long long* tp = h + (i - 1) * 12;
+        acc[0] += t[3] - tp[10];               // SpMV: end of the previous vector kernel -> rows done on CTA 0 (launch gap included)
+        acc[1] += t[4] - t[3];                 // last CTA: reduction + LL stores to all ranks
+        acc[2] += t[5] - t[4];                 // gap until the vector kernel runs
+        acc[3] += t[6] - t[5];                 // vector kernel: wait for the all-reduce words of every rank
+        acc[4] += t[10] - t[6];                // vector kernel body + r.r reduction + halo flag
+        acc[7] += t[10] - tp[10];              // whole iteration
+      }
     }
     const double m = 1e-3 / (i1 - 10);
-    fprintf(stderr, "[femb dist trace] rank %d: push %.1f | k1 wait %.1f body %.1f | k2 wait %.1f body %.1f | k3 wait %.1f body %.1f | iteration %.1f us\n",
-            rank, acc[0] * m, acc[1] * m, acc[2] * m, acc[3] * m, acc[4] * m, acc[5] * m, acc[6] * m, acc[7] * m);
+    if (classic)
+      fprintf(stderr, "[femb dist trace] rank %d: push %.1f | k1 wait %.1f body %.1f | k2 wait %.1f body %.1f | k3 wait %.1f body %.1f | iteration %.1f us\n",
+              rank, acc[0] * m, acc[1] * m, acc[2] * m, acc[3] * m, acc[4] * m, acc[5] * m, acc[6] * m, acc[7] * m);
+    else
+      fprintf(stderr, "[femb dist trace] rank %d: spmv %.1f | reduce+send %.1f | gap %.1f | allreduce wait %.1f | vector body %.1f | iteration %.1f us\n",
+              rank, acc[0] * m, acc[1] * m, acc[2] * m, acc[3] * m, acc[4] * m, acc[7] * m);
   }
   return FEMB_OK;
 }

@@ -89,10 +89,13 @@ __device__ __forceinline__ void cg_k1_epilogue3_n(double dot, double e0, double 
         double rs_new = rs - 2.0 * alpha * b + alpha * alpha * c;
         if (!(rs_new > 0.0)) rs_new = 0.0;  // cancellation at machine-precision convergence
         const double beta = rs_new / (rs + eps);
+        // The recurrence value only feeds beta.  Convergence is decided by cg_merged_kernel on the exactly summed r.r of the
+        // updated residual (the reference's test, solver.py:208-212): the estimate carries an absolute error ~ eps_mach * rs
+        // and can be <= tol^2 (or clip to 0) one step before the true norm is, e.g. at the finite-termination step of a
+        // small system.  A clipped estimate gives beta = 0, i.e. a steepest-descent restart, never a false "converged".
         st->alpha = alpha, st->beta = beta, st->rs_new = rs_new;
         st->fin = 0;
-        if (sqrt(rs_new) < tol) st->fin = 1, st->fin_status = 0;            // solver.py:210-212 (after the u/r update)
-        else if (guards && !isfinite(beta)) st->fin = 1, st->fin_status = 1;  // solver.py:216-218
+        if (guards && !isfinite(beta)) st->fin = 1, st->fin_status = 1;  // solver.py:216-218
       }
     }
   }
@@ -162,11 +165,13 @@ __global__ void __launch_bounds__(TMA_THREADS) spmv_tma_kernel(long long n, long
                                                                const double* __restrict__ val, const double* __restrict__ x,
                                                                double* __restrict__ y, const unsigned char* __restrict__ mask,
                                                                double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards,
-                                                               const double* __restrict__ rvec, double tol) {
-  if (st && st->stop) return;
+                                                               const double* __restrict__ rvec, double tol, long long pin) {
+  pdl_launch_dependents();
   double extra[2] = {0.0, 0.0};
-  const double dot = spmv_tma_rows<LR, true>(n, nnz, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED, 0x7fffffffffffffffll, NoHaloWait(),
-                                             rvec, rvec ? extra : nullptr);
+  const double dot = spmv_tma_rows<LR, true, TMA_THREADS, TMA_STAGES, TMA_CAP, NoHaloWait, PdlWait>(
+      n, nnz, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED, 0x7fffffffffffffffll, NoHaloWait(), rvec, rvec ? extra : nullptr, PdlWait(),
+      st ? &st->stop : nullptr, pin);
+  if (st && st->stop) return;  // block-uniform: the flag is only written by the previous kernel's last CTA
   if (FUSED) {
     if (rvec) cg_k1_epilogue3_n<TMA_THREADS>(dot, extra[0], extra[1], partial, st, eps, guards & 1, tol);
     else cg_k1_epilogue_n<TMA_THREADS>(dot, partial, st, eps, guards & 1);
@@ -350,7 +355,9 @@ __global__ void __launch_bounds__(VEC_THREADS) cg_direction_kernel(long long n, 
 // merged loop, second kernel: all scalars were fixed by the SpMV's last CTA (cg_k1_epilogue3_n)
 __global__ void __launch_bounds__(VEC_THREADS) cg_merged_kernel(long long n, double* __restrict__ u, double* __restrict__ r, double* __restrict__ p,
                                                                 const double* __restrict__ Ap, double* __restrict__ partial,
-                                                                CGState* __restrict__ st, int max_iter) {
+                                                                CGState* __restrict__ st, int max_iter, double tol) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->stop) return;
   const double alpha = st->alpha, beta = st->beta;
   const bool move_p = st->fin == 0;
@@ -377,7 +384,10 @@ __global__ void __launch_bounds__(VEC_THREADS) cg_merged_kernel(long long n, dou
     a = block_sum<VEC_THREADS>(a);
     if (threadIdx.x == 0) {
       st->ticket2 = 0;
-      if (!move_p) {
+      st->rs_new = a;  // the reported residual is the exactly summed one
+      if (sqrt(a) < tol) {  // solver.py:210-212: break after the u / r update (p is not part of the result)
+        st->stop = 1, st->status = 0, st->iterations = st->it + 1;
+      } else if (!move_p) {
         st->stop = 1, st->status = st->fin_status, st->iterations = st->it + 1;
       } else {
         st->rs_old = a;  // exactly summed r.r of the new residual: the next recurrence starts from it
@@ -460,6 +470,8 @@ static int pick_lanes(long long n, long long nnz, int block = 1) {
 }
 
 static thread_local long long nnz_hint = 0;  // set by the callers right before launch_spmv (the TMA kernel clamps its copies to nnz)
+static thread_local bool pdl_hint = false;   // launch the next TMA SpMV with the programmatic-serialization attribute (graph loop only)
+static thread_local long long pin_hint = 0;  // leading nonzeros staged evict_last (spmv_pin_entries), 0 outside solves
 
 template <bool FUSED>
 static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const int* crow, const int* col, const double* val, const double* x,
@@ -469,7 +481,8 @@ static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const 
 #define FEMB_TMA(LRV)                                                                                                              \
   {                                                                                                                                \
     cudaFuncSetAttribute(spmv_tma_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);                 \
-    spmv_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, TMA_SMEM, s>>>(n, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
+    launch_pdl(spmv_tma_kernel<LRV, FUSED>, grid, TMA_THREADS, TMA_SMEM, s, pdl_hint, n, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, \
+               guards, rvec, tol, pin_hint);                                                                                     \
   }
 #define FEMB_BSR(LRV)                                                                                                              \
   {                                                                                                                                \
@@ -568,20 +581,6 @@ extern "C" int femb_csr_jacobi(int64_t n, const int32_t* crow, const int32_t* co
   return FEMB_OK;
 }
 
-// Stream capture is illegal on the legacy default stream (torch's default current stream), so the solve runs on a private
-// non-blocking stream that is ordered after the caller's stream by an event; the call blocks until the solve is done.
-static cudaStream_t solver_stream(cudaStream_t user) {
-  static thread_local cudaStream_t s = nullptr;
-  static thread_local cudaEvent_t ev = nullptr;
-  if (!s) {
-    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-  }
-  cudaEventRecord(ev, user);
-  cudaStreamWaitEvent(s, ev, 0);
-  return s;
-}
-
 struct CsrRef {
   long long nnz;  // scalar nonzeros, or 3x3 blocks when block == 3
   const int *crow, *col;
@@ -595,8 +594,9 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   FEMB_CHECK_ARG(n > 0 && nmat >= 1 && nmat <= 8 && F && u && work && result_host, "null pointer / n <= 0 / nmat not in 1..8");
   if (check_every < 1) check_every = 16;
   spmv_apply_env_once();
-  cudaStream_t s = solver_stream(as_stream(stream));
-  FEMB_CHECK_ARG(s != nullptr, "could not create the solver stream");
+  SolveCtx* ctx = solve_ctx(as_stream(stream));  // private capture-capable stream of the current device, ordered after the caller's
+  if (!ctx) return FEMB_ERR_CUDA;
+  cudaStream_t s = ctx->stream;
   const int guards = minv ? 0 : 1;  // the reference's PCG loop carries no guards and no eps (solver.py:795-810)
   if (minv) eps = 0.0;
   double *r = work, *p = work + n, *Ap = work + 2 * n;
@@ -634,9 +634,15 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
     const int last = nmat - 1;
     nnz_hint = mats[last].nnz;
     if (merged) {
+      // PDL pair: only when the loop is exactly [TMA SpMV, merged vector kernel] (one matrix); the first SpMV of the graph
+      // depends on the previous graph launch the ordinary way
+      const bool pdl = pdl_enabled() && nmat == 1 && lanes[last] >= 100 && lanes[last] < 200;
+      pdl_hint = pdl && k > 0;
+      pin_hint = pdl ? spmv_pin_entries(mats[last].nnz) : 0;
       launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
                         guards | (last ? 2 : 0), r, tol);
-      cg_merged_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, r, p, Ap, partial, st, max_iter);
+      pdl_hint = false, pin_hint = 0;
+      launch_pdl(cg_merged_kernel, g2, VEC_THREADS, 0, s, pdl, n, u, r, p, Ap, partial, st, max_iter, tol);
     } else {
       launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
                         guards | (last ? 2 : 0));
@@ -652,15 +658,10 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   FEMB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
   // Host polling is pipelined one graph deep: graph l+1 is already queued while the stop flag of graph l travels back
   // (kernels after the stop are no-ops), so the GPU never idles on the host round trip.
-  static thread_local CGState* hst = nullptr;  // [2] pinned
-  static thread_local cudaEvent_t ev[2] = {nullptr, nullptr}, tev[2] = {nullptr, nullptr};
-  if (!hst) {
-    FEMB_CUDA(cudaMallocHost(&hst, 2 * sizeof(CGState)));
-    for (int k = 0; k < 2; ++k) {
-      FEMB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
-      FEMB_CUDA(cudaEventCreate(&tev[k]));
-    }
-  }
+  static_assert(2 * sizeof(CGState) <= SOLVE_PINNED_BYTES, "pinned status buffer");
+  CGState* hst = static_cast<CGState*>(ctx->pinned);  // [2] pinned
+  cudaEvent_t* ev = ctx->poll_ev;
+  cudaEvent_t* tev = ctx->time_ev;
   int rc = FEMB_OK;
   const int launches = (max_iter + check_every - 1) / check_every;
   hst[0].stop = hst[1].stop = 0;

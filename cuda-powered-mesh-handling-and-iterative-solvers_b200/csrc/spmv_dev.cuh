@@ -154,6 +154,15 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsign
                "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
+// L2 residency of the matrix head: when the operator is only a few times larger than the 126 MB L2 (the per-rank block of a
+// strong-scaled solve), the first `pin` bytes of val/col are staged with an evict_last policy and so survive from one SpMV
+// to the next, while the rest keeps streaming evict_first; those tiles then cost no HBM traffic.  At 1 GPU on the 64 M-tet
+// operator (1.9 GB) the pinned share is 3 % and changes nothing; at 8 GPUs (241 MB per rank) it is a quarter of the stream.
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 static __device__ int g_spmv_l2_hint = 1;  // per translation unit; FEMB_SPMV_L2HINT=0 switches the hint off (A/B runs)
 static inline void spmv_apply_env_once() {  // call outside stream capture, before the first launch
   static thread_local int done_for = -1;
@@ -165,17 +174,59 @@ static inline void spmv_apply_env_once() {  // call outside stream capture, befo
     cudaMemcpyToSymbol(g_spmv_l2_hint, &v, sizeof(int));
   }
 }
+// nonzeros (from the start of val/col) to keep L2-resident across SpMVs of one solve: FEMB_SPMV_PIN_MB overrides the rule
+inline long long spmv_pin_entries(long long nnz) {
+  static const double env_mb = getenv("FEMB_SPMV_PIN_MB") ? atof(getenv("FEMB_SPMV_PIN_MB")) : -1.0;
+  const double bytes = 12.0 * (double)nnz;
+  double pin_mb = env_mb;
+  if (pin_mb < 0.0) pin_mb = bytes <= 600e6 ? 48.0 : 0.0;  // only when the operator is within ~5x of L2
+  return (long long)std::min(bytes, pin_mb * 1e6) / 12;
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// Both kernels of a CG iteration are launched with cudaLaunchAttributeProgrammaticStreamSerialization inside the graph:
+// a kernel signals `launch_dependents` as soon as it starts, so the next kernel's CTAs become resident while this one
+// drains, run their prologue (barrier init, first TMA stages of the read-only matrix) and park in `griddepcontrol.wait`
+// until this grid has completed and flushed.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+struct PdlWait {
+  __device__ __forceinline__ void operator()() const { pdl_wait(); }
+};
+struct NoDep {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((unsigned)block), cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+inline bool pdl_enabled() {
+  static const bool on = getenv("FEMB_NO_PDL") == nullptr;
+  return on;
+}
 
 constexpr int TMA_THREADS = 128, TMA_STAGES = 2, TMA_CAP = 2304, TMA_CTAS_PER_SM = 4;
 constexpr size_t TMA_SMEM = (size_t)TMA_STAGES * TMA_CAP * 12;
 
 // Needs TMA_SMEM bytes of dynamic shared memory and blockDim.x == THREADS.  Returns this thread's partial of y.x (fused).
-template <int LR, bool NC, int THREADS = TMA_THREADS, int STAGES = TMA_STAGES, int CAP = TMA_CAP, typename Wait = NoHaloWait>
+// `dep` runs once after the first stages are in flight and before anything but the (read-only) matrix is touched: the PDL
+// wait of graph-captured loops.  `stop` (read after dep) aborts the tile loop: the staged copies are drained first, a CTA must
+// not exit with bulk copies still landing in its shared memory.  `pin` = leading nonzeros staged evict_last (see above).
+template <int LR, bool NC, int THREADS = TMA_THREADS, int STAGES = TMA_STAGES, int CAP = TMA_CAP, typename Wait = NoHaloWait,
+          typename Dep = NoDep>
 __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, const int* __restrict__ crow, const int* __restrict__ col,
                                                 const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
                                                 const unsigned char* __restrict__ mask, bool accumulate, bool fused,
                                                 long long halo_row = 0x7fffffffffffffffll, Wait wait = Wait(),
-                                                const double* __restrict__ rvec = nullptr, double* extra = nullptr) {
+                                                const double* __restrict__ rvec = nullptr, double* extra = nullptr, Dep dep = Dep(),
+                                                const int* stop = nullptr, long long pin = 0) {
   // rvec/extra (merged-reduction CG): extra[0] += y_r * rvec_r, extra[1] += y_r * y_r for the rows this thread finishes
   constexpr int R = THREADS / LR;
   extern __shared__ __align__(128) unsigned char tma_smem[];
@@ -186,7 +237,7 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
   const int tid = threadIdx.x, sub = tid % LR, lr = tid / LR;
   const long long ntiles = (n + R - 1) / R;
   const bool use_hint = g_spmv_l2_hint != 0;
-  const unsigned long long pol = l2_evict_first_policy();
+  const unsigned long long pol = l2_evict_first_policy(), pol_keep = l2_evict_last_policy();
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,8 +262,9 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&full[s], (unsigned)cnt * 12u);
     if (use_hint) {
-      bulk_g2s_hint(vbuf + (size_t)s * CAP, val + a0, (unsigned)cnt * 8u, &full[s], pol);
-      bulk_g2s_hint(cbuf + (size_t)s * CAP, col + a0, (unsigned)cnt * 4u, &full[s], pol);
+      const unsigned long long pl = (long long)a0 + cnt <= pin ? pol_keep : pol;
+      bulk_g2s_hint(vbuf + (size_t)s * CAP, val + a0, (unsigned)cnt * 8u, &full[s], pl);
+      bulk_g2s_hint(cbuf + (size_t)s * CAP, col + a0, (unsigned)cnt * 4u, &full[s], pl);
     } else {
       bulk_g2s(vbuf + (size_t)s * CAP, val + a0, (unsigned)cnt * 8u, &full[s]);
       bulk_g2s(cbuf + (size_t)s * CAP, col + a0, (unsigned)cnt * 4u, &full[s]);
@@ -229,6 +281,17 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
   double dot = 0.0;
   unsigned phase_bits = 0;  // parity per stage
   bool waited = false;
+  dep();  // everything above touched only crow/col/val; x, y, rvec, mask-independent state below may come from the previous kernel
+  if (stop) {  // sticky stop flag (block-uniform through shared memory): drain what was staged, then leave
+    __shared__ int stop_sh;
+    if (tid == 0) stop_sh = *(volatile const int*)stop;
+    __syncthreads();
+    if (stop_sh) {
+      for (int k = 0; k < STAGES - 1; ++k)
+        if (blockIdx.x + (long long)k * gridDim.x < ntiles && base[k % STAGES] >= 0) mbar_wait(&full[k % STAGES], 0u);
+      return 0.0;
+    }
+  }
   for (long long k = 0;; ++k) {
     const long long t = blockIdx.x + k * gridDim.x;
     if (t >= ntiles) break;

@@ -124,6 +124,50 @@ def setup_poisson_p1(coords, elements, rank, world, dev):
     return part, plan, DistOperator(part, crow, col, val, dev), cl
 
 
+def parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N, rel_tol=1e-11, max_iter=20000):
+    """Solve K u = f (f = 1 lumped, z = 0 Dirichlet) to |r| < rel_tol |f| on `world` GPUs, then the same problem on ONE GPU
+    (rank 0 assembles the global operator and runs the single-GPU loop), and compare: iterations within +-1, u within 1e-8
+    relative (north-star tolerances).  Returns the dict printed as `parity` in the bench line."""
+    import element as el
+    no = part.n_owned
+    vol = torch.zeros(part.n_local, dtype=torch.float64, device=dev)
+    v = el.compute_tetrahedral_volumes(cl, part.elements_local, device=dev, dtype=torch.float64) / 4
+    vol.index_add_(0, part.elements_local.reshape(-1), v.repeat_interleave(4))   # ghost elements included: owned entries are complete
+    Fp = (vol[:no] * mask).contiguous()
+    nf = (Fp * Fp).sum()
+    dist.all_reduce(nf)
+    tol = rel_tol * float(nf.sqrt().item())
+    uN, infoN = op.solve(Fp, mask, tol=tol, max_iter=max_iter, check_every=50)
+    full = torch.zeros(N, dtype=torch.float64, device=dev)
+    full[part.owned_global] = uN
+    Ffull = torch.zeros(N, dtype=torch.float64, device=dev)
+    Ffull[part.owned_global] = Fp
+    dist.all_reduce(full)
+    dist.all_reduce(Ffull)
+    out = None
+    if rank == 0:
+        from . import meshgen
+        n = round(N ** (1.0 / 3.0)) - 1
+        _, tets = meshgen.kuhn_cube(n, device=dev)
+        gplan = ops.CsrPlan(tets, N, dev)
+        crow, col = gplan.pattern(1)
+        vals = gplan.assemble_c3d4(coords, "poisson")
+        gmask = (coords[:, 2] != 0).to(torch.uint8).contiguous()
+        u1, info1 = ops.cg_solve(crow, col, vals, Ffull, mask=gmask, tol=tol, max_iter=max_iter, check_every=50)
+        # true residual of the N-GPU solution on the 1-GPU operator
+        res = (Ffull - ops.spmv(crow, col, vals, full)) * gmask
+        err = float((full - u1).abs().max() / u1.abs().max())
+        out = {"problem": f"K u = f, f = 1 lumped, z = 0 fixed, |r| < {rel_tol:g} |f| (abs tol {tol:.3e})",
+               "iterations_N": infoN["iterations"], "iterations_1gpu": info1["iterations"], "status_N": infoN["status"],
+               "status_1gpu": info1["status"], "rel_err_u": err, "rs_N": infoN["rs"], "rs_1gpu": info1["rs"],
+               "true_residual_N_over_f": float(res.norm() / Ffull.norm()), "u_max": float(u1.max()),
+               "ok": bool(infoN["status"] == "converged" and info1["status"] == "converged"
+                          and abs(infoN["iterations"] - info1["iterations"]) <= 1 and err < 1e-8)}
+        del gplan, crow, col, vals, tets
+    dist.barrier()
+    return out
+
+
 def bench(args, dev, rank, world, metric, unit):
     """bench.py's N>1 arm: strong scaling of the 64M-tet Poisson CG (BASELINE config 4)."""
     import json
@@ -131,7 +175,7 @@ def bench(args, dev, rank, world, metric, unit):
     import sys
     from . import meshgen
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-    from bench import ClockSampler, peaks
+    from bench import ClockSampler, peaks, workload_config
 
     n, K, W = args.n, args.steps, max(args.warmup, 3)
     sampler = ClockSampler(dev.index or 0)   # started first (nvidia-smi needs ~1 s on an 8-GPU box); stopped after a load soak
@@ -167,6 +211,26 @@ def bench(args, dev, rank, world, metric, unit):
     for _ in range(4):                         # untimed: the same loop again so the clock sampler sees >= 0.5 s of this load
         op.solve(F, mask, tol=0.0, max_iter=1500, check_every=100)
     clocks = sampler.stop()
+    # ---- the other half of the metric: assembled elements/s, aggregate (every rank assembles its own rows; elements that touch
+    # rows of several ranks are recomputed by each of them, so the job's rate is global elements / slowest rank)
+    val = torch.empty(plan.nnz_nodes, dtype=torch.float64, device=dev)   # all local rows (owned + the partial ghost rows)
+    for _ in range(3):
+        plan.assemble_c3d4(cl, "poisson", out=val, check_singular=False)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a0.record()
+    for _ in range(5):
+        plan.assemble_c3d4(cl, "poisson", out=val, check_singular=False)
+    a1.record()
+    torch.cuda.synchronize()
+    ms_asm = torch.tensor([a0.elapsed_time(a1) / 5], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms_asm, op=dist.ReduceOp.MAX)
+    m_loc = torch.tensor([part.elements_local.shape[0]], dtype=torch.float64, device=dev)
+    m_sum = m_loc.clone()
+    dist.all_reduce(m_sum)
+    # ---- parity, driver-visible: a fixed-tolerance solve on N GPUs against the same solve on ONE GPU (rank 0, global operator)
+    parity = parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N)
     nnz_tot = torch.tensor([op.nnz], dtype=torch.float64, device=dev)
     dist.all_reduce(nnz_tot)
     halo = torch.tensor([op.halo_bytes], dtype=torch.float64, device=dev)
@@ -180,11 +244,17 @@ def bench(args, dev, rank, world, metric, unit):
             "metric": metric, "value": round(K / (ms_loop * 1e-3), 2), "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(ms_loop / K, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"P1 tet Poisson, Kuhn cube n={n}: {M} C3D4 tets, {N} nodes, CSR nnz {nnz} (BASELINE config 4); "
-                                   "step = one CG iteration of the reference loop", "index_dtype": "int32 CSR / int64 API connectivity",
-                       "l2": "total CSR operator %.2f GB over %d GPUs" % (nnz * 12 / 1e9, world), "tol": 0.0,
-                       "partition": f"RCB on node coordinates, {world} parts, halo exchange + all-reduce over NVLink peer memory (no NCCL in the loop)",
-                       "max_halo_bytes_per_rank": int(halo.item()), "setup_s": round(t_setup, 2)},
+            "config": workload_config(n, M, N, nnz),
+            "impl_details": {"index_dtype": "int32 CSR / int64 API connectivity",
+                             "partition": f"RCB on node coordinates, {world} parts, halo exchange + all-reduce over NVLink peer memory (no NCCL in the loop)",
+                             "max_halo_bytes_per_rank": int(halo.item()), "setup_s": round(t_setup, 2),
+                             "l2_per_rank": "CSR operator %.0f MB per rank vs 126 MB L2; the leading 48 MB are staged evict_last" % (nnz * 12 / 1e6 / world)},
+            "parity": parity,
+            "assembly": {"metric": "assembled_elems_per_s", "value": round(M / (float(ms_asm.item()) * 1e-3), 1), "ms": round(float(ms_asm.item()), 3),
+                         "what": "fused coords -> CSR values of each rank's own rows, max over ranks; aggregate = global elements / that time",
+                         "elements_assembled_all_ranks": int(m_sum.item()), "redundancy": round(float(m_sum.item()) / M, 4),
+                         "algorithmic_bytes": M * 32 + N * 24 + nnz * 8,
+                         "frac": round((M * 32 + N * 24 + nnz * 8) / (float(ms_asm.item()) * 1e-3) / 1e9 / (hbm * world), 4)},
             "clocks": clocks,
             "e2e": {"value": round(K / (float(ms2.item()) * 1e-3), 2), "unit": unit, "h2d_bytes_per_step": int(N * 8 / K),
                     "d2h_bytes_per_step": int(N * 8 / K),

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -417,9 +418,17 @@ class CsrPlan:
         self.n_nodes = int(n_nodes) if n_nodes is not None else (int(conn.max().item()) + 1 if self.M else 1)
         h, nnz = C.c_void_p(), C.c_int64()
         with torch.cuda.device(self.dev):
-            check(lib.femb_csr_plan_create(_p(conn), _fp(conn), self.M, self.nen, self.n_nodes, _stream(self.dev), C.byref(h), C.byref(nnz)),
-                  "femb_csr_plan_create")
+            try:
+                check(lib.femb_csr_plan_create(_p(conn), _fp(conn), self.M, self.nen, self.n_nodes, _stream(self.dev), C.byref(h), C.byref(nnz)),
+                      "femb_csr_plan_create")
+            except _lib.FembError as exc:
+                if "outside [0, n_nodes)" in str(exc):   # the reference's gathers raise an index error for such connectivity
+                    raise IndexError(f"connectivity holds a node index outside [0, {self.n_nodes})") from exc
+                raise
         self.handle, self.nnz_nodes = h, nnz.value
+        # device bytes held by the plan (conn32, incidences, slot table, pattern, P1 records once built): bounds the plan cache
+        L = self.M * self.nen
+        self.nbytes = L * (8 + self.nen) + 8 * (self.n_nodes + 1) + 4 * self.nnz_nodes + (20 * L if self.nen == 4 else 0)
         self._fin = weakref.finalize(self, lib.femb_csr_plan_destroy, h)
         self._patterns = {}
 
@@ -487,19 +496,25 @@ class CsrPlan:
 
 
 _PLAN_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+PLAN_CACHE_BYTES = int(float(os.environ.get("FEMB_PLAN_CACHE_GB", "16")) * 2 ** 30)   # a 64 M-tet plan holds ~8 GB of HBM
 
 
 def cached_plan(elements, n_nodes, device) -> CsrPlan:
-    """Plans are keyed on the connectivity tensor's identity/version so that repeated operator applications on
-    the same mesh (every CG iteration of the reference calls compute_nodal_forces) reuse one plan."""
-    e = torch.as_tensor(elements)
-    key = (e.data_ptr(), tuple(e.shape), e.dtype, e._version, str(e.device), int(n_nodes), str(device))
+    """Plans are cached per connectivity TENSOR (object identity + in-place version counter) so that repeated operator
+    applications on the same mesh (every CG iteration of the reference calls compute_nodal_forces) reuse one plan.
+    Only torch tensors handed in by the caller are cached: numpy arrays / lists have no version counter, so an in-place
+    renumbering would silently reuse a stale plan -- they get a fresh plan per call.  The cache is bounded by the device
+    bytes the plans hold (FEMB_PLAN_CACHE_GB, default 16), least recently used first, and by 8 entries."""
+    if not torch.is_tensor(elements):
+        return CsrPlan(torch.as_tensor(elements).clone(), n_nodes, device)
+    e = elements
+    key = (id(e), e.data_ptr(), tuple(e.shape), e.dtype, e._version, str(e.device), int(n_nodes), str(device))
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         plan = CsrPlan(e, n_nodes, device)
-        plan._keepalive = e   # keeps data_ptr from being recycled while cached
+        plan._keepalive = e   # keeps id() / data_ptr from being recycled while cached
         _PLAN_CACHE[key] = plan
-        while len(_PLAN_CACHE) > 8:
+        while len(_PLAN_CACHE) > 1 and (len(_PLAN_CACHE) > 8 or sum(p.nbytes for p in _PLAN_CACHE.values()) > PLAN_CACHE_BYTES):
             _PLAN_CACHE.popitem(last=False)
     else:
         _PLAN_CACHE.move_to_end(key)

@@ -29,7 +29,9 @@ from femb200 import ops as _ops  # noqa: E402
 def _dof_mask(n_nodes, ndof, fixed, dev):
     mask = torch.ones((n_nodes, ndof), device=dev, dtype=torch.uint8)
     if fixed is not None and torch.as_tensor(fixed).numel():
-        mask[torch.as_tensor(fixed).to(dev).long()] = 0
+        f = torch.as_tensor(fixed).to(dev)
+        # u[rbe2] = 0 in the reference (solver.py:161) accepts an index list or a boolean node mask
+        mask[f if f.dtype == torch.bool else f.long()] = 0
     return mask.reshape(-1).contiguous()
 
 

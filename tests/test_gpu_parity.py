@@ -369,8 +369,16 @@ def test_shell_cg(api):
     K = sh.compute_s3_K_matrix(c3, s3, MB, MB, **KW)
     u, info = sv.stable_conjugate_gradient_shell_solver(K, s3, T(g["F"]), T(g["fixed"]), coords=c3, tol=1e-9, max_iter=3000,
                                                         return_info=True, **KW)
+    # Why this is looser than the solid CG tests (+-1 iteration, 1e-8): the reference's S3 element matrix has identically zero
+    # rows and columns for w and theta_z (shell.py:404-438: membrane rows act on u, v; bending rows on theta_x, theta_y), so the
+    # rotated global operator is singular on every flat patch.  CG on a semi-definite system has no unique iterate: the
+    # component of u in the null space is whatever rounding leaves there, and the iteration at which |r| first dips below tol
+    # moves with the summation order (the reference itself gives 25 iterations more or less between torch builds / thread
+    # counts).  What IS pinned: the same stopping test is met, the residual of the returned u really is below tol, and the
+    # solution agrees with the reference to 1e-6 of its largest entry.
     assert info["status"] == "converged" and abs(info["iterations"] - int(g["it"])) <= 25
     close(u, g["u"], 1e-6)
+    assert info["rs"] ** 0.5 < 1e-9
 
 
 def test_kuhn20_known_counts_and_cg(api, O):
@@ -468,6 +476,51 @@ def test_hybrid_cascade(api, O):
     assert st == "converged" and rel_err(N(u), uo) <= 1e-8
 
 
+def _sampled_rows_vs_oracle(O, coords, conn, crow, col, vals, ndof, Ke_fn, nsample, seed, tol=1e-12):
+    """Oracle check at full size: CSR rows of `nsample` random nodes.  The elements touching the sampled nodes are pulled to
+    the host, their matrices come from the oracle (`Ke_fn(coords_np, conn_np)`), the sampled rows are accumulated in numpy
+    and compared with the device rows: columns bit-exact, values within `tol` of the row's largest entry."""
+    Nn = coords.shape[0]
+    g = torch.Generator().manual_seed(seed)
+    nodes = torch.unique(torch.randint(0, Nn, (nsample,), generator=g)).to(conn.device)
+    sel = torch.isin(conn, nodes).any(dim=1)
+    eids = torch.nonzero(sel).reshape(-1)
+    sub = conn[eids]
+    used, inv = torch.unique(sub, return_inverse=True)
+    cs, es, gl = N(coords[used]), N(inv), N(used)
+    Ke = Ke_fn(cs, es)                                                # oracle element matrices on the sub-mesh
+    nen = es.shape[1]
+    node_set = set(N(nodes).tolist())
+    crow_h, rows_dev = None, []
+    # rows of the sampled nodes from the device CSR
+    r_idx = (nodes.reshape(-1, 1) * ndof + torch.arange(ndof, device=nodes.device)).reshape(-1)
+    lo, hi = crow[r_idx.long()].long(), crow[r_idx.long() + 1].long()
+    worst = 0.0
+    acc = {}
+    for e in range(es.shape[0]):                                      # python loop: ~24 incidences per sampled node
+        ge = gl[es[e]]
+        for a in range(nen):
+            if int(ge[a]) not in node_set:
+                continue
+            for al in range(ndof):
+                row = acc.setdefault(int(ge[a]) * ndof + al, {})
+                kr = Ke[e, a * ndof + al]
+                for b in range(nen):
+                    for be in range(ndof):
+                        c = int(ge[b]) * ndof + be
+                        row[c] = row.get(c, 0.0) + float(kr[b * ndof + be])
+    lo_h, hi_h, r_h = N(lo), N(hi), N(r_idx)
+    for k in range(r_h.shape[0]):
+        cols = N(col[lo_h[k]:hi_h[k]])
+        v = N(vals[lo_h[k]:hi_h[k]])
+        ref = acc[int(r_h[k])]
+        assert cols.tolist() == sorted(ref), (int(r_h[k]), cols.tolist(), sorted(ref))      # pattern bit-exact (explicit zeros kept)
+        rv = np.array([ref[c] for c in cols.tolist()])
+        worst = max(worst, float(np.abs(v - rv).max() / np.abs(rv).max()))
+    assert worst <= tol, worst
+    return int(nodes.numel()), int(eids.numel()), worst
+
+
 def test_full_size_properties_c4():
     """BASELINE config 4 at full size (Kuhn n=220, 63.9 M tets, 10.8 M nodes) through size-independent properties:
     known counts, 2S+K=4M, Laplace null space, symmetry of the assembled operator, bit-reproducible assembly, and the
@@ -501,8 +554,16 @@ def test_full_size_properties_c4():
     assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), 1.0)              # symmetric operator
     Ke = el.compute_c3d4_poisson_K_matrix(c, t, **KW)
     v3 = plan.assemble(Ke, 1)
+    # oracle values at full size (node ids >= 2^23 included): 10 k random element matrices and the CSR rows of 2 k random nodes
+    from oracle import fem_oracle as O
+    ids = torch.randint(0, M, (10_000,), generator=torch.Generator().manual_seed(5)).to(DEV)
+    used, inv = torch.unique(t[ids], return_inverse=True)
+    Ko = O.c3d4_poisson_K(N(c[used]), N(inv))
+    assert float(np.abs(N(Ke[ids]) - Ko).max()) <= 1e-12 * float(np.abs(Ko).max())
     del Ke
     assert float((v3 - v1).abs().max()) <= 1e-12 * float(v1.abs().max())
+    nn, ne, worst = _sampled_rows_vs_oracle(O, c, t, crow, col, v1, 1, O.c3d4_poisson_K, 2000, seed=6)
+    assert nn > 1900 and ne > 20 * nn * 0.9
     # 100 CG iterations reduce the residual and keep fixed rows at zero
     mask = (c[:, 2] != 0).to(torch.uint8).contiguous()
     F = torch.full((Nn, 1), 1.0 / Nn, dtype=torch.float64, device=DEV)
@@ -536,6 +597,14 @@ def test_full_size_properties_c2():
     x = torch.randn(c.shape[0], 3, dtype=torch.float64, device=DEV, generator=torch.Generator(DEV).manual_seed(2))
     y1, y2 = ops.spmv(crow, col, vals, x), el.compute_nodal_forces(K, e10, x, **KW)
     assert float((y1 - y2).abs().max()) <= 1e-12 * float(y2.abs().max())
+    # oracle values at full size: 10 k random element matrices (reference rule, element.py:1191-1239) and the CSR rows of 500 random nodes
+    from oracle import fem_oracle as O
+    ids = torch.randint(0, K.shape[0], (10_000,), generator=torch.Generator().manual_seed(7)).to(DEV)
+    used, inv = torch.unique(e10[ids], return_inverse=True)
+    Ko = O.c3d10_K(N(c[used]), N(inv), E, NU)
+    assert float(np.abs(N(K[ids]) - Ko).max()) <= 1e-12 * float(np.abs(Ko).max())
+    nn, ne, worst = _sampled_rows_vs_oracle(O, c, e10, crow, col, vals, 3, lambda cs, es: O.c3d10_K(cs, es, E, NU), 500, seed=8)
+    assert nn > 450
 
 
 def test_edge_cases_topology_and_assembly(api, O):
@@ -845,3 +914,95 @@ def test_region_growing_partition(api, O):
     e2 = torch.tensor([[0, 2], [1, 3]])
     gr, _ = sd.region_growing_partition(e2, 1, 4, device=DEV, first_seed=0)
     assert N(gr[0]).tolist() == [0, 1]
+
+
+def test_plan_rejects_out_of_range_connectivity(api):
+    """A node index outside [0, n_nodes) raises like the reference's gathers do (IndexError), instead of corrupting the plan."""
+    el = api[0]
+    t = torch.tensor([[0, 1, 2, 3], [1, 2, 3, 7]])
+    with pytest.raises(IndexError):
+        el.CsrPlan(t, 5, DEV)
+    with pytest.raises(IndexError):
+        el.CsrPlan(torch.tensor([[0, 1, 2, -1]]), 5, DEV)
+    assert el.CsrPlan(t, 8, DEV).nnz_nodes > 0
+
+
+def test_cg_exact_convergence_test_on_small_systems(api, O):
+    """The merged-reduction loop takes beta from the recurrence r.r - 2 alpha r.Ap + alpha^2 Ap.Ap, but decides convergence on
+    the exactly summed r.r (reference solver.py:208-212).  On tiny systems CG terminates in a handful of steps with a
+    residual drop of many orders in ONE step -- where the recurrence value is pure cancellation noise.  Large load magnitudes
+    make the absolute error of the recurrence exceed tol^2."""
+    el, _, sv = api
+    from femb200 import ops
+    for n, scale, tol in ((1, 1.0, 1e-10), (2, 1e6, 1e-6), (2, 1e8, 1e-4), (3, 1e3, 1e-9)):
+        from femb200 import meshgen
+        c, t = meshgen.kuhn_cube(n, jitter=0.1 if n > 1 else 0.0)
+        plan = el.CsrPlan(t, c.shape[0], DEV)
+        crow, col = plan.pattern(1)
+        vals = plan.assemble_c3d4(c, "poisson")
+        mask = (c[:, 2] != 0).to(torch.uint8).to(DEV)
+        F = (torch.arange(c.shape[0], dtype=torch.float64).reshape(-1, 1) + 1.0) * scale
+        u, info = ops.cg_solve(crow, col, vals, F.to(DEV), mask=mask, tol=tol, max_iter=200, check_every=4)
+        assert info["status"] == "converged", (n, scale, info)
+        r = (F.to(DEV).reshape(-1) - ops.spmv(crow, col, vals, u.reshape(-1))) * mask
+        true_norm = float(r.norm())
+        # the reported rs is the exactly summed r.r of the returned iterate (recomputed here with a different summation order)
+        assert true_norm < tol * (1 + 1e-6) and abs(info["rs"] ** 0.5 - true_norm) <= 1e-6 * max(true_norm, 1e-300) + 1e-12 * scale, (n, scale, info, true_norm)
+        Kp = O.c3d4_poisson_K(N(c), N(t))
+        ou, oit, ost = O.stable_cg(Kp, N(t), N(F), np.flatnonzero(N(c)[:, 2] == 0), tol=tol, max_iter=200, ndof=1)
+        assert ost == "converged" and abs(info["iterations"] - oit) <= 1, (n, scale, info, oit)
+
+
+def test_boolean_fixed_node_mask(api):
+    """`u[rbe2] = 0` in the reference accepts a boolean node mask as well as an index list (solver.py:161)."""
+    el, _, sv = api
+    from femb200 import meshgen
+    c, t = meshgen.kuhn_cube(3, jitter=0.1)
+    K = el.compute_c3d4_K_matrix(c, t, E, NU, **KW)
+    F = torch.zeros(c.shape[0], 3, dtype=torch.float64)
+    F[c[:, 2] == 1, 2] = 0.1
+    fixed_idx = torch.nonzero(c[:, 2] == 0).reshape(-1)
+    u1, i1 = sv.stable_conjugate_gradient_solver(K, t, F, fixed_idx, tol=1e-9, return_info=True, verbose=False, **KW)
+    u2, i2 = sv.stable_conjugate_gradient_solver(K, t, F, c[:, 2] == 0, tol=1e-9, return_info=True, verbose=False, **KW)
+    assert i1["iterations"] == i2["iterations"] and torch.equal(u1, u2)
+
+
+def test_numpy_connectivity_is_not_cached(api):
+    """cached_plan keys torch tensors on identity + version; numpy connectivity edited in place must not reuse a stale plan."""
+    el = api[0]
+    from femb200 import meshgen, ops
+    c, t = meshgen.kuhn_cube(2)
+    tn = N(t).copy()
+    K = el.compute_c3d4_K_matrix(c, t, E, NU, **KW)
+    x = torch.randn(c.shape[0], 3, dtype=torch.float64)
+    y1 = el.compute_nodal_forces(K, tn, x, **KW)
+    perm = np.random.default_rng(0).permutation(c.shape[0])
+    tn[:] = perm[tn]                                   # in-place renumbering of the ndarray
+    y2 = el.compute_nodal_forces(K, tn, x, **KW)
+    inv = np.argsort(perm)
+    y2_expected = el.compute_nodal_forces(K, torch.as_tensor(tn.copy()), x, **KW)
+    assert torch.equal(y2, y2_expected) and not torch.equal(y1, y2)
+    tt = t.clone()
+    p1 = ops.cached_plan(tt, c.shape[0], DEV)
+    assert ops.cached_plan(tt, c.shape[0], DEV) is p1
+    tt[0, 0] = tt[0, 0]                                # bumps the version counter
+    assert ops.cached_plan(tt, c.shape[0], DEV) is not p1
+
+
+def test_solves_on_two_devices_in_one_thread(api):
+    """Streams / events / pinned status of the graph-captured solves are per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    el, _, sv = api
+    from femb200 import meshgen
+    c, t = meshgen.kuhn_cube(4, jitter=0.1)
+    F = torch.zeros(c.shape[0], 3, dtype=torch.float64)
+    F[c[:, 2] == 1, 2] = 0.1
+    fixed = torch.nonzero(c[:, 2] == 0).reshape(-1)
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        K = el.compute_c3d4_K_matrix(c, t, E, NU, device=dev, dtype=torch.float64)
+        u, info = sv.stable_conjugate_gradient_solver(K, t, F, fixed, tol=1e-9, device=dev, return_info=True, verbose=False)
+        assert info["status"] == "converged" and str(u.device) == dev
+        outs.append(u.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
