@@ -469,7 +469,9 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
         }
       }
     }
-    __threadfence_system();
+    // peer stores must be performed before this CTA's ticket (the halo flag follows the last ticket); CTAs whose threads all
+    // lie beyond the boundary rows stored nothing remotely and skip the system-scope fence
+    if (blockIdx.x * (long long)blockDim.x < n - bp.n_interior) __threadfence_system();
   }
   for (long long i = gtid; i < n_plain; i += gsz) {
     const double pi = p[i], ri = r[i] - alpha * Ap[i];
@@ -976,7 +978,7 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   const bool pdl = pdl_enabled() && !classic;
   const long long pin = classic ? 0 : spmv_pin_entries(nnz);
   // with PDL the next SpMV's CTAs (4 x 128 threads per SM) become resident beside the vector kernel: leave them room
-  static const int vec_waves = getenv("FEMB_DIST_VEC_WAVES") ? atoi(getenv("FEMB_DIST_VEC_WAVES")) : 6;
+  static const int vec_waves = getenv("FEMB_DIST_VEC_WAVES") ? atoi(getenv("FEMB_DIST_VEC_WAVES")) : 8;
   const int g2m = pdl ? grid_for(n, DV_THREADS, vec_waves) : g2;
   for (int k = 0; k < check_every; ++k) {
     if (!folded && nnbr > 0) dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
@@ -985,8 +987,8 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
       dist_update_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, eps, guards);
       dist_direction_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, r, st, tol, eps, guards, max_iter, bp);
     } else {
-      launch_dist_spmv3(lr, g1, s, pdl && k > 0, pe, n, nnz, crow, col, val, Ap, mask, r, partial, st, n_interior, pin);
-      launch_pdl(dist_merged_vec_kernel, g2m, DV_THREADS, 0, s, pdl, pe, n, u, r, Ap, partial, st, tol, eps, guards, max_iter, bp);
+      launch_dist_spmv3(lr, g1, s, pdl && k > 0 && (pdl_mode() & 2), pe, n, nnz, crow, col, val, Ap, mask, r, partial, st, n_interior, pin);
+      launch_pdl(dist_merged_vec_kernel, g2m, DV_THREADS, 0, s, pdl && (pdl_mode() & 1), pe, n, u, r, Ap, partial, st, tol, eps, guards, max_iter, bp);
     }
   }
   cudaError_t ce = cudaStreamEndCapture(s, &graph);
@@ -1038,7 +1040,7 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   if (trace && fin->it > 20) {  // average phase times over iterations 10..min(it,TRACE_ITERS)-1 (microseconds)
     static long long h[TRACE_ITERS * 12];
     cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
-    const int i1 = std::min(fin->it, TRACE_ITERS) - 1;
+    const int i1 = std::min(fin->it, TRACE_ITERS) - 2;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 10; i < i1; ++i) {
       const long long* t = h + i * 12;
@@ -1052,13 +1054,14 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
         acc[6] += t[10] - t[9];                // k3 body
         acc[7] += (h + (i + 1) * 12)[0] - t[0];  // whole iteration
       } else {
-        const long long* tp = h + (i - 1) * 12;
-        acc[0] += t[3] - tp[10];               // SpMV: end of the previous vector kernel -> rows done on CTA 0 (launch gap included)
-        acc[1] += t[4] - t[3];                 // last CTA: reduction + LL stores to all ranks
+        // slot 10 is stamped after st->it was advanced: row i holds the END of iteration i-1's vector kernel there
+        const long long* tn = h + (i + 1) * 12;
+        acc[0] += t[3] - t[10];                // SpMV: end of the previous vector kernel -> rows done on CTA 0 (launch gap included)
+        acc[1] += t[4] - t[3];                 // SpMV tail of the other CTAs + last CTA: reduction + LL stores to all ranks
         acc[2] += t[5] - t[4];                 // gap until the vector kernel runs
         acc[3] += t[6] - t[5];                 // vector kernel: wait for the all-reduce words of every rank
-        acc[4] += t[10] - t[6];                // vector kernel body + r.r reduction + halo flag
-        acc[7] += t[10] - tp[10];              // whole iteration
+        acc[4] += tn[10] - t[6];               // vector kernel body + r.r reduction + halo flag
+        acc[7] += tn[10] - t[10];              // whole iteration
       }
     }
     const double m = 1e-3 / (i1 - 10);

@@ -612,6 +612,8 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
     gmax = std::max(gmax, g1[m]);
   }
   const int g2 = grid_for(n, VEC_THREADS, 8);
+  static const int vec_waves = getenv("FEMB_VEC_WAVES") ? atoi(getenv("FEMB_VEC_WAVES")) : 8;
+  const int g2v = grid_for(n, VEC_THREADS, vec_waves);  // merged vector kernel (A/B: room for the next SpMV's early CTAs)
   Scratch scr(s);
   double* partial;
   CGState* st;
@@ -637,12 +639,12 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
       // PDL pair: only when the loop is exactly [TMA SpMV, merged vector kernel] (one matrix); the first SpMV of the graph
       // depends on the previous graph launch the ordinary way
       const bool pdl = pdl_enabled() && nmat == 1 && lanes[last] >= 100 && lanes[last] < 200;
-      pdl_hint = pdl && k > 0;
+      pdl_hint = pdl && k > 0 && (pdl_mode() & 2);
       pin_hint = pdl ? spmv_pin_entries(mats[last].nnz) : 0;
       launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
                         guards | (last ? 2 : 0), r, tol);
       pdl_hint = false, pin_hint = 0;
-      launch_pdl(cg_merged_kernel, g2, VEC_THREADS, 0, s, pdl, n, u, r, p, Ap, partial, st, max_iter, tol);
+      launch_pdl(cg_merged_kernel, g2v, VEC_THREADS, 0, s, pdl && (pdl_mode() & 1), n, u, r, p, Ap, partial, st, max_iter, tol);
     } else {
       launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
                         guards | (last ? 2 : 0));

@@ -179,7 +179,8 @@ inline long long spmv_pin_entries(long long nnz) {
   static const double env_mb = getenv("FEMB_SPMV_PIN_MB") ? atof(getenv("FEMB_SPMV_PIN_MB")) : -1.0;
   const double bytes = 12.0 * (double)nnz;
   double pin_mb = env_mb;
-  if (pin_mb < 0.0) pin_mb = bytes <= 600e6 ? 48.0 : 0.0;  // only when the operator is within ~5x of L2
+  if (pin_mb < 0.0) pin_mb = 0.0;  // measured on the 8-GPU per-rank problem (243 MB operator): 0 / 24 / 48 / 72 / 96 MB pinned ->
+                                   // 57.9 / 58.8 / 59.8 / 62.7 / 63.2 us per CG iteration -- the pinned lines displace the vectors; off
   return (long long)std::min(bytes, pin_mb * 1e6) / 12;
 }
 
@@ -207,10 +208,16 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
   cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
-inline bool pdl_enabled() {
-  static const bool on = getenv("FEMB_NO_PDL") == nullptr;
-  return on;
+// bit 0: the vector kernel is launched programmatically behind the SpMV, bit 1: the SpMV behind the vector kernel.
+// Measured (1 GPU, us per CG iteration, 64 M-tet operator / the 8-GPU per-rank operator): mode 0 507.1 / 57.5, mode 1
+// 533.1 / 57.6 (vector CTAs parked beside the running SpMV slow it down), mode 2 503.4 / 57.3, mode 3 648.9 / 57.7.
+// Graph launch gaps are already ~1-2 us, so only mode 2 (the SpMV's barrier init and first TMA stages overlap the vector
+// kernel's tail) is kept as the default.
+inline int pdl_mode() {
+  static const int m = getenv("FEMB_NO_PDL") ? 0 : (getenv("FEMB_PDL_MODE") ? atoi(getenv("FEMB_PDL_MODE")) : 2);
+  return m;
 }
+inline bool pdl_enabled() { return pdl_mode() != 0; }
 
 constexpr int TMA_THREADS = 128, TMA_STAGES = 2, TMA_CAP = 2304, TMA_CTAS_PER_SM = 4;
 constexpr size_t TMA_SMEM = (size_t)TMA_STAGES * TMA_CAP * 12;

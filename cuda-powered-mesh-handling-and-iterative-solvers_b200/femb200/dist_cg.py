@@ -124,7 +124,7 @@ def setup_poisson_p1(coords, elements, rank, world, dev):
     return part, plan, DistOperator(part, crow, col, val, dev), cl
 
 
-def parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N, rel_tol=1e-11, max_iter=20000):
+def parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N, rel_tol=1e-10, max_iter=20000):
     """Solve K u = f (f = 1 lumped, z = 0 Dirichlet) to |r| < rel_tol |f| on `world` GPUs, then the same problem on ONE GPU
     (rank 0 assembles the global operator and runs the single-GPU loop), and compare: iterations within +-1, u within 1e-8
     relative (north-star tolerances).  Returns the dict printed as `parity` in the bench line."""
@@ -133,7 +133,7 @@ def parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N, rel_tol=
     vol = torch.zeros(part.n_local, dtype=torch.float64, device=dev)
     v = el.compute_tetrahedral_volumes(cl, part.elements_local, device=dev, dtype=torch.float64) / 4
     vol.index_add_(0, part.elements_local.reshape(-1), v.repeat_interleave(4))   # ghost elements included: owned entries are complete
-    Fp = (vol[:no] * mask).contiguous()
+    Fp = (vol[:no] * mask * float(N)).contiguous()        # f = N: entries O(1), far from the reference's absolute 1e-30 guards
     nf = (Fp * Fp).sum()
     dist.all_reduce(nf)
     tol = rel_tol * float(nf.sqrt().item())
@@ -157,7 +157,7 @@ def parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N, rel_tol=
         # true residual of the N-GPU solution on the 1-GPU operator
         res = (Ffull - ops.spmv(crow, col, vals, full)) * gmask
         err = float((full - u1).abs().max() / u1.abs().max())
-        out = {"problem": f"K u = f, f = 1 lumped, z = 0 fixed, |r| < {rel_tol:g} |f| (abs tol {tol:.3e})",
+        out = {"problem": f"K u = f, f = N lumped, z = 0 fixed, |r| < {rel_tol:g} |f| (abs tol {tol:.3e})",
                "iterations_N": infoN["iterations"], "iterations_1gpu": info1["iterations"], "status_N": infoN["status"],
                "status_1gpu": info1["status"], "rel_err_u": err, "rs_N": infoN["rs"], "rs_1gpu": info1["rs"],
                "true_residual_N_over_f": float(res.norm() / Ffull.norm()), "u_max": float(u1.max()),
