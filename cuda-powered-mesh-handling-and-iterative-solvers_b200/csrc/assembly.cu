@@ -12,22 +12,7 @@
 
 #include "common.cuh"
 
-struct femb_csr_plan {
-  long long M = 0, N = 0, nnzn = 0;
-  int nen = 0, max_row = 0, max_inc = 0;
-  int* conn32 = nullptr;    // [M,nen]
-  int* inc_ptr = nullptr;   // [N+1]
-  int* inc = nullptr;       // [M*nen] flat slot e*nen+a, grouped by node, ascending
-  int* node_ptr = nullptr;  // [N+1]
-  int* node_col = nullptr;  // [nnzn] sorted within a row
-  unsigned char* inc_slots = nullptr;  // [M*nen*nen] position of conn[e][b] in the row of the incidence's node (max_row <= 255)
-  // P1 fused-assembly acceleration structure (built lazily): per tile of 32 consecutive rows, step-major records
-  // rec[tile_ptr[t]*32 + step*32 + lane] = {other node 1, 2, 3, their three row slots packed in bytes}; x = -1 pads
-  int4* rec = nullptr;
-  int* tile_ptr = nullptr;          // [ntiles+1] in steps
-  unsigned char* pdiag = nullptr;   // [N] slot of the diagonal entry
-  long long ntiles = 0, total_steps = 0;
-};
+#include "plan.cuh"
 
 namespace femb {
 
@@ -763,6 +748,7 @@ static void plan_free(femb_csr_plan* p) {
   cudaFree(p->rec);
   cudaFree(p->tile_ptr);
   cudaFree(p->pdiag);
+  femb::block_plan_free(p->blk);
   delete p;
 }
 
@@ -977,6 +963,18 @@ extern "C" int femb_csr_assemble_c3d4(femb_csr_plan* p, int kind, const double* 
   cudaStream_t s = as_stream(stream);
   const int grid = grid_for(p->N, W, 16);
   static const bool no_tiles = getenv("FEMB_ASM_ROWS") != nullptr;  // A/B switch: previous thread-per-row kernel
+  // Block-owned assembly (assembly_blocks.cu) is opt-in (FEMB_ASM_BLOCKS=1): on the 64 M-tet mesh it measured 2.65 ms against
+  // 2.54 ms for the row-tile kernel below -- each element is computed once instead of four times, but the colour-ordered
+  // shared-memory adds and coordinate gathers saturate the shared-memory pipe (ncu: l1tex 79 %, 43 % of the wavefronts are
+  // bank conflicts; profiles/r02_ncu_assembly_blocks.txt).
+  static const bool use_blocks = getenv("FEMB_ASM_BLOCKS") != nullptr && !no_tiles;
+  if (kind == 0 && p->max_row <= 255 && p->M > 0 && use_blocks && !p->blk_failed) {
+    if (!p->blk) {  // built at the first call: the clustering needs coordinates
+      const int rc = block_plan_build(p, coords, s);
+      if (rc != FEMB_OK) return rc;
+    }
+    if (p->blk) return block_assemble(p, coords, vals, flag, s);
+  }
   if (kind == 0 && p->inc_slots && (size_t)p->max_row * 8 * 128 <= 160 * 1024 && !no_tiles) {
     constexpr int BD = 128;
     if (!p->rec) {  // lazily built, topology only
