@@ -473,7 +473,8 @@ constexpr size_t BLK_SMEM_LIMIT = 110 * 1024;  // two CTAs per SM
 
 size_t block_smem(const BlockPlan* bp) { return sizeof(double) * ((size_t)bp->max_acc + 3 * (size_t)(bp->R + bp->max_halo)) + sizeof(unsigned) * bp->R; }
 
-// 0 = built, 1 = this R does not fit (try a smaller one), < 0 = error
+// FEMB_OK = built, BLK_TOO_BIG = this R does not fit (try a smaller one), BLK_DEGENERATE = an element repeats a node, else = error
+constexpr int BLK_TOO_BIG = -100, BLK_DEGENERATE = -101;
 int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, BlockPlan** out) {
   const long long N = p->N, M = p->M;
   const long long nblocks = (N + R - 1) / R;
@@ -547,7 +548,7 @@ int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, Blo
   }
   FEMB_CUDA(cudaMemcpyAsync(&bp->max_acc, dmax, sizeof(int), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
-  if (bp->max_acc > 65535 || sizeof(double) * (size_t)bp->max_acc > BLK_SMEM_LIMIT) return 1;
+  if (bp->max_acc > 65535 || sizeof(double) * (size_t)bp->max_acc > BLK_SMEM_LIMIT) return BLK_TOO_BIG;
   // ---- (block, element) pairs, sorted by block then element id
   int* cnt;
   long long* off;
@@ -555,18 +556,18 @@ int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, Blo
   FEMB_CUDA(scr.alloc(&off, (size_t)M + 1));
   count_pairs<<<grid_for(M + 1, 256), 256, 0, s>>>(p->conn32, M, rank, R, cnt);
   FEMB_LAUNCH_CHECK();
-  if (device_scan_ll<int>(scr, cnt, off, M + 1, s) != FEMB_OK) return -1;
+  if (device_scan_ll<int>(scr, cnt, off, M + 1, s) != FEMB_OK) return FEMB_ERR_CUDA;
   long long total = 0;
   FEMB_CUDA(cudaMemcpyAsync(&total, off + M, sizeof(long long), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
-  if (total >= (1ll << 31) - 1) return 1;
+  if (total >= (1ll << 31) - 1) return BLK_TOO_BIG;
   bp->total = total;
   unsigned long long *keys0, *keys;
   FEMB_CUDA(scr.alloc(&keys0, (size_t)std::max<long long>(total, 1)));
   FEMB_CUDA(scr.alloc(&keys, (size_t)std::max<long long>(total, 1)));
   if (M > 0) emit_pairs<<<grid_for(M, 256), 256, 0, s>>>(p->conn32, M, rank, R, off, keys0);
   FEMB_LAUNCH_CHECK();
-  if (sort_keys_u64(scr, keys0, keys, total, 32 + bits_for(nblocks + 1), s) != FEMB_OK) return -1;
+  if (sort_keys_u64(scr, keys0, keys, total, 32 + bits_for(nblocks + 1), s) != FEMB_OK) return FEMB_ERR_CUDA;
   FEMB_CUDA(cudaMalloc(&bp->blk_eptr, sizeof(int) * (nblocks + 1)));
   ptr_from_keys<<<grid_for(total + 1, 256), 256, 0, s>>>(keys, total, nblocks, bp->blk_eptr);
   FEMB_LAUNCH_CHECK();
@@ -577,11 +578,11 @@ int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, Blo
   FEMB_CUDA(scr.alloc(&hoff, (size_t)total + 1));
   count_halo<<<grid_for(total + 1, 256), 256, 0, s>>>(keys, total, p->conn32, rank, R, hcnt);
   FEMB_LAUNCH_CHECK();
-  if (device_scan_ll<int>(scr, hcnt, hoff, total + 1, s) != FEMB_OK) return -1;
+  if (device_scan_ll<int>(scr, hcnt, hoff, total + 1, s) != FEMB_OK) return FEMB_ERR_CUDA;
   long long htotal = 0;
   FEMB_CUDA(cudaMemcpyAsync(&htotal, hoff + total, sizeof(long long), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
-  if (htotal >= (1ll << 31) - 1) return 1;
+  if (htotal >= (1ll << 31) - 1) return BLK_TOO_BIG;
   unsigned long long *hk0, *hk1, *huniq;
   long long* dnh;
   FEMB_CUDA(scr.alloc(&hk0, (size_t)std::max<long long>(htotal, 1)));
@@ -590,7 +591,7 @@ int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, Blo
   FEMB_CUDA(scr.alloc(&dnh, 1));
   if (total > 0) emit_halo<<<grid_for(total, 256), 256, 0, s>>>(keys, total, p->conn32, rank, R, hoff, hk0);
   FEMB_LAUNCH_CHECK();
-  if (sort_keys_u64(scr, hk0, hk1, htotal, 32 + bits_for(nblocks + 1), s) != FEMB_OK) return -1;
+  if (sort_keys_u64(scr, hk0, hk1, htotal, 32 + bits_for(nblocks + 1), s) != FEMB_OK) return FEMB_ERR_CUDA;
   {
     size_t tb = 0;
     FEMB_CUDA(cub::DeviceSelect::Unique(nullptr, tb, hk1, huniq, dnh, (int)htotal, s));
@@ -616,7 +617,7 @@ int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, Blo
   FEMB_CUDA(cudaMemcpyAsync(hstats, stats, sizeof(hstats), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
   bp->max_halo = hstats[3];
-  if (R + bp->max_halo > 65535 || block_smem(bp) > BLK_SMEM_LIMIT) return 1;
+  if (R + bp->max_halo > 65535 || block_smem(bp) > BLK_SMEM_LIMIT) return BLK_TOO_BIG;
   uint4* rtmp;
   unsigned* rtmp2;
   FEMB_CUDA(scr.alloc(&rtmp, (size_t)std::max<long long>(total, 1)));
@@ -627,7 +628,7 @@ int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, Blo
   FEMB_LAUNCH_CHECK();
   FEMB_CUDA(cudaMemcpyAsync(hstats, stats, sizeof(hstats), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
-  if (hstats[2]) return 2;  // an element with a repeated node: the batched row updates need distinct entries -> row-tile kernel
+  if (hstats[2]) return BLK_DEGENERATE;  // an element with a repeated node: the batched row updates need distinct entries -> row-tile kernel
   unsigned char* color;
   int* dest;
   FEMB_CUDA(scr.alloc(&color, (size_t)std::max<long long>(total, 1)));
@@ -641,7 +642,7 @@ int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, Blo
   FEMB_CUDA(cudaMemcpyAsync(hstats, stats, sizeof(hstats), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
   bp->max_colors = hstats[0], bp->max_elems = hstats[1];
-  if (hstats[2] || bp->max_elems > 65535) return 1;
+  if (hstats[2] || bp->max_elems > 65535) return BLK_TOO_BIG;
   FEMB_CUDA(cudaMalloc(&bp->rec, sizeof(uint4) * std::max<long long>(total, 1)));
   FEMB_CUDA(cudaMalloc(&bp->rec2, sizeof(unsigned) * std::max<long long>(total, 1)));
   if (total > 0) permute_records<<<grid_for(total, 256), 256, 0, s>>>(rtmp, rtmp2, dest, total, bp->rec, bp->rec2);
@@ -649,7 +650,7 @@ int try_build(femb_csr_plan* p, const double* coords, int R, cudaStream_t s, Blo
   FEMB_CUDA(cudaStreamSynchronize(s));
   guard.keep = true;
   *out = bp;
-  return 0;
+  return FEMB_OK;
 }
 
 }  // namespace
@@ -663,11 +664,11 @@ int block_plan_build(femb_csr_plan* p, const double* coords, cudaStream_t s) {
   FEMB_CUDA(cudaEventCreate(&t0));
   FEMB_CUDA(cudaEventCreate(&t1));
   cudaEventRecord(t0, s);
-  int rc = 1;
-  for (int R = r_env > 0 ? r_env : 256; R >= 64 && rc == 1; R /= 2) {
+  int rc = BLK_TOO_BIG;
+  for (int R = r_env > 0 ? r_env : 256; R >= 64 && rc == BLK_TOO_BIG; R /= 2) {
     BlockPlan* bp = nullptr;
     rc = try_build(p, coords, R, s, &bp);
-    if (rc == 0) p->blk = bp;
+    if (rc == FEMB_OK) p->blk = bp;
     if (r_env > 0) break;
   }
   cudaEventRecord(t1, s);
@@ -676,8 +677,8 @@ int block_plan_build(femb_csr_plan* p, const double* coords, cudaStream_t s) {
   cudaEventElapsedTime(&ms, t0, t1);
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
-  if (rc < 0) return FEMB_ERR_CUDA;
-  if (rc >= 1) p->blk_failed = true;
+  if (rc == BLK_TOO_BIG || rc == BLK_DEGENERATE) p->blk_failed = true;
+  else if (rc != FEMB_OK) return rc;
   if (p->blk) p->blk->build_ms = ms;
   if (getenv("FEMB_ASM_VERBOSE") && p->blk)
     fprintf(stderr, "[femb] block plan: R=%d blocks=%lld listed elements=%lld (%.3fx of %lld) colours<=%d elems/block<=%d halo<=%d acc<=%d smem=%zu B, built in %.1f ms\n",

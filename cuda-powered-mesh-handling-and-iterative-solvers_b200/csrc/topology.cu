@@ -5,6 +5,17 @@
 // packed into 64-bit words and the entity ids are ordered with stable LSD radix-sort passes (cub), least significant
 // word first.  Run lengths in the sorted stream give "appears once" (surface) and "appears twice" (shared); outputs are
 // produced with flag + exclusive-scan compaction, so their order is exactly the reference's.
+//
+// Default path (entities_build_buckets): nine radix passes over 256 M (key, id) pairs cost 55 ms on the 64 M-tet mesh, 60x
+// the bytes the answer needs.  Instead every entity is dropped into the bucket of its SMALLEST node (one counting pass, one
+// scatter pass: ~24 faces per bucket on a tet mesh), and duplicates are matched inside the bucket by one warp: every lane
+// ranks its entity against all others of the bucket by (rest of the tuple, entity id), reading them as warp-wide broadcasts
+// from shared memory.  Buckets are in node order and the in-bucket rank is the lexicographic order of the remaining nodes, so shared
+// pairs come out in exactly the order of the sorted tuples (lower entity id first); surface entities (rare) are appended to
+// a list that is then sorted by their slot-major position.  The scatter order inside a bucket is arbitrary (atomics), the
+// ranks are not: outputs are deterministic.  Buckets larger than BUCKET_MAX (a node of extreme valence) fall back to the
+// radix path.
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -41,6 +52,10 @@ struct femb_entity_plan {
   int* order = nullptr;   // [T] entity ids (e*nf+f) in lexicographic order of their canonical tuples
   int* sscan = nullptr;   // [T+1] exclusive scan of "appears once" flags in the surface routine's slot-major order
   int* pscan = nullptr;   // [T+1] exclusive scan of "first of a pair" flags in sorted order
+  // bucket path: the answers themselves, compact
+  bool buckets = false;
+  int* surf_pos = nullptr;    // [K] slot-major positions (slot*M+e) of the entities that appear once, ascending
+  uint2* pair_ents = nullptr; // [S] (entity a, entity b), a < b, in lexicographic order of the shared tuple
 };
 
 namespace femb {
@@ -194,6 +209,354 @@ static int entities_build(femb_entity_plan* p, cudaStream_t s) {
   return FEMB_OK;
 }
 
+// ---- bucket path ---------------------------------------------------------------------------------------------------------
+constexpr int BUCKET_MAX = 4096;   // largest bucket the in-bucket matcher accepts (its cost is quadratic in the bucket size)
+
+// Thread per ELEMENT: its nodes are read once, the nf canonical tuples are formed in registers, and entities with the same
+// smallest node share one atomic (a tet has three faces in the bucket of its smallest node and one in the bucket of its
+// second smallest: 2 atomics instead of 4).
+template <typename I>
+__device__ __forceinline__ void element_tuples(const I* __restrict__ conn, int stride, const EntTable& tab, long long e, int (*t)[4]) {
+  int nd[8];
+  for (int k = 0; k < 8; ++k) nd[k] = k < stride ? (int)ldidx(conn + e * stride + k) : 0;
+  for (int f = 0; f < tab.nf; ++f) {
+    for (int k = 0; k < 4; ++k) t[f][k] = k < tab.nfn ? nd[tab.nodes[f][k]] : 0;
+    for (int a = 1; a < tab.nfn; ++a) {  // insertion sort, nfn <= 4
+      const int v = t[f][a];
+      int b = a - 1;
+      while (b >= 0 && t[f][b] > v) {
+        t[f][b + 1] = t[f][b];
+        --b;
+      }
+      t[f][b + 1] = v;
+    }
+  }
+}
+
+template <typename I>
+__global__ void bucket_count(const I* __restrict__ conn, int stride, EntTable tab, long long M, int* __restrict__ cnt) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < M; e += (long long)gridDim.x * blockDim.x) {
+    int t[6][4];
+    element_tuples(conn, stride, tab, e, t);
+    for (int f = 0; f < tab.nf; ++f) {
+      bool first = true;
+      int c = 0;
+      for (int g = 0; g < tab.nf; ++g) {
+        if (t[g][0] == t[f][0]) {
+          if (g < f) first = false;
+          ++c;
+        }
+      }
+      if (first) atomicAdd(cnt + t[f][0], c);
+    }
+  }
+}
+
+// record of a scattered entity: key = (t1 << 32 | t2) (the bucket is t0), t3 (4-node entities only), entity id
+template <typename I>
+__global__ void bucket_scatter(const I* __restrict__ conn, int stride, EntTable tab, long long M, const int* __restrict__ bptr, int* __restrict__ cur,
+                               unsigned long long* __restrict__ key, int* __restrict__ key3, int* __restrict__ ent) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < M; e += (long long)gridDim.x * blockDim.x) {
+    int t[6][4];
+    element_tuples(conn, stride, tab, e, t);
+    for (int f = 0; f < tab.nf; ++f) {
+      bool first = true;
+      int c = 0;
+      for (int g = 0; g < tab.nf; ++g) {
+        if (t[g][0] == t[f][0]) {
+          if (g < f) first = false;
+          ++c;
+        }
+      }
+      if (!first) continue;
+      int pos = bptr[t[f][0]] + atomicAdd(cur + t[f][0], c);
+      for (int g = f; g < tab.nf; ++g) {
+        if (t[g][0] != t[f][0]) continue;
+        key[pos] = (unsigned long long)(unsigned)t[g][1] << 32 | (unsigned long long)(unsigned)(tab.nfn > 2 ? t[g][2] : 0);
+        if (key3) key3[pos] = t[g][3];
+        ent[pos] = (int)(e * tab.nf + g);
+        ++pos;
+      }
+    }
+  }
+}
+
+// One WARP per bucket.  Lane l owns the bucket's entries l, l+32, ...; the bucket is staged in the warp's shared-memory
+// slice (buckets above BUCKET_STAGE entries are read from global memory instead), and every lane walks ALL entries of the
+// bucket -- the same address for the whole warp, i.e. one broadcast read and no divergence -- to find for its own entry:
+//   mult     how many entries carry the same tuple            lowest   whether it has the smallest entity id among them
+//   partner  the other entry of its group                      rank     its position in the order (tuple, entity id)
+// rank is a permutation of 0..cnt-1, so writing "is the first of exactly two" to flag[rank] sorts those flags by tuple; a
+// head's output position inside the bucket is the number of heads before it (ballot + popc per 32 ranks).
+//   appears once        -> appended to the surface list (slot-major position; the list is sorted afterwards)
+//   first of exactly two -> pairbuf[bucket start + head rank] = (entity, partner entity)      lane 0: npairs[bucket]
+constexpr int BUCKET_STAGE = 64;
+constexpr int MATCH_WARPS = 8;
+
+template <bool WIDE>
+__global__ void __launch_bounds__(MATCH_WARPS * 32) bucket_match(const int* __restrict__ bptr, long long nb, const unsigned long long* __restrict__ gkey,
+                                                                  const int* __restrict__ gkey3, const int* __restrict__ gent, EntTable tab, long long M,
+                                                                  int* __restrict__ npairs, uint2* __restrict__ pairbuf, unsigned char* __restrict__ gflag,
+                                                                  int* __restrict__ surf_list, int* __restrict__ surf_count) {
+  __shared__ unsigned long long skey[MATCH_WARPS][BUCKET_STAGE];
+  __shared__ int skey3[WIDE ? MATCH_WARPS : 1][BUCKET_STAGE];
+  __shared__ int sent[MATCH_WARPS][BUCKET_STAGE];
+  __shared__ unsigned char sflag[MATCH_WARPS][BUCKET_STAGE];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long warp = (long long)blockIdx.x * MATCH_WARPS + w, nwarps = (long long)gridDim.x * MATCH_WARPS;
+  // software pipeline over the warp's buckets: the bounds of bucket b + 2*nwarps and the records of bucket b + nwarps are
+  // requested before bucket b is sorted (two dependent global loads per bucket would otherwise be fully exposed)
+  int q0 = 0, q1 = 0, r0 = 0, r1 = 0;  // bounds of the next / next-but-one bucket
+  if (warp < nb) q0 = bptr[warp], q1 = bptr[warp + 1];
+  if (warp + nwarps < nb) r0 = bptr[warp + nwarps], r1 = bptr[warp + nwarps + 1];
+  unsigned long long pkey = 0ull;
+  int pk3 = 0, pen = 0;
+  if (lane < q1 - q0 && q1 - q0 <= 32) {
+    pkey = gkey[q0 + lane], pen = gent[q0 + lane];
+    if (WIDE) pk3 = gkey3[q0 + lane];
+  }
+  for (long long b = warp; b < nb; b += nwarps) {
+    const int s0 = q0, cnt = q1 - q0;
+    const unsigned long long ckey = pkey;
+    const int ck3 = pk3, cen = pen;
+    q0 = r0, q1 = r1;
+    if (b + 2 * nwarps < nb) r0 = bptr[b + 2 * nwarps], r1 = bptr[b + 2 * nwarps + 1];
+    if (b + nwarps < nb && lane < q1 - q0 && q1 - q0 <= 32) {
+      pkey = gkey[q0 + lane], pen = gent[q0 + lane];
+      if (WIDE) pk3 = gkey3[q0 + lane];
+    }
+    if (cnt == 0) continue;
+    if (cnt <= 32) {
+      // Fast path (a tet mesh has ~24 faces per bucket): one entry per lane, bitonic sort of the warp by tuple (15
+      // compare-exchange steps over shuffles), then equal tuples are neighbours: a group of one is a surface entity, a group
+      // of exactly two a shared pair (lower entity id first), and the heads are already in tuple order.
+      unsigned long long key = lane < cnt ? ckey : ~0ull;
+      int k3 = WIDE ? (lane < cnt ? ck3 : 0x7fffffff) : 0;
+      int en = lane < cnt ? cen : 0;
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
+          const int ok3 = WIDE ? __shfl_xor_sync(0xffffffffu, k3, j) : 0;
+          const int oe = __shfl_xor_sync(0xffffffffu, en, j);
+          const bool o_less = ok < key || (WIDE && ok == key && ok3 < k3);
+          const bool o_more = key < ok || (WIDE && ok == key && k3 < ok3);
+          const bool want_min = ((lane & k) == 0) == ((lane & j) == 0);
+          if (want_min ? o_less : o_more) key = ok, k3 = ok3, en = oe;
+        }
+      }
+      const unsigned long long kp1 = __shfl_up_sync(0xffffffffu, key, 1), kn1 = __shfl_down_sync(0xffffffffu, key, 1),
+                               kn2 = __shfl_down_sync(0xffffffffu, key, 2);
+      const int tp1 = WIDE ? __shfl_up_sync(0xffffffffu, k3, 1) : 0, tn1 = WIDE ? __shfl_down_sync(0xffffffffu, k3, 1) : 0,
+                tn2 = WIDE ? __shfl_down_sync(0xffffffffu, k3, 2) : 0;
+      const int en1 = __shfl_down_sync(0xffffffffu, en, 1);
+      const bool on = lane < cnt;
+      const bool eq_prev = lane > 0 && kp1 == key && (!WIDE || tp1 == k3);
+      const bool eq_n1 = lane + 1 < cnt && kn1 == key && (!WIDE || tn1 == k3);
+      const bool eq_n2 = lane + 2 < cnt && kn2 == key && (!WIDE || tn2 == k3);
+      const bool once = on && !eq_prev && !eq_n1, head = on && !eq_prev && eq_n1 && !eq_n2;
+      const unsigned bal = __ballot_sync(0xffffffffu, head);
+      if (head) pairbuf[s0 + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)min(en, en1), (unsigned)max(en, en1));
+      if (once) {
+        const int e = en / tab.nf, f = en - e * tab.nf;
+        surf_list[atomicAdd(surf_count, 1)] = (int)((long long)tab.surf_slot[f] * M + e);
+      }
+      if (lane == 0) npairs[b] = __popc(bal);
+      continue;
+    }
+    const bool staged = cnt <= BUCKET_STAGE;
+    const unsigned long long* kp = gkey + s0;
+    const int* k3p = WIDE ? gkey3 + s0 : nullptr;
+    const int* ep = gent + s0;
+    unsigned char* fp = gflag + s0;
+    if (staged) {
+      for (int i = lane; i < cnt; i += 32) {
+        skey[w][i] = kp[i], sent[w][i] = ep[i];
+        if (WIDE) skey3[w][i] = k3p[i];
+      }
+      kp = skey[w], ep = sent[w], fp = sflag[w];
+      if (WIDE) k3p = skey3[w];
+    }
+    __syncwarp();
+    // pass 1: classify my entries, publish head flags by rank
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      const int i = i0 + lane;
+      const bool on = i < cnt;
+      const unsigned long long mk = on ? kp[i] : 0ull;
+      const int mk3 = (WIDE && on) ? k3p[i] : 0, me = on ? ep[i] : 0;
+      int mult = 0, partner = 0, rank = 0;
+      bool lowest = true;
+      for (int j = 0; j < cnt; ++j) {
+        const unsigned long long kj = kp[j];
+        const int ej = ep[j];
+        const int k3j = WIDE ? k3p[j] : 0;
+        const bool same = kj == mk && (!WIDE || k3j == mk3);
+        const bool before = kj < mk || (kj == mk && WIDE && k3j < mk3) || (same && ej < me);
+        mult += same;
+        rank += before;
+        if (same && j != i) partner = j, lowest &= ej > me;
+      }
+      const bool head = on && mult == 2 && lowest;
+      if (on) fp[rank] = head ? 1 : 0;
+      if (on && mult == 1) {
+        const int e = me / tab.nf, f = me - e * tab.nf;
+        surf_list[atomicAdd(surf_count, 1)] = (int)((long long)tab.surf_slot[f] * M + e);
+      }
+      if (!staged) __threadfence_block();
+      __syncwarp();
+      (void)head, (void)partner;  // the flags are complete only after the last chunk -> pass 2
+    }
+    {
+      // pass 2 (rare): recompute rank / head of my entries and count the heads before each of them from the published flags
+      __syncwarp();
+      int total = 0;
+      for (int r0 = 0; r0 < cnt; r0 += 32) total += __popc(__ballot_sync(0xffffffffu, r0 + lane < cnt && fp[r0 + lane]));
+      for (int i0 = 0; i0 < cnt; i0 += 32) {
+        const int i = i0 + lane;
+        const bool on = i < cnt;
+        const unsigned long long mk = on ? kp[i] : 0ull;
+        const int mk3 = (WIDE && on) ? k3p[i] : 0, me = on ? ep[i] : 0;
+        int mult = 0, partner = 0, rank = 0;
+        bool lowest = true;
+        for (int j = 0; j < cnt; ++j) {
+          const unsigned long long kj = kp[j];
+          const int ej = ep[j];
+          const int k3j = WIDE ? k3p[j] : 0;
+          const bool same = kj == mk && (!WIDE || k3j == mk3);
+          const bool before = kj < mk || (kj == mk && WIDE && k3j < mk3) || (same && ej < me);
+          mult += same;
+          rank += before;
+          if (same && j != i) partner = j, lowest &= ej > me;
+        }
+        if (on && mult == 2 && lowest) {
+          int hb = 0;
+          for (int r = 0; r < rank; ++r) hb += fp[r];
+          pairbuf[s0 + hb] = make_uint2((unsigned)me, (unsigned)ep[partner]);
+        }
+      }
+      if (lane == 0) npairs[b] = total;
+    }
+    __syncwarp();
+  }
+}
+
+// pairs of bucket b: pairbuf[bptr[b] .. +npairs[b]) -> out[pbase[b] ..); 8 lanes per bucket
+__global__ void bucket_compact_pairs(const int* __restrict__ bptr, const int* __restrict__ npairs, const int* __restrict__ pbase, long long nb,
+                                     const uint2* __restrict__ pairbuf, uint2* __restrict__ out) {
+  const int sub = threadIdx.x & 7;
+  for (long long b = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3; b < nb; b += ((long long)gridDim.x * blockDim.x) >> 3) {
+    const int np = npairs[b];
+    const long long src = bptr[b], dst = pbase[b];
+    for (int k = sub; k < np; k += 8) out[dst + k] = pairbuf[src + k];
+  }
+}
+
+template <typename I>
+__global__ void write_surface_list(const I* __restrict__ conn, int stride, EntTable tab, const int* __restrict__ surf_pos, long long K, long long M,
+                                   long long* __restrict__ faces, long long* __restrict__ extra) {
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < K; o += (long long)gridDim.x * blockDim.x) {
+    const long long pos = surf_pos[o];
+    const int slot = (int)(pos / M);
+    const long long e = pos - (long long)slot * M;
+    int f = 0;
+    for (int q = 0; q < tab.nf; ++q)
+      if (tab.surf_slot[q] == slot) f = q;
+    for (int c = 0; c < tab.nfn; ++c) faces[o * tab.nfn + c] = ldidx(conn + e * stride + tab.nodes[f][c]);
+    extra[o] = ldidx(conn + e * stride + tab.extra[f]);
+  }
+}
+
+__global__ void write_shared_list(EntTable tab, const uint2* __restrict__ pair_ents, long long S, long long* __restrict__ pairs) {
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < S; o += (long long)gridDim.x * blockDim.x) {
+    const uint2 q = pair_ents[o];
+    long long* p = pairs + 4 * o;
+    p[0] = q.x / tab.nf, p[1] = q.x % tab.nf, p[2] = q.y / tab.nf, p[3] = q.y % tab.nf;
+  }
+}
+
+// FEMB_OK = done, TOPO_NOT_APPLICABLE = a bucket is too large (use the radix path), anything else = error
+constexpr int TOPO_NOT_APPLICABLE = -100;
+template <typename I>
+static int entities_build_buckets(femb_entity_plan* p, cudaStream_t s) {
+  const I* conn = static_cast<const I*>(p->conn);
+  const long long T = p->T, M = p->M;
+  const EntTable tab = p->tab;
+  Scratch scr(s);
+  int* dmax;
+  FEMB_CUDA(scr.alloc(&dmax, 2));
+  FEMB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(int), s));
+  max_node_kernel<I><<<grid_for(M * p->stride, 256), 256, 0, s>>>(conn, M * p->stride, dmax);
+  int hmax = 0;
+  FEMB_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaStreamSynchronize(s));
+  const long long nb = (long long)hmax + 1;
+  int *cnt, *bptr, *cur, *npairs, *pbase, *ent, *surf_list;
+  uint2* pairbuf;
+  FEMB_CUDA(scr.alloc(&cnt, nb + 1));
+  FEMB_CUDA(scr.alloc(&bptr, nb + 1));
+  FEMB_CUDA(scr.alloc(&cur, nb + 1));
+  FEMB_CUDA(scr.alloc(&npairs, nb + 1));
+  FEMB_CUDA(scr.alloc(&pbase, nb + 1));
+  FEMB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (nb + 1), s));
+  FEMB_CUDA(cudaMemsetAsync(cur, 0, sizeof(int) * (nb + 1), s));
+  FEMB_CUDA(cudaMemsetAsync(npairs, 0, sizeof(int) * (nb + 1), s));
+  bucket_count<I><<<grid_for(M, 256), 256, 0, s>>>(conn, p->stride, tab, M, cnt);
+  FEMB_LAUNCH_CHECK();
+  size_t tb = 0, tb2 = 0;
+  FEMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, bptr, (int)(nb + 1), s));
+  FEMB_CUDA(cub::DeviceReduce::Max(nullptr, tb2, cnt, dmax + 1, (int)nb, s));
+  void* tmp;
+  FEMB_CUDA(scr.alloc((char**)&tmp, std::max(tb, tb2)));
+  FEMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, bptr, (int)(nb + 1), s));
+  FEMB_CUDA(cub::DeviceReduce::Max(tmp, tb2, cnt, dmax + 1, (int)nb, s));
+  int maxb = 0;
+  FEMB_CUDA(cudaMemcpyAsync(&maxb, dmax + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaStreamSynchronize(s));
+  if (maxb > BUCKET_MAX) return TOPO_NOT_APPLICABLE;
+  const bool wide = tab.nfn > 3;
+  unsigned long long* key;
+  int* key3 = nullptr;
+  unsigned char* gflag;
+  FEMB_CUDA(scr.alloc(&key, T));
+  if (wide) FEMB_CUDA(scr.alloc(&key3, T));
+  FEMB_CUDA(scr.alloc(&ent, T));
+  FEMB_CUDA(scr.alloc(&pairbuf, T));
+  FEMB_CUDA(scr.alloc(&gflag, T));
+  FEMB_CUDA(scr.alloc(&surf_list, T + 1));
+  int* surf_count = surf_list + T;
+  FEMB_CUDA(cudaMemsetAsync(surf_count, 0, sizeof(int), s));
+  bucket_scatter<I><<<grid_for(M, 256), 256, 0, s>>>(conn, p->stride, tab, M, bptr, cur, key, key3, ent);
+  FEMB_LAUNCH_CHECK();
+  const int mgrid = grid_for(nb, MATCH_WARPS, 8);
+  if (wide) bucket_match<true><<<mgrid, MATCH_WARPS * 32, 0, s>>>(bptr, nb, key, key3, ent, tab, M, npairs, pairbuf, gflag, surf_list, surf_count);
+  else bucket_match<false><<<mgrid, MATCH_WARPS * 32, 0, s>>>(bptr, nb, key, key3, ent, tab, M, npairs, pairbuf, gflag, surf_list, surf_count);
+  FEMB_LAUNCH_CHECK();
+  FEMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, npairs, pbase, (int)(nb + 1), s));
+  int hs = 0, hk = 0;
+  FEMB_CUDA(cudaMemcpyAsync(&hs, pbase + nb, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaMemcpyAsync(&hk, surf_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaStreamSynchronize(s));
+  p->S = hs, p->K = hk;
+  if (hs > 0) {
+    FEMB_CUDA(cudaMallocAsync((void**)&p->pair_ents, sizeof(uint2) * (size_t)hs, s));
+    bucket_compact_pairs<<<grid_for(nb * 8, 256), 256, 0, s>>>(bptr, npairs, pbase, nb, pairbuf, p->pair_ents);
+    FEMB_LAUNCH_CHECK();
+  }
+  if (hk > 0) {
+    FEMB_CUDA(cudaMallocAsync((void**)&p->surf_pos, sizeof(int) * (size_t)hk, s));
+    int bits = 1;
+    while ((1ll << bits) < T) ++bits;
+    size_t tb3 = 0;
+    FEMB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb3, surf_list, p->surf_pos, hk, 0, bits, s));
+    void* tmp3;
+    FEMB_CUDA(scr.alloc((char**)&tmp3, tb3));
+    FEMB_CUDA(cub::DeviceRadixSort::SortKeys(tmp3, tb3, surf_list, p->surf_pos, hk, 0, bits, s));
+  }
+  p->buckets = true;
+  return FEMB_OK;
+}
+
 template <typename T>
 __global__ void surface_normals_kernel(const T* __restrict__ coords, const long long* __restrict__ faces, const long long* __restrict__ extra,
                                        long long K, int nfn, int second, T* __restrict__ out) {
@@ -255,6 +618,8 @@ static void entities_free(femb_entity_plan* p) {
   cudaFree(p->order);
   cudaFree(p->sscan);
   cudaFree(p->pscan);
+  cudaFree(p->surf_pos);
+  cudaFree(p->pair_ents);
   delete p;
 }
 
@@ -275,7 +640,11 @@ extern "C" int femb_entities_create(int ent_kind, const void* conn, int ib, int6
     return FEMB_ERR_ARG;
   }
   int rc = FEMB_OK;
-  if (M > 0) {
+  static const bool force_radix = getenv("FEMB_TOPO_RADIX") != nullptr;  // A/B switch: the radix-sort path
+  if (M > 0 && !force_radix) {
+    rc = ib == 8 ? entities_build_buckets<long long>(p, as_stream(stream)) : entities_build_buckets<int>(p, as_stream(stream));
+  }
+  if (M > 0 && (force_radix || rc == TOPO_NOT_APPLICABLE)) {
     if (cudaMalloc(&p->order, sizeof(int) * p->T) != cudaSuccess || cudaMalloc(&p->sscan, sizeof(int) * (p->T + 1)) != cudaSuccess ||
         cudaMalloc(&p->pscan, sizeof(int) * (p->T + 1)) != cudaSuccess) {
       entities_free(p);
@@ -298,6 +667,13 @@ extern "C" int femb_entities_surface(femb_entity_plan* p, int64_t* faces, int64_
   FEMB_CHECK_ARG(p != nullptr, "plan");
   if (p->T == 0 || p->K == 0) return FEMB_OK;
   cudaStream_t s = as_stream(stream);
+  if (p->buckets) {
+    const int g = grid_for(p->K, 256);
+    if (p->ib == 8) write_surface_list<long long><<<g, 256, 0, s>>>((const long long*)p->conn, p->stride, p->tab, p->surf_pos, p->K, p->M, (long long*)faces, (long long*)extra);
+    else write_surface_list<int><<<g, 256, 0, s>>>((const int*)p->conn, p->stride, p->tab, p->surf_pos, p->K, p->M, (long long*)faces, (long long*)extra);
+    FEMB_LAUNCH_CHECK();
+    return FEMB_OK;
+  }
   const int grid = grid_for(p->T, 256);
   if (p->ib == 8) write_surface<long long><<<grid, 256, 0, s>>>((const long long*)p->conn, p->stride, p->tab, p->sscan, p->T, p->M, (long long*)faces, (long long*)extra);
   else write_surface<int><<<grid, 256, 0, s>>>((const int*)p->conn, p->stride, p->tab, p->sscan, p->T, p->M, (long long*)faces, (long long*)extra);
@@ -308,6 +684,11 @@ extern "C" int femb_entities_surface(femb_entity_plan* p, int64_t* faces, int64_
 extern "C" int femb_entities_shared(femb_entity_plan* p, int64_t* pairs, femb_stream stream) {
   FEMB_CHECK_ARG(p != nullptr, "plan");
   if (p->T == 0 || p->S == 0) return FEMB_OK;
+  if (p->buckets) {
+    write_shared_list<<<grid_for(p->S, 256), 256, 0, as_stream(stream)>>>(p->tab, p->pair_ents, p->S, (long long*)pairs);
+    FEMB_LAUNCH_CHECK();
+    return FEMB_OK;
+  }
   write_shared<<<grid_for(p->T, 256), 256, 0, as_stream(stream)>>>(p->tab, p->order, p->pscan, p->T, (long long*)pairs);
   FEMB_LAUNCH_CHECK();
   return FEMB_OK;

@@ -78,12 +78,22 @@ def mass_points(kind) -> list:
 
 # ----------------------------------------------------------------------------- element kernels
 
-def c3d4(what, coords, elements, E=0.0, nu=0.0, device="cuda:0", dtype=torch.float32):
+def _out_buffer(out, shape, dev, dtype):
+    """`out=` (additive to the reference API): reuse a caller-owned result buffer instead of allocating a new one per call --
+    at 64 M tets a [M,4,4] fp64 result is 8.2 GB, and a fresh cudaMalloc of that size costs 15x the kernel."""
+    if out is None:
+        return torch.empty(shape, device=dev, dtype=dtype)
+    if tuple(out.shape) != tuple(shape) or out.dtype != dtype or out.device != torch.device(dev) or not out.is_contiguous():
+        raise ValueError(f"out= must be a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}")
+    return out
+
+
+def c3d4(what, coords, elements, E=0.0, nu=0.0, device="cuda:0", dtype=torch.float32, out=None):
     dev = cuda_device(device)
     x, conn = real(coords, dev, dtype), index(elements, dev)
     M = conn.shape[0]
     shape = {0: (M, 4, 3), 1: (M, 6, 12), 2: (M, 12, 12), 3: (M, 4, 4), 4: (M, 12, 12), 5: (M,)}[what]
-    out = torch.empty(shape, device=dev, dtype=dtype)
+    out = _out_buffer(out, shape, dev, dtype)
     flag = torch.zeros(1, device=dev, dtype=torch.int32)
     with torch.cuda.device(dev):
         check(lib.femb_c3d4(what, _p(x), _fp(x), _p(conn), _fp(conn), M, float(E), float(nu), _p(out), _p(flag), _stream(dev)), "femb_c3d4")
@@ -105,7 +115,7 @@ def volumes(kind, coords, elements, device="cuda:0", dtype=torch.float32):
 _NEN = {C3D4: 4, C3D6: 6, C3D8: 8, C3D10: 10, C3D15: 15, C3D20: 20, S3: 3, S4: 4}
 
 
-def solid(kind, what, coords, elements, points, E=0.0, nu=0.0, device="cuda:0", dtype=torch.float32):
+def solid(kind, what, coords, elements, points, E=0.0, nu=0.0, device="cuda:0", dtype=torch.float32, out=None):
     """points: list of [xi,eta,zeta,w] rows (host)."""
     dev = cuda_device(device)
     x, conn = real(coords, dev, dtype), index(elements, dev)
@@ -114,7 +124,7 @@ def solid(kind, what, coords, elements, points, E=0.0, nu=0.0, device="cuda:0", 
         conn = conn[:, :nen].contiguous()
     M, nd, nq = conn.shape[0], 3 * nen, len(points)
     shape = {0: (M, 3, 3), 1: (M, nen, 3), 2: (M, 6, nd), 3: (M, nd, nd), 4: (nq, M, nd, nd), 5: (M, nd, nd), 6: (M, nd, nd)}[what]
-    out = torch.empty(shape, device=dev, dtype=dtype)
+    out = _out_buffer(out, shape, dev, dtype)
     flat = [v for row in points for v in row]
     with torch.cuda.device(dev):
         check(lib.femb_solid(kind, what, _p(x), _fp(x), _p(conn), _fp(conn), M, _host_doubles(flat), nq, float(E), float(nu), _p(out),

@@ -263,14 +263,14 @@ def compute_c3d4_shape_gradients(coords, elements, device="cuda:0", dtype=torch.
     return _ops.c3d4(0, coords, elements, device=device, dtype=dtype)
 
 
-def compute_c3d4_K_matrix(coords, elements, E, nu, device="cuda:0", dtype=torch.float32):
-    """K = B^T D B V, [M,12,12] (element.py:883-903)."""
-    return _ops.c3d4(2, coords, elements, E, nu, device, dtype)
+def compute_c3d4_K_matrix(coords, elements, E, nu, device="cuda:0", dtype=torch.float32, out=None):
+    """K = B^T D B V, [M,12,12] (element.py:883-903).  `out=` (additive): write into a caller-owned buffer."""
+    return _ops.c3d4(2, coords, elements, E, nu, device, dtype, out=out)
 
 
-def compute_c3d4_poisson_K_matrix(coords, elements, device="cuda:0", dtype=torch.float32):
+def compute_c3d4_poisson_K_matrix(coords, elements, device="cuda:0", dtype=torch.float32, out=None):
     """Scalar Laplace stiffness V G G^T [M,4,4].  Not in the reference (parity unpinned); additive."""
-    return _ops.c3d4(3, coords, elements, device=device, dtype=dtype)
+    return _ops.c3d4(3, coords, elements, device=device, dtype=dtype, out=out)
 
 
 def compute_c3d4_M_matrix(coords, elements, rho, device="cuda:0", dtype=torch.float32):
@@ -298,13 +298,13 @@ def c3d10_integration_points(device="cuda:0", dtype=torch.float32):
     return _points_out(_ops.C3D10, device, dtype)
 
 
-def _solid(kind, what, coords, elements, integral_point, device, dtype, E=0.0, nu=0.0, single_point=True):
+def _solid(kind, what, coords, elements, integral_point, device, dtype, E=0.0, nu=0.0, single_point=True, out=None):
     pts = _pts(kind, integral_point, dtype, single_point=single_point)
-    return _ops.solid(kind, what, coords, elements, pts, E, nu, device, dtype)
+    return _ops.solid(kind, what, coords, elements, pts, E, nu, device, dtype, out=out)
 
 
-def _solid_K(kind, coords, elements, E, nu, integral_point, single, device, dtype):
-    return _solid(kind, 3 if single else 4, coords, elements, integral_point, device, dtype, E, nu, single_point=False)
+def _solid_K(kind, coords, elements, E, nu, integral_point, single, device, dtype, out=None):
+    return _solid(kind, 3 if single else 4, coords, elements, integral_point, device, dtype, E, nu, single_point=False, out=out)
 
 
 def _solid_M(kind, coords, elements, rho, integral_point, device, dtype):
@@ -330,9 +330,10 @@ def compute_c3d10_B_matrix(coords, elements, integral_point, device="cuda:0", dt
     return _solid(_ops.C3D10, 2, coords, elements, integral_point, device, dtype)
 
 
-def compute_c3d10_K_matrix(coords, elements, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32):
-    """sum_q w_q detJ_q B^T D B with signed detJ; single=False -> [n_int,M,30,30] unweighted (element.py:1191-1239)."""
-    return _solid_K(_ops.C3D10, coords, elements, E, nu, integral_point, single, device, dtype)
+def compute_c3d10_K_matrix(coords, elements, E, nu, integral_point=None, single=True, device="cuda:0", dtype=torch.float32, out=None):
+    """sum_q w_q detJ_q B^T D B with signed detJ; single=False -> [n_int,M,30,30] unweighted (element.py:1191-1239).
+    `out=` (additive): write into a caller-owned buffer."""
+    return _solid_K(_ops.C3D10, coords, elements, E, nu, integral_point, single, device, dtype, out=out)
 
 
 def compute_c3d10_element_stress(coords, elements, displacement, E, nu, integral_point=None, single=True, device="cuda:0",
