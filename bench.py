@@ -224,6 +224,8 @@ def run_gpu(args):
 
     if world > 1:
         from femb200 import dist_cg
+        if args.config == 2:
+            return dist_cg.bench_config2(args, dev, rank, world, METRIC, UNIT)
         return dist_cg.bench(args, dev, rank, world, METRIC, UNIT)
 
     sampler = ClockSampler(local)          # started first: nvidia-smi needs up to a second before its first sample
@@ -521,6 +523,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--n", type=int, default=220, help="Kuhn cube cells per edge (220 -> 63.9M tets)")
     ap.add_argument("--impl", default="femb200", choices=["femb200", "reference"])
+    ap.add_argument("--config", type=int, default=4, choices=[4, 2], help="BASELINE config: 4 = P1 Poisson 64 M tets (headline); "
+                    "2 = P2 elasticity 2 M tets, Jacobi-PCG (multi-GPU line: torchrun ... bench.py --gpus N --config 2)")
+    ap.add_argument("--n2", type=int, default=69, help="Kuhn cube cells per edge of config 2 (69 -> 1.97 M C3D10 tets)")
     ap.add_argument("--cpu-n", type=int, default=96, help="cube size of the CPU sample")
     ap.add_argument("--cpu-iters", type=int, default=20)
     ap.add_argument("--cpu-base-n", type=int, default=64, help="cube size of the cpu_baseline sample inside the GPU arm (~10 s of CPU work)")

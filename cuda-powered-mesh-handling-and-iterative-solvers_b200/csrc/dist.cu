@@ -339,12 +339,50 @@ __global__ void __launch_bounds__(DV_THREADS) dist_direction_kernel(Peers pe, lo
 // Reduction slots are double-buffered by epoch parity: with a single all-rank wait per iteration a fast rank could
 // otherwise overwrite a slot a slow rank has not read yet.
 // =====================================================================================================================
+// epilogue of the merged-reduction SpMV (scalar CSR and 3x3 block-CSR kernels): per-CTA partials of the three sums, the last
+// CTA adds them in index order and sends the rank's sums to every rank as LL words (data + epoch in one 8-byte store)
+template <int THREADS>
+__device__ __forceinline__ void ll_reduce_send(const Peers& pe, double dot, double e0, double e1, double* __restrict__ partial, DistState* st) {
+  const double t0 = block_sum<THREADS>(dot), t1 = block_sum<THREADS>(e0), t2 = block_sum<THREADS>(e1);
+  const int G = gridDim.x;
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = t0, partial[G + blockIdx.x] = t1, partial[2 * G + blockIdx.x] = t2;
+    __threadfence();
+    last = atomicAdd(&st->ticket1, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int k = threadIdx.x; k < G; k += THREADS)
+      a[0] += ((volatile double*)partial)[k], a[1] += ((volatile double*)partial)[G + k], a[2] += ((volatile double*)partial)[2 * G + k];
+    a[0] = block_sum<THREADS>(a[0]), a[1] = block_sum<THREADS>(a[1]), a[2] = block_sum<THREADS>(a[2]);
+    __shared__ double sums[3];
+    __shared__ long long eB;
+    if (threadIdx.x == 0) {
+      st->ticket1 = 0;
+      eB = st->epochB + 1;
+      st->epochB = eB;
+      sums[0] = a[0], sums[1] = a[1], sums[2] = a[2];
+    }
+    __syncthreads();
+    // 6 words to each of the P ranks (own included), one thread per word: data and epoch travel in the same 8-byte store
+    const int par = (int)(eB & 1);
+    for (int t = threadIdx.x; t < 6 * pe.P; t += THREADS) {
+      const int q = t / 6, w = t - 6 * q;
+      ll_store(&pe.hdr[q]->ll[par][pe.rank][w], sums[w >> 1], w & 1, eB);
+    }
+    if (threadIdx.x == 0) trace_stamp(st, 4);
+  }
+}
+
 template <int LR, bool NC>
 __global__ void __launch_bounds__(TMA_THREADS) dist_spmv3_kernel(Peers pe, long long n_owned, long long nnz, const int* __restrict__ crow,
                                                                  const int* __restrict__ col, const double* __restrict__ val,
                                                                  double* __restrict__ y, const unsigned char* __restrict__ mask,
-                                                                 const double* __restrict__ rvec, double* __restrict__ partial, DistState* st,
-                                                                 long long n_interior, long long pin) {
+                                                                 const double* __restrict__ rvec, const double* __restrict__ wvec,
+                                                                 double* __restrict__ partial, DistState* st, long long n_interior, long long pin) {
   pdl_launch_dependents();
   SymHeader* me = pe.hdr[pe.rank];
   __shared__ int nbr[MAXP];
@@ -363,47 +401,80 @@ __global__ void __launch_bounds__(TMA_THREADS) dist_spmv3_kernel(Peers pe, long 
   double extra[2] = {0.0, 0.0};
   const double dot = spmv_tma_rows<LR, NC, TMA_THREADS, TMA_STAGES, TMA_CAP, LazyHalo, PdlWait>(
       n_owned, nnz, crow, col, val, x, y, mask, false, true, pe.nnbr > 0 ? n_interior : 0x7fffffffffffffffll, hw, rvec, extra, PdlWait(), &st->stop,
-      pin);
+      pin, wvec);
   if (st->stop) return;  // set before this kernel (block-uniform) or by a spin timeout (status 3: the solve is lost anyway)
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 3);
-  const double t0 = block_sum<TMA_THREADS>(dot), t1 = block_sum<TMA_THREADS>(extra[0]), t2 = block_sum<TMA_THREADS>(extra[1]);
-  const int G = gridDim.x;
-  __shared__ bool last;
-  if (threadIdx.x == 0) {
-    partial[blockIdx.x] = t0, partial[G + blockIdx.x] = t1, partial[2 * G + blockIdx.x] = t2;
-    __threadfence();
-    last = atomicAdd(&st->ticket1, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (last) {
-    __threadfence();
-    double a[3] = {0.0, 0.0, 0.0};
-    for (int k = threadIdx.x; k < G; k += TMA_THREADS)
-      a[0] += ((volatile double*)partial)[k], a[1] += ((volatile double*)partial)[G + k], a[2] += ((volatile double*)partial)[2 * G + k];
-    a[0] = block_sum<TMA_THREADS>(a[0]), a[1] = block_sum<TMA_THREADS>(a[1]), a[2] = block_sum<TMA_THREADS>(a[2]);
-    __shared__ double sums[3];
-    __shared__ long long eB;
-    if (threadIdx.x == 0) {
-      st->ticket1 = 0;
-      eB = st->epochB + 1;
-      st->epochB = eB;
-      sums[0] = a[0], sums[1] = a[1], sums[2] = a[2];
+  ll_reduce_send<TMA_THREADS>(pe, dot, extra[0], extra[1], partial, st);
+}
+
+// 3x3 block-CSR twin (3-dof operators: every elasticity solver of the reference): warp per block row as the single-GPU
+// spmv_bsr3_vec_kernel (krylov.cu) -- lanes 0..26 = (block, position) of three consecutive blocks per step -- on the owned
+// block rows, interior rows first; a warp waits for the halo flags when it reaches its first boundary row.  x = p in the
+// symmetric buffer, dof-level numbering 3 * (local node) + component.
+constexpr int DBSR_THREADS = 256;
+template <int U>
+__global__ void __launch_bounds__(DBSR_THREADS) dist_spmv3_bsr3_kernel(Peers pe, long long nb, const int* __restrict__ brow, const int* __restrict__ bcol,
+                                                                       const double* __restrict__ bval, double* __restrict__ y,
+                                                                       const unsigned char* __restrict__ mask, const double* __restrict__ rvec,
+                                                                       const double* __restrict__ wvec, double* __restrict__ partial, DistState* st,
+                                                                       long long nb_interior) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (st->stop) return;
+  SymHeader* me = pe.hdr[pe.rank];
+  const double* x = sym_p(me);
+  const int lane = threadIdx.x & 31;
+  const int boff = lane / 9, pos = lane - 9 * boff, cx = pos % 3;  // lanes 27..31: boff = 3 -> idle
+  const bool active = lane < 27;
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long epochA = st->epochA;
+  bool waited = pe.nnbr == 0;
+  double dot = 0.0, e0 = 0.0, e1 = 0.0;
+  for (long long r = gw; r < nb; r += nw) {
+    if (!waited && r >= nb_interior) {  // first boundary row of this warp: its columns may be ghosts
+      if (lane < pe.nnbr) spin_until(me->flagA + pe.nbr[lane], epochA, st);
+      __syncwarp();
+      waited = true;
     }
-    __syncthreads();
-    // 6 words to each of the P ranks (own included), one thread per word: data and epoch travel in the same 8-byte store
-    const int par = (int)(eB & 1);
-    for (int t = threadIdx.x; t < 6 * pe.P; t += TMA_THREADS) {
-      const int q = t / 6, w = t - 6 * q;
-      ll_store(&pe.hdr[q]->ll[par][pe.rank][w], sums[w >> 1], w & 1, eB);
+    const int a = __ldg(brow + r), e = __ldg(brow + r + 1);
+    double acc = 0.0;
+    if (active) {
+      int b = a + boff;
+      for (; b + 3 * (U - 1) < e; b += 3 * U) {
+        double v[U], xv[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          v[q] = ld_stream(bval + (size_t)(b + 3 * q) * 9 + pos);
+          xv[q] = __ldg(x + 3ll * ld_stream(bcol + b + 3 * q) + cx);
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) acc += v[q] * xv[q];
+      }
+      for (; b < e; b += 3) acc += ld_stream(bval + (size_t)b * 9 + pos) * __ldg(x + 3ll * ld_stream(bcol + b) + cx);
     }
-    if (threadIdx.x == 0) trace_stamp(st, 4);
+    acc += __shfl_down_sync(0xffffffffu, acc, 9) + __shfl_down_sync(0xffffffffu, acc, 18);
+    acc += __shfl_down_sync(0xffffffffu, acc, 1) + __shfl_down_sync(0xffffffffu, acc, 2);
+    if (lane == 0 || lane == 3 || lane == 6) {
+      const long long i = 3 * r + lane / 3;
+      double sv = acc;
+      if (mask && !mask[i]) sv = 0.0;
+      const double w = wvec ? wvec[i] : 1.0;
+      dot += sv * __ldg(x + i);
+      e0 += sv * (w * rvec[i]), e1 += sv * (sv * w);
+      y[i] = sv;
+    }
   }
+  if (st->stop == 3) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 3);
+  ll_reduce_send<DBSR_THREADS>(pe, dot, e0, e1, partial, st);
 }
 
 __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, long long n, double* __restrict__ u, double* __restrict__ r,
-                                                                     const double* __restrict__ Ap, double* __restrict__ partial,
-                                                                     DistState* st, double tol, double eps, int guards, int max_iter,
-                                                                     BoundaryPush bp) {
+                                                                     const double* __restrict__ Ap, const double* __restrict__ minv,
+                                                                     double* __restrict__ partial, DistState* st, double tol, double eps,
+                                                                     int guards, int max_iter, BoundaryPush bp) {
+  // minv != nullptr: Jacobi-PCG (solver.py:766-812): z = minv .* r, the sums are r.z, p = z + beta p; the three sums of the
+  // SpMV carry the same weights, so rs_new below is the recurrence of r.z
   pdl_launch_dependents();
   pdl_wait();
   if (st->stop) return;
@@ -457,11 +528,12 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
     for (long long b = gtid; b < n - bp.n_interior; b += gsz) {
       const long long i = bp.n_interior + b;
       const double pi = p[i], ri = r[i] - alpha * Ap[i];
+      const double zi = minv ? minv[i] * ri : ri;
       u[i] += alpha * pi;
       r[i] = ri;
-      dot += ri * ri;
+      dot += ri * zi;
       if (move_p) {
-        const double v = ri + beta * pi;
+        const double v = zi + beta * pi;
         p[i] = v;
         for (int e = bp.ptr[b]; e < bp.ptr[b + 1]; ++e) {
           const int k = bp.k[e];
@@ -475,10 +547,11 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
   }
   for (long long i = gtid; i < n_plain; i += gsz) {
     const double pi = p[i], ri = r[i] - alpha * Ap[i];
+    const double zi = minv ? minv[i] * ri : ri;
     u[i] += alpha * pi;
     r[i] = ri;
-    dot += ri * ri;
-    if (move_p) p[i] = ri + beta * pi;
+    dot += ri * zi;
+    if (move_p) p[i] = zi + beta * pi;
   }
   const double t = block_sum<DV_THREADS>(dot);
   __shared__ bool last;
@@ -540,6 +613,28 @@ __global__ void dist_final_check(Peers pe, DistState* st, double tol) {
     for (int q = 0; q < pe.P; ++q) a += __longlong_as_double((long long)(((unsigned long long)halves[2 * q + 1] << 32) | halves[2 * q]));
     st->rs_new = a;  // the reported residual is the exactly summed one
     if (sqrt(a) < tol && st->status == 2) st->stop = 1, st->status = 0, st->iterations = st->it;
+  }
+}
+
+// plain block-CSR product for the setup (Ap = A u): every warp waits for the neighbours' halo of this epoch first
+__global__ void __launch_bounds__(DBSR_THREADS) dist_bsr3_plain_kernel(Peers pe, long long nb, const int* __restrict__ brow, const int* __restrict__ bcol,
+                                                                       const double* __restrict__ bval, double* __restrict__ y, DistState* st) {
+  SymHeader* me = pe.hdr[pe.rank];
+  const double* x = sym_p(me);
+  const int lane = threadIdx.x & 31;
+  const int boff = lane / 9, pos = lane - 9 * boff, cx = pos % 3;
+  const bool active = lane < 27;
+  if (lane < pe.nnbr) spin_until(me->flagA + pe.nbr[lane], st->epochA, st);
+  __syncwarp();
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = gw; r < nb; r += nw) {
+    const int a = __ldg(brow + r), e = __ldg(brow + r + 1);
+    double acc = 0.0;
+    if (active)
+      for (int b = a + boff; b < e; b += 3) acc += ld_stream(bval + (size_t)b * 9 + pos) * __ldg(x + 3ll * ld_stream(bcol + b) + cx);
+    acc += __shfl_down_sync(0xffffffffu, acc, 9) + __shfl_down_sync(0xffffffffu, acc, 18);
+    acc += __shfl_down_sync(0xffffffffu, acc, 1) + __shfl_down_sync(0xffffffffu, acc, 2);
+    if (lane == 0 || lane == 3 || lane == 6) y[3 * r + lane / 3] = acc;
   }
 }
 
@@ -812,13 +907,13 @@ static void launch_dist_spmv(int lr, int grid, cudaStream_t s, const Peers& pe, 
 }
 
 static void launch_dist_spmv3(int lr, int grid, cudaStream_t s, bool pdl, const Peers& pe, long long n, long long nnz, const int* crow,
-                              const int* col, const double* val, double* y, const unsigned char* mask, const double* rvec, double* partial,
-                              DistState* st, long long n_interior, long long pin) {
+                              const int* col, const double* val, double* y, const unsigned char* mask, const double* rvec, const double* wvec,
+                              double* partial, DistState* st, long long n_interior, long long pin) {
 #define FEMB_DSPMV3(LRV)                                                                                                    \
   {                                                                                                                         \
     cudaFuncSetAttribute(dist_spmv3_kernel<LRV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);         \
-    launch_pdl(dist_spmv3_kernel<LRV, true>, grid, TMA_THREADS, TMA_SMEM, s, pdl, pe, n, nnz, crow, col, val, y, mask, rvec, partial, st, \
-               n_interior, pin);                                                                                            \
+    launch_pdl(dist_spmv3_kernel<LRV, true>, grid, TMA_THREADS, TMA_SMEM, s, pdl, pe, n, nnz, crow, col, val, y, mask, rvec, wvec, partial, \
+               st, n_interior, pin);                                                                                        \
   }
   switch (lr) {
     case 1: FEMB_DSPMV3(1) break;
@@ -875,8 +970,9 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
                                   double* u, double* work, void* const* sym_host, int nnbr,
                                   const int32_t* nbr_host, const int32_t* send_ptr_host, const int32_t* send_idx,
                                   const int64_t* ghost_off_host, const int32_t* bptr, const uint8_t* bk, const int32_t* boff, double tol,
-                                  int max_iter, double eps, int check_every, femb_cg_result* result_host, femb_stream stream) {
+                                  int max_iter, double eps, int check_every, int block, femb_cg_result* result_host, femb_stream stream) {
   FEMB_CHECK_ARG(nranks >= 1 && nranks <= MAXP && rank >= 0 && rank < nranks && nnbr >= 0 && nnbr < MAXP, "rank/nranks/nnbr");
+  FEMB_CHECK_ARG(block == 1 || (block == 3 && n_owned % 3 == 0 && n_interior % 3 == 0), "block in {1,3}; block 3 needs 3 rows per node");
   FEMB_CHECK_ARG(n_owned > 0 && crow && col && val && F && u && work && sym_host && result_host, "null pointer / n_owned <= 0");
   if (check_every < 1) check_every = 16;
   spmv_apply_env_once();
@@ -892,7 +988,12 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   const long long n = n_owned;
   double *r = work, *Ap = work + n;
   const int lr = tma_pick_lr(n, nnz);
-  const int g1 = tma_grid(n, lr);
+  int g1 = tma_grid(n, lr);
+  if (block == 3) {  // warp per block row, persistent: every CTA that fits on the device
+    int per_sm = 0;
+    FEMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dist_spmv3_bsr3_kernel<4>, DBSR_THREADS, 0));
+    g1 = (int)std::max<long long>(1, std::min<long long>((n / 3 + DBSR_THREADS / 32 - 1) / (DBSR_THREADS / 32), (long long)SMS * std::max(per_sm, 1)));
+  }
   const int g2 = grid_for(n, DV_THREADS, 8);
   const int gp = std::max(1, std::min(64, (pe.send_ptr[nnbr] + 255) / 256));
   Scratch scr(s);
@@ -913,14 +1014,15 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   // ---- setup: p <- mask.*u, halo, Ap = A u, r = mask.*(F - Ap), p = r, rs_old = allreduce(r.r)   (solver.py:163-181)
   dist_load_p<<<g2, DV_THREADS, 0, s>>>(pe, n, u, mask);
   dist_push_kernel<<<gp, 256, 0, s>>>(pe, send_idx, st);
-  launch_dist_spmv<false>(lr, g1, s, pe, n, nnz, crow, col, val, Ap, nullptr, nullptr, st, 0);
+  if (block == 3) dist_bsr3_plain_kernel<<<g1, DBSR_THREADS, 0, s>>>(pe, n / 3, crow, col, val, Ap, st);
+  else launch_dist_spmv<false>(lr, g1, s, pe, n, nnz, crow, col, val, Ap, nullptr, nullptr, st, 0);
   dist_init_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, F, Ap, mask, minv, r, partial, st);
   dist_init_finish<<<1, 32, 0, s>>>(pe, st, max_iter);
   FEMB_LAUNCH_CHECK();
   // default: three kernels per iteration in a CUDA graph.  FEMB_DIST_PERSISTENT=1 (and PCG) selects the single persistent
   // cooperative kernel, which measured slower so far (grid-wide software barriers cost more than launch boundaries)
   static const bool use_persistent = getenv("FEMB_DIST_PERSISTENT") != nullptr;
-  if (use_persistent || minv) {
+  if (use_persistent && block == 1) {
     // ---- iterations: one persistent cooperative kernel
     PersistArgs pa;
     pa.pe = pe, pa.n = n, pa.n_interior = n_interior, pa.crow = crow, pa.col = col, pa.val = val, pa.F = F, pa.minv = minv, pa.mask = mask;
@@ -974,7 +1076,8 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
   const bool folded = bptr != nullptr && nnbr > 0 && n_interior > 0 && !getenv("FEMB_DIST_SEPARATE_PUSH");
   BoundaryPush bp{folded ? bptr : nullptr, bk, boff, n_interior};
   // FEMB_DIST_CLASSIC=1: the three-kernel loop k1/k2/k3 (two waited all-reduces); default: merged reduction m1/m2
-  static const bool classic = getenv("FEMB_DIST_CLASSIC") != nullptr;
+  static const bool classic_env = getenv("FEMB_DIST_CLASSIC") != nullptr;
+  const bool classic = classic_env && block == 1 && !minv;  // the three-kernel loop exists for scalar CSR without a preconditioner
   const bool pdl = pdl_enabled() && !classic;
   const long long pin = classic ? 0 : spmv_pin_entries(nnz);
   // with PDL the next SpMV's CTAs (4 x 128 threads per SM) become resident beside the vector kernel: leave them room
@@ -987,8 +1090,14 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
       dist_update_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, u, r, Ap, partial, st, eps, guards);
       dist_direction_kernel<<<g2, DV_THREADS, 0, s>>>(pe, n, r, st, tol, eps, guards, max_iter, bp);
     } else {
-      launch_dist_spmv3(lr, g1, s, pdl && k > 0 && (pdl_mode() & 2), pe, n, nnz, crow, col, val, Ap, mask, r, partial, st, n_interior, pin);
-      launch_pdl(dist_merged_vec_kernel, g2m, DV_THREADS, 0, s, pdl && (pdl_mode() & 1), pe, n, u, r, Ap, partial, st, tol, eps, guards, max_iter, bp);
+      const bool pdl_s = pdl && k > 0 && (pdl_mode() & 2);
+      if (block == 3)
+        launch_pdl(dist_spmv3_bsr3_kernel<4>, g1, DBSR_THREADS, 0, s, pdl_s, pe, n / 3, crow, col, val, Ap, mask, (const double*)r, minv, partial, st,
+                   n_interior / 3);
+      else
+        launch_dist_spmv3(lr, g1, s, pdl_s, pe, n, nnz, crow, col, val, Ap, mask, r, minv, partial, st, n_interior, pin);
+      launch_pdl(dist_merged_vec_kernel, g2m, DV_THREADS, 0, s, pdl && (pdl_mode() & 1), pe, n, u, r, Ap, minv, partial, st, tol, eps, guards, max_iter,
+                 bp);
     }
   }
   cudaError_t ce = cudaStreamEndCapture(s, &graph);

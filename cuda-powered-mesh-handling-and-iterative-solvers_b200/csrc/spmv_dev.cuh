@@ -233,7 +233,9 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
                                                 const unsigned char* __restrict__ mask, bool accumulate, bool fused,
                                                 long long halo_row = 0x7fffffffffffffffll, Wait wait = Wait(),
                                                 const double* __restrict__ rvec = nullptr, double* extra = nullptr, Dep dep = Dep(),
-                                                const int* stop = nullptr, long long pin = 0) {
+                                                const int* stop = nullptr, long long pin = 0, const double* __restrict__ wvec = nullptr) {
+  // wvec (merged-reduction Jacobi-PCG): the two extra sums carry the preconditioner's diagonal, extra[0] += y_r w_r rvec_r,
+  // extra[1] += y_r^2 w_r
   // rvec/extra (merged-reduction CG): extra[0] += y_r * rvec_r, extra[1] += y_r * y_r for the rows this thread finishes
   constexpr int R = THREADS / LR;
   extern __shared__ __align__(128) unsigned char tma_smem[];
@@ -313,7 +315,7 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
     }
     const long long r = t * R + lr;
     int ra = 0, rb = 0;
-    double x_own = 0.0, y_prev = 0.0, r_own = 0.0;
+    double x_own = 0.0, y_prev = 0.0, r_own = 0.0, w_own = 1.0;
     bool keep = true;
     if (r < n) {
       ra = __ldg(crow + r), rb = __ldg(crow + r + 1);
@@ -322,6 +324,7 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
           x_own = ld_x<NC>(x + r);
           if (mask) keep = mask[r] != 0;
           if (rvec) r_own = rvec[r];
+          if (wvec) w_own = wvec[r];
         }
         if (accumulate) y_prev = y[r];
       }
@@ -360,7 +363,7 @@ __device__ __forceinline__ double spmv_tma_rows(long long n, long long nnz, cons
       if (fused) {
         if (!keep) sum = 0.0;
         dot += sum * x_own;
-        if (extra) extra[0] += sum * r_own, extra[1] += sum * sum;
+        if (extra) extra[0] += sum * (w_own * r_own), extra[1] += sum * (sum * w_own);
       }
       y[r] = sum;
     }

@@ -46,6 +46,9 @@ SIGNATURES = {
     "femb_shell_extrude": [c_vp, c_vp, c_vp, c_i32, c_i64, c_f64, c_f64, c_vp, c_vp],
     "femb_extrude_connectivity": [c_vp, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp],
     "femb_to_c3d4": [c_i32, c_vp, c_i32, c_i64, c_vp, c_vp],
+    "femb_p2_create": [c_vp, c_i32, c_i64, c_i64, c_vp, C.POINTER(c_vp), C.POINTER(c_i64)],
+    "femb_p2_fill": [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
+    "femb_p2_destroy": [c_vp],
     "femb_entities_create": [c_i32, c_vp, c_i32, c_i64, c_i32, c_vp, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_i64)],
     "femb_entities_surface": [c_vp, c_vp, c_vp, c_vp],
     "femb_entities_shared": [c_vp, c_vp, c_vp],
@@ -88,7 +91,7 @@ SIGNATURES = {
     "femb_dist_reset": [c_vp, c_vp],
     "femb_dist_cg_solve": [c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_vp), c_i32,
                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_vp, C.POINTER(c_i64), c_vp, c_vp, c_vp, c_f64, c_i32, c_f64, c_i32,
-                           C.POINTER(CGResult), c_vp],
+                           c_i32, C.POINTER(CGResult), c_vp],
 }
 _RESTYPES = {"femb_last_error": C.c_char_p}
 

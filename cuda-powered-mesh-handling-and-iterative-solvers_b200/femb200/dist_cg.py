@@ -18,22 +18,25 @@ from ._lib import CGResult, check, lib
 
 
 class DistOperator:
-    """A row-partitioned CSR operator plus its peer-memory halo plan on this rank."""
+    """A row-partitioned operator plus its peer-memory halo plan on this rank.
+    block = 1: scalar CSR over the local nodes (crow, col, val[nnz]); block = 3: 3x3 block-CSR of a 3-dof operator (crow / col =
+    node pattern, val = [nnzb,3,3] blocks): vectors, halo lists and the boundary table are then dof-level (3*node + c)."""
 
-    def __init__(self, part: partition.LocalPart, crow, col, val, device):
-        self.part, self.dev = part, torch.device(device)
+    def __init__(self, part: partition.LocalPart, crow, col, val, device, block=1):
+        self.part, self.dev, self.block = part, torch.device(device), int(block)
         self.rank, self.P = part.rank, part.nparts
         no = part.n_owned
         nnz = int(crow[no].item())
         self.crow, self.col, self.val = crow[:no + 1].contiguous(), col[:nnz].contiguous(), val[:nnz].contiguous()
         self.nnz = nnz
+        B = self.block
         # ---- symmetric buffers: header + p[max n_local over ranks]
         sizes = [None] * self.P
         dist.all_gather_object(sizes, {"n_owned": no, "ghost_base": part.ghost_base, "n_local": part.n_local, "recv_off": part.recv_off})
         self.sizes = sizes
         hdr = lib.femb_dist_header_bytes()
         nmax = max(s["n_local"] for s in sizes)
-        self.sym_bytes = hdr + 8 * nmax
+        self.sym_bytes = hdr + 8 * nmax * B
         own, handle = C.c_void_p(), (C.c_char * 64)()
         with torch.cuda.device(self.dev):
             check(lib.femb_dist_alloc(self.sym_bytes, C.byref(own), handle), "femb_dist_alloc")
@@ -56,13 +59,17 @@ class DistOperator:
         nb = part.neighbors
         self.nnbr = len(nb)
         self.nbr = (C.c_int32 * max(1, self.nnbr))(*nb)
+        def dofs(t):     # node-level indices / offsets -> dof-level, component fastest (the ghost blocks use the same interleaving)
+            t = torch.as_tensor(t)
+            return t if B == 1 else (t.reshape(-1, 1) * B + torch.arange(B, device=t.device)).reshape(-1)
+
         ptrs, idx = [0], []
         for q in nb:
-            idx.append(part.send_idx[q].to(torch.int32))
-            ptrs.append(ptrs[-1] + int(part.send_idx[q].numel()))
+            idx.append(dofs(part.send_idx[q]).to(torch.int32))
+            ptrs.append(ptrs[-1] + B * int(part.send_idx[q].numel()))
         self.send_ptr = (C.c_int32 * (self.nnbr + 1))(*ptrs)
         self.send_idx = (torch.cat(idx) if idx else torch.zeros(1, dtype=torch.int32)).to(self.dev).contiguous()
-        self.ghost_off = (C.c_int64 * max(1, self.nnbr))(*[sizes[q]["ghost_base"] + sizes[q]["recv_off"][self.rank] for q in nb])
+        self.ghost_off = (C.c_int64 * max(1, self.nnbr))(*[B * (sizes[q]["ghost_base"] + sizes[q]["recv_off"][self.rank]) for q in nb])
         self.halo_bytes = 8 * ptrs[-1]
         # destinations of every boundary row (CSR over rows n_interior..n_owned): lets the direction kernel store boundary
         # values straight into the neighbours' ghost slots instead of running a separate push kernel
@@ -75,6 +82,15 @@ class DistOperator:
             assert int(rows.min().item()) >= ni, "send rows must be boundary rows"
             order = torch.sort(rows, stable=True).indices
             rows, ks, offs = rows[order], ks[order], offs[order]
+            if B > 1:       # every boundary node row becomes B dof rows with the same destinations, offsets scaled
+                c = torch.arange(B, device=rows.device)
+                nrow = rows.numel()
+                rows = (rows.reshape(-1, 1) * B + c).reshape(-1)                      # dof rows, still grouped by node
+                ks = ks.reshape(-1, 1).expand(nrow, B).reshape(-1)
+                offs = (offs.reshape(-1, 1) * B + c).reshape(-1)
+                order = torch.sort(rows, stable=True).indices
+                rows, ks, offs = rows[order], ks[order], offs[order]
+            ni, no = ni * B, no * B
             cnt = torch.bincount(rows - ni, minlength=no - ni)
             bptr = torch.zeros(no - ni + 1, dtype=torch.int64, device=rows.device)
             bptr[1:] = torch.cumsum(cnt, 0)
@@ -82,8 +98,20 @@ class DistOperator:
             self.bk = ks.to(torch.uint8).to(self.dev).contiguous()
             self.boff = offs.to(torch.int32).to(self.dev).contiguous()
 
-    def solve(self, F_owned, mask_owned=None, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, check_every=16, minv=None):
+    def jacobi(self, mask_owned=None):
+        """1 / diag of the owned rows (0 where the mask fixes the dof or the diagonal vanishes): the corrected Jacobi diagonal."""
         no = self.part.n_owned
+        out = torch.empty(no * self.block, device=self.dev, dtype=torch.float64)
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            if self.block == 3:
+                check(lib.femb_bsr3_jacobi(no, ops._p(self.crow), ops._p(self.col), ops._p(self.val), ops._p(mask_owned), ops._p(out), st), "femb_bsr3_jacobi")
+            else:
+                check(lib.femb_csr_jacobi(no, ops._p(self.crow), ops._p(self.col), ops._p(self.val), ops._p(mask_owned), ops._p(out), st), "femb_csr_jacobi")
+        return out
+
+    def solve(self, F_owned, mask_owned=None, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, check_every=16, minv=None):
+        no = self.part.n_owned * self.block
         Ff = F_owned.to(self.dev, torch.float64).reshape(-1).contiguous()
         u = torch.zeros(no, device=self.dev, dtype=torch.float64) if u_init is None else \
             u_init.to(self.dev, torch.float64).reshape(-1).clone().contiguous()
@@ -93,11 +121,11 @@ class DistOperator:
         with torch.cuda.device(self.dev):
             check(lib.femb_dist_reset(self.own, st), "femb_dist_reset")
             dist.barrier()          # every rank's flags are zero before anyone starts pushing
-            check(lib.femb_dist_cg_solve(self.rank, self.P, no, int(getattr(self.part, "n_interior", 0)), self.nnz, ops._p(self.crow),
+            check(lib.femb_dist_cg_solve(self.rank, self.P, no, self.block * int(getattr(self.part, "n_interior", 0)), self.nnz, ops._p(self.crow),
                                          ops._p(self.col), ops._p(self.val), ops._p(Ff), ops._p(mask_owned), ops._p(minv), ops._p(u),
                                          ops._p(work), self.sym, self.nnbr, self.nbr, self.send_ptr,
                                          ops._p(self.send_idx), self.ghost_off, ops._p(self.bptr), ops._p(self.bk), ops._p(self.boff),
-                                         float(tol), int(max_iter), float(eps), int(check_every),
+                                         float(tol), int(max_iter), float(eps), int(check_every), self.block,
                                          C.byref(res), st), "femb_dist_cg_solve")
             dist.barrier()          # nobody frees / resets while a peer may still be storing
         info = {"iterations": res.iterations, "status": ops.STATUS.get(res.status, "?"), "rs": res.rs, "loop_ms": res.loop_ms}
@@ -122,6 +150,60 @@ def setup_poisson_p1(coords, elements, rank, world, dev):
     crow, col = plan.pattern(1)
     val = plan.assemble_c3d4(cl, "poisson")
     return part, plan, DistOperator(part, crow, col, val, dev), cl
+
+
+def setup_from_elements(K, elements, n_nodes, ndof, rank, world, dev, coords=None):
+    """Replicated element matrices K [M,nd,nd] + connectivity -> this rank's rows of the assembled operator (scalar CSR for
+    ndof = 1, 3x3 block-CSR for ndof = 3) with its halo plan.  Every rank assembles the elements touching its nodes: no
+    communication.  Returns (part, DistOperator)."""
+    elements = torch.as_tensor(elements).to(dev).long()
+    labels = partition.rcb_labels(torch.as_tensor(coords).to(dev), world) if coords is not None else partition.block_labels(n_nodes, world, dev)
+    part = partition.build_local_part(elements, labels, rank, world)
+    Kl = torch.as_tensor(K).to(dev)[part.element_ids].to(torch.float64).contiguous()
+    plan = ops.CsrPlan(part.elements_local, part.n_local, dev)
+    brow, bcol = plan.pattern(1)
+    vals = plan.assemble(Kl, ndof)
+    del Kl
+    if ndof == 3:
+        A = ops.Bsr3.from_csr_values(brow, bcol, vals)
+        return part, DistOperator(part, brow, bcol, A.bval, dev, block=3)
+    if ndof == 1:
+        return part, DistOperator(part, brow, bcol, vals, dev, block=1)
+    raise ValueError("the multi-GPU route supports 1 or 3 dofs per node")
+
+
+def solve_replicated(K, elements, F, fixed, u_init=None, tol=1e-10, max_iter=1000, eps=1e-30, jacobi=False, minv=None, coords=None,
+                     device=None, check_every=16):
+    """The solver API's multi-GPU route (one process per GPU, torch.distributed initialised, NCCL): every rank passes the same
+    (K, elements, F [N,ndof], fixed); rows are partitioned over the ranks, each rank assembles and solves its block over NVLink
+    peer memory, and the full solution comes back on every rank.  `jacobi=True` builds the corrected Jacobi diagonal from the
+    assembled rows; `minv` [N,ndof] (replicated) supplies one."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    F = torch.as_tensor(F).to(dev, torch.float64)
+    N, ndof = F.shape
+    part, op = setup_from_elements(K, elements, N, ndof, rank, world, dev, coords)
+    try:
+        og = part.owned_global
+        mask = torch.ones((N, ndof), dtype=torch.uint8, device=dev)
+        if fixed is not None and torch.as_tensor(fixed).numel():
+            f = torch.as_tensor(fixed).to(dev)
+            mask[f if f.dtype == torch.bool else f.long()] = 0
+        mo = mask[og].reshape(-1).contiguous()
+        mv = None
+        if minv is not None:
+            mv = torch.as_tensor(minv).to(dev, torch.float64)[og].reshape(-1).contiguous()
+        elif jacobi:
+            mv = op.jacobi(mo)
+        u0 = None if u_init is None else torch.as_tensor(u_init).to(dev, torch.float64)[og].reshape(-1)
+        u, info = op.solve(F[og].reshape(-1), mo, u_init=u0, tol=tol, max_iter=max_iter, eps=eps, check_every=check_every, minv=mv)
+        full = torch.zeros((N, ndof), dtype=torch.float64, device=dev)
+        full[og] = u.reshape(-1, ndof)
+        dist.all_reduce(full)
+    finally:
+        op.close()
+    info["ranks"] = world
+    return full, info
 
 
 def parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N, rel_tol=1e-10, max_iter=20000):
@@ -265,6 +347,123 @@ def bench(args, dev, rank, world, metric, unit):
                          "frac": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9 / (hbm * world), 4), "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes": bytes_iter},
         }
+        print(json.dumps(out), flush=True)
+    op.close()
+    dist.destroy_process_group()
+
+
+def bench_config2(args, dev, rank, world, metric, unit):
+    """`bench.py --config 2` on N >= 1 GPUs: BASELINE config 2 (P2 tet linear elasticity, ~2 M C3D10 tets, fp64): element K and
+    assembly of each rank's rows (aggregate elements/s), then Jacobi-PCG iterations/s on the 3x3 block-CSR operator over NVLink
+    peer memory, with a fixed-tolerance parity solve against the single-GPU loop."""
+    import json
+    import os
+    import sys
+    import element as el
+    from . import meshgen
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from bench import ClockSampler, peaks
+    n, K_it, W = args.n2, args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(dev.index or 0)
+    c1, t1 = meshgen.kuhn_cube(n, device=dev)
+    coords, e10 = meshgen.p1_to_p2_lattice(n, meshgen.swap01(t1), device=dev)
+    del c1, t1
+    M, N = e10.shape[0], coords.shape[0]
+    labels = partition.rcb_labels(coords, world)
+    part = partition.build_local_part(e10, labels, rank, world)
+    cl = partition.localize(coords, part).contiguous()
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    # ---- element K + assembly of this rank's rows
+    Kl = el.compute_c3d10_K_matrix(cl, part.elements_local, 1.0, 0.3, device=dev, dtype=torch.float64)
+    plan = ops.CsrPlan(part.elements_local, part.n_local, dev)
+    brow, bcol = plan.pattern(1)
+    vals = plan.assemble(Kl, 3)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a0, a1, a2 = ev(), ev(), ev()
+    a0.record()
+    for _ in range(3):
+        el.compute_c3d10_K_matrix(cl, part.elements_local, 1.0, 0.3, device=dev, dtype=torch.float64, out=Kl)
+    a1.record()
+    for _ in range(3):
+        plan.assemble(Kl, 3, out=vals)
+    a2.record()
+    torch.cuda.synchronize()
+    t_asm = torch.tensor([a0.elapsed_time(a1) / 3, a1.elapsed_time(a2) / 3], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_asm, op=dist.ReduceOp.MAX)
+    del Kl
+    A = ops.Bsr3.from_csr_values(brow, bcol, vals)
+    op = DistOperator(part, brow, bcol, A.bval, dev, block=3)
+    del A, vals
+    og = part.owned_global
+    mask = torch.ones((part.n_owned, 3), dtype=torch.uint8, device=dev)
+    mask[coords[og, 2] == 0] = 0
+    mask = mask.reshape(-1).contiguous()
+    ntop = float((coords[:, 2] == 1).sum())
+    F = torch.zeros((part.n_owned, 3), dtype=torch.float64, device=dev)
+    F[coords[og, 2] == 1, 2] = 1.0 / ntop
+    F = F.reshape(-1).contiguous()
+    minv = op.jacobi(mask)
+    op.solve(F, mask, tol=0.0, max_iter=max(W, 50), check_every=50, minv=minv)
+    torch.cuda.synchronize()
+    dist.barrier()
+    _, info = op.solve(F, mask, tol=0.0, max_iter=K_it, check_every=min(K_it, 50), minv=minv)
+    ms = torch.tensor([info["loop_ms"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    for _ in range(3):
+        op.solve(F, mask, tol=0.0, max_iter=400, check_every=100, minv=minv)
+    clocks = sampler.stop()
+    # ---- parity: |r|_M < 1e-9 |F| on N GPUs vs the single-GPU block-CSR loop (rank 0 assembles the global operator)
+    nf = (F * F).sum()
+    dist.all_reduce(nf)
+    tol = 1e-9 * float(nf.sqrt().item())
+    uN, infoN = op.solve(F, mask, tol=tol, max_iter=20000, check_every=50, minv=minv)
+    full = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+    full[og] = uN.reshape(-1, 3)
+    dist.all_reduce(full)
+    nnzb = torch.tensor([op.nnz], dtype=torch.float64, device=dev)
+    dist.all_reduce(nnzb)
+    parity = None
+    if rank == 0:
+        Kg = el.compute_c3d10_K_matrix(coords, e10, 1.0, 0.3, device=dev, dtype=torch.float64)
+        gplan = ops.CsrPlan(e10, N, dev)
+        gb, gc = gplan.pattern(1)
+        G = ops.Bsr3.from_csr_values(gb, gc, gplan.assemble(Kg, 3))
+        del Kg
+        gm = torch.ones((N, 3), dtype=torch.uint8, device=dev)
+        gm[coords[:, 2] == 0] = 0
+        gm = gm.reshape(-1).contiguous()
+        gF = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+        gF[coords[:, 2] == 1, 2] = 1.0 / ntop
+        u1, info1 = G.cg_solve(gF, mask=gm, minv=G.jacobi(gm), tol=tol, max_iter=20000, check_every=50)
+        err = float((full - u1).abs().max() / u1.abs().max())
+        parity = {"problem": f"P2 elasticity, z = 0 fixed, unit load on z = 1, Jacobi-PCG to sqrt(r.z) < {tol:.3e}",
+                  "iterations_N": infoN["iterations"], "iterations_1gpu": info1["iterations"], "status_N": infoN["status"],
+                  "status_1gpu": info1["status"], "rel_err_u": err,
+                  "ok": bool(infoN["status"] == info1["status"] == "converged" and abs(infoN["iterations"] - info1["iterations"]) <= 1 and err < 1e-8)}
+        del G, gplan
+    dist.barrier()
+    hbm, peak_src = peaks()
+    nnz = int(nnzb.item()) * 9
+    ms_it = float(ms.item()) / K_it
+    bytes_csr = nnz * 12 + 3 * N * 20 + 11 * 3 * N * 8            # SURVEY 8d: scalar-CSR SpMV + 11 vector passes (Jacobi-PCG)
+    if rank == 0:
+        msK, msA = float(t_asm[0].item()), float(t_asm[1].item())
+        out = {"metric": metric, "value": round(1e3 / ms_it, 2), "unit": unit, "n_gpus": world, "steps": K_it, "warmup": W,
+               "ms_per_step": round(ms_it, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": f"P2 tet linear elasticity, Kuhn n={n}: {M} C3D10 tets, {N} nodes, {3 * N} dofs, CSR nnz {nnz} "
+                                      "(BASELINE config 2); step = one Jacobi-PCG iteration (solver.py:766-812)", "tol": 0.0,
+                          "l2": "CSR operator %.1f GB in total" % (nnz * 12 / 1e9)},
+               "impl_details": {"partition": f"RCB on node coordinates, {world} parts; 3x3 block-CSR rows per rank; halo + all-reduce over NVLink peer memory"},
+               "clocks": clocks, "parity": parity,
+               "roofline": {"kernel": "whole Jacobi-PCG iteration (dist_spmv3_bsr3 + dist_merged_vec), aggregate over ranks", "bound": "hbm",
+                            "achieved": round(bytes_csr / (ms_it * 1e-3) / 1e9, 1), "peak": hbm * world, "unit": "GB/s",
+                            "frac": round(bytes_csr / (ms_it * 1e-3) / 1e9 / (hbm * world), 4), "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes": bytes_csr, "note": "scalar-CSR byte count of SURVEY 8d; the block layout moves 0.71 of it"},
+               "assembly": {"metric": "assembled_elems_per_s", "value": round(M / ((msK + msA) * 1e-3), 1), "element_K_ms": round(msK, 3),
+                            "assemble_ms": round(msA, 3), "what": "element K + assembly of each rank's rows, max over ranks; aggregate = global elements / that time"},
+               "gpu_launches": 2 * K_it + 5}
         print(json.dumps(out), flush=True)
     op.close()
     dist.destroy_process_group()

@@ -505,6 +505,31 @@ class CsrPlan:
         return out
 
 
+def p1_to_p2(coords, elements, device, dtype):
+    """Mid-edge insertion on the device (csrc/refine.cu): (coords' [N+E,3] dtype, conn10 [M,10] int32, edges [E,2] int32 = end
+    points of new node N+r).  Numbering = the reference's first-encounter order (element.py:777-833)."""
+    dev = cuda_device(device)
+    x = torch.as_tensor(coords).to(dev)
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.to(torch.float64)
+    x = x.contiguous()
+    conn = index(elements, dev)
+    M, N = conn.shape[0], x.shape[0]
+    h, ne = C.c_void_p(), C.c_int64()
+    with torch.cuda.device(dev):
+        check(lib.femb_p2_create(_p(conn), _fp(conn), M, N, _stream(dev), C.byref(h), C.byref(ne)), "femb_p2_create")
+        try:
+            E = ne.value
+            conn10 = torch.empty((M, 10), device=dev, dtype=torch.int32)
+            xo = torch.empty((N + E, 3), device=dev, dtype=dtype)
+            edges = torch.empty((E, 2), device=dev, dtype=torch.int32)
+            check(lib.femb_p2_fill(h, _p(conn), _fp(conn), _p(x), _fp(x), xo.element_size(), _p(conn10), _p(xo), _p(edges), _stream(dev)),
+                  "femb_p2_fill")
+        finally:
+            lib.femb_p2_destroy(h)
+    return xo, conn10, edges
+
+
 _PLAN_CACHE: "collections.OrderedDict" = collections.OrderedDict()
 PLAN_CACHE_BYTES = int(float(os.environ.get("FEMB_PLAN_CACHE_GB", "16")) * 2 ** 30)   # a 64 M-tet plan holds ~8 GB of HBM
 

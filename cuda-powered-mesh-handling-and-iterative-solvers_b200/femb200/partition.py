@@ -40,6 +40,12 @@ def rcb_labels(coords: torch.Tensor, nparts: int) -> torch.Tensor:
     return labels
 
 
+def block_labels(n_nodes: int, nparts: int, device="cpu") -> torch.Tensor:
+    """Coordinate-free partition: contiguous node-id ranges of (almost) equal size.  What the solver API falls back to when the
+    caller gives no coordinates (the reference's solvers take none); its quality is that of the mesh numbering."""
+    return (torch.arange(n_nodes, device=device) * nparts // max(n_nodes, 1)).clamp_(max=nparts - 1)
+
+
 @dataclass
 class LocalPart:
     rank: int

@@ -215,38 +215,24 @@ def identify_tetrahedral_shared_faces(elements, device="cuda:0"):
 
 
 def c3d4_to_c3d10(coords, elements, rbe2_ids=None, rbe3_ids=None, dtype=torch.float32, device=None):
-    """Mid-edge insertion with the reference's first-encounter numbering (element.py:777-833), done with parallel device
-    primitives instead of a Python dict loop: an edge's new id is N + (rank of its first occurrence in element-major,
+    """Mid-edge insertion with the reference's first-encounter numbering (element.py:777-833) as device kernels
+    (csrc/refine.cu: one stable radix sort of the edge keys, a max-scan of the group heads, a prefix sum over the first
+    occurrences) instead of a Python dict loop: an edge's new id is N + (rank of its first occurrence in element-major,
     slot (0,1),(1,2),(2,0),(0,3),(1,3),(2,3) order).  Returns (coords', elems[int32], rbe2', rbe3') on the CPU like the
-    reference unless `device` is given."""
+    reference unless `device` is given.  Mid points are formed in the precision of `coords` (the reference uses Python
+    floats, i.e. fp64, for fp64 input) and then cast to `dtype`."""
     dev = torch.as_tensor(elements).device if device is None else torch.device(device)
-    work = dev if dev.type == "cuda" else (torch.device("cuda:0") if torch.cuda.is_available() else dev)
-    x = torch.as_tensor(coords).to(work)
-    e = torch.as_tensor(elements).to(work).long()
-    N, M = x.shape[0], e.shape[0]
-    slots = torch.tensor([[0, 1], [1, 2], [2, 0], [0, 3], [1, 3], [2, 3]], device=work)
-    pr = e[:, slots]                                     # [M,6,2]
-    lo, hi = pr.min(dim=2).values, pr.max(dim=2).values
-    key = (lo * N + hi).reshape(-1)
-    uniq, inv = torch.unique(key, return_inverse=True)
-    first = torch.full((uniq.numel(),), key.numel(), device=work, dtype=torch.long)
-    first.scatter_reduce_(0, inv, torch.arange(key.numel(), device=work), reduce="amin")
-    rank = torch.empty_like(first)
-    rank[torch.argsort(first)] = torch.arange(uniq.numel(), device=work)
-    mids = (N + rank[inv]).reshape(M, 6)
-    new_elems = torch.cat([e, mids], dim=1).to(torch.int32)
-    ulo, uhi = uniq // N, uniq % N
-    mid_xyz = torch.empty((uniq.numel(), 3), device=work, dtype=x.dtype)
-    mid_xyz[rank] = (x[ulo] + x[uhi]) / 2
-    new_coords = torch.cat([x, mid_xyz], dim=0).to(dtype)
+    work = dev if dev.type == "cuda" else torch.device("cuda:0")
+    x = torch.as_tensor(coords)
+    N = x.shape[0]
+    new_coords, new_elems, edges = _ops.p1_to_p2(x, elements, work, dtype)
 
     def grow(ids):
         if ids is None:
             return torch.tensor([], dtype=torch.int32)
         m = torch.zeros(N, dtype=torch.bool, device=work)
         m[torch.as_tensor(ids).to(work).long()] = True
-        both = torch.zeros(uniq.numel(), dtype=torch.bool, device=work)
-        both[rank] = m[ulo] & m[uhi]
+        both = m[edges[:, 0].long()] & m[edges[:, 1].long()]
         return torch.cat([torch.nonzero(m).reshape(-1), N + torch.nonzero(both).reshape(-1)]).to(torch.int32)
 
     out_dev = torch.device("cpu") if device is None else dev

@@ -83,14 +83,29 @@ def _cg(K, elements, F, dev, **kw):
     return _Assembled(K, elements, N, ndof, dev).cg_solve(F, **kw)
 
 
+def _distributed_world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def stable_conjugate_gradient_solver(K, elements, F, rbe2, u_init=None, tol=1e-10, max_iter=1000, device="cuda:0", dtype=torch.float64,
-                                     eps=1e-30, return_info=False, verbose=True):
+                                     eps=1e-30, return_info=False, verbose=True, distributed=False, coords=None):
     """Projected CG with node fixing (solver.py:144-229).  K: element matrices [M,nd,nd] (assembled internally) or a
-    torch CSR tensor.  Arithmetic is fp64 (the reference's default); the result is cast to `dtype`."""
+    torch CSR tensor.  Arithmetic is fp64 (the reference's default); the result is cast to `dtype`.
+    `distributed=True` (additive; one process per GPU with torch.distributed initialised, every rank passing the same
+    arguments): rows are partitioned over the ranks -- by recursive coordinate bisection when `coords` is given, by node-id
+    ranges otherwise -- each rank assembles its rows from K and the loop runs over NVLink peer memory (femb200.dist_cg); the
+    full solution is returned on every rank.  Same iterates as the single-GPU loop up to summation order."""
     dev = _ops.cuda_device(device)
     F = torch.as_tensor(F).to(dev)
     N, ndof = F.shape
-    u, info = _cg(K, elements, F, dev, mask=_dof_mask(N, ndof, rbe2, dev), u_init=u_init, tol=tol, max_iter=max_iter, eps=eps)
+    if distributed and _distributed_world() > 1:
+        from femb200 import dist_cg
+        if K.layout == torch.sparse_csr:
+            raise ValueError("distributed=True assembles each rank's rows from element matrices: pass K as [M,nd,nd]")
+        u, info = dist_cg.solve_replicated(K, elements, F, rbe2, u_init=u_init, tol=tol, max_iter=max_iter, eps=eps, coords=coords, device=dev)
+    else:
+        u, info = _cg(K, elements, F, dev, mask=_dof_mask(N, ndof, rbe2, dev), u_init=u_init, tol=tol, max_iter=max_iter, eps=eps)
     if verbose:
         _report("CG", info, max_iter)
     u = u.to(dtype)
@@ -293,13 +308,20 @@ def compute_diagonal_preconditioner(K, elements, N, device="cuda:0", dtype=torch
 
 
 def preconditioned_conjugate_gradient_solver(K, elements, F, M_inv, u_init=None, tol=1e-8, max_iter=1000, device="cuda:0",
-                                             dtype=torch.float32, return_info=False, verbose=True):
+                                             dtype=torch.float32, return_info=False, verbose=True, distributed=False, coords=None):
     """Textbook Jacobi-PCG exactly as the reference writes it (solver.py:766-812): z = M_inv*r, converged iff
-    sqrt(r.z) < tol, no node fixing, no guards.  The loop runs in fp64 on the device; the result is cast to `dtype`."""
+    sqrt(r.z) < tol, no node fixing, no guards.  The loop runs in fp64 on the device; the result is cast to `dtype`.
+    `distributed=True`: the multi-GPU route of stable_conjugate_gradient_solver (M_inv replicated, [N,ndof])."""
     dev = _ops.cuda_device(device)
     F = torch.as_tensor(F).to(dev)
-    minv = torch.as_tensor(M_inv).to(dev, torch.float64).reshape(-1).contiguous()
-    u, info = _cg(K, elements, F, dev, mask=None, minv=minv, u_init=u_init, tol=tol, max_iter=max_iter, eps=0.0)
+    if distributed and _distributed_world() > 1:
+        from femb200 import dist_cg
+        u, info = dist_cg.solve_replicated(K, elements, F, None, u_init=u_init, tol=tol, max_iter=max_iter, eps=0.0,
+                                           minv=torch.as_tensor(M_inv).reshape(F.shape), coords=coords, device=dev)
+        minv = None
+    else:
+        minv = torch.as_tensor(M_inv).to(dev, torch.float64).reshape(-1).contiguous()
+        u, info = _cg(K, elements, F, dev, mask=None, minv=minv, u_init=u_init, tol=tol, max_iter=max_iter, eps=0.0)
     if verbose:
         if info["status"] == "converged":
             print(f"Converged after {info['iterations']} iterations.")

@@ -144,6 +144,17 @@ int femb_stress_helper(int what, const void* in, int fp, int64_t M, void* out, f
  * c3d20_to_c3d4 :1852-1896.  out[k*M,4] int64, k = 8/6/3/24. */
 int femb_to_c3d4(int kind, const void* conn, int ib, int64_t M, int64_t* out, femb_stream stream);
 
+/* c3d4_to_c3d10 :777-833 (P1 -> P2 mid-edge insertion; the reference is a Python dict loop).  New node ids are handed out
+ * in first-encounter order over (element-major, edge slots (0,1),(1,2),(2,0),(0,3),(1,3),(2,3)): bit-exact numbering.
+ * Count-then-fill: create returns the number of distinct edges E; fill writes conn10[M,10] int32, coords_out[N+E,3]
+ * (fp_out = 4 or 8; mid points are (x_lo + x_hi) / 2) and edges[E,2] int32 = the end points behind new node N + r (used
+ * by the caller to grow its RBE2 / RBE3 node sets).  Any of the three outputs may be NULL. */
+typedef struct femb_p2_plan femb_p2_plan;
+int femb_p2_create(const void* conn, int ib, int64_t M, int64_t n_nodes, femb_stream stream, femb_p2_plan** plan, int64_t* n_edges);
+int femb_p2_fill(femb_p2_plan* plan, const void* conn, int ib, const void* coords, int fp_in, int fp_out, int32_t* conn10,
+                 void* coords_out, int32_t* edges, femb_stream stream);
+int femb_p2_destroy(femb_p2_plan* plan);
+
 /* ---------------------------------------------------------------------------------------------
  * Topology (bit-exact): faces of solids, edges of shells
  *   surface: compute_tetrahedral_surface_faces_with_fourth_node :543-579, hex :1293-1334, wedge :2234-2283,
@@ -341,14 +352,18 @@ int femb_dist_close(void* ptr);
 int femb_dist_free(void* ptr);
 int femb_dist_reset(void* own_sym, femb_stream stream); /* zero the flags; callers barrier across ranks afterwards */
 
-/* The reference's projected CG (solver.py:144-229) on row-partitioned data.  Local CSR = owned rows only, columns in
- * local numbering [owned | ghost]; F, mask, u are owned-only.  sym_host[P] = every rank's symmetric buffer as mapped in
- * this process.  For neighbour k: nbr_host[k] = its rank, send_idx[send_ptr_host[k]..send_ptr_host[k+1]) = my owned
- * entries it needs, ghost_off_host[k] = index in ITS p where my block starts.  The halo exchange and both all-reduces
- * are peer stores + epoch flags inside ONE persistent cooperative kernel per solve (FEMB_DIST_GRAPH=1 selects the
- * four-kernels-per-iteration CUDA graph instead); there is no NCCL call.  Rows [0,n_interior) must not reference ghost
- * columns (their SpMV overlaps the exchange); pass 0 if the rows are not ordered that way.  minv != NULL = Jacobi-PCG.
- * work = 2*n_owned. */
+/* The reference's projected CG (solver.py:144-229) / Jacobi-PCG (:766-812, minv != NULL) on row-partitioned data.
+ * Local operator = owned rows only, columns in local numbering [owned | ghost]; F, mask, minv, u are owned-only.
+ *   block = 1: scalar CSR (crow[n_owned+1], col, val[nnz]);
+ *   block = 3: 3x3 block-CSR of a 3-dof operator (crow/col = node-level pattern of the n_owned/3 owned nodes, val = nnz
+ *              row-major blocks); rows, halo lists and the boundary table are dof-level (3*node + component).
+ * sym_host[P] = every rank's symmetric buffer as mapped in this process.  For neighbour k: nbr_host[k] = its rank,
+ * send_idx[send_ptr_host[k]..send_ptr_host[k+1]) = my owned entries it needs, ghost_off_host[k] = index in ITS p where my
+ * block starts.  One iteration = two kernels in a CUDA graph (merged-reduction loop): SpMV + three dot products, then one
+ * vector pass; the halo exchange is peer stores + epoch flags, the all-reduce "LL" words (value and epoch in one 8-byte
+ * store) -- there is no NCCL call in the loop.  Convergence is tested on the exactly summed r.r (r.z) one SpMV late, so the
+ * returned state is the reference's at its break.  Rows [0,n_interior) must not reference ghost columns (their SpMV
+ * overlaps the exchange); pass 0 if the rows are not ordered that way.  work = 2*n_owned. */
 int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t n_interior, int64_t nnz, const int32_t* crow,
                        const int32_t* col, const double* val, const double* F, const uint8_t* mask, const double* minv,
                        double* u, double* work,
@@ -356,9 +371,9 @@ int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t n_interior
                        const int32_t* send_idx, const int64_t* ghost_off_host,
                        /* optional (NULL = separate push kernel): CSR over the boundary rows [n_interior,n_owned) of their
                         * destinations, bk = neighbour index, boff = offset in that neighbour's ghost block; lets the
-                        * direction update store boundary values straight into the neighbours' ghost slots */
+                        * vector kernel store boundary values straight into the neighbours' ghost slots */
                        const int32_t* bptr, const uint8_t* bk, const int32_t* boff, double tol, int max_iter, double eps,
-                       int check_every, femb_cg_result* result_host, femb_stream stream);
+                       int check_every, int block, femb_cg_result* result_host, femb_stream stream);
 
 #ifdef __cplusplus
 }

@@ -52,8 +52,60 @@ def main():
         print(f"dist_gpu_check world={world}: iterations {info['iterations']} (oracle {ito}), rel err {err:.2e}, "
               f"neighbors {part.neighbors}, ghosts {part.n_ghost}, loop {info['loop_ms']:.2f} ms -> {'OK' if ok else 'FAIL'}", flush=True)
     op.close()
+    ok = ok and check_elasticity_routes(rank, world, dev)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+def check_elasticity_routes(rank, world, dev):
+    """3-dof operators over several GPUs through the solver API (distributed=True): 3x3 block-CSR rows per rank, projected CG
+    and Jacobi-PCG, P1 (node-id partition) and P2 (RCB on coordinates), against the single-process oracle / single-GPU loop."""
+    import element as el
+    import solver as sv
+    from femb200 import meshgen
+    from oracle import fem_oracle as O
+    ok = True
+    n = int(os.environ.get("FEMB_CHECK_NE", "6"))
+    c, t = meshgen.kuhn_cube(n, jitter=0.15)
+    K = el.compute_c3d4_K_matrix(c, t, 1.0, 0.3, device=dev, dtype=torch.float64)
+    fixed = torch.nonzero(c[:, 2] == 0).reshape(-1)
+    F = torch.zeros(c.shape[0], 3, dtype=torch.float64)
+    F[c[:, 2] == 1, 2] = 1.0 / float((c[:, 2] == 1).sum())
+    u, info = sv.stable_conjugate_gradient_solver(K, t, F, fixed, tol=1e-9, max_iter=5000, device=dev, return_info=True, verbose=False,
+                                                  distributed=True)
+    u2, info2 = sv.stable_conjugate_gradient_solver(K, t, F, fixed, tol=1e-9, max_iter=5000, device=dev, return_info=True, verbose=False,
+                                                    distributed=True)
+    assert torch.equal(u, u2) and info["iterations"] == info2["iterations"]          # deterministic, flags survive a second solve
+    if rank == 0:
+        uo, ito, st = O.stable_cg(K.cpu().numpy(), t.numpy(), F.numpy(), fixed.numpy(), tol=1e-9, max_iter=5000)
+        err = np.abs(u.cpu().numpy() - uo).max() / np.abs(uo).max()
+        good = st == "converged" and info["status"] == "converged" and abs(info["iterations"] - ito) <= 1 and err < 1e-8
+        print(f"dist_gpu_check world={world} P1 elasticity (block-CSR, node-id partition): iterations {info['iterations']} (oracle {ito}), "
+              f"rel err {err:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+        ok = ok and good
+    # Jacobi-PCG with the corrected diagonal, P2 elements, RCB partition on the P2 coordinates
+    c2, e10, _, _ = el.c3d4_to_c3d10(c, meshgen.swap01(t), dtype=torch.float64)
+    e10 = e10.long()
+    K2 = el.compute_c3d10_K_matrix(c2, e10, 1.0, 0.3, device=dev, dtype=torch.float64)
+    fixed2 = torch.nonzero(c2[:, 2] == 0).reshape(-1)
+    F2 = torch.zeros(c2.shape[0], 3, dtype=torch.float64)
+    F2[c2[:, 2] == 1, 2] = 1.0 / float((c2[:, 2] == 1).sum())
+    Minv = sv.compute_diagonal_preconditioner(K2, e10, c2.shape[0], device=dev, dtype=torch.float64)
+    Minv[fixed2.to(Minv.device)] = 0.0              # fixed rows: M_inv = 0 keeps them at zero in the BC-less PCG loop (SURVEY 8c)
+    up, ip = sv.preconditioned_conjugate_gradient_solver(K2, e10, F2, Minv, tol=1e-9, max_iter=5000, device=dev, dtype=torch.float64,
+                                                         return_info=True, verbose=False, distributed=True, coords=c2)
+    if rank == 0:
+        u1, i1 = sv.preconditioned_conjugate_gradient_solver(K2, e10, F2, Minv, tol=1e-9, max_iter=5000, device=dev, dtype=torch.float64,
+                                                             return_info=True, verbose=False)
+        err = float((up - u1).abs().max() / u1.abs().max())
+        good = ip["status"] == i1["status"] == "converged" and abs(ip["iterations"] - i1["iterations"]) <= 1 and err < 1e-8
+        print(f"dist_gpu_check world={world} P2 elasticity Jacobi-PCG (block-CSR, RCB): iterations {ip['iterations']} (1 GPU {i1['iterations']}), "
+              f"rel err {err:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+        ok = ok and good
+    dist.barrier()
+    return ok
 
 
 if __name__ == "__main__":

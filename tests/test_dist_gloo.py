@@ -136,3 +136,25 @@ def test_rcb_is_balanced_and_deterministic():
             sent = parts[r].owned_global[parts[r].send_idx[q]]
             o = parts[q].recv_off[r]
             assert torch.equal(sent, parts[q].ghost_global[o:o + parts[q].recv_cnt[r]])
+
+
+def test_block_partition_halo_plans_agree():
+    """The coordinate-free partition of the solver API's multi-GPU route (node-id ranges): balanced, every node owned once,
+    and the pairwise halo plans agree like the RCB ones."""
+    from femb200 import partition
+    c, t, _ = _problem(7)
+    N = c.shape[0]
+    for P in (2, 3, 5):
+        lab = partition.block_labels(N, P)
+        cnt = torch.bincount(lab, minlength=P)
+        assert cnt.sum() == N and cnt.max() - cnt.min() <= 1 and bool((lab[1:] >= lab[:-1]).all())
+        parts = [partition.build_local_part(t, lab, r, P) for r in range(P)]
+        owned = torch.cat([p.owned_global for p in parts])
+        assert torch.equal(torch.sort(owned).values, torch.arange(N))
+        for r in range(P):
+            assert parts[r].n_interior <= parts[r].n_owned
+            for q in parts[r].neighbors:
+                sent = parts[r].owned_global[parts[r].send_idx[q]]
+                o = parts[q].recv_off[r]
+                assert torch.equal(sent, parts[q].ghost_global[o:o + parts[q].recv_cnt[r]])
+                assert int(parts[r].send_idx[q].min()) >= parts[r].n_interior      # only boundary rows are sent

@@ -1009,3 +1009,38 @@ def test_solves_on_two_devices_in_one_thread(api):
         assert info["status"] == "converged" and str(u.device) == dev
         outs.append(u.cpu())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_p1_to_p2_kernel_vs_oracle(api, O):
+    """c3d4_to_c3d10 as device kernels (csrc/refine.cu): the reference's first-encounter numbering (element.py:777-833) on a
+    shuffled, renumbered mesh (bit-exact connectivity), mid points, int32 / int64 input, and the RBE set growth rule
+    (a mid node joins a set when both end points are in it, :806-809) against a Python-set restatement."""
+    el = api[0]
+    from femb200 import meshgen
+    c, t = meshgen.kuhn_cube(5, jitter=0.2)
+    g = torch.Generator().manual_seed(11)
+    perm = torch.randperm(c.shape[0], generator=g)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(c.shape[0])
+    c2, t2 = c[perm], inv[t][torch.randperm(t.shape[0], generator=g)]
+    oc, oe = O.c3d4_to_c3d10(N(c2), N(t2))
+    rb2 = torch.nonzero(c2[:, 2] < 0.3).reshape(-1)
+    rb3 = torch.nonzero(c2[:, 0] > 0.7).reshape(-1)
+    for conn in (t2, t2.to(torch.int32)):
+        nc, ne, r2, r3 = el.c3d4_to_c3d10(c2, conn, rb2, rb3, dtype=torch.float64)
+        assert ne.dtype == torch.int32 and nc.dtype == torch.float64 and nc.device.type == "cpu"
+        same(ne, oe)
+        close(nc, oc, 1e-15)
+        for got, base in ((r2, rb2), (r3, rb3)):
+            want = set(base.tolist())
+            for e in range(oe.shape[0]):
+                for (a, b), m in zip(((0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)), oe[e, 4:].tolist()):
+                    if int(oe[e, a]) in want and int(oe[e, b]) in want and int(oe[e, a]) < c2.shape[0] and int(oe[e, b]) < c2.shape[0]:
+                        want.add(m)
+            assert set(got.tolist()) == want and got.dtype == torch.int32
+    nc32, _, _, _ = el.c3d4_to_c3d10(c2, t2, dtype=torch.float32, device=DEV)
+    assert nc32.dtype == torch.float32 and nc32.device.type == "cuda"
+    close(nc32.double(), oc, 1e-6)
+    # empty mesh
+    nc0, ne0, _, _ = el.c3d4_to_c3d10(c2, torch.zeros((0, 4), dtype=torch.int64), dtype=torch.float64)
+    assert ne0.shape == (0, 10) and nc0.shape == c2.shape
