@@ -565,7 +565,7 @@ def spmv(crow, col, val, x):
     y = torch.empty(n, device=dev, dtype=torch.float64)
     with torch.cuda.device(dev):
         check(lib.femb_spmv(n, val.numel(), _p(crow), _p(col), _p(val), _p(xx), _p(y), _stream(dev)), "femb_spmv")
-    return y.reshape(x.shape)
+    return y.reshape(x.shape) if x.numel() == n else y          # rectangular operators (restriction) return [n]
 
 
 def jacobi(crow, col, val, mask=None):

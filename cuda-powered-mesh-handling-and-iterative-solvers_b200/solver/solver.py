@@ -562,10 +562,12 @@ def static_structure_solver(coords, force, fixed, c3d4=None, c3d6=None, c3d8=Non
 
 
 def hybrid_subdivided_solver(coords, elements, levels, load_fn, fixed_fn, E=None, nu=None, kind="elasticity", tol=1e-8, max_iter=10000,
-                             device="cuda:0", verbose=True):
+                             device="cuda:0", verbose=True, mode="multilevel"):
     """Additive API for the reference's announced "hybrid solver of iterative and inverse methods with sub-divided mesh"
-    (README.md:7; the notebook stops before any solve loop): direct solve on the coarse C3D4 mesh, then `levels` uniform
-    refinements (c3d4_to_c3d10 + c3d10_to_c3d4), each solved by the reference CG loop warm-started from the prolongated
-    coarser solution.  See femb200/hybrid.py.  Returns (u_fine, coords_fine, elements_fine, info)."""
+    (README.md:7; the notebook stops before any solve loop): the coarse C3D4 mesh is solved directly (dense Cholesky) and
+    refined `levels` times (c3d4_to_c3d10 + c3d10_to_c3d4).  mode="multilevel": CG on the finest mesh preconditioned by a
+    V-cycle over the hierarchy with the direct solve at the bottom; mode="cascade": every level solved by the reference CG
+    loop warm-started from the prolongated coarser solution.  See femb200/hybrid.py.
+    Returns (u_fine, coords_fine, elements_fine, info)."""
     from femb200 import hybrid
-    return hybrid.hybrid_solve(coords, elements, levels, load_fn, fixed_fn, E, nu, kind, tol, max_iter, device, _el, verbose)
+    return hybrid.hybrid_solve(coords, elements, levels, load_fn, fixed_fn, E, nu, kind, tol, max_iter, device, _el, verbose, mode)
