@@ -437,6 +437,11 @@ __global__ void __launch_bounds__(DBSR_THREADS) dist_spmv3_bsr3_kernel(Peers pe,
       waited = true;
     }
     const int a = __ldg(brow + r), e = __ldg(brow + r + 1);
+    double r_own = 0.0, w_own = 1.0;  // requested before the block loop (see spmv_bsr3_vec_kernel)
+    if (lane == 0 || lane == 3 || lane == 6) {
+      r_own = rvec[3 * r + lane / 3];
+      if (wvec) w_own = wvec[3 * r + lane / 3];
+    }
     double acc = 0.0;
     if (active) {
       int b = a + boff;
@@ -458,9 +463,8 @@ __global__ void __launch_bounds__(DBSR_THREADS) dist_spmv3_bsr3_kernel(Peers pe,
       const long long i = 3 * r + lane / 3;
       double sv = acc;
       if (mask && !mask[i]) sv = 0.0;
-      const double w = wvec ? wvec[i] : 1.0;
       dot += sv * __ldg(x + i);
-      e0 += sv * (w * rvec[i]), e1 += sv * (sv * w);
+      e0 += sv * (w_own * r_own), e1 += sv * (sv * w_own);
       y[i] = sv;
     }
   }

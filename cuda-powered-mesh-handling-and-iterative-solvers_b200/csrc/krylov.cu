@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(long long n, const i
                                                             const double* __restrict__ val, const double* __restrict__ x,
                                                             double* __restrict__ y, const unsigned char* __restrict__ mask,
                                                             double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards,
-                                                            const double* __restrict__ rvec, double tol) {
+                                                            const double* __restrict__ rvec, double tol, const double* __restrict__ wvec) {
   if (st && st->stop) return;
   const bool accumulate = (guards & 2) != 0;  // y += A x (operator given as a sum of matrices)
   guards &= 1;
@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(long long n, const i
       if (FUSED) {
         if (mask && !mask[r]) sum = 0.0;
         dot += sum * __ldg(x + r);
-        if (rvec) e0 += sum * rvec[r], e1 += sum * sum;
+        if (rvec) {  // merged-reduction sums; wvec = the Jacobi diagonal of PCG (z = wvec .* r)
+          const double w = wvec ? wvec[r] : 1.0;
+          e0 += sum * (w * rvec[r]), e1 += sum * (sum * w);
+        }
       }
       y[r] = sum;
     }
@@ -153,7 +156,8 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(long long n, 
                                                                    const double* __restrict__ val, const double* __restrict__ x,
                                                                    double* __restrict__ y, const unsigned char* __restrict__ mask,
                                                                    double* __restrict__ partial, CGState* __restrict__ st, double eps,
-                                                                   int guards, const double* __restrict__ rvec, double tol) {
+                                                                   int guards, const double* __restrict__ rvec, double tol,
+                                                                   const double* __restrict__ wvec) {
   if (st && st->stop) return;
   const double dot = spmv_stream_rows<LR, true>(n, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED);
   if (FUSED) cg_k1_epilogue(dot, partial, st, eps, guards & 1);
@@ -165,12 +169,13 @@ __global__ void __launch_bounds__(TMA_THREADS) spmv_tma_kernel(long long n, long
                                                                const double* __restrict__ val, const double* __restrict__ x,
                                                                double* __restrict__ y, const unsigned char* __restrict__ mask,
                                                                double* __restrict__ partial, CGState* __restrict__ st, double eps, int guards,
-                                                               const double* __restrict__ rvec, double tol, long long pin) {
+                                                               const double* __restrict__ rvec, double tol, long long pin,
+                                                               const double* __restrict__ wvec) {
   pdl_launch_dependents();
   double extra[2] = {0.0, 0.0};
   const double dot = spmv_tma_rows<LR, true, TMA_THREADS, TMA_STAGES, TMA_CAP, NoHaloWait, PdlWait>(
       n, nnz, crow, col, val, x, y, mask, (guards & 2) != 0, FUSED, 0x7fffffffffffffffll, NoHaloWait(), rvec, rvec ? extra : nullptr, PdlWait(),
-      st ? &st->stop : nullptr, pin);
+      st ? &st->stop : nullptr, pin, wvec);
   if (st && st->stop) return;  // block-uniform: the flag is only written by the previous kernel's last CTA
   if (FUSED) {
     if (rvec) cg_k1_epilogue3_n<TMA_THREADS>(dot, extra[0], extra[1], partial, st, eps, guards & 1, tol);
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(TMA_THREADS) spmv_bsr3_tma_kernel(long long nb
                                                                     const double* __restrict__ x, double* __restrict__ y,
                                                                     const unsigned char* __restrict__ mask, double* __restrict__ partial,
                                                                     CGState* __restrict__ st, double eps, int guards,
-                                                                    const double* __restrict__ rvec, double tol) {
+                                                                    const double* __restrict__ rvec, double tol, const double* __restrict__ wvec) {
   if (st && st->stop) return;
   const double dot = spmv_bsr3_tma_rows<LR, true>(nb, nnzb, brow, bcol, bval, x, y, mask, (guards & 2) != 0, FUSED);
   if (FUSED) cg_k1_epilogue_n<TMA_THREADS>(dot, partial, st, eps, guards & 1);
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(BSRV_THREADS) spmv_bsr3_vec_kernel(long long n
                                                                      const double* __restrict__ x, double* __restrict__ y,
                                                                      const unsigned char* __restrict__ mask, double* __restrict__ partial,
                                                                      CGState* __restrict__ st, double eps, int guards,
-                                                                     const double* __restrict__ rvec, double tol) {
+                                                                     const double* __restrict__ rvec, double tol, const double* __restrict__ wvec) {
   if (st && st->stop) return;
   const bool accumulate = (guards & 2) != 0;
   guards &= 1;
@@ -218,8 +223,16 @@ __global__ void __launch_bounds__(BSRV_THREADS) spmv_bsr3_vec_kernel(long long n
   const bool active = lane < 27;
   const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
   double dot = 0.0;
+  const bool owner = lane == 0 || lane == 3 || lane == 6;  // these lanes finish row 3r + lane/3
   for (long long r = gw; r < nb; r += nw) {
     const int a = __ldg(brow + r), e = __ldg(brow + r + 1);
+    // the row's own vector entries are requested before the block loop: r and minv stream from DRAM, and loading them after
+    // the shuffles put a full memory latency at the end of every row (merged Jacobi-PCG: 2.06 ms instead of 1.46 per iteration)
+    double r_own = 0.0, w_own = 1.0;
+    if (MERGED && owner) {
+      r_own = rvec[3 * r + lane / 3];
+      if (wvec) w_own = wvec[3 * r + lane / 3];
+    }
     double acc = 0.0;
     if (active) {
       int b = a + boff;
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(BSRV_THREADS) spmv_bsr3_vec_kernel(long long n
       if (FUSED) {
         if (mask && !mask[i]) sv = 0.0;
         dot += sv * __ldg(x + i);
-        if (MERGED) e0 += sv * rvec[i], e1 += sv * sv;
+        if (MERGED) e0 += sv * (w_own * r_own), e1 += sv * (sv * w_own);
       }
       y[i] = sv;
     }
@@ -354,8 +367,9 @@ __global__ void __launch_bounds__(VEC_THREADS) cg_direction_kernel(long long n, 
 
 // merged loop, second kernel: all scalars were fixed by the SpMV's last CTA (cg_k1_epilogue3_n)
 __global__ void __launch_bounds__(VEC_THREADS) cg_merged_kernel(long long n, double* __restrict__ u, double* __restrict__ r, double* __restrict__ p,
-                                                                const double* __restrict__ Ap, double* __restrict__ partial,
-                                                                CGState* __restrict__ st, int max_iter, double tol) {
+                                                                const double* __restrict__ Ap, const double* __restrict__ minv,
+                                                                double* __restrict__ partial, CGState* __restrict__ st, int max_iter, double tol) {
+  // minv != nullptr: Jacobi-PCG (solver.py:766-812): z = minv .* r, the exact sum is r.z, p = z + beta p
   pdl_launch_dependents();
   pdl_wait();
   if (st->stop) return;
@@ -364,10 +378,11 @@ __global__ void __launch_bounds__(VEC_THREADS) cg_merged_kernel(long long n, dou
   double dot = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double pi = p[i], ri = r[i] - alpha * Ap[i];
+    const double zi = minv ? minv[i] * ri : ri;
     u[i] += alpha * pi;
     r[i] = ri;
-    dot += ri * ri;
-    if (move_p) p[i] = ri + beta * pi;
+    dot += ri * zi;
+    if (move_p) p[i] = zi + beta * pi;
   }
   const double t = block_sum<VEC_THREADS>(dot);
   __shared__ bool last;
@@ -476,26 +491,26 @@ static thread_local long long pin_hint = 0;  // leading nonzeros staged evict_la
 template <bool FUSED>
 static void launch_spmv(int lanes, int grid, cudaStream_t s, long long n, const int* crow, const int* col, const double* val, const double* x,
                         double* y, const unsigned char* mask, double* partial, CGState* st, double eps, int guards,
-                        const double* rvec = nullptr, double tol = 0.0) {
-#define FEMB_SPMV_ARGS n, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol
+                        const double* rvec = nullptr, double tol = 0.0, const double* wvec = nullptr) {
+#define FEMB_SPMV_ARGS n, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol, wvec
 #define FEMB_TMA(LRV)                                                                                                              \
   {                                                                                                                                \
     cudaFuncSetAttribute(spmv_tma_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);                 \
     launch_pdl(spmv_tma_kernel<LRV, FUSED>, grid, TMA_THREADS, TMA_SMEM, s, pdl_hint, n, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, \
-               guards, rvec, tol, pin_hint);                                                                                     \
+               guards, rvec, tol, pin_hint, wvec);                                                                               \
   }
 #define FEMB_BSR(LRV)                                                                                                              \
   {                                                                                                                                \
     cudaFuncSetAttribute(spmv_bsr3_tma_kernel<LRV, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSR_SMEM);            \
-    spmv_bsr3_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, BSR_SMEM, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
+    spmv_bsr3_tma_kernel<LRV, FUSED><<<grid, TMA_THREADS, BSR_SMEM, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol, wvec); \
   }
   switch (lanes) {
 #define FEMB_BSRV(UV)                                                                                                              \
   {                                                                                                                                \
     if (FUSED && rvec)                                                                                                             \
-      spmv_bsr3_vec_kernel<FUSED, UV, FUSED><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
+      spmv_bsr3_vec_kernel<FUSED, UV, FUSED><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol, wvec); \
     else                                                                                                                           \
-      spmv_bsr3_vec_kernel<FUSED, UV, false><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol); \
+      spmv_bsr3_vec_kernel<FUSED, UV, false><<<grid, BSRV_THREADS, 0, s>>>(n / 3, nnz_hint, crow, col, val, x, y, mask, partial, st, eps, guards, rvec, tol, wvec); \
   }
     case 300: FEMB_BSRV(4) break;
     case 301: FEMB_BSRV(2) break;
@@ -602,11 +617,14 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   double *r = work, *p = work + n, *Ap = work + 2 * n;
   int lanes[8], g1[8], gmax = 1;
   for (int m = 0; m < nmat; ++m) lanes[m] = pick_lanes(n, mats[m].nnz, mats[m].block);
-  // merged-reduction loop (2 kernels, 7 vector passes per iteration) for plain CG on every SpMV kernel that sums the two extra
-  // dot products; PCG, the LDG-streaming / block-TMA A/B kernels and FEMB_CG_CLASSIC=1 take the three-kernel loop
+  // merged-reduction loop (2 kernels, 7 vector passes per iteration) for CG and Jacobi-PCG (the preconditioner's diagonal weights
+  // the two extra sums) on every SpMV kernel that forms them; the LDG-streaming / block-TMA A/B kernels and FEMB_CG_CLASSIC=1
+  // take the three-kernel loop
   static const bool classic_env = getenv("FEMB_CG_CLASSIC") != nullptr;
   const int ll = lanes[nmat - 1];
-  const bool merged = !classic_env && !minv && (ll >= 300 || (ll >= 100 && ll < 200) || ll < 0);
+  // (block-CSR Jacobi-PCG keeps the three-kernel loop: on the 2 M-tet P2 operator the merged block SpMV measured 1.96 ms per
+  // iteration against 1.47 ms -- the warp-per-block-row kernel is latency-bound and pays for the two extra streamed vectors)
+  const bool merged = !classic_env && ((ll >= 300 && !minv) || (ll >= 100 && ll < 200) || ll < 0);
   for (int m = 0; m < nmat; ++m) {
     g1[m] = spmv_grid(n, lanes[m], merged && m == nmat - 1);  // one grid per matrix: setup (plain) and loop (fused) launches share it
     gmax = std::max(gmax, g1[m]);
@@ -642,9 +660,9 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
       pdl_hint = pdl && k > 0 && (pdl_mode() & 2);
       pin_hint = pdl ? spmv_pin_entries(mats[last].nnz) : 0;
       launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
-                        guards | (last ? 2 : 0), r, tol);
+                        guards | (last ? 2 : 0), r, tol, minv);
       pdl_hint = false, pin_hint = 0;
-      launch_pdl(cg_merged_kernel, g2v, VEC_THREADS, 0, s, pdl && (pdl_mode() & 1), n, u, r, p, Ap, partial, st, max_iter, tol);
+      launch_pdl(cg_merged_kernel, g2v, VEC_THREADS, 0, s, pdl && (pdl_mode() & 1), n, u, r, p, Ap, minv, partial, st, max_iter, tol);
     } else {
       launch_spmv<true>(lanes[last], g1[last], s, n, mats[last].crow, mats[last].col, mats[last].val, p, Ap, mask, partial, st, eps,
                         guards | (last ? 2 : 0));
