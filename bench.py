@@ -315,6 +315,14 @@ def run_gpu(args):
     ms_call = c0.elapsed_time(c1)
     ms_loop = info["loop_ms"]
     assert info["iterations"] == K, info
+    # a K-step loop of a few milliseconds is at the mercy of one clock ramp: the same EXACTLY-K-step solve is repeated until
+    # >= 50 ms have been timed in total and the median is reported (`timed_repeats` in the line)
+    loops = [ms_loop]
+    while sum(loops) < 50.0 and len(loops) < 25:
+        _, info_r = ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=K, check_every=min(K, 50))
+        loops.append(info_r["loop_ms"])
+    loops.sort()
+    ms_loop = loops[len(loops) // 2]
     bytes_iter = bytes_spmv + 9 * N * 8
 
     # ---- e2e: public solver API, load vector from pinned host memory, solution read back to the host
@@ -374,7 +382,7 @@ def run_gpu(args):
         "e2e": {"value": round(K / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(F_host.numel() * 8 / K),
                 "d2h_bytes_per_step": int(u_host.numel() * 8 / K),
                 "note": f"one solver-API call of {K} iterations: F pinned host -> device, CG, u -> pinned host; bytes are per call / K"},
-        "gpu_launches": (3 if os.environ.get("FEMB_CG_CLASSIC") else 2) * K + 4,
+        "gpu_launches": (3 if os.environ.get("FEMB_CG_CLASSIC") else 2) * K + 4, "timed_repeats": len(loops),
         "roofline": {"kernel": "spmv_tma_kernel<1,false> (TMA-pipelined CSR SpMV; its fused twin is CG step k1)", "bound": "hbm",
                      "achieved": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
                      "frac": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9 / hbm, 4), "traffic": ncu_traffic(n, "spmv_tma_kernel"), "peak_source": peak_src,
