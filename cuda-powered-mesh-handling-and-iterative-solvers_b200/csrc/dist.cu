@@ -545,9 +545,6 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
         }
       }
     }
-    // peer stores must be performed before this CTA's ticket (the halo flag follows the last ticket); CTAs whose threads all
-    // lie beyond the boundary rows stored nothing remotely and skip the system-scope fence
-    if (blockIdx.x * (long long)blockDim.x < n - bp.n_interior) __threadfence_system();
   }
   for (long long i = gtid; i < n_plain; i += gsz) {
     const double pi = p[i], ri = r[i] - alpha * Ap[i];
@@ -557,6 +554,11 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
     dot += ri * zi;
     if (move_p) p[i] = zi + beta * pi;
   }
+  // Peer stores must be performed before this CTA's ticket (the halo flag follows the last ticket).  The system-scope fence
+  // sits AFTER the interior rows: by then the remote stores issued above have long been acknowledged, so it returns at once
+  // instead of exposing an NVLink round trip in the CTAs that own boundary rows.  CTAs whose threads all lie beyond the
+  // boundary rows stored nothing remotely and skip it.
+  if (bp.ptr && blockIdx.x * (long long)blockDim.x < n - bp.n_interior) __threadfence_system();
   const double t = block_sum<DV_THREADS>(dot);
   __shared__ bool last;
   if (threadIdx.x == 0) {
