@@ -40,6 +40,8 @@ struct SymHeader {
   // receiver knows a value is complete the moment it sees the epoch.  Words 0..5 = lo/hi of p.Ap, r.Ap, Ap.Ap (epoch B),
   // words 6..7 = lo/hi of the exactly summed r.r (epoch C).
   volatile unsigned long long ll[2][MAXP][8];
+  volatile long long flagS[MAXP];  // start barrier of the iteration graph (rank q has finished its setup and enqueued its loop)
+  long long pad2[MAXP];
 };
 static_assert(sizeof(SymHeader) % 256 == 0, "header keeps p 256-byte aligned");
 
@@ -216,7 +218,12 @@ __global__ void __launch_bounds__(DV_THREADS) dist_update_kernel(Peers pe, long 
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 5);
   wait_flags(me->flagB, all, pe.P, st->epochB, st);
-  if (st->stop) return;
+  {  // block-uniform (one read per CTA): CTA 0 may raise the flag below while this CTA is still on its way here
+    __shared__ int stop_now;
+    if (threadIdx.x == 0) stop_now = st->stop;
+    __syncthreads();
+    if (stop_now) return;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 6);
   const double pAp = sum_slots(me->redB, pe.P);
   const double alpha = st->rs_old / (pAp + eps);
@@ -275,7 +282,12 @@ __global__ void __launch_bounds__(DV_THREADS) dist_direction_kernel(Peers pe, lo
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 8);
   wait_flags(me->flagC, all, pe.P, st->epochC, st);
-  if (st->stop) return;
+  {  // block-uniform (one read per CTA), see dist_update_kernel
+    __shared__ int stop_now;
+    if (threadIdx.x == 0) stop_now = st->stop;
+    __syncthreads();
+    if (stop_now) return;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 9);
   const double rs_new = sum_slots(me->redC, pe.P);
   const double beta = rs_new / (st->rs_old + eps);
@@ -496,8 +508,11 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
       else halves[t] = it > 0 ? ll_wait(&me->ll[pc][q][w], eC, st) : 0u;
     }
   }
+  // block-uniform exit on a spin timeout (status 3): ONE read per CTA, broadcast through shared memory
+  __shared__ int stop_now;
+  if (threadIdx.x == 0) stop_now = st->stop;
   __syncthreads();
-  if (st->stop) return;
+  if (stop_now) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(st, 6);
   if (threadIdx.x < 4) {  // sums in rank order: identical on every rank and CTA
     double a = 0.0;
@@ -510,13 +525,21 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
   // rs_old is the exactly summed r.r of the previous update (it arrived one SpMV ago): the reference's convergence test
   // (solver.py:208-212) is applied to IT, one SpMV late, before anything of this iteration is applied -- u and r are then
   // exactly the reference's state at its break.  The recurrence value below only feeds beta.
-  if (it > 0 && sqrt(rs_old) < tol) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->stop = 1, st->status = 0, st->iterations = it, st->rs_new = rs_old;
-    return;
-  }
+  // The stop flag is raised by the LAST CTA to take a ticket, never earlier: a CTA that is still on its way to the checks
+  // above must not see it change under its feet (a flag set by the first CTA to get here split slower CTAs -- some warps left
+  // at the check, the others went on without the scalars warp 0 computes and applied a garbage update to their rows).
+  const bool converged = it > 0 && sqrt(rs_old) < tol;
   const double alpha = rs_old / (pAp + eps);
-  if (guards && (fabs(pAp) < eps || pAp < 0.0 || !isfinite(alpha))) {  // solver.py:187-198, same verdict on every rank/CTA
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->stop = 1, st->status = 1, st->iterations = it + 1, st->pAp = pAp, st->rs_new = rs_old;
+  const bool broke = !converged && guards && (fabs(pAp) < eps || pAp < 0.0 || !isfinite(alpha));  // solver.py:187-198, same verdict everywhere
+  if (converged || broke) {
+    if (threadIdx.x == 0 && atomicAdd(&st->ticket2, 1u) == gridDim.x - 1) {
+      st->ticket2 = 0;
+      st->rs_new = rs_old;
+      if (converged) st->status = 0, st->iterations = it;
+      else st->status = 1, st->iterations = it + 1, st->pAp = pAp;
+      __threadfence();
+      st->stop = 1;
+    }
     return;
   }
   double rs_new = rs_old - 2.0 * alpha * rAp + alpha * alpha * ApAp;
@@ -545,6 +568,11 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
         }
       }
     }
+    // peer stores must be performed before this CTA's ticket (the halo flag follows the last ticket); CTAs whose threads all
+    // lie beyond the boundary rows stored nothing remotely and skip the system-scope fence.  (Placing the fence after the
+    // interior rows instead measured SLOWER at 4 and 8 GPUs, 26 -> 31 us and 16.5 -> 18.4 us for this kernel: a system fence
+    // waits for every earlier write of the thread, and by then those are the whole u / r / p update.)
+    if (blockIdx.x * (long long)blockDim.x < n - bp.n_interior) __threadfence_system();
   }
   for (long long i = gtid; i < n_plain; i += gsz) {
     const double pi = p[i], ri = r[i] - alpha * Ap[i];
@@ -554,11 +582,6 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
     dot += ri * zi;
     if (move_p) p[i] = zi + beta * pi;
   }
-  // Peer stores must be performed before this CTA's ticket (the halo flag follows the last ticket).  The system-scope fence
-  // sits AFTER the interior rows: by then the remote stores issued above have long been acknowledged, so it returns at once
-  // instead of exposing an NVLink round trip in the CTAs that own boundary rows.  CTAs whose threads all lie beyond the
-  // boundary rows stored nothing remotely and skip it.
-  if (bp.ptr && blockIdx.x * (long long)blockDim.x < n - bp.n_interior) __threadfence_system();
   const double t = block_sum<DV_THREADS>(dot);
   __shared__ bool last;
   if (threadIdx.x == 0) {
@@ -602,6 +625,16 @@ __global__ void __launch_bounds__(DV_THREADS) dist_merged_vec_kernel(Peers pe, l
     }
     if (threadIdx.x == 0) trace_stamp(st, 10);
   }
+}
+
+// Cross-rank barrier in front of the iteration graph.  Capturing and instantiating the graph costs each rank's HOST a
+// millisecond of jittery work during which its GPU idles; without this kernel the ranks would enter iteration 0 hundreds of
+// microseconds apart and the early ones would spend that time inside their first all-reduce wait -- 5 us per iteration on a
+// 20-iteration solve.  It is enqueued after the instantiation, right in front of the timing event and the first graph launch.
+__global__ void dist_start_barrier(Peers pe, DistState* st) {
+  SymHeader* me = pe.hdr[pe.rank];
+  if (threadIdx.x < pe.P) pe.hdr[threadIdx.x]->flagS[pe.rank] = 1;
+  if (threadIdx.x < pe.P) spin_until(me->flagS + threadIdx.x, 1, st);
 }
 
 // after the last graph: the loop tests convergence one SpMV late, so an update that converged in the very last iteration
@@ -1112,6 +1145,8 @@ extern "C" int femb_dist_cg_solve(int rank, int nranks, int64_t n_owned, int64_t
     return FEMB_ERR_CUDA;
   }
   FEMB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  if (!getenv("FEMB_DIST_NO_UPLOAD")) FEMB_CUDA(cudaGraphUpload(exec, s));  // the first launch must not pay for the upload inside the loop
+  if (!getenv("FEMB_DIST_NO_START_BARRIER")) dist_start_barrier<<<1, 32, 0, s>>>(pe, st);
   DistState* hst = static_cast<DistState*>(ctx->pinned);  // [2] pinned
   cudaEvent_t* ev = ctx->poll_ev;
   cudaEvent_t* tev = ctx->time_ev;

@@ -676,6 +676,7 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
     return FEMB_ERR_CUDA;
   }
   FEMB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  FEMB_CUDA(cudaGraphUpload(exec, s));  // the first launch must not pay for the upload inside the loop
   // Host polling is pipelined one graph deep: graph l+1 is already queued while the stop flag of graph l travels back
   // (kernels after the stop are no-ops), so the GPU never idles on the host round trip.
   static_assert(2 * sizeof(CGState) <= SOLVE_PINNED_BYTES, "pinned status buffer");

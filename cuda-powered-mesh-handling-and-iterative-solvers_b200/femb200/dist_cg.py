@@ -8,6 +8,8 @@ halo offsets, and for a barrier after flags are reset.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 import time
 
 import torch
@@ -220,6 +222,21 @@ def parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N, rel_tol=
     dist.all_reduce(nf)
     tol = rel_tol * float(nf.sqrt().item())
     uN, infoN = op.solve(Fp, mask, tol=tol, max_iter=max_iter, check_every=50)
+    uN2, infoN2 = op.solve(Fp, mask, tol=tol, max_iter=max_iter, check_every=50)     # determinism: a second solve is bit-identical
+    same = torch.tensor([1 if (torch.equal(uN, uN2) and infoN2["iterations"] == infoN["iterations"]) else 0], device=dev)
+    if int(same.item()) == 0 and os.environ.get("FEMB_DIST_DEBUG"):
+        d = torch.nonzero(uN != uN2).reshape(-1)
+        dd = d[1:] - d[:-1]
+        runs = int((dd != 1).sum()) + 1
+        big = (uN.abs() > 10 * float(uN2.abs().max())).sum()
+        big2 = (uN2.abs() > 10 * float(uN.abs().max())).sum()
+        print(f"[femb dist debug] rank {rank}: {d.numel()} of {uN.numel()} entries differ in {runs} runs, index range [{int(d.min())}, {int(d.max())}], "
+              f"n_interior {part.n_interior}, n_owned {part.n_owned}; first: idx {d[:4].tolist()} a {uN[d[:4]].tolist()} b {uN2[d[:4]].tolist()}; "
+              f"last idx {d[-4:].tolist()}; max|a| {float(uN.abs().max()):.3e} max|b| {float(uN2.abs().max()):.3e} outliers a {int(big)} b {int(big2)}; "
+              f"a-b max {float((uN - uN2).abs().max()):.3e}; u ptr {uN.data_ptr():#x} {uN2.data_ptr():#x} sym {int(op.own.value):#x}+{op.sym_bytes}; "
+              f"its {infoN['iterations']} {infoN2['iterations']}", file=sys.stderr, flush=True)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    del uN2
     full = torch.zeros(N, dtype=torch.float64, device=dev)
     full[part.owned_global] = uN
     Ffull = torch.zeros(N, dtype=torch.float64, device=dev)
@@ -239,11 +256,14 @@ def parity_check(coords, part, plan, op, cl, mask, rank, world, dev, N, rel_tol=
         # true residual of the N-GPU solution on the 1-GPU operator
         res = (Ffull - ops.spmv(crow, col, vals, full)) * gmask
         err = float((full - u1).abs().max() / u1.abs().max())
-        out = {"problem": f"K u = f, f = N lumped, z = 0 fixed, |r| < {rel_tol:g} |f| (abs tol {tol:.3e})",
+        labels = partition.rcb_labels(coords, world)
+        per_rank = [float((full - u1)[labels == q].abs().max() / u1.abs().max()) for q in range(world)]
+        out = {"repeat_bitwise_equal": bool(int(same.item())), "rel_err_u_per_rank": per_rank,
+               "problem": f"K u = f, f = N lumped, z = 0 fixed, |r| < {rel_tol:g} |f| (abs tol {tol:.3e})",
                "iterations_N": infoN["iterations"], "iterations_1gpu": info1["iterations"], "status_N": infoN["status"],
                "status_1gpu": info1["status"], "rel_err_u": err, "rs_N": infoN["rs"], "rs_1gpu": info1["rs"],
                "true_residual_N_over_f": float(res.norm() / Ffull.norm()), "u_max": float(u1.max()),
-               "ok": bool(infoN["status"] == "converged" and info1["status"] == "converged"
+               "ok": bool(infoN["status"] == "converged" and info1["status"] == "converged" and int(same.item()) == 1
                           and abs(infoN["iterations"] - info1["iterations"]) <= 1 and err < 1e-8)}
         del gplan, crow, col, vals, tets
     dist.barrier()
