@@ -41,7 +41,7 @@ def peaks():
 
 def ncu_traffic(n, kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture, only for the workload size it was captured on."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         d = json.load(open(path))
         return d[kernel]["traffic_bytes"] if d.get("n") == n else None
@@ -386,7 +386,7 @@ def run_gpu(args):
         "roofline": {"kernel": "spmv_tma_kernel<1,false> (TMA-pipelined CSR SpMV; its fused twin is CG step k1)", "bound": "hbm",
                      "achieved": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
                      "frac": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9 / hbm, 4), "traffic": ncu_traffic(n, "spmv_tma_kernel"), "peak_source": peak_src,
-                     "traffic_source": "profiles/r01_traffic.json (ncu --set full capture of this kernel on this workload; null for other sizes)",
+                     "traffic_source": "profiles/r02_traffic.json (ncu --set full capture of this kernel on this workload; null for other sizes)",
                      "ms_per_launch": round(ms_spmv, 4), "algorithmic_bytes": bytes_spmv},
         "cg_iteration": {"ms": round(ms_loop / K, 4), "algorithmic_bytes": bytes_iter,
                          "achieved_GBps": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9, 1),
