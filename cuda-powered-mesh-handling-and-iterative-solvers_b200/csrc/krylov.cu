@@ -622,9 +622,11 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   // take the three-kernel loop
   static const bool classic_env = getenv("FEMB_CG_CLASSIC") != nullptr;
   const int ll = lanes[nmat - 1];
-  // (block-CSR Jacobi-PCG keeps the three-kernel loop: on the 2 M-tet P2 operator the merged block SpMV measured 1.96 ms per
-  // iteration against 1.47 ms -- the warp-per-block-row kernel is latency-bound and pays for the two extra streamed vectors)
-  const bool merged = !classic_env && ((ll >= 300 && !minv) || (ll >= 100 && ll < 200) || ll < 0);
+  // (3x3 block-CSR keeps the three-kernel loop for CG and PCG alike: on the 2 M-tet P2 operator the merged block SpMV measured
+  // 1.96 ms per iteration against 1.49 ms (CG) / 1.47 ms (PCG) -- the warp-per-block-row kernel is latency-bound and pays for the
+  // two extra streamed vectors; FEMB_BSR_MERGED=1 selects the merged loop for A/B runs)
+  static const bool bsr_merged = getenv("FEMB_BSR_MERGED") != nullptr;
+  const bool merged = !classic_env && ((ll >= 300 && bsr_merged) || (ll >= 100 && ll < 200) || ll < 0);
   for (int m = 0; m < nmat; ++m) {
     g1[m] = spmv_grid(n, lanes[m], merged && m == nmat - 1);  // one grid per matrix: setup (plain) and loop (fused) launches share it
     gmax = std::max(gmax, g1[m]);
