@@ -57,48 +57,22 @@ class DistOperator:
                     check(lib.femb_dist_open(hb, C.byref(ptr)), "femb_dist_open")
                 self.sym[q] = ptr.value
                 self._opened.append(ptr)
-        # ---- halo plan
-        nb = part.neighbors
+        # ---- halo plan (partition.halo_tables: pure torch, covered by the CPU tests)
+        tb = partition.halo_tables(part, sizes, B)
+        nb = tb["nbr"]
         self.nnbr = len(nb)
         self.nbr = (C.c_int32 * max(1, self.nnbr))(*nb)
-        def dofs(t):     # node-level indices / offsets -> dof-level, component fastest (the ghost blocks use the same interleaving)
-            t = torch.as_tensor(t)
-            return t if B == 1 else (t.reshape(-1, 1) * B + torch.arange(B, device=t.device)).reshape(-1)
-
-        ptrs, idx = [0], []
-        for q in nb:
-            idx.append(dofs(part.send_idx[q]).to(torch.int32))
-            ptrs.append(ptrs[-1] + B * int(part.send_idx[q].numel()))
-        self.send_ptr = (C.c_int32 * (self.nnbr + 1))(*ptrs)
-        self.send_idx = (torch.cat(idx) if idx else torch.zeros(1, dtype=torch.int32)).to(self.dev).contiguous()
-        self.ghost_off = (C.c_int64 * max(1, self.nnbr))(*[B * (sizes[q]["ghost_base"] + sizes[q]["recv_off"][self.rank]) for q in nb])
-        self.halo_bytes = 8 * ptrs[-1]
-        # destinations of every boundary row (CSR over rows n_interior..n_owned): lets the direction kernel store boundary
-        # values straight into the neighbours' ghost slots instead of running a separate push kernel
+        self.send_ptr = (C.c_int32 * (self.nnbr + 1))(*tb["send_ptr"])
+        self.send_idx = tb["send_idx"].to(self.dev).contiguous()
+        self.ghost_off = (C.c_int64 * max(1, self.nnbr))(*tb["ghost_off"])
+        self.halo_bytes = 8 * tb["send_ptr"][-1]
+        # destinations of every boundary row (CSR over rows n_interior..n_owned): lets the vector kernel store boundary values
+        # straight into the neighbours' ghost slots instead of running a separate push kernel
         self.bptr = self.bk = self.boff = None
-        ni = int(getattr(part, "n_interior", 0))
-        if self.nnbr and ni > 0:
-            rows = torch.cat([part.send_idx[q] for q in nb])
-            ks = torch.cat([torch.full((part.send_idx[q].numel(),), k, dtype=torch.int64) for k, q in enumerate(nb)]).to(rows.device)
-            offs = torch.cat([torch.arange(part.send_idx[q].numel()) for q in nb]).to(rows.device)
-            assert int(rows.min().item()) >= ni, "send rows must be boundary rows"
-            order = torch.sort(rows, stable=True).indices
-            rows, ks, offs = rows[order], ks[order], offs[order]
-            if B > 1:       # every boundary node row becomes B dof rows with the same destinations, offsets scaled
-                c = torch.arange(B, device=rows.device)
-                nrow = rows.numel()
-                rows = (rows.reshape(-1, 1) * B + c).reshape(-1)                      # dof rows, still grouped by node
-                ks = ks.reshape(-1, 1).expand(nrow, B).reshape(-1)
-                offs = (offs.reshape(-1, 1) * B + c).reshape(-1)
-                order = torch.sort(rows, stable=True).indices
-                rows, ks, offs = rows[order], ks[order], offs[order]
-            ni, no = ni * B, no * B
-            cnt = torch.bincount(rows - ni, minlength=no - ni)
-            bptr = torch.zeros(no - ni + 1, dtype=torch.int64, device=rows.device)
-            bptr[1:] = torch.cumsum(cnt, 0)
-            self.bptr = bptr.to(torch.int32).to(self.dev).contiguous()
-            self.bk = ks.to(torch.uint8).to(self.dev).contiguous()
-            self.boff = offs.to(torch.int32).to(self.dev).contiguous()
+        if tb["bptr"] is not None:
+            self.bptr = tb["bptr"].to(self.dev).contiguous()
+            self.bk = tb["bk"].to(self.dev).contiguous()
+            self.boff = tb["boff"].to(self.dev).contiguous()
 
     def jacobi(self, mask_owned=None):
         """1 / diag of the owned rows (0 where the mask fixes the dof or the diagonal vanishes): the corrected Jacobi diagonal."""

@@ -116,3 +116,51 @@ def localize(vec_global: torch.Tensor, part: LocalPart) -> torch.Tensor:
     """Rows of a replicated global [N, ...] array in local numbering (owned, zero padding up to ghost_base, ghost)."""
     pad = torch.zeros((part.ghost_base - part.n_owned,) + tuple(vec_global.shape[1:]), dtype=vec_global.dtype, device=vec_global.device)
     return torch.cat([vec_global[part.owned_global], pad, vec_global[part.ghost_global]], dim=0)
+
+
+def halo_tables(part: LocalPart, sizes, block: int = 1):
+    """The halo plan of one rank as flat tables for the device loop (pure torch, no device needed; femb_dist_cg_solve's arguments).
+    `sizes[q]` = {"ghost_base", "recv_off"} of every rank q.  `block` dofs per node: rows, offsets and counts become dof-level
+    (`block*node + c`, component fastest -- the ghost blocks of the receiver use the same interleaving).  Returns a dict:
+      nbr        neighbour ranks (ascending)
+      send_ptr   [nnbr+1] prefix into send_idx per neighbour
+      send_idx   owned dof rows to push to each neighbour, in the receiver's ghost order
+      ghost_off  per neighbour: dof index in ITS p vector where my block starts
+      bptr/bk/boff  CSR over the boundary dof rows [n_interior*block, n_owned*block): neighbour index and offset inside that
+                 neighbour's block for every destination of the row (None when the rows are not ordered interior-first)
+    """
+    B = int(block)
+    nb = list(part.neighbors)
+
+    def dofs(t):
+        t = torch.as_tensor(t)
+        return t if B == 1 else (t.reshape(-1, 1) * B + torch.arange(B, device=t.device)).reshape(-1)
+
+    ptrs, idx = [0], []
+    for q in nb:
+        idx.append(dofs(part.send_idx[q]).to(torch.int32))
+        ptrs.append(ptrs[-1] + B * int(part.send_idx[q].numel()))
+    out = {"nbr": nb, "send_ptr": ptrs, "send_idx": torch.cat(idx) if idx else torch.zeros(1, dtype=torch.int32),
+           "ghost_off": [B * (sizes[q]["ghost_base"] + sizes[q]["recv_off"][part.rank]) for q in nb],
+           "bptr": None, "bk": None, "boff": None}
+    ni, no = int(getattr(part, "n_interior", 0)), part.n_owned
+    if nb and ni > 0:
+        rows = torch.cat([part.send_idx[q] for q in nb])
+        ks = torch.cat([torch.full((part.send_idx[q].numel(),), k, dtype=torch.int64) for k, q in enumerate(nb)]).to(rows.device)
+        offs = torch.cat([torch.arange(part.send_idx[q].numel()) for q in nb]).to(rows.device)
+        assert int(rows.min().item()) >= ni, "send rows must be boundary rows"
+        if B > 1:       # every boundary node row becomes B dof rows with the same destinations, offsets scaled
+            c = torch.arange(B, device=rows.device)
+            nrow = rows.numel()
+            rows = (rows.reshape(-1, 1) * B + c).reshape(-1)
+            ks = ks.reshape(-1, 1).expand(nrow, B).reshape(-1)
+            offs = (offs.reshape(-1, 1) * B + c).reshape(-1)
+        order = torch.sort(rows, stable=True).indices
+        rows, ks, offs = rows[order], ks[order], offs[order]
+        ni, no = ni * B, no * B
+        cnt = torch.bincount(rows - ni, minlength=no - ni)
+        bptr = torch.zeros(no - ni + 1, dtype=torch.int64, device=rows.device)
+        bptr[1:] = torch.cumsum(cnt, 0)
+        out["bptr"], out["bk"], out["boff"] = bptr.to(torch.int32), ks.to(torch.uint8), offs.to(torch.int32)
+    return out
+

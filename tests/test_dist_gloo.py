@@ -158,3 +158,42 @@ def test_block_partition_halo_plans_agree():
                 o = parts[q].recv_off[r]
                 assert torch.equal(sent, parts[q].ghost_global[o:o + parts[q].recv_cnt[r]])
                 assert int(parts[r].send_idx[q].min()) >= parts[r].n_interior      # only boundary rows are sent
+
+
+@pytest.mark.parametrize("block", [1, 3])
+@pytest.mark.parametrize("kind", ["rcb", "ids"])
+def test_halo_tables_deliver_every_ghost(block, kind):
+    """partition.halo_tables (the flat tables femb_dist_cg_solve receives) emulated on the host: every rank "pushes" through
+    send_idx / ghost_off (the separate push kernel) and through the boundary-row table bptr / bk / boff (the push folded into the
+    vector kernel); both must fill every ghost dof of every rank with the owner's value, for 1 and 3 dofs per node."""
+    from femb200 import partition
+    c, t, _ = _problem(6)
+    N, P, B = c.shape[0], 4, block
+    lab = partition.rcb_labels(c, P) if kind == "rcb" else partition.block_labels(N, P)
+    parts = [partition.build_local_part(t, lab, r, P) for r in range(P)]
+    sizes = [{"ghost_base": p.ghost_base, "recv_off": p.recv_off, "n_local": p.n_local} for p in parts]
+    tabs = [partition.halo_tables(p, sizes, B) for p in parts]
+    g = torch.Generator().manual_seed(3)
+    xg = torch.randn(N, B, dtype=torch.float64, generator=g)                 # a global vector
+    for mode in ("push", "folded"):
+        # local p vectors: owned part filled, ghosts poisoned
+        x = [torch.full((p.n_local * B,), float("nan"), dtype=torch.float64) for p in parts]
+        for r, p in enumerate(parts):
+            x[r][:p.n_owned * B] = xg[p.owned_global].reshape(-1)
+        for r, (p, tb) in enumerate(zip(parts, tabs)):
+            if mode == "push" or tb["bptr"] is None:      # (no interior rows on this rank: the library keeps the push kernel)
+                for k, q in enumerate(tb["nbr"]):
+                    a, b = tb["send_ptr"][k], tb["send_ptr"][k + 1]
+                    x[q][tb["ghost_off"][k]: tb["ghost_off"][k] + (b - a)] = x[r][tb["send_idx"][a:b].long()]
+            else:
+                ni = p.n_interior * B
+                assert tb["bptr"].numel() == (p.n_owned - p.n_interior) * B + 1
+                for row in range(tb["bptr"].numel() - 1):
+                    for e in range(int(tb["bptr"][row]), int(tb["bptr"][row + 1])):
+                        k = int(tb["bk"][e])
+                        x[tb["nbr"][k]][tb["ghost_off"][k] + int(tb["boff"][e])] = x[r][ni + row]
+        for r, p in enumerate(parts):
+            gb = p.ghost_base * B
+            want = xg[p.ghost_global].reshape(-1)
+            assert torch.equal(x[r][gb: gb + p.n_ghost * B], want), (mode, r)
+            assert gb % 16 == 0                                              # ghosts start on their own 128-byte line
