@@ -102,5 +102,5 @@ u2, info2 = ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=a.iter
 out["cg"] = {"ms_per_iter": round(info2["loop_ms"] / a.iters, 3), "iters_per_s": round(a.iters / info2["loop_ms"] * 1e3, 1)}
 u4, info4 = A.cg_solve(F, mask=mask, tol=0.0, max_iter=a.iters, check_every=min(a.iters, 50))
 out["cg_bsr3"] = {"ms_per_iter": round(info4["loop_ms"] / a.iters, 3), "iters_per_s": round(a.iters / info4["loop_ms"] * 1e3, 1),
-                  "loop": "classic (3 kernels)" if os.environ.get("FEMB_CG_CLASSIC") else "merged (2 kernels)"}
+                  "loop": "merged (2 kernels)" if os.environ.get("FEMB_BSR_MERGED") and not os.environ.get("FEMB_CG_CLASSIC") else "classic (3 kernels)"}
 print(json.dumps(out), flush=True)
