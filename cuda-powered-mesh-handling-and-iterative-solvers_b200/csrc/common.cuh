@@ -80,6 +80,14 @@ struct SolveCtx {
   cudaEvent_t order_ev = nullptr;
   cudaEvent_t poll_ev[2] = {nullptr, nullptr}, time_ev[2] = {nullptr, nullptr};
   void* pinned = nullptr;  // SOLVE_PINNED_BYTES of page-locked host memory (two status structs)
+  // iteration-graph cache of the single-GPU CG (krylov.cu): the scalars / per-CTA partials live in a persistent device buffer so
+  // that a repeated solve with the same operator, vectors and parameters finds every address baked into the graph unchanged and
+  // re-launches the instantiated graph instead of capturing + instantiating again (~1 ms per solve: most of a small solve)
+  void* dev_scratch = nullptr;
+  size_t dev_scratch_bytes = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  unsigned char graph_key[512];
+  size_t graph_key_bytes = 0;
 };
 constexpr size_t SOLVE_PINNED_BYTES = 1024;
 // context of the CURRENT device with its stream ordered after `user`; nullptr (and set_error) on any CUDA failure

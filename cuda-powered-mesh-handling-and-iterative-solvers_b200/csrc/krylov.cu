@@ -634,11 +634,19 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   const int g2 = grid_for(n, VEC_THREADS, 8);
   static const int vec_waves = getenv("FEMB_VEC_WAVES") ? atoi(getenv("FEMB_VEC_WAVES")) : 8;
   const int g2v = grid_for(n, VEC_THREADS, vec_waves);  // merged vector kernel (A/B: room for the next SpMV's early CTAs)
-  Scratch scr(s);
-  double* partial;
-  CGState* st;
-  FEMB_CUDA(scr.alloc(&partial, (size_t)std::max(3 * gmax, g2)));
-  FEMB_CUDA(scr.alloc(&st, 1));
+  // scalars + per-CTA partials: persistent per (thread, device), so their addresses survive from one solve to the next (graph cache)
+  const size_t need = 256 + sizeof(double) * (size_t)std::max(3 * gmax, g2);
+  if (ctx->dev_scratch_bytes < need) {
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr, ctx->graph_key_bytes = 0;
+    FEMB_CUDA(cudaStreamSynchronize(s));
+    if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
+    ctx->dev_scratch = nullptr, ctx->dev_scratch_bytes = 0;
+    FEMB_CUDA(cudaMalloc(&ctx->dev_scratch, need + need / 2));
+    ctx->dev_scratch_bytes = need + need / 2;
+  }
+  static_assert(sizeof(CGState) <= 256, "state slot");
+  CGState* st = static_cast<CGState*>(ctx->dev_scratch);
+  double* partial = reinterpret_cast<double*>(static_cast<unsigned char*>(ctx->dev_scratch) + 256);
   // ---- setup (solver.py:163-181)
   if (mask) cg_mask_kernel<<<g2, VEC_THREADS, 0, s>>>(n, u, mask);
   for (int m = 0; m < nmat; ++m)
@@ -646,9 +654,31 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   cg_init_kernel<<<g2, VEC_THREADS, 0, s>>>(n, F, Ap, mask, minv, r, p, partial);
   cg_init_finish<<<1, VEC_THREADS, 0, s>>>(g2, partial, st, max_iter);
   FEMB_LAUNCH_CHECK();
-  // ---- capture `check_every` iterations into one graph
+  // ---- `check_every` iterations as one graph: re-used when every value baked into it is unchanged
+  struct GraphKey {
+    long long n;
+    int nmat, check_every, max_iter, guards, merged, pdl, lanes[8], g1[8], g2, g2v;
+    long long nnz[8];
+    const void *crow[8], *col[8], *val[8];
+    int block[8];
+    const void *mask, *minv, *u, *work, *st, *partial;
+    double tol, eps;
+    long long pin;
+  } key;
+  memset(&key, 0, sizeof(key));
+  static_assert(sizeof(GraphKey) <= sizeof(ctx->graph_key), "graph key buffer");
+  key.n = n, key.nmat = nmat, key.check_every = check_every, key.max_iter = max_iter, key.guards = guards, key.merged = merged ? 1 : 0;
+  key.pdl = pdl_mode(), key.g2 = g2, key.g2v = g2v, key.mask = mask, key.minv = minv, key.u = u, key.work = work, key.st = st, key.partial = partial;
+  key.tol = tol, key.eps = eps, key.pin = spmv_pin_entries(mats[nmat - 1].nnz);
+  for (int m = 0; m < nmat; ++m) {
+    key.lanes[m] = lanes[m], key.g1[m] = g1[m];
+    key.nnz[m] = mats[m].nnz, key.crow[m] = mats[m].crow, key.col[m] = mats[m].col, key.val[m] = mats[m].val, key.block[m] = mats[m].block;
+  }
+  static const bool no_cache = getenv("FEMB_NO_GRAPH_CACHE") != nullptr;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  if (!no_cache && ctx->graph_exec && ctx->graph_key_bytes == sizeof(key) && memcmp(ctx->graph_key, &key, sizeof(key)) == 0) exec = ctx->graph_exec;
+  if (!exec) {
   FEMB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   for (int k = 0; k < check_every; ++k) {
     for (int m = 0; m + 1 < nmat; ++m)
@@ -678,7 +708,12 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
     return FEMB_ERR_CUDA;
   }
   FEMB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
   FEMB_CUDA(cudaGraphUpload(exec, s));  // the first launch must not pay for the upload inside the loop
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  ctx->graph_exec = exec, ctx->graph_key_bytes = sizeof(key);
+  memcpy(ctx->graph_key, &key, sizeof(key));
+  }
   // Host polling is pipelined one graph deep: graph l+1 is already queued while the stop flag of graph l travels back
   // (kernels after the stop are no-ops), so the GPU never idles on the host round trip.
   static_assert(2 * sizeof(CGState) <= SOLVE_PINNED_BYTES, "pinned status buffer");
@@ -712,9 +747,11 @@ static int cg_solve_impl(int64_t n, int nmat, const CsrRef* mats, const double* 
   }
   float ms = 0.f;
   if (rc == FEMB_OK) cudaEventElapsedTime(&ms, tev[0], tev[1]);
-  cudaGraphExecDestroy(exec);
-  cudaGraphDestroy(graph);
-  if (rc != FEMB_OK) return rc;
+  if (rc != FEMB_OK) {  // a failed launch may have left the graph in an undefined state: drop it
+    cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->graph_exec = nullptr, ctx->graph_key_bytes = 0;
+    return rc;
+  }
   result_host->iterations = fin->stop ? fin->iterations : max_iter;
   result_host->status = fin->stop ? fin->status : 2;
   result_host->rs = fin->rs_new;

@@ -1086,3 +1086,42 @@ def test_hybrid_multilevel_config5(api):
     mask[fixed_fn(cp)] = 0
     uo, io = ops.cg_solve(crow, col, vals, load1(cp, tp), mask=mask, tol=1e-12, max_iter=5000)
     assert ip["status"] == io["status"] == "converged" and float((up - uo).abs().max()) <= 1e-8 * float(uo.abs().max())
+
+
+def test_graph_cache_repeated_and_changed_solves(api, O):
+    """The instantiated iteration graph is re-used when a solve repeats with identical arguments (same operator, vectors,
+    tolerance): results stay bit-identical; any changed argument (tolerance, iteration cap, load, mask, another operator, another
+    size) gives the result of a fresh solve.  FEMB_NO_GRAPH_CACHE=1 disables the cache for A/B runs."""
+    el = api[0]
+    from femb200 import meshgen, ops
+    outs = {}
+    for n in (4, 5):
+        c, t = meshgen.kuhn_cube(n, jitter=0.1)
+        plan = el.CsrPlan(t, c.shape[0], DEV)
+        crow, col = plan.pattern(1)
+        vals = plan.assemble_c3d4(c, "poisson")
+        mask = (c[:, 2] != 0).to(torch.uint8).to(DEV)
+        F = torch.linspace(1.0, 2.0, c.shape[0], dtype=torch.float64).reshape(-1, 1).to(DEV)
+        Kp = O.c3d4_poisson_K(N(c), N(t))
+        fixed = np.flatnonzero(N(c)[:, 2] == 0)
+        for rep in range(3):                                   # same buffers from the caching allocator -> cache hits
+            u, info = ops.cg_solve(crow, col, vals, F, mask=mask, tol=1e-9, max_iter=500)
+            outs.setdefault((n, "a"), []).append((u.clone(), info["iterations"]))
+        assert all(torch.equal(outs[(n, "a")][0][0], x[0]) and x[1] == outs[(n, "a")][0][1] for x in outs[(n, "a")])
+        uo, ito, _ = O.stable_cg(Kp, N(t), N(F), fixed, tol=1e-9, max_iter=500, ndof=1)
+        assert abs(outs[(n, "a")][0][1] - ito) <= 1 and rel_err(N(outs[(n, "a")][0][0]), uo) <= 1e-8
+        # changed tolerance / cap / load / mask
+        u2, i2 = ops.cg_solve(crow, col, vals, F, mask=mask, tol=1e-4, max_iter=500)
+        uo2, ito2, _ = O.stable_cg(Kp, N(t), N(F), fixed, tol=1e-4, max_iter=500, ndof=1)
+        assert abs(i2["iterations"] - ito2) <= 1 and i2["iterations"] < outs[(n, "a")][0][1]
+        u3, i3 = ops.cg_solve(crow, col, vals, F, mask=mask, tol=1e-9, max_iter=7)
+        assert i3["iterations"] == 7 and i3["status"] == "maxiter"
+        u4, i4 = ops.cg_solve(crow, col, vals, 3.0 * F, mask=mask, tol=1e-9, max_iter=500)
+        uo4, ito4, _ = O.stable_cg(Kp, N(t), 3.0 * N(F), fixed, tol=1e-9, max_iter=500, ndof=1)
+        assert abs(i4["iterations"] - ito4) <= 1 and rel_err(N(u4), uo4) <= 1e-8
+        mask2 = ((c[:, 2] != 0) & (c[:, 0] != 1)).to(torch.uint8).to(DEV)
+        u5, i5 = ops.cg_solve(crow, col, vals, F, mask=mask2, tol=1e-9, max_iter=500)
+        uo5, ito5, _ = O.stable_cg(Kp, N(t), N(F), np.flatnonzero((N(c)[:, 2] == 0) | (N(c)[:, 0] == 1)), tol=1e-9, max_iter=500, ndof=1)
+        assert abs(i5["iterations"] - ito5) <= 1 and rel_err(N(u5), uo5) <= 1e-8
+        u6, i6 = ops.cg_solve(crow, col, vals, F, mask=mask, tol=1e-9, max_iter=500)            # back to the first arguments
+        assert torch.equal(u6, outs[(n, "a")][0][0])
