@@ -1,22 +1,27 @@
 // Multi-GPU conjugate gradient over NVLink peer memory (one process per GPU, rows partitioned).
 //
 // The reference has no distributed code.  Each rank owns a block of rows (local numbering [owned, interior rows first |
-// padding to a cache line | ghost]) and keeps its search direction p in a cudaIpc-shared "symmetric" buffer.  One CG
-// iteration is three kernels in one CUDA graph:
-//   k1    TMA-pipelined SpMV on the owned rows (spmv_dev.cuh): interior row tiles first; a CTA waits for halo flag A of its
-//         neighbours only before its first boundary tile.  p.Ap partial; the last CTA stores the rank's partial into
-//         slot[rank] of EVERY rank's reduction array and raises flag B everywhere
-//   k2    waits for flag B of all ranks, sums the P partials in rank order (deterministic, identical on every rank),
-//         guards/alpha, u += alpha p, r -= alpha Ap, r.r partial -> slot[rank] everywhere, flag C
-//   k3    waits for flag C, rs_new, convergence test / beta (identical on every rank), p = r + beta p; the thread that
-//         updates a boundary row also stores the new value straight into the ghost slots of the neighbours that need it
-//         (st.global on mapped peer pointers through NVSwitch); the last CTA raises flag A on the neighbours
-// There is no NCCL call and no host involvement inside the loop: the "collectives" are peer stores plus epoch flags.
+// padding to a cache line | ghost]) and keeps its search direction p in a cudaIpc-shared "symmetric" buffer.  One iteration
+// of CG / Jacobi-PCG is TWO kernels in one CUDA graph (merged-reduction loop, default):
+//   m1    SpMV on the owned rows -- scalar CSR: the TMA-pipelined row tiles of spmv_dev.cuh; 3-dof operators: 3x3 block-CSR,
+//         warp per block row -- interior rows first; a CTA (warp) waits for halo flag A of its neighbours only before its first
+//         boundary tile (row).  Partials of p.Ap, z.Ap, (M^-1 Ap).Ap; the last CTA sends the rank's sums to every rank as
+//         "LL words": (epoch << 32 | half of a double) in ONE 8-byte store, so value and flag arrive together (no system
+//         fence, no separate flag)
+//   m2    waits for the words of all ranks, sums them in rank order (identical on every rank), alpha, beta from the recurrence,
+//         u += alpha p, r -= alpha Ap, p = z + beta p in one pass; the thread that updates a boundary row stores the new value
+//         straight into the ghost slots of the neighbours that need it (st.global on mapped peer pointers through NVSwitch);
+//         the last CTA raises flag A on the neighbours and sends the exactly summed r.z (consumed one SpMV later: that is where
+//         the reference's convergence test is applied, so the returned state is the reference's at its break)
+// FEMB_DIST_CLASSIC=1 keeps round 1's three-kernel loop (k1 SpMV + p.Ap, k2 update + r.r, k3 direction + halo push; slot stores,
+// system fence and flag stores for the two waited all-reduces) for scalar CSR without a preconditioner, for A/B runs.
+// There is no NCCL call and no host involvement inside the loop: the "collectives" are peer stores plus epochs.
 // All spin loops carry a timeout so a lost rank turns into an error, not a hang.  Lessons measured on 8 B200:
 // let ONE thread per CTA read the reduction slots (every thread doing it made the slot line an L2 hot spot worth 17 us per
 // kernel); read x through the read-only path (plain loads cost 17 %), which is safe because ghosts start on their own
 // 128-byte line and are first touched after flag A while L1 is flushed at every launch; a single persistent cooperative
-// kernel with software grid barriers (dist_cg_persistent_kernel, FEMB_DIST_PERSISTENT=1) is slower than launch boundaries.
+// kernel with software grid barriers (dist_cg_persistent_kernel, FEMB_DIST_PERSISTENT=1) is slower than launch boundaries; a
+// stop flag must only ever be raised by the LAST CTA of a kernel (profiles/r02_race_note.md).
 #include <cstdlib>
 
 #include "spmv_dev.cuh"
