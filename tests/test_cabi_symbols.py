@@ -35,6 +35,44 @@ def test_argument_validation_without_gpu():
     assert _lib.lib.femb_default_points(6, buf) == 6 and buf[2] == -0.5773502588272095   # fp32-rounded (quirk q1)
 
 
+def test_round2_entry_points_validate_arguments_without_gpu():
+    """femb_p2_* (c3d4_to_c3d10 kernels), femb_dist_cg_solve's `block` argument and femb_entities_create reject bad arguments before
+    touching the device; the additive keyword arguments of the mirror keep the reference's positional order intact."""
+    import inspect
+    import sys
+    from femb200 import _lib
+    L = _lib.lib
+    h, ne = ctypes.c_void_p(), ctypes.c_int64()
+    assert L.femb_p2_create(None, 3, 0, 1, None, ctypes.byref(h), ctypes.byref(ne)) == 1 and b"ib" in L.femb_last_error()
+    assert L.femb_p2_create(None, 8, 0, 0, None, ctypes.byref(h), ctypes.byref(ne)) == 1          # n_nodes >= 1
+    assert L.femb_p2_create(None, 8, 400_000_000, 10, None, ctypes.byref(h), ctypes.byref(ne)) == 1 and b"int32" in L.femb_last_error()
+    assert L.femb_p2_create(None, 8, 0, 5, None, ctypes.byref(h), ctypes.byref(ne)) == 0 and ne.value == 0   # empty mesh: no device work
+    assert L.femb_p2_destroy(h) == 0
+    res = _lib.CGResult()
+    sym = (ctypes.c_void_p * 2)()
+    rc = L.femb_dist_cg_solve(0, 2, 9, 0, 1, None, None, None, None, None, None, None, None, sym, 0, None, None, None, None, None, None, None,
+                              1e-8, 10, 1e-30, 16, 2, ctypes.byref(res), None)
+    assert rc == 1 and b"block" in L.femb_last_error()
+    rc = L.femb_dist_cg_solve(0, 2, 10, 0, 1, None, None, None, None, None, None, None, None, sym, 0, None, None, None, None, None, None, None,
+                              1e-8, 10, 1e-30, 16, 3, ctypes.byref(res), None)
+    assert rc == 1                                                                                     # 10 rows are not 3 per node
+    rc = L.femb_dist_cg_solve(5, 2, 9, 0, 1, None, None, None, None, None, None, None, None, sym, 0, None, None, None, None, None, None, None,
+                              1e-8, 10, 1e-30, 16, 1, ctypes.byref(res), None)
+    assert rc == 1 and b"rank" in L.femb_last_error()
+    assert L.femb_dist_header_bytes() % 256 == 0
+    sys.path.insert(0, os.path.join(PKG, "solver"))
+    import element, solver
+    sig = inspect.signature(solver.stable_conjugate_gradient_solver)
+    assert list(sig.parameters)[:10] == ["K", "elements", "F", "rbe2", "u_init", "tol", "max_iter", "device", "dtype", "eps"]
+    assert sig.parameters["distributed"].default is False and sig.parameters["coords"].default is None
+    sig = inspect.signature(solver.preconditioned_conjugate_gradient_solver)
+    assert list(sig.parameters)[:9] == ["K", "elements", "F", "M_inv", "u_init", "tol", "max_iter", "device", "dtype"]
+    assert sig.parameters["tol"].default == 1e-8 and sig.parameters["distributed"].default is False
+    assert list(inspect.signature(element.c3d4_to_c3d10).parameters)[:5] == ["coords", "elements", "rbe2_ids", "rbe3_ids", "dtype"]
+    assert inspect.signature(element.compute_c3d10_K_matrix).parameters["out"].default is None
+    assert inspect.signature(solver.hybrid_subdivided_solver).parameters["mode"].default == "multilevel"
+
+
 def test_mirror_api_names():
     """Every hot-path function of the reference's three modules exists with the reference's parameter names."""
     import inspect
