@@ -341,7 +341,7 @@ def run_gpu(args):
     while time.perf_counter() - t_soak < 0.5:
         ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=200, check_every=50)
     clocks = sampler.stop()
-    # ---- topology on the same mesh (bit-exact face lists; sort-based, HBM-bound on its radix passes)
+    # ---- topology on the same mesh (bit-exact face lists; buckets by smallest node + in-warp sort, csrc/topology.cu)
     topo = None
     if not args.no_topo:
         try:
@@ -354,11 +354,11 @@ def run_gpu(args):
             torch.cuda.synchronize()
             ms_topo = t0e.elapsed_time(t1e)
             bytes_topo = M * 4 * 8 + faces.numel() * 8 + extra.numel() * 8 + pairs.numel() * 8   # conn in, face lists out
-            topo = {"what": "tet surface faces + fourth node and shared-face pairs in one pass (canonical tuples, radix sort, run classification)",
+            topo = {"what": "tet surface faces + fourth node and shared-face pairs in one pass (faces bucketed by smallest node, one warp sorts a bucket)",
                     "ms": round(ms_topo, 2), "elems_per_s": round(M / (ms_topo * 1e-3), 1), "surface_faces": int(faces.shape[0]),
                     "shared_pairs": int(pairs.shape[0]), "algorithmic_bytes": bytes_topo,
                     "frac": round(bytes_topo / (ms_topo * 1e-3) / 1e9 / hbm, 4),
-                    "note": "sort traffic (4 faces x 64 M tets, two 64-bit radix passes) is implementation overhead, not counted"}
+                    "note": "bucket records (12 B per face written, read once) and per-bucket pair lists are implementation overhead, not counted"}
             del faces, extra, pairs
         except Exception as exc:  # noqa: BLE001
             topo = {"error": f"{type(exc).__name__}: {exc}"}

@@ -8,11 +8,12 @@
 //
 // Default path (entities_build_buckets): nine radix passes over 256 M (key, id) pairs cost 55 ms on the 64 M-tet mesh, 60x
 // the bytes the answer needs.  Instead every entity is dropped into the bucket of its SMALLEST node (one counting pass, one
-// scatter pass: ~24 faces per bucket on a tet mesh), and duplicates are matched inside the bucket by one warp: every lane
-// ranks its entity against all others of the bucket by (rest of the tuple, entity id), reading them as warp-wide broadcasts
-// from shared memory.  Buckets are in node order and the in-bucket rank is the lexicographic order of the remaining nodes, so shared
-// pairs come out in exactly the order of the sorted tuples (lower entity id first); surface entities (rare) are appended to
-// a list that is then sorted by their slot-major position.  The scatter order inside a bucket is arbitrary (atomics), the
+// scatter pass: ~24 faces per bucket on a tet mesh), and duplicates are matched inside the bucket by one warp: a bitonic
+// sort of the warp by the rest of the tuple (buckets above 32 entries: every lane ranks its entity against all others of the
+// bucket, read as warp-wide broadcasts from shared memory).  Buckets are in node order and the in-bucket order is the
+// lexicographic order of the remaining nodes, so shared pairs come out in exactly the order of the sorted tuples (lower
+// entity id first); surface entities (rare) are appended to a list that is then sorted by their slot-major position.
+// 6.9 ms on that mesh (DESIGN.md section 3.2 has the steps and their measured effect).  The scatter order inside a bucket is arbitrary (atomics), the
 // ranks are not: outputs are deterministic.  Buckets larger than BUCKET_MAX (a node of extreme valence) fall back to the
 // radix path.
 #include <cstdlib>
@@ -56,6 +57,10 @@ struct femb_entity_plan {
   bool buckets = false;
   int* surf_pos = nullptr;    // [K] slot-major positions (slot*M+e) of the entities that appear once, ascending
   uint2* pair_ents = nullptr; // [S] (entity a, entity b), a < b, in lexicographic order of the shared tuple
+  // ... or, uncompacted, per bucket: pairs of bucket b = pairbuf[bptr[b] .. +pbase[b+1]-pbase[b]), output rows from pbase[b]
+  uint2* pairbuf = nullptr;
+  int *bptr = nullptr, *pbase = nullptr;
+  long long nb = 0;
 };
 
 namespace femb {
@@ -281,6 +286,107 @@ __global__ void bucket_scatter(const I* __restrict__ conn, int stride, EntTable 
   }
 }
 
+// Tetrahedron faces -- the entity kind of the large meshes -- without the table-driven loops above (whose runtime indices
+// put the tuples in local memory): the four sorted triples are formed in registers, and lanes of a warp whose elements have
+// the same bucket share ONE atomic (neighbouring elements of a mesh generator's or a partitioner's ordering usually have the
+// same smallest node: the six tets of a Kuhn cube all do).  Three faces of a tet hold its smallest node (all four when the
+// element repeats that node), the fourth goes to the bucket of its own smallest node.
+struct TetFaces {
+  int t[4][3];   // ascending node triples of the faces (012)(013)(123)(023), element.py:722-727
+  int m, tb;     // bucket of the faces holding the element's smallest node / bucket of the remaining face
+  bool has_b;
+};
+
+template <typename I>
+__device__ __forceinline__ TetFaces tet_faces(const I* __restrict__ conn, int stride, long long e) {
+  int n[4];
+  if (stride == 4 && sizeof(I) == 8) {
+    long long q[4];
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(conn + 4 * e));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) n[k] = (int)q[k];
+  } else if (stride == 4) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(conn) + e);
+    n[0] = q.x, n[1] = q.y, n[2] = q.z, n[3] = q.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) n[k] = (int)ldidx(conn + e * stride + k);
+  }
+  TetFaces r;
+  constexpr int F[4][3] = {{0, 1, 2}, {0, 1, 3}, {1, 2, 3}, {0, 2, 3}};
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    int a = n[F[f][0]], b = n[F[f][1]], c = n[F[f][2]];
+    const int lo = min(a, b), hi = max(a, b);
+    r.t[f][0] = min(lo, c);
+    r.t[f][2] = max(hi, c);
+    r.t[f][1] = max(lo, min(hi, c));
+  }
+  r.m = min(min(n[0], n[1]), min(n[2], n[3]));
+  r.has_b = false, r.tb = 0;
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+    if (r.t[f][0] != r.m) r.has_b = true, r.tb = r.t[f][0];   // at most one face lacks the smallest node
+  return r;
+}
+
+template <typename I>
+__global__ void __launch_bounds__(256) tet_bucket_count(const I* __restrict__ conn, int stride, long long M, int* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  for (long long base = blockIdx.x * (long long)blockDim.x + threadIdx.x - lane; base < M; base += (long long)gridDim.x * blockDim.x) {
+    const long long e = base + lane;
+    const bool on = e < M;
+    TetFaces r;
+    if (on) r = tet_faces(conn, stride, e);
+    const bool hb = on && r.has_b;
+    // idle lanes carry distinct negative keys: they match nobody
+    const unsigned ma = __match_any_sync(0xffffffffu, on ? r.m : ~lane), mb = __match_any_sync(0xffffffffu, hb ? r.tb : ~lane);
+    const unsigned four = __ballot_sync(0xffffffffu, on && !r.has_b);
+    if (on && lane == __ffs(ma) - 1) atomicAdd(cnt + r.m, 3 * __popc(ma) + __popc(ma & four));
+    if (hb && lane == __ffs(mb) - 1) atomicAdd(cnt + r.tb, __popc(mb));
+  }
+}
+
+template <typename I>
+__global__ void __launch_bounds__(256) tet_bucket_scatter(const I* __restrict__ conn, int stride, long long M, const int* __restrict__ bptr,
+                                                          int* __restrict__ cur, unsigned long long* __restrict__ key, int* __restrict__ ent) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  for (long long base = blockIdx.x * (long long)blockDim.x + threadIdx.x - lane; base < M; base += (long long)gridDim.x * blockDim.x) {
+    const long long e = base + lane;
+    const bool on = e < M;
+    TetFaces r;
+    if (on) r = tet_faces(conn, stride, e);
+    const bool hb = on && r.has_b;
+    const unsigned ma = __match_any_sync(0xffffffffu, on ? r.m : ~lane), mb = __match_any_sync(0xffffffffu, hb ? r.tb : ~lane);
+    const unsigned four = __ballot_sync(0xffffffffu, on && !r.has_b);
+    // the lowest lane of a group reserves the group's slots
+    const int la = __ffs(ma) - 1, lb = __ffs(mb) - 1;
+    const int ga = __popc(ma);
+    int pa = 0, pb = 0;
+    if (on && lane == la) pa = bptr[r.m] + atomicAdd(cur + r.m, 3 * ga + __popc(ma & four));
+    if (hb && lane == lb) pb = bptr[r.tb] + atomicAdd(cur + r.tb, __popc(mb));
+    // slot of a lane's i-th face in the group's range: i * (lanes in the group) + (rank of the lane) -- one store instruction
+    // of the warp then fills consecutive slots (1.93 -> 1.65 ms on the 64 M-tet mesh against three slots per lane); the fourth
+    // faces of elements that repeat their smallest node come last.  Two elements per thread (connectivity of both requested
+    // before the first atomic round trip) measured the same: not kept.
+    const int base_a = __shfl_sync(0xffffffffu, pa, la);
+    pa = base_a + __popc(ma & lt);
+    const int pa4 = base_a + 3 * ga + __popc(ma & four & lt);
+    pb = __shfl_sync(0xffffffffu, pb, lb) + __popc(mb & lt);
+    if (!on) continue;
+    int ia = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const bool in_a = r.t[f][0] == r.m;
+      const int pos = in_a ? (ia < 3 ? pa + ia * ga : pa4) : pb;
+      ia += in_a;
+      key[pos] = (unsigned long long)(unsigned)r.t[f][1] << 32 | (unsigned long long)(unsigned)r.t[f][2];
+      ent[pos] = (int)(e * 4 + f);
+    }
+  }
+}
+
 // One WARP per bucket.  Lane l owns the bucket's entries l, l+32, ...; the bucket is staged in the warp's shared-memory
 // slice (buckets above BUCKET_STAGE entries are read from global memory instead), and every lane walks ALL entries of the
 // bucket -- the same address for the whole warp, i.e. one broadcast read and no divergence -- to find for its own entry:
@@ -293,11 +399,55 @@ __global__ void bucket_scatter(const I* __restrict__ conn, int stride, EntTable 
 constexpr int BUCKET_STAGE = 64;
 constexpr int MATCH_WARPS = 8;
 
+// Fast path of bucket_match: one entry per lane, bitonic sort of the warp by tuple (15 compare-exchange steps over
+// shuffles); equal tuples are then neighbours: a group of one is a surface entity, a group of exactly two a shared pair
+// (lower entity id first), and the heads are already in tuple order.
+template <typename K, bool WIDE>
+__device__ __forceinline__ void bucket_sort_emit(K key, int k3, int en, int lane, int cnt, int s0, long long b, const EntTable& tab, long long M,
+                                                 int* __restrict__ npairs, uint2* __restrict__ pairbuf, int* __restrict__ surf_list,
+                                                 int* __restrict__ surf_count) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const K ok = __shfl_xor_sync(0xffffffffu, key, j);
+      const int oe = __shfl_xor_sync(0xffffffffu, en, j);
+      const bool want_min = ((lane & k) == 0) == ((lane & j) == 0);
+      if (!WIDE) {  // one min/max with the direction as its predicate; equal keys keep their own entity on both sides
+        const K nk = want_min ? min(key, ok) : max(key, ok);
+        en = nk != key ? oe : en;
+        key = nk;
+      } else {
+        const int ok3 = __shfl_xor_sync(0xffffffffu, k3, j);
+        const bool o_less = ok < key || (ok == key && ok3 < k3);
+        const bool o_more = key < ok || (ok == key && k3 < ok3);
+        if (want_min ? o_less : o_more) key = ok, k3 = ok3, en = oe;
+      }
+    }
+  }
+  const K kp1 = __shfl_up_sync(0xffffffffu, key, 1), kn1 = __shfl_down_sync(0xffffffffu, key, 1), kn2 = __shfl_down_sync(0xffffffffu, key, 2);
+  const int tp1 = WIDE ? __shfl_up_sync(0xffffffffu, k3, 1) : 0, tn1 = WIDE ? __shfl_down_sync(0xffffffffu, k3, 1) : 0,
+            tn2 = WIDE ? __shfl_down_sync(0xffffffffu, k3, 2) : 0;
+  const int en1 = __shfl_down_sync(0xffffffffu, en, 1);
+  const bool on = lane < cnt;
+  const bool eq_prev = lane > 0 && kp1 == key && (!WIDE || tp1 == k3);
+  const bool eq_n1 = lane + 1 < cnt && kn1 == key && (!WIDE || tn1 == k3);
+  const bool eq_n2 = lane + 2 < cnt && kn2 == key && (!WIDE || tn2 == k3);
+  const bool once = on && !eq_prev && !eq_n1, head = on && !eq_prev && eq_n1 && !eq_n2;
+  const unsigned bal = __ballot_sync(0xffffffffu, head);
+  if (head) pairbuf[s0 + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)min(en, en1), (unsigned)max(en, en1));
+  if (once) {
+    const int e = en / tab.nf, f = en - e * tab.nf;
+    surf_list[atomicAdd(surf_count, 1)] = (int)((long long)tab.surf_slot[f] * M + e);
+  }
+  if (lane == 0) npairs[b] = __popc(bal);
+}
+
 template <bool WIDE>
 __global__ void __launch_bounds__(MATCH_WARPS * 32) bucket_match(const int* __restrict__ bptr, long long nb, const unsigned long long* __restrict__ gkey,
                                                                   const int* __restrict__ gkey3, const int* __restrict__ gent, EntTable tab, long long M,
                                                                   int* __restrict__ npairs, uint2* __restrict__ pairbuf, unsigned char* __restrict__ gflag,
-                                                                  int* __restrict__ surf_list, int* __restrict__ surf_count) {
+                                                                  int* __restrict__ surf_list, int* __restrict__ surf_count, bool key32) {
   __shared__ unsigned long long skey[MATCH_WARPS][BUCKET_STAGE];
   __shared__ int skey3[WIDE ? MATCH_WARPS : 1][BUCKET_STAGE];
   __shared__ int sent[MATCH_WARPS][BUCKET_STAGE];
@@ -327,42 +477,18 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) bucket_match(const int* __re
     }
     if (cnt == 0) continue;
     if (cnt <= 32) {
-      // Fast path (a tet mesh has ~24 faces per bucket): one entry per lane, bitonic sort of the warp by tuple (15
-      // compare-exchange steps over shuffles), then equal tuples are neighbours: a group of one is a surface entity, a group
-      // of exactly two a shared pair (lower entity id first), and the heads are already in tuple order.
-      unsigned long long key = lane < cnt ? ckey : ~0ull;
-      int k3 = WIDE ? (lane < cnt ? ck3 : 0x7fffffff) : 0;
-      int en = lane < cnt ? cen : 0;
-#pragma unroll
-      for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
-          const int ok3 = WIDE ? __shfl_xor_sync(0xffffffffu, k3, j) : 0;
-          const int oe = __shfl_xor_sync(0xffffffffu, en, j);
-          const bool o_less = ok < key || (WIDE && ok == key && ok3 < k3);
-          const bool o_more = key < ok || (WIDE && ok == key && k3 < ok3);
-          const bool want_min = ((lane & k) == 0) == ((lane & j) == 0);
-          if (want_min ? o_less : o_more) key = ok, k3 = ok3, en = oe;
-        }
+      // Fast path (a tet mesh has ~24 faces per bucket): bucket_sort_emit, one entry per lane.
+      // 3-node tuples whose two remaining nodes lie within 65534 ids of the bucket's node (every bucket of a mesh numbered
+      // with any locality) sort on ONE 32-bit word -- two shuffles per compare-exchange step instead of three.
+      bool narrow = false;
+      if (!WIDE && key32) {
+        const unsigned d2 = lane < cnt ? (unsigned)ckey - (unsigned)b : 0u, d1 = lane < cnt ? (unsigned)(ckey >> 32) - (unsigned)b : 0u;
+        narrow = __reduce_max_sync(0xffffffffu, max(d1, d2)) < 65535u;
+        if (narrow) bucket_sort_emit<unsigned, false>(lane < cnt ? (d1 << 16 | d2) : ~0u, 0, lane < cnt ? cen : 0, lane, cnt, s0, b, tab, M, npairs, pairbuf, surf_list, surf_count);
       }
-      const unsigned long long kp1 = __shfl_up_sync(0xffffffffu, key, 1), kn1 = __shfl_down_sync(0xffffffffu, key, 1),
-                               kn2 = __shfl_down_sync(0xffffffffu, key, 2);
-      const int tp1 = WIDE ? __shfl_up_sync(0xffffffffu, k3, 1) : 0, tn1 = WIDE ? __shfl_down_sync(0xffffffffu, k3, 1) : 0,
-                tn2 = WIDE ? __shfl_down_sync(0xffffffffu, k3, 2) : 0;
-      const int en1 = __shfl_down_sync(0xffffffffu, en, 1);
-      const bool on = lane < cnt;
-      const bool eq_prev = lane > 0 && kp1 == key && (!WIDE || tp1 == k3);
-      const bool eq_n1 = lane + 1 < cnt && kn1 == key && (!WIDE || tn1 == k3);
-      const bool eq_n2 = lane + 2 < cnt && kn2 == key && (!WIDE || tn2 == k3);
-      const bool once = on && !eq_prev && !eq_n1, head = on && !eq_prev && eq_n1 && !eq_n2;
-      const unsigned bal = __ballot_sync(0xffffffffu, head);
-      if (head) pairbuf[s0 + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)min(en, en1), (unsigned)max(en, en1));
-      if (once) {
-        const int e = en / tab.nf, f = en - e * tab.nf;
-        surf_list[atomicAdd(surf_count, 1)] = (int)((long long)tab.surf_slot[f] * M + e);
-      }
-      if (lane == 0) npairs[b] = __popc(bal);
+      if (!narrow)
+        bucket_sort_emit<unsigned long long, WIDE>(lane < cnt ? ckey : ~0ull, WIDE ? (lane < cnt ? ck3 : 0x7fffffff) : 0, lane < cnt ? cen : 0, lane, cnt, s0, b,
+                                                   tab, M, npairs, pairbuf, surf_list, surf_count);
       continue;
     }
     const bool staged = cnt <= BUCKET_STAGE;
@@ -467,11 +593,32 @@ __global__ void write_surface_list(const I* __restrict__ conn, int stride, EntTa
   }
 }
 
-__global__ void write_shared_list(EntTable tab, const uint2* __restrict__ pair_ents, long long S, long long* __restrict__ pairs) {
+// one 32-byte store per pair: a warp writes 1 KB of complete sectors (four 8-byte stores per lane would touch every line 4x)
+template <int NF>
+__global__ void write_shared_list(int nf_rt, const uint2* __restrict__ pair_ents, long long S, long long* __restrict__ pairs) {
+  const unsigned nf = NF ? NF : nf_rt;
   for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < S; o += (long long)gridDim.x * blockDim.x) {
-    const uint2 q = pair_ents[o];
-    long long* p = pairs + 4 * o;
-    p[0] = q.x / tab.nf, p[1] = q.x % tab.nf, p[2] = q.y / tab.nf, p[3] = q.y % tab.nf;
+    const uint2 q = __ldg(pair_ents + o);
+    const long long a = q.x / nf, b = q.x % nf, c = q.y / nf, d = q.y % nf;
+    asm volatile("st.global.v4.s64 [%0], {%1,%2,%3,%4};" ::"l"(pairs + 4 * o), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+  }
+}
+
+// The same straight from the per-bucket pair lists (8 lanes per bucket, ~12 pairs per bucket on a tet mesh): no compaction
+// pass, the 32-byte rows of consecutive buckets are consecutive in the output.
+template <int NF>
+__global__ void write_shared_buckets(int nf_rt, const int* __restrict__ bptr, const int* __restrict__ pbase, long long nb,
+                                     const uint2* __restrict__ pairbuf, long long* __restrict__ pairs) {
+  const unsigned nf = NF ? NF : nf_rt;
+  const int sub = threadIdx.x & 7;
+  for (long long b = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3; b < nb; b += ((long long)gridDim.x * blockDim.x) >> 3) {
+    const long long dst = pbase[b], src = bptr[b];
+    const int np = pbase[b + 1] - (int)dst;
+    for (int k = sub; k < np; k += 8) {
+      const uint2 q = __ldg(pairbuf + src + k);
+      const long long a = q.x / nf, bb = q.x % nf, c = q.y / nf, d = q.y % nf;
+      asm volatile("st.global.v4.s64 [%0], {%1,%2,%3,%4};" ::"l"(pairs + 4 * (dst + k)), "l"(a), "l"(bb), "l"(c), "l"(d) : "memory");
+    }
   }
 }
 
@@ -491,17 +638,31 @@ static int entities_build_buckets(femb_entity_plan* p, cudaStream_t s) {
   FEMB_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
   const long long nb = (long long)hmax + 1;
+  // FEMB_TOPO_OPT (A/B switches, default all on): 1 = blocks walk the elements in order (no grid cap: the buckets a block
+  // fills stay in L2 until their last contributor has passed), 2 = tet fast path, 4 = 32-bit in-bucket keys, 8 = the plan
+  // keeps the per-bucket pair lists (no compaction pass)
+  const int opt = getenv("FEMB_TOPO_OPT") ? atoi(getenv("FEMB_TOPO_OPT")) : 15;   // read per call: tools/topo_rate.py sweeps it
+  const bool keep_lists = (opt & 8) != 0;
   int *cnt, *bptr, *cur, *npairs, *pbase, *ent, *surf_list;
   uint2* pairbuf;
   FEMB_CUDA(scr.alloc(&cnt, nb + 1));
-  FEMB_CUDA(scr.alloc(&bptr, nb + 1));
   FEMB_CUDA(scr.alloc(&cur, nb + 1));
   FEMB_CUDA(scr.alloc(&npairs, nb + 1));
-  FEMB_CUDA(scr.alloc(&pbase, nb + 1));
+  if (keep_lists) {  // owned by the plan (released by entities_free, also on the error paths of the caller)
+    FEMB_CUDA(cudaMallocAsync((void**)&p->bptr, sizeof(int) * (size_t)(nb + 1), s));
+    FEMB_CUDA(cudaMallocAsync((void**)&p->pbase, sizeof(int) * (size_t)(nb + 1), s));
+    bptr = p->bptr, pbase = p->pbase, p->nb = nb;
+  } else {
+    FEMB_CUDA(scr.alloc(&bptr, nb + 1));
+    FEMB_CUDA(scr.alloc(&pbase, nb + 1));
+  }
   FEMB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (nb + 1), s));
   FEMB_CUDA(cudaMemsetAsync(cur, 0, sizeof(int) * (nb + 1), s));
   FEMB_CUDA(cudaMemsetAsync(npairs, 0, sizeof(int) * (nb + 1), s));
-  bucket_count<I><<<grid_for(M, 256), 256, 0, s>>>(conn, p->stride, tab, M, cnt);
+  const int egrid = grid_for(M, 256, (opt & 1) ? (1 << 20) : 64);
+  const bool tets = (opt & 2) && tab.nf == 4 && tab.nfn == 3 && p->stride >= 4;
+  if (tets) tet_bucket_count<I><<<egrid, 256, 0, s>>>(conn, p->stride, M, cnt);
+  else bucket_count<I><<<egrid, 256, 0, s>>>(conn, p->stride, tab, M, cnt);
   FEMB_LAUNCH_CHECK();
   size_t tb = 0, tb2 = 0;
   FEMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, bptr, (int)(nb + 1), s));
@@ -521,16 +682,23 @@ static int entities_build_buckets(femb_entity_plan* p, cudaStream_t s) {
   FEMB_CUDA(scr.alloc(&key, T));
   if (wide) FEMB_CUDA(scr.alloc(&key3, T));
   FEMB_CUDA(scr.alloc(&ent, T));
-  FEMB_CUDA(scr.alloc(&pairbuf, T));
+  if (keep_lists) {
+    FEMB_CUDA(cudaMallocAsync((void**)&p->pairbuf, sizeof(uint2) * (size_t)T, s));
+    pairbuf = p->pairbuf;
+  } else {
+    FEMB_CUDA(scr.alloc(&pairbuf, T));
+  }
   FEMB_CUDA(scr.alloc(&gflag, T));
   FEMB_CUDA(scr.alloc(&surf_list, T + 1));
   int* surf_count = surf_list + T;
   FEMB_CUDA(cudaMemsetAsync(surf_count, 0, sizeof(int), s));
-  bucket_scatter<I><<<grid_for(M, 256), 256, 0, s>>>(conn, p->stride, tab, M, bptr, cur, key, key3, ent);
+  if (tets) tet_bucket_scatter<I><<<egrid, 256, 0, s>>>(conn, p->stride, M, bptr, cur, key, ent);
+  else bucket_scatter<I><<<egrid, 256, 0, s>>>(conn, p->stride, tab, M, bptr, cur, key, key3, ent);
   FEMB_LAUNCH_CHECK();
   const int mgrid = grid_for(nb, MATCH_WARPS, 8);
-  if (wide) bucket_match<true><<<mgrid, MATCH_WARPS * 32, 0, s>>>(bptr, nb, key, key3, ent, tab, M, npairs, pairbuf, gflag, surf_list, surf_count);
-  else bucket_match<false><<<mgrid, MATCH_WARPS * 32, 0, s>>>(bptr, nb, key, key3, ent, tab, M, npairs, pairbuf, gflag, surf_list, surf_count);
+  const bool key32 = (opt & 4) && tab.nfn == 3;
+  if (wide) bucket_match<true><<<mgrid, MATCH_WARPS * 32, 0, s>>>(bptr, nb, key, key3, ent, tab, M, npairs, pairbuf, gflag, surf_list, surf_count, false);
+  else bucket_match<false><<<mgrid, MATCH_WARPS * 32, 0, s>>>(bptr, nb, key, key3, ent, tab, M, npairs, pairbuf, gflag, surf_list, surf_count, key32);
   FEMB_LAUNCH_CHECK();
   FEMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, npairs, pbase, (int)(nb + 1), s));
   int hs = 0, hk = 0;
@@ -538,7 +706,7 @@ static int entities_build_buckets(femb_entity_plan* p, cudaStream_t s) {
   FEMB_CUDA(cudaMemcpyAsync(&hk, surf_count, sizeof(int), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
   p->S = hs, p->K = hk;
-  if (hs > 0) {
+  if (hs > 0 && !keep_lists) {
     FEMB_CUDA(cudaMallocAsync((void**)&p->pair_ents, sizeof(uint2) * (size_t)hs, s));
     bucket_compact_pairs<<<grid_for(nb * 8, 256), 256, 0, s>>>(bptr, npairs, pbase, nb, pairbuf, p->pair_ents);
     FEMB_LAUNCH_CHECK();
@@ -620,6 +788,9 @@ static void entities_free(femb_entity_plan* p) {
   cudaFree(p->pscan);
   cudaFree(p->surf_pos);
   cudaFree(p->pair_ents);
+  cudaFree(p->pairbuf);
+  cudaFree(p->bptr);
+  cudaFree(p->pbase);
   delete p;
 }
 
@@ -685,7 +856,17 @@ extern "C" int femb_entities_shared(femb_entity_plan* p, int64_t* pairs, femb_st
   FEMB_CHECK_ARG(p != nullptr, "plan");
   if (p->T == 0 || p->S == 0) return FEMB_OK;
   if (p->buckets) {
-    write_shared_list<<<grid_for(p->S, 256), 256, 0, as_stream(stream)>>>(p->tab, p->pair_ents, p->S, (long long*)pairs);
+    FEMB_CHECK_ARG((reinterpret_cast<uintptr_t>(pairs) & 31) == 0, "pairs must be 32-byte aligned");
+    if (p->pairbuf) {
+      const int gb = grid_for(p->nb * 8, 256, 1 << 20);
+      if (p->tab.nf == 4) write_shared_buckets<4><<<gb, 256, 0, as_stream(stream)>>>(4, p->bptr, p->pbase, p->nb, p->pairbuf, (long long*)pairs);
+      else write_shared_buckets<0><<<gb, 256, 0, as_stream(stream)>>>(p->tab.nf, p->bptr, p->pbase, p->nb, p->pairbuf, (long long*)pairs);
+      FEMB_LAUNCH_CHECK();
+      return FEMB_OK;
+    }
+    const int g = grid_for(p->S, 256, 1 << 20);
+    if (p->tab.nf == 4) write_shared_list<4><<<g, 256, 0, as_stream(stream)>>>(4, p->pair_ents, p->S, (long long*)pairs);
+    else write_shared_list<0><<<g, 256, 0, as_stream(stream)>>>(p->tab.nf, p->pair_ents, p->S, (long long*)pairs);
     FEMB_LAUNCH_CHECK();
     return FEMB_OK;
   }

@@ -175,7 +175,8 @@ int femb_entities_create(int ent_kind, const void* conn, int ib, int64_t M, int 
                          femb_entity_plan** plan, int64_t* n_surface, int64_t* n_shared);
 /* faces[K,nfn] int64 in slot-major order with the element's node order, extra[K] = off-entity node */
 int femb_entities_surface(femb_entity_plan* plan, int64_t* faces, int64_t* extra, femb_stream stream);
-/* pairs[S,2,2] int64 = ((elem,local),(elem,local)), rows lexicographic by sorted tuple, lower element id first */
+/* pairs[S,2,2] int64 = ((elem,local),(elem,local)), rows lexicographic by sorted tuple, lower element id first.
+ * `pairs` must be 32-byte aligned (each row leaves as one 32-byte store). */
 int femb_entities_shared(femb_entity_plan* plan, int64_t* pairs, femb_stream stream);
 int femb_entities_destroy(femb_entity_plan* plan);
 

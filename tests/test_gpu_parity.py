@@ -636,6 +636,34 @@ def test_edge_cases_topology_and_assembly(api, O):
     assert float(y[6:9].abs().max()) == 0.0 and float(y[10:].abs().max()) == 0.0
 
 
+def test_tet_topology_warp_aggregated_buckets(api, O):
+    """The tet fast path of the bucket build (csrc/topology.cu: tet_bucket_count / tet_bucket_scatter, 32-bit in-bucket keys):
+    elements that repeat a node (all four faces in one bucket), node ids far apart inside one bucket (falls back to 64-bit
+    keys bucket by bucket), int32 / int64 ids, [M,4] and [M,10] connectivity, lattice and shuffled element order."""
+    el = api[0]
+    from femb200 import meshgen
+    rng = np.random.default_rng(11)
+    _, e = meshgen.kuhn_cube(6)
+    e = e.clone()
+    e[5, 1] = e[5, 0]                        # repeated node
+    e[9, 3] = e[9, 2]
+    k = int(torch.argmin(e[7]))
+    e[7, (k + 1) % 4] = e[7, k]              # the smallest node twice: no face without it
+    e[11] = e[11, 0]                         # a point
+    far = e.clone()
+    far[far >= 200] += 100_000               # buckets below 200 now hold deltas above 65535
+    for conn in (e, far, far[torch.as_tensor(rng.permutation(far.shape[0]))]):
+        for dt in (torch.int64, torch.int32):
+            for wide in (False, True):
+                c = conn.to(dt)
+                if wide:
+                    c = torch.cat([c, torch.zeros(c.shape[0], 6, dtype=dt)], 1)
+                f, x = el.compute_tetrahedral_surface_faces_with_fourth_node(c, device=DEV)
+                of, ox = O.tet_surface_faces(N(conn))
+                same(f, of); same(x, ox)
+                same(el.identify_tetrahedral_shared_faces(c, device=DEV), O.tet_shared_faces(N(conn)))
+
+
 def test_mixed_family_topology(api, O):
     """Hex / wedge surface extraction on shuffled multi-element meshes against the oracle (bit-exact)."""
     el = api[0]
