@@ -329,14 +329,26 @@ def run_gpu(args):
     F_host = torch.full((N, 1), 1.0 / N, dtype=torch.float64).pin_memory()
     u_host = torch.empty((N, 1), dtype=torch.float64).pin_memory()
     A = torch.sparse_csr_tensor(crow, col, vals, size=(N, N))
-    e0, e1 = ev(), ev()
-    torch.cuda.synchronize()
-    e0.record()
-    u2 = sv.stable_conjugate_gradient_solver(A, tets, F_host.to(dev, non_blocking=True), fixed, tol=0.0, max_iter=K, device=dev, verbose=False)
-    u_host.copy_(u2, non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_e2e = e0.elapsed_time(e1)
+
+    def e2e_call():
+        e0, e1 = ev(), ev()
+        torch.cuda.synchronize()
+        e0.record()
+        u2 = sv.stable_conjugate_gradient_solver(A, tets, F_host.to(dev, non_blocking=True), fixed, tol=0.0, max_iter=K, device=dev, verbose=False)
+        u_host.copy_(u2, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), u2
+
+    # the first call of this path is timed too and reported (`first_call_ms`: it pays the solver's one-time setup for this
+    # operator); the e2e value is the median of repeated calls, EVERY one of which copies F in and u out, until >= 50 ms are timed
+    ms_e2e_first, u2 = e2e_call()
+    e2e_ms = []
+    while (sum(e2e_ms) < 50.0 or len(e2e_ms) < 3) and len(e2e_ms) < 25:
+        ms_c, u2 = e2e_call()
+        e2e_ms.append(ms_c)
+    e2e_ms.sort()
+    ms_e2e = e2e_ms[len(e2e_ms) // 2]
     t_soak = time.perf_counter()           # untimed: keep the same loop running until the sampler has >= 0.5 s under load
     while time.perf_counter() - t_soak < 0.5:
         ops.cg_solve(crow, col, vals, F, mask=mask, tol=0.0, max_iter=200, check_every=50)
@@ -381,7 +393,9 @@ def run_gpu(args):
         "clocks": clocks,
         "e2e": {"value": round(K / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(F_host.numel() * 8 / K),
                 "d2h_bytes_per_step": int(u_host.numel() * 8 / K),
-                "note": f"one solver-API call of {K} iterations: F pinned host -> device, CG, u -> pinned host; bytes are per call / K"},
+                "calls": len(e2e_ms), "first_call_ms": round(ms_e2e_first, 3), "ms_per_call": round(ms_e2e, 3),
+                "note": f"one solver-API call of {K} iterations: F pinned host -> device, CG, u -> pinned host; bytes are per call / K; "
+                        "median over `calls` identical calls after one untimed-in-the-median first call"},
         "gpu_launches": (3 if os.environ.get("FEMB_CG_CLASSIC") else 2) * K + 4, "timed_repeats": len(loops),
         "roofline": {"kernel": "spmv_tma_kernel<1,false> (TMA-pipelined CSR SpMV; its fused twin is CG step k1)", "bound": "hbm",
                      "achieved": round(bytes_spmv / (ms_spmv * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",

@@ -96,12 +96,19 @@ __global__ void pack_keys(const I* __restrict__ conn, int stride, EntTable tab, 
   }
 }
 
+// out[0] = largest node id, out[1] = 1 if any id is negative or does not fit int32 (the buckets are indexed by node id)
 template <typename I>
 __global__ void max_node_kernel(const I* __restrict__ conn, long long total, int* __restrict__ out) {
   int m = 0;
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) m = max(m, (int)ldidx(conn + k));
+  bool bad = false;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+    const long long v = ldidx(conn + k);
+    bad |= v < 0 || v > 0x7ffffffell;
+    m = max(m, (int)v);
+  }
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) out[1] = 1;
 }
 
 template <typename I>
@@ -159,12 +166,14 @@ static int entities_build(femb_entity_plan* p, cudaStream_t s) {
   const EntTable tab = p->tab;
   Scratch scr(s);
   int* dmax;
-  FEMB_CUDA(scr.alloc(&dmax, 1));
-  FEMB_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), s));
+  FEMB_CUDA(scr.alloc(&dmax, 2));
+  FEMB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(int), s));
   max_node_kernel<I><<<grid_for(M * p->stride, 256), 256, 0, s>>>(conn, M * p->stride, dmax);
-  int hmax = 0;
-  FEMB_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, s));
+  int hm[2] = {0, 0};
+  FEMB_CUDA(cudaMemcpyAsync(hm, dmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
+  FEMB_CHECK_ARG(hm[1] == 0, "connectivity holds a negative node id (or one beyond int32)");
+  const int hmax = hm[0];
   int bits = 1;
   while ((1ll << bits) <= hmax) ++bits;
   const int per_pass = std::max(1, std::min(tab.nfn, 64 / bits));
@@ -631,13 +640,14 @@ static int entities_build_buckets(femb_entity_plan* p, cudaStream_t s) {
   const EntTable tab = p->tab;
   Scratch scr(s);
   int* dmax;
-  FEMB_CUDA(scr.alloc(&dmax, 2));
-  FEMB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(int), s));
+  FEMB_CUDA(scr.alloc(&dmax, 3));   // [0] largest id, [1] bad-id flag, [2] largest bucket (below)
+  FEMB_CUDA(cudaMemsetAsync(dmax, 0, 3 * sizeof(int), s));
   max_node_kernel<I><<<grid_for(M * p->stride, 256), 256, 0, s>>>(conn, M * p->stride, dmax);
-  int hmax = 0;
-  FEMB_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, s));
+  int hm[2] = {0, 0};
+  FEMB_CUDA(cudaMemcpyAsync(hm, dmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
-  const long long nb = (long long)hmax + 1;
+  FEMB_CHECK_ARG(hm[1] == 0, "connectivity holds a negative node id (or one beyond int32)");
+  const long long nb = (long long)hm[0] + 1;
   // FEMB_TOPO_OPT (A/B switches, default all on): 1 = blocks walk the elements in order (no grid cap: the buckets a block
   // fills stay in L2 until their last contributor has passed), 2 = tet fast path, 4 = 32-bit in-bucket keys, 8 = the plan
   // keeps the per-bucket pair lists (no compaction pass)
@@ -666,13 +676,13 @@ static int entities_build_buckets(femb_entity_plan* p, cudaStream_t s) {
   FEMB_LAUNCH_CHECK();
   size_t tb = 0, tb2 = 0;
   FEMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, bptr, (int)(nb + 1), s));
-  FEMB_CUDA(cub::DeviceReduce::Max(nullptr, tb2, cnt, dmax + 1, (int)nb, s));
+  FEMB_CUDA(cub::DeviceReduce::Max(nullptr, tb2, cnt, dmax + 2, (int)nb, s));
   void* tmp;
   FEMB_CUDA(scr.alloc((char**)&tmp, std::max(tb, tb2)));
   FEMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, bptr, (int)(nb + 1), s));
-  FEMB_CUDA(cub::DeviceReduce::Max(tmp, tb2, cnt, dmax + 1, (int)nb, s));
+  FEMB_CUDA(cub::DeviceReduce::Max(tmp, tb2, cnt, dmax + 2, (int)nb, s));
   int maxb = 0;
-  FEMB_CUDA(cudaMemcpyAsync(&maxb, dmax + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FEMB_CUDA(cudaMemcpyAsync(&maxb, dmax + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
   FEMB_CUDA(cudaStreamSynchronize(s));
   if (maxb > BUCKET_MAX) return TOPO_NOT_APPLICABLE;
   const bool wide = tab.nfn > 3;

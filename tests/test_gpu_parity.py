@@ -953,6 +953,10 @@ def test_plan_rejects_out_of_range_connectivity(api):
     with pytest.raises(IndexError):
         el.CsrPlan(torch.tensor([[0, 1, 2, -1]]), 5, DEV)
     assert el.CsrPlan(t, 8, DEV).nnz_nodes > 0
+    # the topology buckets are indexed by node id: a negative id is refused before anything is counted
+    from femb200._lib import FembError
+    with pytest.raises(FembError, match="negative node id"):
+        el.compute_tetrahedral_surface_faces_with_fourth_node(torch.tensor([[0, 1, 2, -1]]), device=DEV)
 
 
 def test_cg_exact_convergence_test_on_small_systems(api, O):
