@@ -9,11 +9,13 @@ A step = one CG iteration of the reference's projected CG (solver.py:144-229) on
 
 Prints ONE JSON line (rank 0).  `value` = CG iterations/s with everything resident in HBM (device events around the
 graph-captured loop), `e2e` = the same through the public solver API with the load vector in pinned host memory and the
-solution read back to the host inside the timed region.  `roofline` is for the dominant kernel (the CSR SpMV).
+solution read back to the host inside the timed region of every call (median of repeated calls; the first call of the
+process is reported as `first_call_ms`).  `roofline` is for the dominant kernel (the CSR SpMV).
 `assembly` reports the second half of the metric (assembled elems/s, fused coords->CSR values) with its own roofline.
 `config2` (1 GPU only) reports BASELINE config 2 beside it: P2 elasticity element K, assembly, block-CSR SpMV, Jacobi-PCG.
-`--impl reference` times the CPU restatement of the reference (oracle/, the numpy port or its C/OpenMP build) on a
-bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref/solver, installed by __graft_entry__.build(); run by
+baseline/ref_arm.py in a subprocess, torch CPU on all host threads) on a bounded sample of the same workload; the C
+restatement under oracle/ is reported beside it as a labelled second baseline (`cpu_baseline.port`).
 """
 import argparse
 import json

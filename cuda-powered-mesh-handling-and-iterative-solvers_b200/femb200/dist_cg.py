@@ -280,16 +280,28 @@ def bench(args, dev, rank, world, metric, unit):
     # e2e through host buffers: load vector from pinned host memory, owned solution back to the host
     F_host = torch.full((no,), 1.0 / N, dtype=torch.float64).pin_memory()
     u_host = torch.empty(no, dtype=torch.float64).pin_memory()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0.record()
-    u2, info2 = op.solve(F_host.to(dev, non_blocking=True), mask, tol=0.0, max_iter=K, check_every=min(K, 50))
-    u_host.copy_(u2, non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+
+    def e2e_call():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        u2, _ = op.solve(F_host.to(dev, non_blocking=True), mask, tol=0.0, max_iter=K, check_every=min(K, 50))
+        u_host.copy_(u2, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # same protocol as the single-GPU line: the first call reported by itself, then the median of repeated calls (each with its
+    # copies, each the maximum over ranks) until >= 50 ms are timed; the loop count is the same on every rank (all-reduced times)
+    e2e_first = e2e_call()
+    e2e_ms = []
+    while (sum(e2e_ms) < 50.0 or len(e2e_ms) < 3) and len(e2e_ms) < 25:
+        e2e_ms.append(e2e_call())
+    e2e_ms.sort()
+    ms2 = torch.tensor([e2e_ms[len(e2e_ms) // 2]], dtype=torch.float64, device=dev)
     for _ in range(4):                         # untimed: the same loop again so the clock sampler sees >= 0.5 s of this load
         op.solve(F, mask, tol=0.0, max_iter=1500, check_every=100)
     clocks = sampler.stop()
@@ -340,7 +352,9 @@ def bench(args, dev, rank, world, metric, unit):
             "clocks": clocks,
             "e2e": {"value": round(K / (float(ms2.item()) * 1e-3), 2), "unit": unit, "h2d_bytes_per_step": int(N * 8 / K),
                     "d2h_bytes_per_step": int(N * 8 / K),
-                    "note": f"one solve call of {K} iterations per rank: F pinned host -> device, CG, owned u -> pinned host; bytes are whole-job per call / K"},
+                    "calls": len(e2e_ms), "first_call_ms": round(e2e_first, 3), "ms_per_call": round(float(ms2.item()), 3),
+                    "note": f"one solve call of {K} iterations per rank: F pinned host -> device, CG, owned u -> pinned host; bytes are "
+                            "whole-job per call / K; median over `calls` identical calls (max over ranks each) after the first call"},
             "gpu_launches": (3 if os.environ.get("FEMB_DIST_CLASSIC") else 2) * K + 5, "timed_repeats": len(loops),
             "roofline": {"kernel": "whole CG iteration (dist_spmv3 + dist_merged_vec: merged-reduction loop, halo push folded in), aggregate over ranks",
                          "bound": "hbm", "achieved": round(bytes_iter / (ms_loop / K * 1e-3) / 1e9, 1), "peak": hbm * world, "unit": "GB/s",
