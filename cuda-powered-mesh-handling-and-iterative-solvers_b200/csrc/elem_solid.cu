@@ -404,6 +404,157 @@ __global__ void __launch_bounds__(512) solid_K_kernel(const T* __restrict__ coor
   if (BULK && tid == 0) bulk_wait_all();  // shared memory must outlive the last copy
 }
 
+// ------------------------------------------------------------------------------------------------
+// C3D10 stiffness, one WARP per element (no CTA barriers: the phases of different warps overlap on the LSU / fp64 pipes).
+// solid_K_kernel above spends its time in the shared-memory pipe (l1tex 87 %, ~640 wavefronts per element): derivative
+// tables, Jacobians and gradients all travel through shared memory at 2 loads per FMA.  Here
+//   phase A  lane (q, h) = (lane/2, lane%2), q < nq <= 16: the point's derivative table lives in REGISTERS for the whole kernel;
+//            J_q (both halves, redundantly), its inverse, the gradients of nodes 5h..5h+4 -> shared gs[q][a][3], w det -> wd[q]
+//   phase B  lane = tile (t, b), 30 tiles: node pairs (2t, b) and (2t+1, b), b >= 2t; per point three 128-bit loads for the two
+//            a-rows (the same five addresses across the warp), three 64-bit loads for the b-row (ten addresses), 18 FMAs;
+//            K_ab = lam S + mu S^T + mu tr(S) I and its mirror image go to the warp's K tile
+//   store    the tile leaves through the TMA engine while the warp is already in phase A of its next element
+// Connectivity is requested two elements ahead and coordinates one element ahead.
+// ------------------------------------------------------------------------------------------------
+constexpr int C10W_WARPS = 4, C10W_MAXQ = 16;
+constexpr int C10W_PER_WARP = 900 + C10W_MAXQ * 30 + C10W_MAXQ + 32;   // K tile | gs | wd | xs   (T units, even)
+
+template <typename T, typename I, int MINB>
+__global__ void __launch_bounds__(C10W_WARPS * 32, MINB) c3d10_K_warp_kernel(const T* __restrict__ coords, const I* __restrict__ conn, long long M,
+                                                                             SolidTab tab, int nq, T lam, T mu, T* __restrict__ out) {
+  constexpr int NEN = 10, ND = 30;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T* kt = reinterpret_cast<T*>(smem_raw) + (size_t)w * C10W_PER_WARP;
+  T* gs = kt + ND * ND;
+  T* wd = gs + C10W_MAXQ * 30;
+  T* xs = wd + C10W_MAXQ;
+  const long long nwarps = (long long)gridDim.x * C10W_WARPS, warp0 = (long long)blockIdx.x * C10W_WARPS + w;
+  // phase-A role
+  const int q = lane >> 1, h = lane & 1;
+  const bool act = q < nq;
+  T dn[NEN][3], wq = 0;
+#pragma unroll
+  for (int a = 0; a < NEN; ++a)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dn[a][k] = act ? (T)tab.dN[((size_t)q * NEN + a) * 3 + k] : T(0);
+  if (act) wq = (T)tab.w[q];
+  // phase-B role
+  int t = 0, b = 0;
+  if (lane < 10) t = 0, b = lane;
+  else if (lane < 18) t = 1, b = lane - 8;
+  else if (lane < 24) t = 2, b = lane - 14;
+  else if (lane < 28) t = 3, b = lane - 18;
+  else t = 4, b = min(lane, 29) - 20;
+  const bool tile = lane < 30;
+  const int a0 = 2 * t, a1 = a0 + 1;
+  // gather pipeline: lane l < 30 owns component l%3 of node l/3
+  const int ga = lane < 30 ? lane / 3 : 0, gc = lane < 30 ? lane - 3 * (lane / 3) : 0;
+  long long n1 = 0;   // node of the element after the current one
+  T xv = 0;           // coordinate of the current element
+  if (warp0 < M) xv = __ldg(coords + 3 * ldidx(conn + warp0 * NEN + ga) + gc);
+  if (warp0 + nwarps < M) n1 = ldidx(conn + (warp0 + nwarps) * NEN + ga);
+  for (long long e = warp0; e < M; e += nwarps) {
+    xs[lane] = xv;
+    __syncwarp();
+    if (e + nwarps < M) xv = __ldg(coords + 3 * n1 + gc);
+    if (e + 2 * nwarps < M) n1 = ldidx(conn + (e + 2 * nwarps) * NEN + ga);
+    // ---- phase A
+    if (act) {
+      T J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) {
+        const T x0 = xs[3 * a], x1 = xs[3 * a + 1], x2 = xs[3 * a + 2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) J[3 * i] += dn[a][i] * x0, J[3 * i + 1] += dn[a][i] * x1, J[3 * i + 2] += dn[a][i] * x2;
+      }
+      T Ji[9];
+      const T det = inv3(J, Ji);
+      if (h == 0) wd[q] = det * wq;
+      T* g = gs + q * 30 + h * 15;
+#pragma unroll
+      for (int aa = 0; aa < 5; ++aa) {
+        const T d0 = h ? dn[aa + 5][0] : dn[aa][0], d1 = h ? dn[aa + 5][1] : dn[aa][1], d2 = h ? dn[aa + 5][2] : dn[aa][2];
+        g[3 * aa] = Ji[0] * d0 + Ji[1] * d1 + Ji[2] * d2;
+        g[3 * aa + 1] = Ji[3] * d0 + Ji[4] * d1 + Ji[5] * d2;
+        g[3 * aa + 2] = Ji[6] * d0 + Ji[7] * d1 + Ji[8] * d2;
+      }
+    }
+    __syncwarp();
+    // ---- phase B
+    T S0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, S1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < nq; ++p) {
+      const T* g = gs + p * 30;
+      const T wt = wd[p];
+      T ar[6];
+      if (sizeof(T) == 8) {  // rows 2t, 2t+1: 48 bytes at a 16-byte aligned offset
+        const double2* v = reinterpret_cast<const double2*>(g + 6 * t);
+        const double2 v0 = v[0], v1 = v[1], v2 = v[2];
+        ar[0] = (T)v0.x, ar[1] = (T)v0.y, ar[2] = (T)v1.x, ar[3] = (T)v1.y, ar[4] = (T)v2.x, ar[5] = (T)v2.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ar[k] = g[6 * t + k];
+      }
+      const T gb0 = g[3 * b], gb1 = g[3 * b + 1], gb2 = g[3 * b + 2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const T u0 = wt * ar[i], u1 = wt * ar[3 + i];
+        S0[3 * i] += u0 * gb0, S0[3 * i + 1] += u0 * gb1, S0[3 * i + 2] += u0 * gb2;
+        S1[3 * i] += u1 * gb0, S1[3 * i + 1] += u1 * gb1, S1[3 * i + 2] += u1 * gb2;
+      }
+    }
+    T k0[9], k1[9];
+    {
+      const T tr0 = mu * (S0[0] + S0[4] + S0[8]), tr1 = mu * (S1[0] + S1[4] + S1[8]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          k0[3 * i + j] = lam * S0[3 * i + j] + mu * S0[3 * j + i] + (i == j ? tr0 : T(0));
+          k1[3 * i + j] = lam * S1[3 * i + j] + mu * S1[3 * j + i] + (i == j ? tr1 : T(0));
+        }
+      // diagonal blocks: one triangle decides both (w g_i g_j and w g_j g_i round differently)
+      if (b == a0) k0[3] = k0[1], k0[6] = k0[2], k0[7] = k0[5];
+      if (b == a1) k1[3] = k1[1], k1[6] = k1[2], k1[7] = k1[5];
+    }
+    // the previous tile must have been read out of shared memory before it is overwritten
+    if (lane == 0) bulk_wait_read();
+    __syncwarp();
+    if (tile) {
+      const bool up1 = b >= a1, mir0 = b > a0, mir1 = b > a1;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          kt[(3 * a0 + i) * ND + 3 * b + j] = k0[3 * i + j];
+          if (mir0) kt[(3 * b + j) * ND + 3 * a0 + i] = k0[3 * i + j];
+          if (up1) kt[(3 * a1 + i) * ND + 3 * b + j] = k1[3 * i + j];
+          if (mir1) kt[(3 * b + j) * ND + 3 * a1 + i] = k1[3 * i + j];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bulk_s2g(out + (size_t)e * ND * ND, kt, (unsigned)(ND * ND * sizeof(T)));
+    }
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+template <typename T, typename I, int MINB>
+static int launch_c3d10_warp(const T* X, const I* C, long long M, SolidTab tab, int nq, T lam, T mu, T* O, cudaStream_t s) {
+  const size_t smem = sizeof(T) * (size_t)C10W_WARPS * C10W_PER_WARP;
+  auto kern = c3d10_K_warp_kernel<T, I, MINB>;
+  FEMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  FEMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C10W_WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int grid = (int)std::min<long long>((M + C10W_WARPS - 1) / C10W_WARPS, (long long)SMS * per_sm);
+  kern<<<grid, C10W_WARPS * 32, smem, s>>>(X, C, M, tab, nq, lam, mu, O);
+  FEMB_LAUNCH_CHECK();
+  return FEMB_OK;
+}
+
 // what 0: J [M,3,3]; 1: gradients [M,NEN,3]; 2: B [M,6,3*NEN] -- single point, one thread per element
 template <typename T, typename I, int NEN>
 __global__ void solid_point_kernel(const T* __restrict__ coords, const I* __restrict__ conn, long long M, SolidTab tab, int what,
@@ -675,6 +826,13 @@ static int solid_dispatch(int what, const void* coords, const void* conn, long l
   const double c = E / ((1 + nu) * (1 - 2 * nu));
   T lam = (T)(c * nu), mu = (T)(c * (1 - 2 * nu) / 2);
   if (what == 6) lam = (T)E, mu = 0;  // E carries rho
+  // C3D10 stiffness with up to 16 points: the warp-per-element kernel (FEMB_SOLID_WARP=0: the CTA-phased kernel below)
+  static const int warp_env = getenv("FEMB_SOLID_WARP") ? atoi(getenv("FEMB_SOLID_WARP")) : 3;
+  if (NEN == 10 && what == 3 && nq <= C10W_MAXQ && warp_env > 0) {
+    if (warp_env == 4) return launch_c3d10_warp<T, I, 4>(X, C, M, tab, nq, lam, mu, O, s);
+    if (warp_env == 2) return launch_c3d10_warp<T, I, 2>(X, C, M, tab, nq, lam, mu, O, s);
+    return launch_c3d10_warp<T, I, 3>(X, C, M, tab, nq, lam, mu, O, s);
+  }
   // elements per CTA: several small CTAs per SM overlap each other's barrier-separated phases
   static const int epb_env = getenv("FEMB_SOLID_EPB") ? atoi(getenv("FEMB_SOLID_EPB")) : 0;
   const int epb = epb_env ? epb_env : (NEN >= 20 ? 2 : 4);

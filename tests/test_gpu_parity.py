@@ -124,6 +124,34 @@ def test_c3d10(api, O):
     same(ne, g["elems10"]); close(nc, g["coords10"], 1e-15)
 
 
+def test_c3d10_K_warp_kernel_cases(api, O):
+    """The warp-per-element C3D10 stiffness kernel (csrc/elem_solid.cu: c3d10_K_warp_kernel) against the oracle on cases the
+    golden fixture does not hold: curved elements (mid nodes off the edge midpoints -> a different Jacobian at every point),
+    more elements than warps in the grid (the gather pipeline wraps), int32 ids, fp32, 1 / 4 / 16 custom points, and 17 points
+    (beyond the kernel's lane layout: the CTA-phased kernel takes over).  Symmetry must be exact: one triangle is mirrored."""
+    el = api[0]
+    from femb200 import meshgen
+    rng = np.random.default_rng(21)
+    c, t = meshgen.kuhn_cube(3, jitter=0.1)
+    c10, e10 = O.c3d4_to_c3d10(c.numpy(), t.numpy())[:2]
+    c10 = c10 + 0.015 * rng.standard_normal(c10.shape)
+    e10 = e10[rng.permutation(e10.shape[0])]
+    big = np.tile(e10, (40, 1))                                   # 6,480 elements: every warp of the grid loops
+    Kref = O.c3d10_K(c10, e10, E, NU)
+    K = el.compute_c3d10_K_matrix(T(c10), T(big), E, NU, **KW)
+    close(K[: e10.shape[0]], Kref)
+    assert torch.equal(K[: e10.shape[0]], K[-e10.shape[0]:])
+    assert torch.equal(K, K.transpose(1, 2))
+    close(el.compute_c3d10_K_matrix(T(c10), T(e10).to(torch.int32), E, NU, **KW), Kref)
+    k32 = el.compute_c3d10_K_matrix(T(c10), T(e10), E, NU, device=DEV)
+    assert k32.dtype == torch.float32
+    close(k32.double(), Kref, 5e-5)
+    for nq in (1, 4, 16, 17):
+        pts = np.concatenate([0.05 + 0.2 * rng.random((nq, 3)), 0.01 + 0.1 * rng.random((nq, 1))], axis=1)
+        close(el.compute_c3d10_K_matrix(T(c10), T(e10), E, NU, integral_point=T(pts), **KW), O.c3d10_K(c10, e10, E, NU, points=pts))
+    close(el.compute_c3d10_K_matrix(T(c10), T(e10[:1]), E, NU, **KW), Kref[:1])
+
+
 def test_c3d8(api):
     el = api[0]
     g = load_golden("hexes")
