@@ -417,17 +417,21 @@ __global__ void __launch_bounds__(512) solid_K_kernel(const T* __restrict__ coor
 // Connectivity is requested two elements ahead and coordinates one element ahead.
 // ------------------------------------------------------------------------------------------------
 constexpr int C10W_WARPS = 4, C10W_MAXQ = 16;
-constexpr int C10W_PER_WARP = 900 + C10W_MAXQ * 30 + C10W_MAXQ + 32;   // K tile | gs | wd | xs   (T units, even)
+constexpr int C10W_GQ = 36;   // gs row stride per point (30 used): with 36 the 128-bit stores of phase A and loads of phase B are conflict-free
+constexpr int C10W_PER_WARP = 900 + C10W_MAXQ * C10W_GQ + C10W_MAXQ + 32;   // K tile | gs | wd | xs   (T units, a multiple of 4)
 
-template <typename T, typename I, int MINB>
+// NQ > 0: the number of points is a compile-time constant (the reference's 11-point rule): phase B unrolls completely and its
+// loads run ahead of the FMAs of earlier points; NQ = 0: any nq_rt <= 16.
+template <typename T, typename I, int MINB, int NQ>
 __global__ void __launch_bounds__(C10W_WARPS * 32, MINB) c3d10_K_warp_kernel(const T* __restrict__ coords, const I* __restrict__ conn, long long M,
-                                                                             SolidTab tab, int nq, T lam, T mu, T* __restrict__ out) {
+                                                                             SolidTab tab, int nq_rt, T lam, T mu, T* __restrict__ out) {
   constexpr int NEN = 10, ND = 30;
+  const int nq = NQ ? NQ : nq_rt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   T* kt = reinterpret_cast<T*>(smem_raw) + (size_t)w * C10W_PER_WARP;
   T* gs = kt + ND * ND;
-  T* wd = gs + C10W_MAXQ * 30;
+  T* wd = gs + C10W_MAXQ * C10W_GQ;
   T* xs = wd + C10W_MAXQ;
   const long long nwarps = (long long)gridDim.x * C10W_WARPS, warp0 = (long long)blockIdx.x * C10W_WARPS + w;
   // phase-A role
@@ -462,29 +466,62 @@ __global__ void __launch_bounds__(C10W_WARPS * 32, MINB) c3d10_K_warp_kernel(con
     // ---- phase A
     if (act) {
       T J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      T xr[30];
+      if (sizeof(T) == 8) {  // the same address for the whole warp: 15 broadcast 128-bit loads
+        const double2* xv2 = reinterpret_cast<const double2*>(xs);
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+          const double2 v = xv2[k];
+          xr[2 * k] = (T)v.x, xr[2 * k + 1] = (T)v.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 30; ++k) xr[k] = xs[k];
+      }
 #pragma unroll
       for (int a = 0; a < NEN; ++a) {
-        const T x0 = xs[3 * a], x1 = xs[3 * a + 1], x2 = xs[3 * a + 2];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) J[3 * i] += dn[a][i] * x0, J[3 * i + 1] += dn[a][i] * x1, J[3 * i + 2] += dn[a][i] * x2;
+        for (int i = 0; i < 3; ++i)
+          J[3 * i] += dn[a][i] * xr[3 * a], J[3 * i + 1] += dn[a][i] * xr[3 * a + 1], J[3 * i + 2] += dn[a][i] * xr[3 * a + 2];
       }
       T Ji[9];
       const T det = inv3(J, Ji);
       if (h == 0) wd[q] = det * wq;
-      T* g = gs + q * 30 + h * 15;
+      // half 0: nodes 0..5 (18 values), half 1: nodes 6..9 (12 values, the last two slots unused) -- both ranges start 16-byte aligned
+      T gv[18];
 #pragma unroll
-      for (int aa = 0; aa < 5; ++aa) {
-        const T d0 = h ? dn[aa + 5][0] : dn[aa][0], d1 = h ? dn[aa + 5][1] : dn[aa][1], d2 = h ? dn[aa + 5][2] : dn[aa][2];
-        g[3 * aa] = Ji[0] * d0 + Ji[1] * d1 + Ji[2] * d2;
-        g[3 * aa + 1] = Ji[3] * d0 + Ji[4] * d1 + Ji[5] * d2;
-        g[3 * aa + 2] = Ji[6] * d0 + Ji[7] * d1 + Ji[8] * d2;
+      for (int aa = 0; aa < 6; ++aa) {
+        const int ah = aa < 4 ? aa + 6 : aa;   // half 1 has no nodes 4, 5: it repeats half 0's (discarded)
+        const T d0 = h ? dn[ah][0] : dn[aa][0], d1 = h ? dn[ah][1] : dn[aa][1], d2 = h ? dn[ah][2] : dn[aa][2];
+        gv[3 * aa] = Ji[0] * d0 + Ji[1] * d1 + Ji[2] * d2;
+        gv[3 * aa + 1] = Ji[3] * d0 + Ji[4] * d1 + Ji[5] * d2;
+        gv[3 * aa + 2] = Ji[6] * d0 + Ji[7] * d1 + Ji[8] * d2;
+      }
+      T* g = gs + q * C10W_GQ + h * 18;
+      if (sizeof(T) == 8) {
+        double2* g2 = reinterpret_cast<double2*>(g);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g2[k] = make_double2((double)gv[2 * k], (double)gv[2 * k + 1]);
+        if (h == 0) {
+#pragma unroll
+          for (int k = 6; k < 9; ++k) g2[k] = make_double2((double)gv[2 * k], (double)gv[2 * k + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) g[k] = gv[k];
+        if (h == 0) {
+#pragma unroll
+          for (int k = 12; k < 18; ++k) g[k] = gv[k];
+        }
       }
     }
     __syncwarp();
     // ---- phase B
     T S0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, S1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = 0; p < nq; ++p) {
-      const T* g = gs + p * 30;
+#pragma unroll
+    for (int p = 0; p < (NQ ? NQ : C10W_MAXQ); ++p) {
+      if (!NQ && p >= nq) break;
+      const T* g = gs + p * C10W_GQ;
       const T wt = wd[p];
       T ar[6];
       if (sizeof(T) == 8) {  // rows 2t, 2t+1: 48 bytes at a 16-byte aligned offset
@@ -527,10 +564,31 @@ __global__ void __launch_bounds__(C10W_WARPS * 32, MINB) c3d10_K_warp_kernel(con
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           kt[(3 * a0 + i) * ND + 3 * b + j] = k0[3 * i + j];
-          if (mir0) kt[(3 * b + j) * ND + 3 * a0 + i] = k0[3 * i + j];
           if (up1) kt[(3 * a1 + i) * ND + 3 * b + j] = k1[3 * i + j];
-          if (mir1) kt[(3 * b + j) * ND + 3 * a1 + i] = k1[3 * i + j];
         }
+      if (sizeof(T) == 8) {
+        // mirror image: row 3b+j holds (K_{a0,b})^T | (K_{a1,b})^T in columns 6t..6t+5 -- 48 bytes, 16-byte aligned: three 128-bit
+        // stores (as 8-byte stores the lanes of a warp hit only the even banks: 144 of the 409 shared-memory wavefronts per
+        // element were these).  For b == a1 the second half lands on the diagonal block written above, with the same values
+        // (symmetrised); for b == a0 the first half would, and the second half belongs to the lane of tile (t, a1): skipped.
+        if (mir0) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            double2* row = reinterpret_cast<double2*>(kt + (3 * b + j) * ND + 6 * t);
+            row[0] = make_double2((double)k0[j], (double)k0[3 + j]);
+            row[1] = make_double2((double)k0[6 + j], (double)k1[j]);
+            row[2] = make_double2((double)k1[3 + j], (double)k1[6 + j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (mir0) kt[(3 * b + j) * ND + 3 * a0 + i] = k0[3 * i + j];
+            if (mir1) kt[(3 * b + j) * ND + 3 * a1 + i] = k1[3 * i + j];
+          }
+      }
     }
     __syncwarp();
     if (lane == 0) {
@@ -541,10 +599,10 @@ __global__ void __launch_bounds__(C10W_WARPS * 32, MINB) c3d10_K_warp_kernel(con
   if (lane == 0) bulk_wait_all();
 }
 
-template <typename T, typename I, int MINB>
+template <typename T, typename I, int MINB, int NQ>
 static int launch_c3d10_warp(const T* X, const I* C, long long M, SolidTab tab, int nq, T lam, T mu, T* O, cudaStream_t s) {
   const size_t smem = sizeof(T) * (size_t)C10W_WARPS * C10W_PER_WARP;
-  auto kern = c3d10_K_warp_kernel<T, I, MINB>;
+  auto kern = c3d10_K_warp_kernel<T, I, MINB, NQ>;
   FEMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   FEMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C10W_WARPS * 32, smem));
@@ -826,12 +884,12 @@ static int solid_dispatch(int what, const void* coords, const void* conn, long l
   const double c = E / ((1 + nu) * (1 - 2 * nu));
   T lam = (T)(c * nu), mu = (T)(c * (1 - 2 * nu) / 2);
   if (what == 6) lam = (T)E, mu = 0;  // E carries rho
-  // C3D10 stiffness with up to 16 points: the warp-per-element kernel (FEMB_SOLID_WARP=0: the CTA-phased kernel below)
+  // C3D10 stiffness with up to 16 points: the warp-per-element kernel (FEMB_SOLID_WARP=0: the CTA-phased kernel below; 2: two CTAs per SM; 5: point loop not unrolled)
   static const int warp_env = getenv("FEMB_SOLID_WARP") ? atoi(getenv("FEMB_SOLID_WARP")) : 3;
   if (NEN == 10 && what == 3 && nq <= C10W_MAXQ && warp_env > 0) {
-    if (warp_env == 4) return launch_c3d10_warp<T, I, 4>(X, C, M, tab, nq, lam, mu, O, s);
-    if (warp_env == 2) return launch_c3d10_warp<T, I, 2>(X, C, M, tab, nq, lam, mu, O, s);
-    return launch_c3d10_warp<T, I, 3>(X, C, M, tab, nq, lam, mu, O, s);
+    if (warp_env == 2) return launch_c3d10_warp<T, I, 2, 0>(X, C, M, tab, nq, lam, mu, O, s);
+    if (warp_env == 5 || nq != 11) return launch_c3d10_warp<T, I, 3, 0>(X, C, M, tab, nq, lam, mu, O, s);   // 5: A/B of the unrolled form
+    return launch_c3d10_warp<T, I, 3, 11>(X, C, M, tab, nq, lam, mu, O, s);
   }
   // elements per CTA: several small CTAs per SM overlap each other's barrier-separated phases
   static const int epb_env = getenv("FEMB_SOLID_EPB") ? atoi(getenv("FEMB_SOLID_EPB")) : 0;
